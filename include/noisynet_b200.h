@@ -1,0 +1,169 @@
+/*
+ * noisynet_b200 -- C ABI of the B200 (sm_100a) NoisyNet hot path.
+ *
+ * The reference (michaelklachko/NoisyNet) is pure Python on PyTorch and has no FFI of its
+ * own; its "operator API" for this path is the set of Python names the drivers import
+ * (noisynet.py:14, models/resnet.py:9-11, models/mobilenet.py:9, main.py:37).  This header
+ * is the boundary a binding for those names sits on: each entry point cites the reference
+ * code it replaces (file:line in the reference tree).  Plain pointers and sizes only; all
+ * pointers are DEVICE pointers unless stated; all tensors are fp32, contiguous, NCHW
+ * (the reference's layout).
+ *
+ * Every function returns 0 on success, non-zero on error (message via nn_last_error()).
+ * Kernels are enqueued on `stream` (a cudaStream_t passed as void*) of device `device`;
+ * nothing synchronises the host.  All entry points are re-entrant per device.
+ */
+#ifndef NOISYNET_B200_H
+#define NOISYNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NN_ABI_VERSION 3
+
+/* ---- common ---------------------------------------------------------------------- */
+
+/* Philox4x32-10 stream: key = seed, counter = (offset + *offset_dev, group index).
+ * offset_dev (device uint64, may be NULL) lets a captured CUDA graph advance the stream
+ * without re-capturing (see nn_rng_advance).  Replaces the global torch generator the
+ * reference draws from (hardware_model.py:59,81,161,297). */
+typedef struct nn_rng {
+    uint64_t seed;
+    uint64_t offset;
+    const uint64_t* offset_dev;
+} nn_rng;
+
+const char* nn_last_error(void);
+int nn_abi_version(void);
+/* sm_count / compute capability of `device`; fails unless the device is sm_100. */
+int nn_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+/* *offset_dev += inc (one thread); graph-capturable. */
+int nn_rng_advance(uint64_t* offset_dev, uint64_t inc, int device, void* stream);
+
+/* ---- a1/a2: UniformQuantize  (hardware_model.py:133-183, quant.py:12-61) ------------- */
+
+/* y = rne(clamp((x-min)/scale + U(-stochastic,stochastic), 0, 2^bits-1)) * scale + min,
+ * scale = max((max-min)/(2^bits-1), 1e-6)  (:148-170).  u_inject (optional, device, n floats
+ * already in [-stochastic, stochastic)) replaces the Philox draw -- parity/test hook.
+ * In place allowed (y == x) -- the reference's `inplace=True` (:141-144). */
+int nn_quantize_fwd(const float* x, float* y, int64_t n, int bits, double min_value,
+                    double max_value, float stochastic, const float* u_inject, nn_rng rng,
+                    int device, void* stream);
+/* Saturated STE (:176-183): gx = gy * 1[min <= x <= max].  Does NOT modify gy. */
+int nn_quantize_bwd(const float* x, const float* gy, float* gx, int64_t n, double min_value,
+                    double max_value, int device, void* stream);
+
+/* ---- a4: AddNoise  (hardware_model.py:291-307) ------------------------------------- */
+/* out = w + w * U(-noise, noise). */
+int nn_weight_noise_fwd(const float* w, float* out, int64_t n, float noise,
+                        const float* u_inject, nn_rng rng, int device, void* stream);
+
+/* ---- reductions used by the noise model (hardware_model.py:44-47, :88) ------------- */
+/* out3[0] = max(x), out3[1] = max|x|, out3[2] = count(x > 0) (as float).  Overwrites out3. */
+int nn_tensor_stats(const float* x, int64_t n, float* out3, int device, void* stream);
+
+/* ---- a9: weight clamp  (noisynet.py:1527-1542, main.py:953-957) -------------------- */
+/* w = clamp(w, -w_max, w_max) in place (skipped if w_max <= 0); absmax_out (optional device
+ * scalar) receives max|w| after the clamp, which the next forward's merged-DAC noise needs
+ * (hardware_model.py:47). */
+int nn_clamp_absmax(float* w, int64_t n, float w_max, float* absmax_out, int device, void* stream);
+
+/* ---- a7 (unfused form): y_noisy = y + z * sqrt(0.1 * (scale / I) * S) --------------- */
+/* hardware_model.py:59 / :81-83 / :125.  scale_dev: device scalar (max|W| merged DAC,
+ * max(x) external DAC).  z_inject / z_export / optional.  stats2 (optional, device[2]) is
+ * ACCUMULATED: [0] += sum|noise| ; [1] = max(stats[1], max(y))  (for nsr, :87). */
+int nn_noise_epilogue(const float* y, const float* S, float* out, int64_t rows, int64_t cols,
+                      const float* scale_dev, float current, const float* z_inject,
+                      float* z_export, float* stats2, nn_rng rng, int device, void* stream);
+
+/* Alternative output-noise models (hardware_model.py:17-41, :122-125).
+ * kind: 1 uniform_ind, 2 uniform_dep (multiplicative), 3 normal_ind, 4 normal_dep,
+ *       5 distort_act.  absmax_dev: device scalar max|y| (kinds 1 and 3). */
+int nn_alt_noise(const float* y, float* out, int64_t n, int kind, float level,
+                 const float* absmax_dev, const float* rnd_inject, nn_rng rng,
+                 int device, void* stream);
+
+/* ---- a5/a6/a7 fused: noisy conv / linear forward ------------------------------------ */
+
+typedef struct nn_conv_geom {
+    int32_t B, Cin, H, W;        /* input  [B, Cin, H, W]   (linear: H = W = 1)            */
+    int32_t Cout, KH, KW;        /* weight [Cout, Cin, KH, KW]                             */
+    int32_t stride, pad;         /* dilation 1, groups 1                                   */
+} nn_conv_geom;                  /* output [B, Cout, OH, OW], OH = (H + 2 pad - KH)/stride + 1 */
+
+enum { NN_NOISE_NONE = 0, NN_NOISE_MERGED = 1, NN_NOISE_EXTERNAL = 2 };
+enum { NN_PREC_FP32 = 0,      /* CUDA-core fp32 FMA (reference arithmetic, any geometry)  */
+       NN_PREC_TF32 = 1,      /* tcgen05 kind::tf32, fp32 accumulate in TMEM              */
+       NN_PREC_BF16 = 2 };    /* tcgen05 kind::f16 (bf16), fp32 accumulate; exact when the
+                                 operands are integer codes (a_code_scale > 0)             */
+
+typedef struct nn_conv_fwd_args {
+    nn_conv_geom g;
+    const float* x;          /* layer input (after any activation quantizer)               */
+    const float* w_eff;      /* weight of the main contraction (quantized / noised / raw).
+                                NULL (with noise_mode > 0) = noise-only mode: `y` is an INPUT
+                                (the clean output computed earlier) and only the sigma^2
+                                contraction + epilogue run -- the two-call flow of
+                                noisynet.py:398 + :415                                     */
+    const float* w_raw;      /* raw parameter for the sigma^2 contraction (noise_mode > 0) */
+    const float* bias;       /* [Cout] or NULL                                             */
+    float* y;                /* clean output  F.conv2d / F.linear  (hardware_model.py:362, :421) */
+    float* y_noisy;          /* y + sigma * z (hardware_model.py:125); NULL iff noise_mode == 0 */
+    int32_t noise_mode;      /* NN_NOISE_*                                                 */
+    float current;           /* I_max in nA (args.layer_currents[layer_num])               */
+    const float* scale_dev;  /* device scalar: max|w_raw| (merged) or max(x) (external)     */
+    const float* z_inject;   /* optional [B,Cout,OH,OW] N(0,1) draws replacing Philox       */
+    float* z_export;         /* optional: the z actually used                              */
+    float* sigma_export;     /* optional: sigma                                            */
+    nn_rng rng;
+    float* stats;            /* optional device[3], ACCUMULATED: [0] += sum conv(x,|W|),
+                                [1] += sum|noise|, [2] = max(., max(y)) (:55-57, :77-79, :87) */
+    int32_t precision;       /* NN_PREC_*                                                  */
+    /* Integer-code mode (NN_PREC_BF16): x holds k_a * a_scale (k_a integer in [0, 2^bits)),
+     * w_eff holds c_w * w_scale (c_w odd/any integer): the operands fed to the tensor core
+     * are the integers themselves (exact in bf16) and the epilogue multiplies by
+     * a_scale * w_scale.  0 disables. */
+    float a_code_scale, w_code_scale;
+    void* workspace;         /* device scratch for packed operands (nn_conv_workspace_bytes) */
+    int64_t workspace_bytes;
+} nn_conv_fwd_args;
+
+int64_t nn_conv_workspace_bytes(const nn_conv_geom* g, int32_t precision);
+int nn_noisy_conv_fwd(const nn_conv_fwd_args* a, int device, void* stream);
+
+/* ---- a10: backward of a5/a6 with the saturated STE fused --------------------------- */
+/* dgrad: gx = conv_transpose(gy, w_eff) * 1[x_lo <= x_pre <= x_hi]   (mask optional: x_pre
+ * NULL disables; it is the STE of the activation quantizer in front of the layer,
+ * hardware_model.py:176-183). */
+typedef struct nn_conv_dgrad_args {
+    nn_conv_geom g;
+    const float* gy;         /* [B,Cout,OH,OW] */
+    const float* w_eff;
+    float* gx;               /* [B,Cin,H,W] */
+    const float* x_pre; double x_lo, x_hi;
+    int32_t precision;
+    void* workspace; int64_t workspace_bytes;
+} nn_conv_dgrad_args;
+int nn_noisy_conv_dgrad(const nn_conv_dgrad_args* a, int device, void* stream);
+
+/* wgrad: gw = (gy^T * im2col(x)) * 1[w_lo <= w_raw <= w_hi]  (mask optional: the STE of the
+ * weight quantizer, hardware_model.py:343 + :176-183).  Deterministic split-K. */
+typedef struct nn_conv_wgrad_args {
+    nn_conv_geom g;
+    const float* gy;
+    const float* x;          /* the layer input used in the forward */
+    float* gw;               /* [Cout,Cin,KH,KW] */
+    const float* w_raw; double w_lo, w_hi;
+    int32_t precision;
+    void* workspace; int64_t workspace_bytes;
+} nn_conv_wgrad_args;
+int64_t nn_conv_wgrad_workspace_bytes(const nn_conv_geom* g, int32_t precision, int device);
+int nn_noisy_conv_wgrad(const nn_conv_wgrad_args* a, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOISYNET_B200_H */

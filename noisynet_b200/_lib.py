@@ -1,0 +1,115 @@
+"""ctypes binding of libnoisynet_b200.so (the C ABI declared in include/noisynet_b200.h).
+
+There is no CPU or eager fallback: if the shared library is missing, or a tensor is not a
+CUDA tensor, the ops raise.  Build with ``python __graft_entry__.py`` (or ``build()``).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libnoisynet_b200.so")
+ABI_VERSION = 3
+
+NOISE_NONE, NOISE_MERGED, NOISE_EXTERNAL = 0, 1, 2
+PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
+
+c_f32p = C.c_void_p      # device pointers travel as void* (int addresses from tensor.data_ptr())
+
+
+class Rng(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("offset", C.c_uint64), ("offset_dev", C.c_void_p)]
+
+
+class ConvGeom(C.Structure):
+    _fields_ = [("B", C.c_int32), ("Cin", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("Cout", C.c_int32), ("KH", C.c_int32), ("KW", C.c_int32),
+                ("stride", C.c_int32), ("pad", C.c_int32)]
+
+
+class ConvFwdArgs(C.Structure):
+    _fields_ = [("g", ConvGeom),
+                ("x", C.c_void_p), ("w_eff", C.c_void_p), ("w_raw", C.c_void_p), ("bias", C.c_void_p),
+                ("y", C.c_void_p), ("y_noisy", C.c_void_p),
+                ("noise_mode", C.c_int32), ("current", C.c_float),
+                ("scale_dev", C.c_void_p), ("z_inject", C.c_void_p), ("z_export", C.c_void_p),
+                ("sigma_export", C.c_void_p),
+                ("rng", Rng),
+                ("stats", C.c_void_p),
+                ("precision", C.c_int32),
+                ("a_code_scale", C.c_float), ("w_code_scale", C.c_float),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+
+
+class ConvDgradArgs(C.Structure):
+    _fields_ = [("g", ConvGeom),
+                ("gy", C.c_void_p), ("w_eff", C.c_void_p), ("gx", C.c_void_p),
+                ("x_pre", C.c_void_p), ("x_lo", C.c_double), ("x_hi", C.c_double),
+                ("precision", C.c_int32),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+
+
+class ConvWgradArgs(C.Structure):
+    _fields_ = [("g", ConvGeom),
+                ("gy", C.c_void_p), ("x", C.c_void_p), ("gw", C.c_void_p),
+                ("w_raw", C.c_void_p), ("w_lo", C.c_double), ("w_hi", C.c_double),
+                ("precision", C.c_int32),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+
+
+# name -> (restype, argtypes); mirrors include/noisynet_b200.h one to one
+SIGNATURES = {
+    "nn_last_error": (C.c_char_p, []),
+    "nn_abi_version": (C.c_int, []),
+    "nn_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "nn_rng_advance": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
+    "nn_quantize_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_double,
+                                  C.c_float, C.c_void_p, Rng, C.c_int, C.c_void_p]),
+    "nn_quantize_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double,
+                                  C.c_int, C.c_void_p]),
+    "nn_weight_noise_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, Rng,
+                                      C.c_int, C.c_void_p]),
+    "nn_tensor_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
+    "nn_clamp_absmax": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
+    "nn_noise_epilogue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                    C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, Rng, C.c_int, C.c_void_p]),
+    "nn_alt_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p,
+                               C.c_void_p, Rng, C.c_int, C.c_void_p]),
+    "nn_conv_workspace_bytes": (C.c_int64, [C.POINTER(ConvGeom), C.c_int32]),
+    "nn_noisy_conv_fwd": (C.c_int, [C.POINTER(ConvFwdArgs), C.c_int, C.c_void_p]),
+    "nn_noisy_conv_dgrad": (C.c_int, [C.POINTER(ConvDgradArgs), C.c_int, C.c_void_p]),
+    "nn_conv_wgrad_workspace_bytes": (C.c_int64, [C.POINTER(ConvGeom), C.c_int32, C.c_int]),
+    "nn_noisy_conv_wgrad": (C.c_int, [C.POINTER(ConvWgradArgs), C.c_int, C.c_void_p]),
+}
+
+_lib = None
+
+
+class NoisyNetLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library (once).  Raises loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise NoisyNetLibraryError(
+            "noisynet_b200: CUDA extension %s not found; build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'`. There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)         # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    v = lib.nn_abi_version()
+    if v != ABI_VERSION:
+        raise NoisyNetLibraryError("noisynet_b200: ABI mismatch: library %d, binding %d (rebuild)" % (v, ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(rc, who=""):
+    if rc != 0:
+        msg = load().nn_last_error()
+        raise NoisyNetLibraryError("%s failed (%d): %s" % (who, rc, msg.decode() if msg else "?"))

@@ -1,0 +1,130 @@
+// Shared device/host helpers for the noisynet_b200 kernels (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/noisynet_b200.h"
+
+// ---------------------------------------------------------------- error plumbing
+extern thread_local char g_nn_err[512];
+
+static inline int nn_fail(const char* fmt, const char* a = "", long long b = 0) {
+    snprintf(g_nn_err, sizeof(g_nn_err), fmt, a, b);
+    return 1;
+}
+
+#define NN_CUDA_OK(expr)                                                              \
+    do {                                                                              \
+        cudaError_t _e = (expr);                                                      \
+        if (_e != cudaSuccess) {                                                      \
+            snprintf(g_nn_err, sizeof(g_nn_err), "%s:%d %s -> %s", __FILE__, __LINE__, \
+                     #expr, cudaGetErrorString(_e));                                  \
+            return 2;                                                                 \
+        }                                                                             \
+    } while (0)
+
+#define NN_SET_DEVICE(dev) NN_CUDA_OK(cudaSetDevice(dev))
+#define NN_LAUNCH_OK() NN_CUDA_OK(cudaGetLastError())
+
+static inline int nn_num_sms(int device) {
+    static int cached[64] = {0};
+    if (device < 0 || device >= 64) return 148;
+    if (!cached[device]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+        cached[device] = v;
+    }
+    return cached[device];
+}
+
+// ---------------------------------------------------------------- Philox4x32-10
+// key = seed, counter = (offset_lo, offset_hi, group_lo, group_hi).  Spec mirrored by
+// oracle/noisynet_oracle.py::philox4x32_10 (tests compare bit-exactly).
+struct NnRng {
+    uint32_t k0, k1, c0, c1;
+};
+
+__device__ __forceinline__ NnRng nn_rng_load(const nn_rng& r) {
+    uint64_t off = r.offset;
+    if (r.offset_dev) off += *r.offset_dev;
+    NnRng s;
+    s.k0 = (uint32_t)r.seed;
+    s.k1 = (uint32_t)(r.seed >> 32);
+    s.c0 = (uint32_t)off;
+    s.c1 = (uint32_t)(off >> 32);
+    return s;
+}
+
+__device__ __forceinline__ uint4 nn_philox(const NnRng& s, uint64_t group) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    uint32_t c0 = s.c0, c1 = s.c1, c2 = (uint32_t)group, c3 = (uint32_t)(group >> 32);
+    uint32_t k0 = s.k0, k1 = s.k1;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// u in [0,1), 24 bits, exact in fp32
+__device__ __forceinline__ float nn_u01(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }
+
+// U[-s, s): fl(fl(u * 2s) - s), two explicit roundings (no FMA contraction)
+__device__ __forceinline__ float nn_usym(uint32_t r, float s) {
+    return __fadd_rn(__fmul_rn(nn_u01(r), __fmul_rn(2.0f, s)), -s);
+}
+
+// Box-Muller on one pair.  u1 = fl(fl(r*2^-32) + 2^-33) in (0,1]; theta = pi*(2*u2-1).
+__device__ __forceinline__ void nn_box_muller(uint32_t ra, uint32_t rb, float& z0, float& z1) {
+    float u1 = __fadd_rn(__fmul_rn(__uint2float_rn(ra), 2.3283064365386963e-10f), 1.1641532182693481e-10f);
+    float u2 = nn_u01(rb);
+    float rad = sqrtf(-2.0f * logf(u1));
+    float th = __fmul_rn(3.14159274101257324f, __fadd_rn(__fmul_rn(2.0f, u2), -1.0f));
+    float sn, cs;
+    __sincosf(th, &sn, &cs);
+    z0 = rad * cs;
+    z1 = rad * sn;
+}
+
+__device__ __forceinline__ void nn_normal4(const NnRng& s, uint64_t group, float z[4]) {
+    uint4 r = nn_philox(s, group);
+    nn_box_muller(r.x, r.y, z[0], z[1]);
+    nn_box_muller(r.z, r.w, z[2], z[3]);
+}
+
+// ---------------------------------------------------------------- float atomics
+__device__ __forceinline__ void nn_atomic_max_float(float* addr, float v) {
+    // valid for any mix of signs: ordered-int trick
+    if (v >= 0.0f) atomicMax((int*)addr, __float_as_int(v));
+    else atomicMin((unsigned int*)addr, __float_as_uint(v));
+}
+
+__device__ __forceinline__ float nn_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float nn_warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// sigma = sqrt(0.1 * (scale / I) * S) with the reference's rounding order
+// (hardware_model.py:59: torch.sqrt(0.1 * (w_max / I) * sigmas)).
+__device__ __forceinline__ float nn_noise_coef(float scale, float current) {
+    return __fmul_rn(0.1f, __fdiv_rn(scale, current));
+}
+__device__ __forceinline__ float nn_sigma(float coef, float S) { return sqrtf(__fmul_rn(coef, S)); }
+
+static inline void nn_out_hw(const nn_conv_geom& g, int& OH, int& OW) {
+    OH = (g.H + 2 * g.pad - g.KH) / g.stride + 1;
+    OW = (g.W + 2 * g.pad - g.KW) / g.stride + 1;
+}

@@ -1,0 +1,378 @@
+// Elementwise / reduction kernels of the NoisyNet hot path (HBM-bound; float4 vectorised,
+// grid sized in multiples of the SM count, Philox drawn in registers -- no separate RNG kernel).
+#include "nn_common.cuh"
+
+thread_local char g_nn_err[512] = "";
+
+extern "C" const char* nn_last_error(void) { return g_nn_err; }
+extern "C" int nn_abi_version(void) { return NN_ABI_VERSION; }
+
+extern "C" int nn_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
+    int sms = 0, maj = 0, min_ = 0;
+    NN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    NN_CUDA_OK(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, device));
+    NN_CUDA_OK(cudaDeviceGetAttribute(&min_, cudaDevAttrComputeCapabilityMinor, device));
+    if (sm_count) *sm_count = sms;
+    if (cc_major) *cc_major = maj;
+    if (cc_minor) *cc_minor = min_;
+    if (maj != 10) return nn_fail("noisynet_b200 is built for sm_100a only; device has compute capability %s%lld", "", (long long)maj);
+    return 0;
+}
+
+static inline int nn_grid_for(int64_t work_items, int threads, int device, int waves = 8) {
+    int64_t blocks = (work_items + threads - 1) / threads;
+    int64_t cap = (int64_t)nn_num_sms(device) * waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+__global__ void k_rng_advance(uint64_t* p, uint64_t inc) { *p += inc; }
+
+extern "C" int nn_rng_advance(uint64_t* offset_dev, uint64_t inc, int device, void* stream) {
+    NN_SET_DEVICE(device);
+    k_rng_advance<<<1, 1, 0, (cudaStream_t)stream>>>(offset_dev, inc);
+    NN_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ a1 quantize fwd
+// One thread = one Philox group = 4 consecutive elements.
+__device__ __forceinline__ float quant_one(float x, float neg_min, float scale, float qmax, float u,
+                                           float min_v) {
+    float t = __fdiv_rn(__fadd_rn(x, neg_min), scale);   // add_(-min).div_(scale)   (:154)
+    t = __fadd_rn(t, u);                                  // add_(noise)              (:162)
+    t = fminf(fmaxf(t, 0.0f), qmax);                      // clamp_(qmin, qmax)       (:166)
+    t = rintf(t);                                         // round_() half-to-even    (:166)
+    return __fadd_rn(__fmul_rn(t, scale), min_v);         // mul_(scale).add_(min)    (:170)
+}
+
+__global__ void __launch_bounds__(256)
+k_quantize_fwd(const float* __restrict__ x, float* __restrict__ y, int64_t n, float neg_min, float min_v,
+               float scale, float qmax, float stoch, const float* __restrict__ u_inject, nn_rng rng) {
+    const NnRng s = nn_rng_load(rng);
+    const int64_t ngroups = (n + 3) >> 2;
+    const bool vec = ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)u_inject) & 15) == 0);
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < ngroups;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = g << 2;
+        float xv[4], uv[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool full = vec && (i0 + 3 < n);
+        if (full) {
+            float4 t = *reinterpret_cast<const float4*>(x + i0);
+            xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xv[j] = (i0 + j < n) ? x[i0 + j] : 0.f;
+        }
+        if (stoch > 0.f) {
+            if (u_inject) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) uv[j] = (i0 + j < n) ? u_inject[i0 + j] : 0.f;
+            } else {
+                uint4 r = nn_philox(s, (uint64_t)g);
+                uv[0] = nn_usym(r.x, stoch); uv[1] = nn_usym(r.y, stoch);
+                uv[2] = nn_usym(r.z, stoch); uv[3] = nn_usym(r.w, stoch);
+            }
+        }
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = quant_one(xv[j], neg_min, scale, qmax, uv[j], min_v);
+        if (full) {
+            *reinterpret_cast<float4*>(y + i0) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (i0 + j < n) y[i0 + j] = o[j];
+        }
+    }
+}
+
+extern "C" int nn_quantize_fwd(const float* x, float* y, int64_t n, int bits, double min_value,
+                               double max_value, float stochastic, const float* u_inject, nn_rng rng,
+                               int device, void* stream) {
+    if (n <= 0) return 0;
+    if (bits < 1 || bits > 16) return nn_fail("nn_quantize_fwd: bits out of range%s (%lld)", "", bits);
+    NN_SET_DEVICE(device);
+    // hardware_model.py:148-151 -- scale computed in doubles, then used as an fp32 scalar
+    double qmax = (double)((1u << bits) - 1u);
+    double scale = (max_value - min_value) / qmax;
+    if (scale < 1e-6) scale = 1e-6;
+    int threads = 256;
+    int grid = nn_grid_for((n + 3) / 4, threads, device);
+    k_quantize_fwd<<<grid, threads, 0, (cudaStream_t)stream>>>(
+        x, y, n, (float)(-min_value), (float)min_value, (float)scale, (float)qmax, stochastic, u_inject, rng);
+    NN_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ a2 quantize bwd (STE)
+__global__ void __launch_bounds__(256)
+k_quantize_bwd(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
+               int64_t n, float lo, float hi) {
+    const bool vec = ((((uintptr_t)x | (uintptr_t)gy | (uintptr_t)gx) & 15) == 0);
+    const int64_t ngroups = (n + 3) >> 2;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < ngroups;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = g << 2;
+        if (vec && i0 + 3 < n) {
+            float4 xv = *reinterpret_cast<const float4*>(x + i0);
+            float4 gv = *reinterpret_cast<const float4*>(gy + i0);
+            gv.x = (xv.x > hi || xv.x < lo) ? 0.f : gv.x;
+            gv.y = (xv.y > hi || xv.y < lo) ? 0.f : gv.y;
+            gv.z = (xv.z > hi || xv.z < lo) ? 0.f : gv.z;
+            gv.w = (xv.w > hi || xv.w < lo) ? 0.f : gv.w;
+            *reinterpret_cast<float4*>(gx + i0) = gv;
+        } else {
+            for (int j = 0; j < 4 && i0 + j < n; ++j) {
+                float xv = x[i0 + j];
+                gx[i0 + j] = (xv > hi || xv < lo) ? 0.f : gy[i0 + j];
+            }
+        }
+    }
+}
+
+extern "C" int nn_quantize_bwd(const float* x, const float* gy, float* gx, int64_t n, double min_value,
+                               double max_value, int device, void* stream) {
+    if (n <= 0) return 0;
+    NN_SET_DEVICE(device);
+    int threads = 256;
+    int grid = nn_grid_for((n + 3) / 4, threads, device);
+    k_quantize_bwd<<<grid, threads, 0, (cudaStream_t)stream>>>(x, gy, gx, n, (float)min_value, (float)max_value);
+    NN_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ a4 AddNoise
+__global__ void __launch_bounds__(256)
+k_weight_noise(const float* __restrict__ w, float* __restrict__ out, int64_t n, float noise,
+               const float* __restrict__ u_inject, nn_rng rng) {
+    const NnRng s = nn_rng_load(rng);
+    const int64_t ngroups = (n + 3) >> 2;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < ngroups;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = g << 2;
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (!u_inject) r = nn_philox(s, (uint64_t)g);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i0 + j < n) {
+                float wv = w[i0 + j];
+                float u = u_inject ? u_inject[i0 + j] : nn_usym(rr[j], noise);
+                out[i0 + j] = __fadd_rn(wv, __fmul_rn(wv, u));      // output.add_(output * U)  (:297-298)
+            }
+        }
+    }
+}
+
+extern "C" int nn_weight_noise_fwd(const float* w, float* out, int64_t n, float noise,
+                                   const float* u_inject, nn_rng rng, int device, void* stream) {
+    if (n <= 0) return 0;
+    NN_SET_DEVICE(device);
+    int threads = 256;
+    int grid = nn_grid_for((n + 3) / 4, threads, device);
+    k_weight_noise<<<grid, threads, 0, (cudaStream_t)stream>>>(w, out, n, noise, u_inject, rng);
+    NN_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ tensor stats: max, max|.|, count>0
+__global__ void k_stats_init(float* out3) {
+    out3[0] = __int_as_float(0xff800000);   // -inf
+    out3[1] = 0.f;
+    out3[2] = 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+k_tensor_stats(const float* __restrict__ x, int64_t n, float* __restrict__ out3) {
+    float mx = __int_as_float(0xff800000), amx = 0.f;
+    unsigned int cnt = 0;
+    const int64_t nvec = (((uintptr_t)x & 15) == 0) ? (n >> 2) : 0;
+    const float4* xv = reinterpret_cast<const float4*>(x);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = xv[i];
+        mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+        amx = fmaxf(fmaxf(amx, fabsf(v.x)), fmaxf(fabsf(v.y), fmaxf(fabsf(v.z), fabsf(v.w))));
+        cnt += (v.x > 0.f) + (v.y > 0.f) + (v.z > 0.f) + (v.w > 0.f);
+    }
+    for (int64_t i = (nvec << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float v = x[i];
+        mx = fmaxf(mx, v); amx = fmaxf(amx, fabsf(v)); cnt += (v > 0.f);
+    }
+    mx = nn_warp_max(mx); amx = nn_warp_max(amx);
+    float c = nn_warp_sum((float)cnt);
+    __shared__ float smx[8], samx[8], sc[8];
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { smx[w] = mx; samx[w] = amx; sc[w] = c; }
+    __syncthreads();
+    if (w == 0) {
+        mx = (l < 8) ? smx[l] : __int_as_float(0xff800000);
+        amx = (l < 8) ? samx[l] : 0.f;
+        c = (l < 8) ? sc[l] : 0.f;
+        mx = nn_warp_max(mx); amx = nn_warp_max(amx); c = nn_warp_sum(c);
+        if (l == 0) {
+            nn_atomic_max_float(out3 + 0, mx);
+            nn_atomic_max_float(out3 + 1, amx);
+            atomicAdd(out3 + 2, c);
+        }
+    }
+}
+
+extern "C" int nn_tensor_stats(const float* x, int64_t n, float* out3, int device, void* stream) {
+    NN_SET_DEVICE(device);
+    k_stats_init<<<1, 1, 0, (cudaStream_t)stream>>>(out3);
+    if (n > 0) {
+        int grid = nn_grid_for((n + 3) / 4, 256, device, 4);
+        k_tensor_stats<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, out3);
+    }
+    NN_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ a9 clamp + absmax
+__global__ void k_zero1(float* p) { *p = 0.f; }
+
+__global__ void __launch_bounds__(256)
+k_clamp_absmax(float* __restrict__ w, int64_t n, float w_max, float* __restrict__ absmax_out) {
+    float amx = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = w[i];
+        if (w_max > 0.f) {
+            float c = fminf(fmaxf(v, -w_max), w_max);
+            if (c != v) w[i] = c;
+            v = c;
+        }
+        amx = fmaxf(amx, fabsf(v));
+    }
+    if (absmax_out) {
+        amx = nn_warp_max(amx);
+        __shared__ float s[8];
+        int wi = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (l == 0) s[wi] = amx;
+        __syncthreads();
+        if (wi == 0) {
+            amx = (l < 8) ? s[l] : 0.f;
+            amx = nn_warp_max(amx);
+            if (l == 0) nn_atomic_max_float(absmax_out, amx);
+        }
+    }
+}
+
+extern "C" int nn_clamp_absmax(float* w, int64_t n, float w_max, float* absmax_out, int device, void* stream) {
+    NN_SET_DEVICE(device);
+    if (absmax_out) k_zero1<<<1, 1, 0, (cudaStream_t)stream>>>(absmax_out);
+    if (n > 0) {
+        int grid = nn_grid_for(n, 256, device, 2);
+        k_clamp_absmax<<<grid, 256, 0, (cudaStream_t)stream>>>(w, n, w_max, absmax_out);
+    }
+    NN_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ a7 unfused epilogue
+// Philox mapping identical to the fused conv epilogue: element (m, n) -> group m*ceil(N/4) + n/4
+// when (rows, cols) = (M, N) row-major; callers with NCHW tensors pass rows = numel/4.. see below.
+// Here the tensor is treated as flat with groups of 4 consecutive elements: rows*cols elements.
+__global__ void __launch_bounds__(256)
+k_noise_epilogue(const float* __restrict__ y, const float* __restrict__ S, float* __restrict__ out, int64_t n,
+                 const float* __restrict__ scale_dev, float current, const float* __restrict__ z_inject,
+                 float* __restrict__ z_export, float* __restrict__ stats2, nn_rng rng) {
+    const NnRng s = nn_rng_load(rng);
+    const float coef = nn_noise_coef(*scale_dev, current);
+    float sum_abs = 0.f, mx = __int_as_float(0xff800000);
+    const int64_t ngroups = (n + 3) >> 2;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < ngroups;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = g << 2;
+        float z[4];
+        if (z_inject) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) z[j] = (i0 + j < n) ? z_inject[i0 + j] : 0.f;
+        } else {
+            nn_normal4(s, (uint64_t)g, z);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i0 + j < n) {
+                float yv = y[i0 + j];
+                float nz = __fmul_rn(z[j], nn_sigma(coef, S[i0 + j]));
+                out[i0 + j] = __fadd_rn(yv, nz);
+                if (z_export) z_export[i0 + j] = z[j];
+                sum_abs += fabsf(nz);
+                mx = fmaxf(mx, yv);
+            }
+        }
+    }
+    if (stats2) {
+        sum_abs = nn_warp_sum(sum_abs);
+        mx = nn_warp_max(mx);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(stats2 + 0, sum_abs);
+            nn_atomic_max_float(stats2 + 1, mx);
+        }
+    }
+}
+
+extern "C" int nn_noise_epilogue(const float* y, const float* S, float* out, int64_t rows, int64_t cols,
+                                 const float* scale_dev, float current, const float* z_inject,
+                                 float* z_export, float* stats2, nn_rng rng, int device, void* stream) {
+    int64_t n = rows * cols;
+    if (n <= 0) return 0;
+    if (!(current > 0.f)) return nn_fail("nn_noise_epilogue: current must be > 0%s", "");
+    NN_SET_DEVICE(device);
+    int grid = nn_grid_for((n + 3) / 4, 256, device);
+    k_noise_epilogue<<<grid, 256, 0, (cudaStream_t)stream>>>(y, S, out, n, scale_dev, current, z_inject,
+                                                              z_export, stats2, rng);
+    NN_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ alternative noise models
+__global__ void __launch_bounds__(256)
+k_alt_noise(const float* __restrict__ y, float* __restrict__ out, int64_t n, int kind, float level,
+            const float* __restrict__ absmax_dev, const float* __restrict__ rnd_inject, nn_rng rng) {
+    const NnRng s = nn_rng_load(rng);
+    const float amax = absmax_dev ? *absmax_dev : 0.f;
+    const int64_t ngroups = (n + 3) >> 2;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < ngroups;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = g << 2;
+        float r[4];
+        if (rnd_inject) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[j] = (i0 + j < n) ? rnd_inject[i0 + j] : 0.f;
+        } else if (kind == 3 || kind == 4) {
+            nn_normal4(s, (uint64_t)g, r);
+        } else {
+            uint4 q = nn_philox(s, (uint64_t)g);
+            r[0] = nn_u01(q.x); r[1] = nn_u01(q.y); r[2] = nn_u01(q.z); r[3] = nn_u01(q.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i0 + j >= n) continue;
+            float yv = y[i0 + j], o;
+            switch (kind) {
+                case 1: o = yv + (r[j] * 2.f - 1.f) * (level * amax); break;               // :25-27
+                case 2: o = yv * (level + r[j] * (1.f / level - level)); break;            // :29-31, :122-123
+                case 3: o = yv + r[j] * (level * amax); break;                              // :33-36
+                case 4: o = yv + r[j] * (level * yv); break;                                // :38-41
+                default: o = yv + yv * ((r[j] * 2.f - 1.f) * level); break;                 // :17-20
+            }
+            out[i0 + j] = o;
+        }
+    }
+}
+
+extern "C" int nn_alt_noise(const float* y, float* out, int64_t n, int kind, float level,
+                            const float* absmax_dev, const float* rnd_inject, nn_rng rng,
+                            int device, void* stream) {
+    if (n <= 0) return 0;
+    if (kind < 1 || kind > 5) return nn_fail("nn_alt_noise: unknown kind%s %lld", "", kind);
+    if ((kind == 1 || kind == 3) && !absmax_dev) return nn_fail("nn_alt_noise: absmax_dev required%s", "");
+    NN_SET_DEVICE(device);
+    int grid = nn_grid_for((n + 3) / 4, 256, device);
+    k_alt_noise<<<grid, 256, 0, (cudaStream_t)stream>>>(y, out, n, kind, level, absmax_dev, rnd_inject, rng);
+    NN_LAUNCH_OK();
+    return 0;
+}

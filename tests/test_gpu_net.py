@@ -1,0 +1,144 @@
+"""Whole-net GPU parity: NoisyNet on the boundary modules (drop-in two-call flow AND the fused
+single-launch flow) against the CPU oracle's restatement of noisynet.Net, which itself is pinned to
+the reference's own Net by tests/test_oracle_golden.py::test_net_step_*.
+
+All random draws (stochastic rounding u, current-noise z) are generated on the CPU, fed to the oracle
+by name and injected into the CUDA ops in call order, so the comparison is elementwise.
+Tolerance: fp32 CUDA-core path 2e-4 (logits/grads; BatchNorm amplifies summation-order noise).
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import noisynet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    import __graft_entry__ as entry
+    entry.build()
+    return torch.device("cuda:0")
+
+
+def _shapes(a, B):
+    c1 = (B, a.fm1, 28, 28)
+    c2 = (B, a.fm2, 10, 10)
+    return dict(ua1=(B, 3, 32, 32), uw0=(a.fm1, 3, 5, 5), z0=c1, ua2=(B, a.fm1, 14, 14), uw1=(a.fm2, a.fm1, 5, 5),
+                z1=c2, ua3=(B, a.fm2 * 25), uw2=(a.fc, a.fm2 * 25), z2=(B, a.fc), ua4=(B, a.fc), uw3=(10, a.fc),
+                z3=(B, 10))
+
+
+def _make_rnd(a, B, q, seed):
+    g = torch.Generator().manual_seed(seed)
+    rnd = {}
+    for k, shp in _shapes(a, B).items():
+        if k.startswith("z"):
+            rnd[k] = torch.randn(shp, generator=g)
+        elif q:
+            rnd[k] = torch.rand(shp, generator=g) - 0.5
+    return rnd
+
+
+def _run_pair(dev, q, fused, widths, B, precision="fp32", steps=1):
+    from noisynet_b200 import ops
+    from noisynet_b200.net import NoisyNet, default_args, make_optimizer, train_step, with_quant
+    oa = O.default_args(q_a=q, q_w=q, quant_max2=4.0, quant_max4=4.5, **widths)
+    torch.manual_seed(1)
+    om = O.OracleNet(oa).init_like_reference()
+    na = default_args(**widths)
+    if q:
+        with_quant(na, q, q)
+    nm = NoisyNet(na, fused=fused, precision=precision).to(dev)
+    nm.load_state_dict({k: v for k, v in om.state_dict().items()}, strict=False)
+    if q:
+        nm.quantize2.running_max = torch.tensor(4.0, device=dev)
+        nm.quantize4.running_max = torch.tensor(4.5, device=dev)
+    oopt, nopt = O.make_optimizer(om, oa), make_optimizer(nm, na)
+    om.train(), nm.train()
+    out = []
+    for s in range(steps):
+        x, lab = O.synthetic_cifar(B, seed=10 + s)
+        rnd = _make_rnd(oa, B, q, 100 + s)
+        oloss, ologits = O.train_step(om, oopt, x, lab, i=s, rnd=rnd)
+        order_u = [rnd[k] for k in ("ua1", "uw0", "ua2", "uw1", "ua3", "uw2", "ua4", "uw3")] if q else []
+        order_z = [rnd[k] for k in ("z0", "z1", "z2", "z3")]
+        with ops.inject_random([u.to(dev) for u in order_u], [z.to(dev) for z in order_z]) as inj:
+            nloss, nlogits = train_step(nm, nopt, x.to(dev), lab.to(dev), i=s)
+            assert not inj["u"] and not inj["z"], "not all injected draws were consumed"
+        out.append((oloss, ologits, nloss.cpu(), nlogits.cpu()))
+    return om, nm, out
+
+
+def _assert_grads_and_weights(om, nm, gtol=3e-4):
+    """Gradients: elementwise, relative to the tensor's max.  Updated weights: Adam's first update is
+    +-lr*sign(g), so a gradient within rounding of zero may flip a weight by 2*lr -> fraction criterion."""
+    ograds = dict(om.named_parameters())
+    for k, p in nm.named_parameters():
+        og = ograds[k].grad
+        assert og is not None and p.grad is not None, k
+        scale = og.abs().max().item() + 1e-12
+        assert (p.grad.cpu() - og).abs().max().item() <= gtol * scale + 1e-7, (k, (p.grad.cpu() - og).abs().max().item(), scale)
+    osd = om.state_dict()
+    for k, v in nm.state_dict().items():
+        if k in osd and v.dtype == torch.float32:
+            bad = ((v.cpu() - osd[k]).abs() > 2e-4 + 2e-3 * osd[k].abs()).float().mean().item()
+            assert bad <= 2e-3, (k, bad)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("q", [0, 4])
+def test_train_step_parity_narrow(dev, q, fused):
+    widths = dict(fm1=9, fm2=12, fc=24)
+    om, nm, out = _run_pair(dev, q, fused, widths, B=8, steps=1)
+    oloss, ologits, nloss, nlogits = out[0]
+    assert torch.allclose(nlogits, ologits, rtol=2e-4, atol=2e-4), (nlogits - ologits).abs().max()
+    assert abs(nloss.item() - oloss.item()) < 2e-4
+    _assert_grads_and_weights(om, nm)
+    # side statistics collected for i < 20 (power, nsr, sparsity) agree with the oracle's
+    for name in ("power", "nsr", "input_sparsity"):
+        a, b = np.asarray(getattr(nm, name)), np.asarray(getattr(om, name))
+        assert a.shape == b.shape == (4, 1)
+        assert np.allclose(a, b, rtol=2e-3), (name, a, b)
+
+
+@pytest.mark.parametrize("q", [0, 4])
+def test_train_step_parity_full_width(dev, q):
+    """NoisyNet default widths (65/120/390), batch 16, fused flow."""
+    om, nm, out = _run_pair(dev, q, True, {}, B=16, steps=1)
+    oloss, ologits, nloss, nlogits = out[0]
+    assert torch.allclose(nlogits, ologits, rtol=5e-4, atol=5e-4), (nlogits - ologits).abs().max()
+    _assert_grads_and_weights(om, nm, gtol=1e-3)
+
+
+def test_weight_clamp_projection(dev):
+    from noisynet_b200.net import NoisyNet, default_args
+    nm = NoisyNet(default_args(fm1=9, fm2=12, fc=24, w_max1=0.05, w_max2=0.01)).to(dev)
+    nm.clamp_weights_()
+    assert nm.conv1.weight.abs().max().item() <= 0.05 and nm.conv2.weight.abs().max().item() <= 0.01
+    assert nm.w_absmax[0][1].item() == pytest.approx(nm.conv1.weight.abs().max().item())
+
+
+def test_training_reduces_loss(dev):
+    """End-to-end sanity at I = 1 nA, 4-bit, in-kernel Philox: the loss of a small learnable problem falls."""
+    from noisynet_b200.net import NoisyNet, default_args, init_like_reference, make_optimizer, train_step, with_quant
+    torch.manual_seed(0)
+    a = with_quant(default_args(), 4, 4)
+    nm = init_like_reference(NoisyNet(a, fused=True)).to(dev)
+    nm.quantize2.running_max = torch.tensor(5.0, device=dev)
+    nm.quantize4.running_max = torch.tensor(5.0, device=dev)
+    nm.collect_stats = False
+    opt = make_optimizer(nm, a)
+    g = torch.Generator().manual_seed(3)
+    protos = torch.randint(0, 16, (10, 3, 32, 32), generator=g).float() / 15
+    lab = torch.randint(0, 10, (256,), generator=g)
+    x = (protos[lab] * 0.7 + 0.3 * torch.randint(0, 16, (256, 3, 32, 32), generator=g).float() / 15)
+    x = (x * 15).round() / 15
+    x, lab = x.to(dev), lab.to(dev)
+    nm.train()
+    losses = [train_step(nm, opt, x, lab, i=100 + s)[0].item() for s in range(30)]
+    assert losses[-1] < 0.5 * losses[0], losses
+    assert all(np.isfinite(losses))
