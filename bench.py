@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the NoisyNet hot path: CIFAR-10 4-bit NoisyNet (I_max = 1 nA) training images/sec.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+A "step" = one full training step (forward, loss, backward, AdamW, weight clamp -- noisynet.py:1276-1542)
+over one batch of synthetic CIFAR-10-shaped 4-bit data (random-init weights; no dataset on disk).
+Workload = BASELINE.json configs[1]: NoisyNet, --current 1 --act_max 5 --w_max1 0.3, --q_a 4 --q_w 4,
+batch 512 per GPU.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FLOP_FWD = {"conv1": 15.288e6, "conv2": 78.0e6, "fc1": 4.68e6, "fc2": 0.0156e6}   # main + sigma^2, per image
+FLOP_STEP = 188.3e6
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=30)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--batch", type=int, default=512, help="per-GPU batch")
+    p.add_argument("--variant", default="q4", choices=["q4", "fp"], help="q4: --q_a 4 --q_w 4; fp: README flags")
+    p.add_argument("--flow", default="fused", choices=["fused", "dropin"])
+    p.add_argument("--precision", default=os.environ.get("NN_BENCH_PRECISION", "auto"))
+    p.add_argument("--graph", type=int, default=int(os.environ.get("NN_BENCH_GRAPH", "1")))
+    p.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--pool", type=int, default=24, help="distinct resident input batches cycled through")
+    return p.parse_args()
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return d, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index=0, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80, "sync_boost": 0x10,
+                 "applications_clocks_setting": 0x2}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.ok:
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------ reference / CPU arm
+def oracle_arm(batch, variant, steps, warmup, seconds=None):
+    """The reference's CPU implementation of the step (oracle port, torch CPU fp32, all host threads)."""
+    from oracle import noisynet_oracle as O
+    q = 4 if variant == "q4" else 0
+    torch.set_num_threads(os.cpu_count() or 1)
+    a = O.default_args(q_a=q, q_w=q, quant_max2=5.0, quant_max4=5.0)
+    torch.manual_seed(0)
+    m = O.OracleNet(a).init_like_reference()
+    opt = O.make_optimizer(m, a)
+    m.train()
+    x, lab = O.synthetic_cifar(batch, seed=0)
+    for s in range(warmup):
+        O.train_step(m, opt, x, lab, i=100)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        O.train_step(m, opt, x, lab, i=100)
+        n += 1
+        el = time.perf_counter() - t0
+        if (seconds is not None and el >= seconds) or (seconds is None and n >= steps):
+            break
+    return {"img_s": n * batch / el, "steps": n, "seconds": el, "cores": torch.get_num_threads(), "batch": batch}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = oracle_arm(args.batch, args.variant, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "NoisyNet CIFAR-10 4-bit training images/sec", "value": r["img_s"], "unit": "img/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / r["steps"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": r["img_s"], "unit": "img/s", "cores": r["cores"], "kind": "port",
+                         "sample": "%d steps of batch %d (oracle port of the reference step, torch CPU fp32)" % (r["steps"], args.batch)},
+        "e2e": {"value": r["img_s"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "NoisyNet CIFAR-10 (conv5x5x65 - conv5x5x120 - fc390 - fc10), I_max=1nA all layers, act_max=5, w_max1=0.3, "
+                        + ("q_a=4 q_w=4 stochastic rounding" if args.variant == "q4" else "README flags (q_a=q_w=0)"),
+            "per_gpu_batch": args.batch, "global_batch": args.batch * world, "parallelism": "dp%d" % world,
+            "flow": args.flow, "l2_policy": "inputs+activations (>400 MB/step) exceed the 126 MB L2; %d distinct input batches cycled" % args.pool}
+
+
+# ------------------------------------------------------------------------------------ our arm
+def build_model(args, dev, precision):
+    from noisynet_b200.net import NoisyNet, default_args, init_like_reference, make_optimizer, with_quant
+    a = default_args()
+    if args.variant == "q4":
+        with_quant(a, 4, 4)
+    m = init_like_reference(NoisyNet(a, fused=(args.flow == "fused"), precision=precision)).to(dev)
+    if args.variant == "q4":      # ranges as after the 5-batch calibration (noisynet.py:1251-1259): fixed running_max
+        m.quantize2.running_max = torch.tensor(5.0, device=dev)
+        m.quantize4.running_max = torch.tensor(5.0, device=dev)
+    m.collect_stats = False       # steady state: i >= 20 (no host-synced side statistics)
+    m.train()
+    return m, a, make_optimizer(m, a, capturable=bool(args.graph))
+
+
+def pick_precision(args, dev):
+    """auto: the tcgen05 path (bf16 integer codes for q4, tf32 otherwise) if it passes a self-check, else fp32."""
+    if args.precision != "auto":
+        return args.precision
+    from noisynet_b200 import ops
+    want = "bf16" if args.variant == "q4" else "tf32"
+    try:
+        x = torch.rand(8, 65, 14, 14, device=dev)
+        w = torch.randn(120, 65, 5, 5, device=dev) * 0.05
+        y0 = ops.noisy_conv_fwd(x, w, precision="fp32")["y"]
+        y1 = ops.noisy_conv_fwd(x, w, precision=want)["y"]
+        gy = torch.randn_like(y0)
+        ops.conv_dgrad(gy, w, x.shape, precision=want)
+        ops.conv_wgrad(gy, x, w.shape, precision=want)
+        torch.cuda.synchronize()
+        if (y0 - y1).abs().max().item() < 5e-2 * y0.abs().max().item():
+            return want
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write("[bench] tcgen05 path unavailable (%s); using fp32 CUDA-core kernels\n" % e)
+    return "fp32"
+
+
+def run_b200(args):
+    from noisynet_b200 import _lib, dp, ops
+    from noisynet_b200.net import train_step
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    rank, world, local = dp.init_from_env()
+    assert torch.cuda.is_available(), "bench.py (impl b200) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    torch.manual_seed(dp.rank_seed(0, rank))
+    precision = pick_precision(args, dev)
+    model, a, opt = build_model(args, dev, precision)
+    red = dp.FlatGradAllReduce(model, world)
+    red.broadcast_parameters(model)
+    B = args.batch
+    gen = torch.Generator().manual_seed(1234 + rank)
+    pool_x = [(torch.randint(0, 16, (B, 3, 32, 32), generator=gen).float() / 15).pin_memory() for _ in range(args.pool)]
+    pool_y = [torch.randint(0, 10, (B,), generator=gen).pin_memory() for _ in range(args.pool)]
+    dev_x = [t.to(dev) for t in pool_x]
+    dev_y = [t.to(dev) for t in pool_y]
+    sx, sy = torch.empty_like(dev_x[0]), torch.empty_like(dev_y[0])   # static inputs for the captured graph
+    loss_out = torch.zeros((), device=dev)
+
+    def step_body(x, y):
+        out = model(x, 0, 100)
+        loss = F.cross_entropy(out, y)
+        red.zero_()
+        loss.backward()
+        red.all_reduce_mean_()
+        opt.step()
+        model.clamp_weights_()
+        loss_out.copy_(loss.detach())
+
+    # eager warm-up (allocator, cudnn heuristics, lazy state)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for s in range(3):
+            step_body(dev_x[s % args.pool], dev_y[s % args.pool])
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    l0 = lib.nn_launch_count()
+    step_body(dev_x[0], dev_y[0])
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.nn_launch_count() - l0)
+
+    graph = None
+    step_ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+    if args.graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with ops.graph_rng(step_ctr, seed=dp.rank_seed(0, rank)):
+                with torch.cuda.graph(graph):
+                    step_body(sx, sy)
+                    ops.rng_advance(step_ctr, 1)
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write("[bench] CUDA-graph capture failed (%s); running eager\n" % e)
+            graph = None
+
+    def run_step(i):
+        if graph is not None:
+            sx.copy_(dev_x[i % args.pool], non_blocking=True)
+            sy.copy_(dev_y[i % args.pool], non_blocking=True)
+            graph.replay()
+        else:
+            step_body(dev_x[i % args.pool], dev_y[i % args.pool])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- timed region 1: inputs resident in HBM ("value")
+    for i in range(max(args.warmup, 3)):
+        run_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        run_step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    t_ms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = t_ms.item()
+    value = world * B * args.steps / (ms * 1e-3)
+    final_loss = loss_out.item()
+
+    # ---------------- timed region 2: end to end through the public API with HOST buffers ("e2e")
+    def e2e_step(i):
+        x = pool_x[i % args.pool].to(dev, non_blocking=True)
+        y = pool_y[i % args.pool].to(dev, non_blocking=True)
+        if graph is not None:
+            sx.copy_(x, non_blocking=True)
+            sy.copy_(y, non_blocking=True)
+            graph.replay()
+        else:
+            step_body(x, y)
+        return loss_out.item()          # device -> host read of the step's result
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e3.record()
+    barrier()
+    t2 = torch.tensor([e2.elapsed_time(e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * args.steps / (t2.item() * 1e-3)
+
+    # ---------------- roofline of the dominant kernel: fused noisy conv forward of conv2, timed live
+    # with CUDA events on the launch stream, same tensors as the step, inputs cycled (> L2 between reps).
+    peaks, peak_kind = load_peaks()
+    roof = None
+    if rank == 0:
+        from noisynet_b200._lib import NOISE_EXTERNAL
+        xs = [torch.rand(B, 65, 14, 14, device=dev).mul_(15).round_().div_(3.0) for _ in range(8)]   # codes * 5/15
+        w_raw = model.conv2.weight.detach()
+        w_eff = ops.quantize_fwd(w_raw, 4, -1.0, 1.0, 0.0) if args.variant == "q4" else w_raw
+        scale = ops.tensor_stats(xs[0])[0:1]
+        reps = 20
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for i in range(3):
+            ops.noisy_conv_fwd(xs[i % 8], w_eff, w_raw, None, 1, 0, noise_mode=NOISE_EXTERNAL, current=1.0,
+                               scale_dev=scale, precision=precision)
+        torch.cuda.synchronize()
+        for i, (a0, a1) in enumerate(evs):
+            a0.record()
+            ops.noisy_conv_fwd(xs[i % 8], w_eff, w_raw, None, 1, 0, noise_mode=NOISE_EXTERNAL, current=1.0,
+                               scale_dev=scale, precision=precision)
+            a1.record()
+        torch.cuda.synchronize()
+        k_ms = sum(a0.elapsed_time(a1) for a0, a1 in evs) / reps
+        flops = FLOP_FWD["conv2"] * B
+        achieved = flops / (k_ms * 1e-3) / 1e12
+        peak = peaks.get("bf16_tflops", 1590.0)
+        roof = {"kernel": "fused noisy conv forward, conv2 (M=%d, N=2x120, K=1625), precision=%s" % (B * 100, precision),
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_kind": peak_kind + " (burst, kernel timed alone)", "kernel_ms": k_ms,
+                "flop_per_launch": flops, "traffic": None,
+                "step_tensor_frac": (world * B * args.steps / (ms * 1e-3)) * FLOP_STEP / world / (peaks.get("bf16_tflops_sustained", 1400.0) * 1e12)}
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = oracle_arm(128, args.variant, 0, 2, seconds=args.cpu_baseline_seconds)
+        cpu = {"value": r["img_s"], "unit": "img/s", "cores": r["cores"], "kind": "port",
+               "sample": "%d steps of batch 128 in %.1f s (oracle port of the reference training step, torch CPU fp32)" % (r["steps"], r["seconds"])}
+    h2d = B * 3 * 32 * 32 * 4 + B * 8
+    line = {
+        "metric": "NoisyNet CIFAR-10 4-bit training images/sec", "value": value, "unit": "img/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[precision],
+        "data": "synthetic", "config": workload_config(args, world),
+        "e2e": {"value": e2e_val, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+        "cuda_graph": graph is not None, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "final_loss": final_loss,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,8 @@ typedef struct nn_rng {
 
 const char* nn_last_error(void);
 int nn_abi_version(void);
+/* number of kernels this library has launched in this process (host-side counter). */
+uint64_t nn_launch_count(void);
 /* sm_count / compute capability of `device`; fails unless the device is sm_100. */
 int nn_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 /* *offset_dev += inc (one thread); graph-capturable. */

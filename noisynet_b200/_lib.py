@@ -60,6 +60,7 @@ class ConvWgradArgs(C.Structure):
 SIGNATURES = {
     "nn_last_error": (C.c_char_p, []),
     "nn_abi_version": (C.c_int, []),
+    "nn_launch_count": (C.c_uint64, []),
     "nn_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "nn_rng_advance": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
     "nn_quantize_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_double,

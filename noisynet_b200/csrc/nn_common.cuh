@@ -27,7 +27,9 @@ static inline int nn_fail(const char* fmt, const char* a = "", long long b = 0) 
     } while (0)
 
 #define NN_SET_DEVICE(dev) NN_CUDA_OK(cudaSetDevice(dev))
-#define NN_LAUNCH_OK() NN_CUDA_OK(cudaGetLastError())
+extern unsigned long long g_nn_launches;
+#define NN_LAUNCH_OK() do { ++g_nn_launches; NN_CUDA_OK(cudaGetLastError()); } while (0)
+#define NN_LAUNCHED(n) (g_nn_launches += (n))
 
 static inline int nn_num_sms(int device) {
     static int cached[64] = {0};

@@ -3,6 +3,8 @@
 #include "nn_common.cuh"
 
 thread_local char g_nn_err[512] = "";
+unsigned long long g_nn_launches = 0;
+extern "C" uint64_t nn_launch_count(void) { return g_nn_launches; }
 
 extern "C" const char* nn_last_error(void) { return g_nn_err; }
 extern "C" int nn_abi_version(void) { return NN_ABI_VERSION; }
@@ -225,6 +227,7 @@ extern "C" int nn_tensor_stats(const float* x, int64_t n, float* out3, int devic
     if (n > 0) {
         int grid = nn_grid_for((n + 3) / 4, 256, device, 4);
         k_tensor_stats<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, out3);
+        NN_LAUNCHED(1);
     }
     NN_LAUNCH_OK();
     return 0;
@@ -261,7 +264,7 @@ k_clamp_absmax(float* __restrict__ w, int64_t n, float w_max, float* __restrict_
 
 extern "C" int nn_clamp_absmax(float* w, int64_t n, float w_max, float* absmax_out, int device, void* stream) {
     NN_SET_DEVICE(device);
-    if (absmax_out) k_zero1<<<1, 1, 0, (cudaStream_t)stream>>>(absmax_out);
+    if (absmax_out) { k_zero1<<<1, 1, 0, (cudaStream_t)stream>>>(absmax_out); NN_LAUNCHED(1); }
     if (n > 0) {
         int grid = nn_grid_for(n, 256, device, 2);
         k_clamp_absmax<<<grid, 256, 0, (cudaStream_t)stream>>>(w, n, w_max, absmax_out);

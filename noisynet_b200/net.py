@@ -79,7 +79,8 @@ class NoisyNet(nn.Module):
         self.nsr = [[] for _ in range(4)]
         self.input_sparsity = [[] for _ in range(4)]
         self.collect_stats = True      # False: never sync for the i < 20 side statistics (benchmark loops)
-        self.w_absmax = {}             # layer index -> device scalar max|W| maintained by clamp_weights_()
+        self.w_absmax = {}             # layer index -> (param version, device scalar max|W|) from clamp_weights_()
+        self._absmax_buf = None
 
     # --- one noisy layer -------------------------------------------------------------------------
     def _layer(self, x, mod, idx, kind, merged, i):
@@ -168,7 +169,10 @@ class NoisyNet(nn.Module):
         a = self.args
         for idx, (mod, wmax) in enumerate(((self.conv1, a.w_max1), (self.conv2, a.w_max2),
                                            (self.linear1, a.w_max3), (self.linear2, a.w_max4))):
-            amax = ops.clamp_absmax_(mod.weight.data, wmax, want_absmax=True)
+            if self._absmax_buf is None or self._absmax_buf.device != mod.weight.device:
+                self._absmax_buf = torch.zeros(4, dtype=torch.float32, device=mod.weight.device)
+            amax = self._absmax_buf[idx:idx + 1]      # persistent storage: stable address under CUDA-graph replay
+            ops.clamp_absmax_(mod.weight.data, wmax, out=amax)
             self.w_absmax[idx] = (mod.weight._version, amax)
 
 
@@ -185,7 +189,7 @@ def init_like_reference(model):
     return model
 
 
-def make_optimizer(model, args, fused=None):
+def make_optimizer(model, args, fused=None, capturable=False):
     """noisynet.py:1135-1169."""
     a = args
     groups = [
@@ -200,6 +204,8 @@ def make_optimizer(model, args, fused=None):
     kw = {}
     if fused is not None:
         kw["fused"] = fused
+    if capturable:
+        kw["capturable"] = True
     return torch.optim.AdamW(groups, lr=a.LR, amsgrad=a.amsgrad, **kw)
 
 

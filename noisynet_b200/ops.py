@@ -193,13 +193,14 @@ def tensor_stats(x):
     return out
 
 
-def clamp_absmax_(w, w_max, want_absmax=True):
+def clamp_absmax_(w, w_max, want_absmax=True, out=None):
     w = w if isinstance(w, torch.Tensor) else w.data
     if not w.is_contiguous():
         raise ValueError("clamp_absmax_: weight must be contiguous")
     _req(w, "weight")
     dev = _dev(w)
-    out = torch.empty(1, dtype=torch.float32, device=w.device) if want_absmax else None
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device=w.device) if want_absmax else None
     _lib.check(_lib.load().nn_clamp_absmax(_p(w), w.numel(), float(w_max), _p(out), dev, _stream(dev)),
                "nn_clamp_absmax")
     return out
