@@ -134,6 +134,12 @@ typedef struct nn_conv_fwd_args {
 } nn_conv_fwd_args;
 
 int64_t nn_conv_workspace_bytes(const nn_conv_geom* g, int32_t precision);
+/* 1 if (geometry, precision) is served for which = 0 forward / 1 dgrad / 2 wgrad.  NN_PREC_FP32 serves
+ * everything; the tcgen05 precisions serve a subset (callers pick NN_PREC_FP32 for the rest). */
+int nn_conv_supported(const nn_conv_geom* g, int32_t precision, int32_t which);
+/* Test/debug hook: synchronises `device` and returns the tcgen05 pipeline watchdog flag (0 = ok);
+ * reset != 0 clears it. */
+int nn_debug_error_flag(int device, int reset);
 int nn_noisy_conv_fwd(const nn_conv_fwd_args* a, int device, void* stream);
 
 /* ---- a10: backward of a5/a6 with the saturated STE fused --------------------------- */

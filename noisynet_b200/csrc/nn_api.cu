@@ -28,6 +28,13 @@ static int check_geom(const nn_conv_geom& g, const char* who) {
     return 0;
 }
 
+extern "C" int nn_conv_supported(const nn_conv_geom* g, int32_t precision, int32_t which) {
+    if (!g || which < 0 || which > 2) return 0;
+    if (precision == NN_PREC_FP32) return 1;
+    if (precision == NN_PREC_BF16) return nn_umma_supports(g, which) ? 1 : 0;
+    return 0;
+}
+
 extern "C" int64_t nn_conv_workspace_bytes(const nn_conv_geom* g, int32_t precision) {
     if (precision == NN_PREC_FP32) return 0;
     return nn_umma_fwd_workspace(g, precision);

@@ -1,8 +1,622 @@
-// placeholder until the tcgen05 kernels land
+// tcgen05 (5th-gen tensor core) implicit-GEMM kernels for the fused noisy conv / linear (sm_100a).
+//
+//   D[m, n] = sum_k A[m, k] * B[n, k]        m = output pixel (b, oh, ow), k = (tap, c), n = output channel
+//
+// * A (im2col of the activations) is never materialised: the layer input is first packed to
+//   NHWC bf16 with the channel count padded to a multiple of 8 (pack_act: this is where activations are
+//   re-coded to their 4-bit integer codes in registers), and 128 producer threads gather 16-byte
+//   channel chunks with cp.async (zero-fill for padding taps) straight into the 128B-swizzled K-major
+//   shared-memory tile the tensor core reads.
+// * B (weights) is packed once per call into the exact swizzled shared-memory image, one contiguous
+//   block per (n-tile, k-block), so a single cp.async.bulk (TMA engine, mbarrier complete_tx) stages it.
+//   Rows of a tile:  [ main weights n_t | g(|w_raw|) n_t | colsum(|w_raw|) 1 | zero pad ]  -> ONE
+//   tcgen05.mma per 16-wide k step feeds the Y, sigma^2 and power-statistic accumulators from one A tile.
+// * Accumulators live in TMEM (128 lanes x n_mma fp32 columns); the epilogue reads them with
+//   tcgen05.ld, applies scale/bias, draws Philox normals, adds sigma*z and writes NCHW fp32.
+// * Warp roles: warps 0-3 cp.async producers, warp 4 MMA issuer (one elected thread) + TMEM alloc,
+//   warp 5 weight bulk-copy issuer; all 8 warps run the epilogue.  2 CTAs/SM (<= 100 KB smem, 256 TMEM
+//   columns each) so one CTA's epilogue overlaps the other's main loop.
+// * Every mbarrier wait is bounded (clock64 watchdog): a protocol bug sets an error flag instead of
+//   hanging the GPU.
+#include <cuda_bf16.h>
+
 #include "nn_common.cuh"
-int nn_umma_conv_fwd(const nn_conv_fwd_args*, int, cudaStream_t) { return nn_fail("tcgen05 path not built%s", ""); }
-int nn_umma_conv_dgrad(const nn_conv_dgrad_args*, int, cudaStream_t) { return nn_fail("tcgen05 path not built%s", ""); }
-int nn_umma_conv_wgrad(const nn_conv_wgrad_args*, int, cudaStream_t) { return nn_fail("tcgen05 path not built%s", ""); }
-int64_t nn_umma_fwd_workspace(const nn_conv_geom*, int) { return 0; }
+
+namespace {
+
+constexpr int UM_BLOCK_M = 128;
+constexpr int UM_BLOCK_K = 64;                       // bf16 per k-block = 128 bytes = one SWIZZLE_128B row
+constexpr int UM_THREADS = 256;
+constexpr int UM_A_STAGE = UM_BLOCK_M * 128;         // 16 KB
+constexpr int UM_MAX_NT = 120;                       // output channels per n-tile when sigma rows are present
+constexpr long long UM_TIMEOUT = 4000000000LL;       // ~2 s of SM clocks
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > UM_TIMEOUT) return false;
+    }
+    return true;
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1): 8-row groups of
+// 1024 bytes (SBO), swizzle atom = 8 rows x 128 B.  Advancing 16 bf16 along K = +32 bytes = +2 units.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// ------------------------------------------------------------------ kernel parameters
+struct UmmaP {
+    int B, H, W, Cp;               // packed input  [B, H, W, Cp] bf16
+    int KH, KW, stride, pad, OH, OW;
+    int M, Cout, n_t, n_mma, num_kb, stages, tmem_cols;
+    int main_col, sig_col, wsum_col;   // accumulator column offsets inside an n-tile, -1 = absent
+    const __nv_bfloat16* xp;
+    const __nv_bfloat16* wp;       // [n_tiles][num_kb][n_mma * 64] bf16, pre-swizzled smem image
+    float y_scale, s_scale;
+    const float* bias;
+    float* y;                      // written iff main_col >= 0 && y != nullptr
+    const float* y_in;             // noise-only mode (main_col < 0): the clean output
+    float* y_noisy;
+    int noise_mode;
+    float current;
+    const float *scale_dev, *z_inject;
+    float *z_export, *sigma_export, *stats;
+    nn_rng rng;
+    const float* mask_x;           // optional STE mask source, same NCHW shape as the output
+    float mask_lo, mask_hi;
+    int* err_flag;
+};
+
+__global__ void __launch_bounds__(UM_THREADS, 2)
+k_conv_umma(const UmmaP p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int S = p.stages;
+    const uint32_t b_stage = (uint32_t)p.n_mma * 128u;
+    const uint32_t a_base = base;
+    const uint32_t b_base = base + (uint32_t)S * UM_A_STAGE;
+    const uint32_t bar_base = b_base + (uint32_t)S * b_stage;       // 8-byte barriers: full[S], empty[S], tmem_full
+    const uint32_t full_bar = bar_base, empty_bar = bar_base + 8u * S, tfull_bar = bar_base + 16u * S;
+    const uint32_t tmem_slot = tfull_bar + 8;
+    const uint32_t abort_slot = tmem_slot + 4;
+    // generic pointers to the two 4-byte slots
+    uint8_t* gen0 = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gen0 + (tmem_slot - base));
+    volatile uint32_t* abort_g = reinterpret_cast<volatile uint32_t*>(gen0 + (abort_slot - base));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * UM_BLOCK_M;
+    const int tile_n = blockIdx.y;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar + 8 * s, 128 + 1);     // 128 cp.async arrivals (noinc) + 1 expect_tx arrival
+            mbar_init(empty_bar + 8 * s, 1);          // tcgen05.commit
+        }
+        mbar_init(tfull_bar, 1);
+        *abort_g = 0;
+        fence_mbar_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_g;
+
+    // ================================================================ main loop roles
+    if (warp < 4) {
+        // ---------------- A producers: one tile row per thread, 8 x 16-byte chunks per k-block
+        const int row = tid;
+        const int m = m0 + row;
+        const bool row_ok = m < p.M;
+        int b = 0, oh = 0, ow = 0;
+        if (row_ok) { const int ohw = p.OH * p.OW; b = m / ohw; int r = m - b * ohw; oh = r / p.OW; ow = r - oh * p.OW; }
+        const int ih0 = oh * p.stride - p.pad, iw0 = ow * p.stride - p.pad;
+        const __nv_bfloat16* xb = p.xp + (size_t)b * p.H * p.W * p.Cp;
+        const uint32_t row_off = (uint32_t)row * 128u;
+        const uint32_t sw = (uint32_t)(row & 7);
+        int c0 = 0, kh = 0, kw = 0;                   // incremental decode of k = (kh, kw, c0)
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+            const int s = kb % S;
+            if (!mbar_wait(empty_bar + 8 * s, ((kb / S) & 1) ^ 1)) { *abort_g = 1; break; }
+            if (*abort_g) break;
+            const uint32_t dst_row = a_base + (uint32_t)s * UM_A_STAGE + row_off;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int ih = ih0 + kh, iw = iw0 + kw;
+                const bool ok = row_ok && kh < p.KH && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
+                const __nv_bfloat16* src = ok ? xb + ((size_t)ih * p.W + iw) * p.Cp + c0 : p.xp;
+                cp_async_16(dst_row + ((((uint32_t)j) ^ sw) << 4), src, ok ? 16u : 0u);
+                c0 += 8;
+                if (c0 >= p.Cp) { c0 = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
+            }
+            cp_async_mbar_arrive_noinc(full_bar + 8 * s);
+        }
+    } else if (warp == 4) {
+        // ---------------- MMA issuer (single thread)
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) |
+                                   ((uint32_t)(UM_BLOCK_M >> 4) << 24);
+            bool ok = true;
+            for (int kb = 0; kb < p.num_kb && ok; ++kb) {
+                const int s = kb % S;
+                if (!mbar_wait(full_bar + 8 * s, (kb / S) & 1)) { *abort_g = 2; ok = false; break; }
+                fence_proxy_async();            // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+                tc_fence_after();
+                const uint64_t ad = umma_desc_sw128(a_base + (uint32_t)s * UM_A_STAGE);
+                const uint64_t bd = umma_desc_sw128(b_base + (uint32_t)s * b_stage);
+#pragma unroll
+                for (int k = 0; k < UM_BLOCK_K / 16; ++k)
+                    umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                umma_commit(empty_bar + 8 * s);           // frees the smem stage when these MMAs retire
+            }
+            umma_commit(tfull_bar);                        // accumulators complete
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ---------------- B loader: one bulk copy (TMA engine) per k-block
+        if (lane == 0) {
+            const __nv_bfloat16* wt = p.wp + (size_t)tile_n * p.num_kb * p.n_mma * 64;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int s = kb % S;
+                if (!mbar_wait(empty_bar + 8 * s, ((kb / S) & 1) ^ 1)) { *abort_g = 3; break; }
+                if (*abort_g) break;
+                mbar_arrive_expect_tx(full_bar + 8 * s, b_stage);
+                bulk_g2s(b_base + (uint32_t)s * b_stage, wt + (size_t)kb * p.n_mma * 64, b_stage, full_bar + 8 * s);
+            }
+        }
+        __syncwarp();
+    }
+
+    // ================================================================ epilogue (all 8 warps)
+    bool acc_ok = mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    if (!acc_ok || *abort_g) {
+        if (tid == 0 && p.err_flag) atomicExch(p.err_flag, 100 + (int)*abort_g);
+    } else {
+        const int q = warp & 3, half = warp >> 2;
+        const int row = q * 32 + lane;
+        const int m = m0 + row;
+        const bool row_ok = m < p.M;
+        const int ohw = p.OH * p.OW;
+        int b = 0, pix = 0;
+        if (row_ok) { b = m / ohw; pix = m - b * ohw; }
+        const size_t out_row = (size_t)b * p.Cout * ohw + pix;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool noise = p.noise_mode != NN_NOISE_NONE;
+        float coef = 0.f;
+        NnRng rs = {0, 0, 0, 0};
+        if (noise) { coef = nn_noise_coef(*p.scale_dev, p.current); rs = nn_rng_load(p.rng); }
+        const int ngrp = (p.Cout + 3) >> 2;
+        const int n_base = tile_n * p.n_t;
+        float s_plain = 0.f, s_abs = 0.f, s_max = __int_as_float(0xff800000);
+        const int nchunks = (p.n_t + 15) >> 4;
+        for (int ci = half; ci < nchunks; ci += 2) {
+            const int cc = ci * 16;
+            float am[16], as[16];
+            if (p.main_col >= 0) tmem_ld16(t_lane + (uint32_t)(p.main_col + cc), am);
+            if (noise) tmem_ld16(t_lane + (uint32_t)(p.sig_col + cc), as);
+            if (!row_ok) continue;
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+                const int n0 = n_base + cc + g4 * 4;
+                if (n0 >= p.Cout || cc + g4 * 4 >= p.n_t) continue;
+                float z[4] = {0.f, 0.f, 0.f, 0.f};
+                if (noise && !p.z_inject) nn_normal4(rs, (uint64_t)m * ngrp + (uint64_t)(n0 >> 2), z);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int n = n0 + j;
+                    if (n >= p.Cout) continue;
+                    const size_t o = out_row + (size_t)n * ohw;
+                    float yv;
+                    if (p.main_col >= 0) {
+                        yv = am[g4 * 4 + j] * p.y_scale;
+                        if (p.bias) yv = __fadd_rn(yv, __ldg(p.bias + n));
+                        if (p.mask_x) { const float xv = __ldg(p.mask_x + o); if (xv > p.mask_hi || xv < p.mask_lo) yv = 0.f; }
+                        if (p.y) p.y[o] = yv;
+                    } else {
+                        yv = __ldg(p.y_in + o);
+                    }
+                    if (noise) {
+                        const float Sv = as[g4 * 4 + j] * p.s_scale;
+                        const float sg = nn_sigma(coef, Sv);
+                        const float zz = p.z_inject ? __ldg(p.z_inject + o) : z[j];
+                        const float nz = __fmul_rn(zz, sg);
+                        p.y_noisy[o] = __fadd_rn(yv, nz);
+                        if (p.z_export) p.z_export[o] = zz;
+                        if (p.sigma_export) p.sigma_export[o] = sg;
+                        if (p.noise_mode == NN_NOISE_MERGED) s_plain += Sv;
+                        s_abs += fabsf(nz);
+                        s_max = fmaxf(s_max, yv);
+                    }
+                }
+            }
+        }
+        if (noise && p.stats) {
+            if (p.wsum_col >= 0 && half == 0) {      // external DAC: row sum of x (*) |w| from the colsum row
+                float ws[16];
+                tmem_ld16(t_lane + (uint32_t)p.wsum_col, ws);
+                if (row_ok) s_plain += ws[0] * p.s_scale;
+            }
+            s_plain = nn_warp_sum(s_plain); s_abs = nn_warp_sum(s_abs); s_max = nn_warp_max(s_max);
+            if (lane == 0) {
+                atomicAdd(p.stats + 0, s_plain);
+                atomicAdd(p.stats + 1, s_abs);
+                nn_atomic_max_float(p.stats + 2, s_max);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
+// ------------------------------------------------------------------ operand packing
+// NCHW fp32 -> NHWC bf16 with Cp (multiple of 8) channels.  inv_scale > 0: integer-code mode, the value
+// written is rne(x * ... ) -- the activation's quantisation code recovered in registers (exact in bf16).
+__global__ void __launch_bounds__(256)
+k_pack_act(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, int B, int C, int HW, int Cp, float code_scale) {
+    const int chunks = Cp >> 3;
+    const int64_t total = (int64_t)B * HW * chunks;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pixel = i % ((int64_t)B * HW);          // pixel index fastest -> coalesced reads
+        const int chunk = (int)(i / ((int64_t)B * HW));
+        const int b = (int)(pixel / HW), p = (int)(pixel - (int64_t)b * HW);
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = chunk * 8 + j;
+            float f = 0.f;
+            if (c < C) {
+                f = __ldg(x + ((int64_t)b * C + c) * HW + p);
+                if (code_scale > 0.f) f = rintf(__fdiv_rn(f, code_scale));
+            }
+            v[j] = __float2bfloat16_rn(f);
+        }
+        *reinterpret_cast<uint4*>(xp + (pixel * Cp + chunk * 8)) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
+// Weights -> pre-swizzled smem image.  mode 0 (forward): rows [main | sigma | wsum], k = tap*Cp + c reads
+// w[n][c][tap].  mode 1 (dgrad): "output channel" r = input channel c_in, k = tap'*Cp + n with the taps
+// flipped: reads w[n][r][KHW-1-tap'] (Cp = padded Cout).
+struct PackWP {
+    const float *w_eff, *w_raw;
+    __nv_bfloat16* wp;
+    int Cout, Cin, KHW, Cp, n_t, n_mma, num_kb, n_tiles;
+    int main_col, sig_col, wsum_col, noise_mode, mode;
+    float w_code_scale;
+};
+
+__global__ void __launch_bounds__(256)
+k_pack_w(const PackWP p) {
+    const int64_t total = (int64_t)p.n_tiles * p.num_kb * p.n_mma * 8;     // one thread per 16-byte chunk
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i & 7);
+        int64_t t = i >> 3;
+        const int r = (int)(t % p.n_mma); t /= p.n_mma;
+        const int kb = (int)(t % p.num_kb);
+        const int tile = (int)(t / p.num_kb);
+        __align__(16) __nv_bfloat16 v[8];
+        int kind = -1, rr = 0;                       // 0 main, 1 sigma, 2 wsum
+        if (p.main_col >= 0 && r >= p.main_col && r < p.main_col + p.n_t) { kind = 0; rr = r - p.main_col; }
+        else if (p.sig_col >= 0 && r >= p.sig_col && r < p.sig_col + p.n_t) { kind = 1; rr = r - p.sig_col; }
+        else if (p.wsum_col >= 0 && r == p.wsum_col) { kind = 2; }
+        const int nrows = p.mode == 0 ? p.Cout : p.Cin;   // number of real "output" rows
+        const int kdim = p.mode == 0 ? p.Cin : p.Cout;    // real channels inside a tap
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = kb * 64 + j * 8 + e;
+            const int tap = k / p.Cp, c = k - tap * p.Cp;
+            float f = 0.f;
+            if (tap < p.KHW && c < kdim && kind >= 0) {
+                if (kind == 2) {
+                    const int n_lo = tile * p.n_t, n_hi = min(nrows, n_lo + p.n_t);
+                    for (int n = n_lo; n < n_hi; ++n) f += fabsf(__ldg(p.w_raw + ((int64_t)n * p.Cin + c) * p.KHW + tap));
+                } else {
+                    const int n = tile * p.n_t + rr;
+                    if (n < nrows) {
+                        if (p.mode == 0) {
+                            const int64_t idx = ((int64_t)n * p.Cin + c) * p.KHW + tap;
+                            if (kind == 0) {
+                                f = __ldg(p.w_eff + idx);
+                                if (p.w_code_scale > 0.f) f = rintf(__fdiv_rn(f, p.w_code_scale));
+                            } else {
+                                const float a = fabsf(__ldg(p.w_raw + idx));
+                                f = (p.noise_mode == NN_NOISE_MERGED) ? a : __fadd_rn(__fmul_rn(a, a), a);
+                            }
+                        } else {
+                            const int64_t idx = ((int64_t)c * p.Cin + n) * p.KHW + (p.KHW - 1 - tap);
+                            f = __ldg(p.w_eff + idx);
+                            if (p.w_code_scale > 0.f) f = rintf(__fdiv_rn(f, p.w_code_scale));
+                        }
+                    }
+                }
+            }
+            v[e] = __float2bfloat16_rn(f);
+        }
+        const int64_t blk = ((int64_t)tile * p.num_kb + kb) * p.n_mma * 64;          // elements
+        const int64_t off = blk + (int64_t)r * 64 + (((j ^ (r & 7))) << 3);           // 128B swizzle
+        *reinterpret_cast<uint4*>(p.wp + off) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
+__global__ void k_clear_flag(int* f) { *f = 0; }
+
+// ------------------------------------------------------------------ host-side planning
+struct Plan {
+    int Cp, K_total, num_kb, n_tiles, n_t, n_mma, tmem_cols, stages, main_col, sig_col, wsum_col;
+    size_t xp_bytes, wp_bytes, smem_bytes;
+};
+
+static inline int pad_to(int v, int a) { return (v + a - 1) / a * a; }
+
+static Plan make_plan(int Cin_k, int KHW, int n_out, bool has_main, bool has_sigma, bool has_wsum, int64_t pixels_in) {
+    Plan pl;
+    pl.Cp = pad_to(Cin_k, 8);
+    pl.K_total = KHW * pl.Cp;
+    pl.num_kb = (pl.K_total + UM_BLOCK_K - 1) / UM_BLOCK_K;
+    const int max_nt = has_sigma ? (has_main ? UM_MAX_NT : 248) : 256;
+    pl.n_tiles = (n_out + max_nt - 1) / max_nt;
+    pl.n_t = pad_to((n_out + pl.n_tiles - 1) / pl.n_tiles, 8);
+    int col = 0;
+    pl.main_col = pl.sig_col = pl.wsum_col = -1;
+    if (has_main) { pl.main_col = col; col += pl.n_t; }
+    if (has_sigma) { pl.sig_col = col; col += pl.n_t; }
+    if (has_wsum) { pl.wsum_col = col; col += 1; }
+    pl.n_mma = pad_to(col, 16);
+    if (pl.n_mma < 16) pl.n_mma = 16;
+    // the epilogue reads 16-column groups: keep every read inside the allocation
+    int need = pl.n_mma;
+    if (has_main) need = max(need, pl.main_col + pad_to(pl.n_t, 16));
+    if (has_sigma) need = max(need, pl.sig_col + pad_to(pl.n_t, 16));
+    if (has_wsum) need = max(need, pl.wsum_col + 16);
+    pl.tmem_cols = 32;
+    while (pl.tmem_cols < need) pl.tmem_cols <<= 1;
+    const int stage_bytes = UM_A_STAGE + pl.n_mma * 128;
+    pl.stages = (100 * 1024 - 2048) / stage_bytes;
+    if (pl.stages > 4) pl.stages = 4;
+    if (pl.stages < 2) pl.stages = 2;
+    if (pl.stages > pl.num_kb) pl.stages = pl.num_kb < 1 ? 1 : pl.num_kb;
+    pl.smem_bytes = 1024 + (size_t)pl.stages * stage_bytes + 16 * pl.stages + 64;
+    pl.xp_bytes = (size_t)pixels_in * pl.Cp * 2;
+    pl.wp_bytes = (size_t)pl.n_tiles * pl.num_kb * pl.n_mma * 64 * 2;
+    return pl;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    dim3 grid((p.M + UM_BLOCK_M - 1) / UM_BLOCK_M, pl.n_tiles);
+    k_conv_umma<<<grid, UM_THREADS, pl.smem_bytes, st>>>(p);
+    NN_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace
+
+// which: 0 forward, 1 dgrad, 2 wgrad
+bool nn_umma_supports(const nn_conv_geom* g, int which) {
+    if (which == 0) return true;
+    if (which == 1) return g->stride == 1 && g->pad <= g->KH - 1 && g->pad <= g->KW - 1;
+    return false;
+}
+
+int64_t nn_umma_fwd_workspace(const nn_conv_geom* g, int precision) {
+    // sized for the larger of forward (input packed) and dgrad (grad_output packed)
+    int OH, OW;
+    nn_out_hw(*g, OH, OW);
+    Plan f = make_plan(g->Cin, g->KH * g->KW, g->Cout, true, true, true, (int64_t)g->B * g->H * g->W);
+    Plan d = make_plan(g->Cout, g->KH * g->KW, g->Cin, true, false, false, (int64_t)g->B * OH * OW);
+    size_t a = align_up(f.xp_bytes, 1024) + align_up(f.wp_bytes, 1024);
+    size_t b = align_up(d.xp_bytes, 1024) + align_up(d.wp_bytes, 1024);
+    return (int64_t)((a > b ? a : b) + 2048);
+}
+
 int64_t nn_umma_wgrad_workspace(const nn_conv_geom*, int, int) { return 0; }
-bool nn_umma_supports(const nn_conv_geom*, int) { return false; }
+
+int* nn_umma_err_flag(int device) {
+    static int* flags[64] = {nullptr};
+    if (device < 0 || device >= 64) return nullptr;
+    if (!flags[device]) {
+        if (cudaMalloc(&flags[device], sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemset(flags[device], 0, sizeof(int));
+    }
+    return flags[device];
+}
+
+extern "C" int nn_debug_error_flag(int device, int reset) {
+    int* f = nn_umma_err_flag(device);
+    if (!f) return -1;
+    int v = 0;
+    if (cudaSetDevice(device) != cudaSuccess) return -1;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+    if (cudaMemcpy(&v, f, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+    if (reset) cudaMemset(f, 0, sizeof(int));
+    return v;
+}
+
+int nn_umma_conv_fwd(const nn_conv_fwd_args* a, int device, cudaStream_t st) {
+    if (a->precision != NN_PREC_BF16)
+        return nn_fail("nn_noisy_conv_fwd: tcgen05 path implements NN_PREC_BF16 only%s", "");
+    const nn_conv_geom& g = a->g;
+    int OH, OW;
+    nn_out_hw(g, OH, OW);
+    const bool has_main = a->w_eff != nullptr;
+    const bool noise = a->noise_mode != NN_NOISE_NONE;
+    const bool has_wsum = noise && a->noise_mode == NN_NOISE_EXTERNAL && a->stats != nullptr;
+    Plan pl = make_plan(g.Cin, g.KH * g.KW, g.Cout, has_main, noise, has_wsum, (int64_t)g.B * g.H * g.W);
+    const size_t need = align_up(pl.xp_bytes, 1024) + align_up(pl.wp_bytes, 1024) + 1024;
+    if (!a->workspace || (size_t)a->workspace_bytes < need)
+        return nn_fail("nn_noisy_conv_fwd: workspace too small%s (need %lld bytes)", "", (long long)need);
+    uint8_t* ws = (uint8_t*)align_up((size_t)a->workspace, 1024);
+    __nv_bfloat16* xp = (__nv_bfloat16*)ws;
+    __nv_bfloat16* wp = (__nv_bfloat16*)(ws + align_up(pl.xp_bytes, 1024));
+    int* err = nn_umma_err_flag(device);
+
+    {   // activations -> NHWC bf16 (integer codes when a_code_scale > 0)
+        const int64_t total = (int64_t)g.B * g.H * g.W * (pl.Cp / 8);
+        int grid = (int)((total + 255) / 256);
+        if (grid > 16 * nn_num_sms(device)) grid = 16 * nn_num_sms(device);
+        k_pack_act<<<grid, 256, 0, st>>>(a->x, xp, g.B, g.Cin, g.H * g.W, pl.Cp, a->a_code_scale);
+        NN_LAUNCH_OK();
+    }
+    {
+        PackWP pw;
+        pw.w_eff = a->w_eff; pw.w_raw = a->w_raw; pw.wp = wp;
+        pw.Cout = g.Cout; pw.Cin = g.Cin; pw.KHW = g.KH * g.KW; pw.Cp = pl.Cp; pw.n_t = pl.n_t; pw.n_mma = pl.n_mma;
+        pw.num_kb = pl.num_kb; pw.n_tiles = pl.n_tiles; pw.main_col = pl.main_col; pw.sig_col = pl.sig_col;
+        pw.wsum_col = pl.wsum_col; pw.noise_mode = a->noise_mode; pw.mode = 0; pw.w_code_scale = a->w_code_scale;
+        const int64_t total = (int64_t)pl.n_tiles * pl.num_kb * pl.n_mma * 8;
+        int grid = (int)((total + 255) / 256);
+        if (grid > 8 * nn_num_sms(device)) grid = 8 * nn_num_sms(device);
+        k_pack_w<<<grid, 256, 0, st>>>(pw);
+        NN_LAUNCH_OK();
+    }
+    UmmaP p;
+    memset(&p, 0, sizeof(p));
+    p.B = g.B; p.H = g.H; p.W = g.W; p.Cp = pl.Cp; p.KH = g.KH; p.KW = g.KW; p.stride = g.stride; p.pad = g.pad;
+    p.OH = OH; p.OW = OW; p.M = g.B * OH * OW; p.Cout = g.Cout; p.n_t = pl.n_t; p.n_mma = pl.n_mma;
+    p.num_kb = pl.num_kb; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
+    p.main_col = pl.main_col; p.sig_col = pl.sig_col; p.wsum_col = pl.wsum_col;
+    p.xp = xp; p.wp = wp;
+    const float as = a->a_code_scale > 0.f ? a->a_code_scale : 1.f;
+    const float wsc = a->w_code_scale > 0.f ? a->w_code_scale : 1.f;
+    p.y_scale = as * wsc; p.s_scale = as;
+    p.bias = a->bias; p.y = has_main ? a->y : nullptr; p.y_in = has_main ? nullptr : a->y; p.y_noisy = a->y_noisy;
+    p.noise_mode = a->noise_mode; p.current = a->current; p.scale_dev = a->scale_dev; p.z_inject = a->z_inject;
+    p.z_export = a->z_export; p.sigma_export = a->sigma_export; p.stats = a->stats; p.rng = a->rng;
+    p.mask_x = nullptr; p.err_flag = err;
+    return launch_umma(p, pl, st);
+}
+
+int nn_umma_conv_dgrad(const nn_conv_dgrad_args* a, int device, cudaStream_t st) {
+    if (a->precision != NN_PREC_BF16)
+        return nn_fail("nn_noisy_conv_dgrad: tcgen05 path implements NN_PREC_BF16 only%s", "");
+    const nn_conv_geom& g = a->g;
+    int OH, OW;
+    nn_out_hw(g, OH, OW);
+    // dgrad(stride 1) == forward conv of gy [B,Cout,OH,OW] with the transposed, tap-flipped weights and
+    // padding K-1-pad, producing [B,Cin,H,W]
+    Plan pl = make_plan(g.Cout, g.KH * g.KW, g.Cin, true, false, false, (int64_t)g.B * OH * OW);
+    const size_t need = align_up(pl.xp_bytes, 1024) + align_up(pl.wp_bytes, 1024) + 1024;
+    if (!a->workspace || (size_t)a->workspace_bytes < need)
+        return nn_fail("nn_noisy_conv_dgrad: workspace too small%s (need %lld bytes)", "", (long long)need);
+    uint8_t* ws = (uint8_t*)align_up((size_t)a->workspace, 1024);
+    __nv_bfloat16* xp = (__nv_bfloat16*)ws;
+    __nv_bfloat16* wp = (__nv_bfloat16*)(ws + align_up(pl.xp_bytes, 1024));
+    {
+        const int64_t total = (int64_t)g.B * OH * OW * (pl.Cp / 8);
+        int grid = (int)((total + 255) / 256);
+        if (grid > 16 * nn_num_sms(device)) grid = 16 * nn_num_sms(device);
+        k_pack_act<<<grid, 256, 0, st>>>(a->gy, xp, g.B, g.Cout, OH * OW, pl.Cp, 0.f);
+        NN_LAUNCH_OK();
+    }
+    {
+        PackWP pw;
+        pw.w_eff = a->w_eff; pw.w_raw = nullptr; pw.wp = wp;
+        pw.Cout = g.Cout; pw.Cin = g.Cin; pw.KHW = g.KH * g.KW; pw.Cp = pl.Cp; pw.n_t = pl.n_t; pw.n_mma = pl.n_mma;
+        pw.num_kb = pl.num_kb; pw.n_tiles = pl.n_tiles; pw.main_col = pl.main_col; pw.sig_col = -1; pw.wsum_col = -1;
+        pw.noise_mode = 0; pw.mode = 1; pw.w_code_scale = 0.f;
+        const int64_t total = (int64_t)pl.n_tiles * pl.num_kb * pl.n_mma * 8;
+        int grid = (int)((total + 255) / 256);
+        if (grid > 8 * nn_num_sms(device)) grid = 8 * nn_num_sms(device);
+        k_pack_w<<<grid, 256, 0, st>>>(pw);
+        NN_LAUNCH_OK();
+    }
+    UmmaP p;
+    memset(&p, 0, sizeof(p));
+    p.B = g.B; p.H = OH; p.W = OW; p.Cp = pl.Cp; p.KH = g.KH; p.KW = g.KW; p.stride = 1; p.pad = g.KH - 1 - g.pad;
+    p.OH = g.H; p.OW = g.W; p.M = g.B * g.H * g.W; p.Cout = g.Cin; p.n_t = pl.n_t; p.n_mma = pl.n_mma;
+    p.num_kb = pl.num_kb; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
+    p.main_col = pl.main_col; p.sig_col = -1; p.wsum_col = -1;
+    p.xp = xp; p.wp = wp; p.y_scale = 1.f; p.s_scale = 1.f;
+    p.y = a->gx; p.noise_mode = NN_NOISE_NONE;
+    p.mask_x = a->x_pre; p.mask_lo = (float)a->x_lo; p.mask_hi = (float)a->x_hi;
+    p.err_flag = nn_umma_err_flag(device);
+    if (g.KH != g.KW && (g.KH - 1 - g.pad) != (g.KW - 1 - g.pad))
+        return nn_fail("nn_noisy_conv_dgrad: non-square kernels not supported on the tcgen05 path%s", "");
+    return launch_umma(p, pl, st);
+}
+
+int nn_umma_conv_wgrad(const nn_conv_wgrad_args*, int, cudaStream_t) {
+    return nn_fail("nn_noisy_conv_wgrad: tcgen05 wgrad not built yet%s; use NN_PREC_FP32", "");
+}

@@ -233,6 +233,18 @@ def alt_noise(y, kind, level, rnd=None, rng=None):
     return out
 
 
+def _pick_prec(prec, g, which):
+    """tcgen05 precisions serve a subset of geometries; the rest run on the fp32 CUDA-core kernels."""
+    if prec != PREC_FP32 and not _lib.load().nn_conv_supported(C.byref(g), int(prec), which):
+        return PREC_FP32
+    return prec
+
+
+def error_flag(dev=0, reset=True):
+    """Synchronises and returns the tcgen05 pipeline watchdog flag (0 = ok)."""
+    return _lib.load().nn_debug_error_flag(int(dev), 1 if reset else 0)
+
+
 def _geom(x_shape, w_shape, stride, pad):
     B, Cin, H, W = x_shape
     Cout, Cin2, KH, KW = w_shape
@@ -258,6 +270,7 @@ def noisy_conv_fwd(x, w_eff, w_raw=None, bias=None, stride=1, pad=0, noise_mode=
     prec = _prec(precision)
     wshape = (w_eff if w_eff is not None else w_raw).shape
     g, OH, OW = _geom(x.shape, wshape, stride, pad)
+    prec = _pick_prec(prec, g, 0)
     oshape = (g.B, g.Cout, OH, OW)
     a = ConvFwdArgs()
     a.g = g
@@ -316,6 +329,7 @@ def conv_dgrad(gy, w_eff, x_shape, stride=1, pad=0, x_pre=None, x_lo=0.0, x_hi=0
     dev = _dev(gy)
     prec = _prec(precision)
     g, OH, OW = _geom(x_shape, w_eff.shape, stride, pad)
+    prec = _pick_prec(prec, g, 1)
     gx = gy.new_empty(tuple(x_shape))
     a = ConvDgradArgs()
     a.g = g
@@ -324,7 +338,11 @@ def conv_dgrad(gy, w_eff, x_shape, stride=1, pad=0, x_pre=None, x_lo=0.0, x_hi=0
         x_pre = _req(x_pre, "x_pre")
         a.x_pre, a.x_lo, a.x_hi = _p(x_pre), float(x_lo), float(x_hi)
     a.precision = int(prec)
-    _lib.check(_lib.load().nn_noisy_conv_dgrad(C.byref(a), dev, _stream(dev)), "nn_noisy_conv_dgrad")
+    lib = _lib.load()
+    ws = _workspace(dev, lib.nn_conv_workspace_bytes(C.byref(g), int(prec)), "fwd")
+    a.workspace = _p(ws)
+    a.workspace_bytes = 0 if ws is None else ws.numel()
+    _lib.check(lib.nn_noisy_conv_dgrad(C.byref(a), dev, _stream(dev)), "nn_noisy_conv_dgrad")
     return gx
 
 
@@ -333,6 +351,7 @@ def conv_wgrad(gy, x, w_shape, stride=1, pad=0, w_raw=None, w_lo=0.0, w_hi=0.0, 
     dev = _dev(gy)
     prec = _prec(precision)
     g, OH, OW = _geom(x.shape, w_shape, stride, pad)
+    prec = _pick_prec(prec, g, 2)
     gw = gy.new_empty(tuple(w_shape))
     a = ConvWgradArgs()
     a.g = g

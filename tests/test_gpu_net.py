@@ -118,7 +118,8 @@ def test_weight_clamp_projection(dev):
     from noisynet_b200.net import NoisyNet, default_args
     nm = NoisyNet(default_args(fm1=9, fm2=12, fc=24, w_max1=0.05, w_max2=0.01)).to(dev)
     nm.clamp_weights_()
-    assert nm.conv1.weight.abs().max().item() <= 0.05 and nm.conv2.weight.abs().max().item() <= 0.01
+    f32 = lambda v: torch.tensor(v, dtype=torch.float32).item()        # the clamp bound as the fp32 the kernel sees
+    assert nm.conv1.weight.abs().max().item() <= f32(0.05) and nm.conv2.weight.abs().max().item() <= f32(0.01)
     assert nm.w_absmax[0][1].item() == pytest.approx(nm.conv1.weight.abs().max().item())
 
 
