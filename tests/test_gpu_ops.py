@@ -331,8 +331,8 @@ def test_philox_normal_epilogue_matches_spec(dev):
     assert abs((zb ** 3).mean().item()) < 1e-2 and abs((zb ** 4).mean().item() - 3) < 3e-2
     # independent across channels / pixels: lag correlations ~ 0
     zc = rb["z"]
-    assert abs((zc[:, 0] * zc[:, 1]).mean().item()) < 5e-3
-    assert abs((zc[:, :, :, :-1] * zc[:, :, :, 1:]).mean().item()) < 2e-3
+    assert abs((zc[:, 0] * zc[:, 1]).mean().item()) < 2e-2        # 50k samples: sigma = 4.5e-3
+    assert abs((zc[:, :, :, :-1] * zc[:, :, :, 1:]).mean().item()) < 3e-3   # 3.1M samples: sigma = 5.6e-4
 
 
 def test_alt_noise_models(dev, golden):
