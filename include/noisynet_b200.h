@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NN_ABI_VERSION 3
+#define NN_ABI_VERSION 4
 
 /* ---- common ---------------------------------------------------------------------- */
 
@@ -72,6 +72,21 @@ int nn_tensor_stats(const float* x, int64_t n, float* out3, int device, void* st
  * scalar) receives max|w| after the clamp, which the next forward's merged-DAC noise needs
  * (hardware_model.py:47). */
 int nn_clamp_absmax(float* w, int64_t n, float w_max, float* absmax_out, int device, void* stream);
+
+/* ---- optimizer step adjacent to a9 (noisynet.py:1163 AdamW, :1520 optimizer.step(), :1527-1542 clamp) --
+ * One launch for all parameter tensors: torch.optim.AdamW update (decoupled weight decay, bias-corrected,
+ * no amsgrad) with grads pre-multiplied by grad_scale (the 1/world of the gradient mean), then
+ * clamp(+-clamp) if clamp > 0, then absmax_out[0] = max|p| (optional).  *step_dev is incremented first and
+ * used as the step count (device-resident: CUDA-graph replay safe).  `tensors` is a HOST array. */
+#define NN_ADAMW_MAX_TENSORS 24
+typedef struct nn_adamw_tensor {
+    float* p; const float* g; float* m; float* v;
+    int64_t n;
+    float lr, weight_decay, clamp;
+    float* absmax_out;
+} nn_adamw_tensor;
+int nn_adamw_step(const nn_adamw_tensor* tensors, int count, float beta1, float beta2, float eps,
+                  float grad_scale, int64_t* step_dev, int device, void* stream);
 
 /* ---- a7 (unfused form): y_noisy = y + z * sqrt(0.1 * (scale / I) * S) --------------- */
 /* hardware_model.py:59 / :81-83 / :125.  scale_dev: device scalar (max|W| merged DAC,
@@ -153,6 +168,7 @@ typedef struct nn_conv_dgrad_args {
     float* gx;               /* [B,Cin,H,W] */
     const float* x_pre; double x_lo, x_hi;
     int32_t precision;
+    float w_code_scale;      /* > 0: w_eff holds integer codes * w_code_scale (exact bf16 operand), see fwd */
     void* workspace; int64_t workspace_bytes;
 } nn_conv_dgrad_args;
 int nn_noisy_conv_dgrad(const nn_conv_dgrad_args* a, int device, void* stream);
@@ -166,6 +182,7 @@ typedef struct nn_conv_wgrad_args {
     float* gw;               /* [Cout,Cin,KH,KW] */
     const float* w_raw; double w_lo, w_hi;
     int32_t precision;
+    float a_code_scale;      /* > 0: x holds integer codes * a_code_scale (exact bf16 operand), see fwd */
     void* workspace; int64_t workspace_bytes;
 } nn_conv_wgrad_args;
 int64_t nn_conv_wgrad_workspace_bytes(const nn_conv_geom* g, int32_t precision, int device);

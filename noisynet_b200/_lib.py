@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libnoisynet_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 NOISE_NONE, NOISE_MERGED, NOISE_EXTERNAL = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
@@ -44,7 +44,7 @@ class ConvDgradArgs(C.Structure):
     _fields_ = [("g", ConvGeom),
                 ("gy", C.c_void_p), ("w_eff", C.c_void_p), ("gx", C.c_void_p),
                 ("x_pre", C.c_void_p), ("x_lo", C.c_double), ("x_hi", C.c_double),
-                ("precision", C.c_int32),
+                ("precision", C.c_int32), ("w_code_scale", C.c_float),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
@@ -52,8 +52,14 @@ class ConvWgradArgs(C.Structure):
     _fields_ = [("g", ConvGeom),
                 ("gy", C.c_void_p), ("x", C.c_void_p), ("gw", C.c_void_p),
                 ("w_raw", C.c_void_p), ("w_lo", C.c_double), ("w_hi", C.c_double),
-                ("precision", C.c_int32),
+                ("precision", C.c_int32), ("a_code_scale", C.c_float),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+
+
+class AdamWTensor(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
+                ("n", C.c_int64), ("lr", C.c_float), ("weight_decay", C.c_float), ("clamp", C.c_float),
+                ("absmax_out", C.c_void_p)]
 
 
 # name -> (restype, argtypes); mirrors include/noisynet_b200.h one to one
@@ -69,6 +75,8 @@ SIGNATURES = {
                                   C.c_int, C.c_void_p]),
     "nn_weight_noise_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, Rng,
                                       C.c_int, C.c_void_p]),
+    "nn_adamw_step": (C.c_int, [C.POINTER(AdamWTensor), C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                C.c_void_p, C.c_int, C.c_void_p]),
     "nn_tensor_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
     "nn_clamp_absmax": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "nn_noise_epilogue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,

@@ -414,7 +414,172 @@ k_pack_w(const PackWP p) {
     }
 }
 
-__global__ void k_clear_flag(int* f) { *f = 0; }
+// ------------------------------------------------------------------ wgrad on tcgen05 (MN-major operands)
+//   D[n, kcol] = sum_m gy[m, n] * im2col(x)[m, kcol]      n = output channel (128 TMEM lanes),
+//   kcol = tap * Cp + c (up to 256 accumulator columns per CTA), reduction over output pixels m.
+// Both operands are read from NHWC bf16 packs, i.e. contiguous along their M / N dimension: they are staged
+// as MN-major SWIZZLE_128B tiles  [MN atom of 64 elements][64 reduction rows][128 B]  (LBO = MN-atom stride,
+// SBO = 1024 = stride of 8 reduction rows; one UMMA_K = 16 rows = 2048 B).  Split over m across CTAs,
+// partial sums to a workspace, fixed-order reduce (deterministic) that also applies the STE mask.
+struct WgUP {
+    int B, H, W, Cp;                 // xp  [B,H,W,Cp]       (layer input, NHWC bf16)
+    int KH, KW, stride, pad, OH, OW;
+    int Mpix, Cout, Coutp;           // gyp [Mpix, Coutp]    (grad_output, NHWC bf16)
+    int Ktot, NT, ktot_pad;          // Ktot = KH*KW*Cp, NT = accumulator columns per CTA, ktot_pad = tiles * NT
+    int num_kb, kb_per_split, stages, tmem_cols;
+    const __nv_bfloat16 *xp, *gyp;
+    float* partial;                  // [splits][Cout][ktot_pad]
+    int* err_flag;
+};
+
+__global__ void __launch_bounds__(UM_THREADS, 2)
+k_wgrad_umma(const WgUP p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int S = p.stages;
+    const uint32_t b_stage = (uint32_t)p.NT * 128u;                 // 64 rows x NT bf16
+    const uint32_t a_base = base, b_base = base + (uint32_t)S * UM_A_STAGE;
+    const uint32_t bar_base = b_base + (uint32_t)S * b_stage;
+    const uint32_t full_bar = bar_base, empty_bar = bar_base + 8u * S, tfull_bar = bar_base + 16u * S;
+    const uint32_t tmem_slot = tfull_bar + 8, abort_slot = tmem_slot + 4, tab_base = (abort_slot + 4 + 15u) & ~15u;
+    uint8_t* gen0 = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gen0 + (tmem_slot - base));
+    volatile uint32_t* abort_g = reinterpret_cast<volatile uint32_t*>(gen0 + (abort_slot - base));
+    int4* tab = reinterpret_cast<int4*>(gen0 + (tab_base - base));  // per 16-byte column chunk: {kh, kw, c0, valid}
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile_k = blockIdx.x, tile_n = blockIdx.y, split = blockIdx.z;
+    const int kb0 = split * p.kb_per_split;
+    const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+    const int nkb = max(0, kb1 - kb0);
+    const int nchunk = p.NT >> 3;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full_bar + 8 * s, 128); mbar_init(empty_bar + 8 * s, 1); }
+        mbar_init(tfull_bar, 1);
+        *abort_g = 0;
+        fence_mbar_init();
+    }
+    for (int q = tid; q < nchunk; q += UM_THREADS) {
+        const int kcol = tile_k * p.NT + q * 8;
+        const int tap = kcol / p.Cp, c0 = kcol - tap * p.Cp;
+        const int kh = tap / p.KW, kw = tap - kh * p.KW;
+        tab[q] = make_int4(kh, kw, c0, (kcol < p.Ktot) ? 1 : 0);
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_g;
+
+    if (warp < 4) {
+        const int r = tid & 63, grp = tid >> 6;
+        const uint32_t sw = (uint32_t)(r & 7);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % S;
+            if (!mbar_wait(empty_bar + 8 * s, ((i / S) & 1) ^ 1)) { *abort_g = 1; break; }
+            if (*abort_g) break;
+            const int m = (kb0 + i) * 64 + r;
+            const bool m_ok = m < p.Mpix;
+            int b = 0, oh = 0, ow = 0;
+            if (m_ok) { const int ohw = p.OH * p.OW; b = m / ohw; int t = m - b * ohw; oh = t / p.OW; ow = t - oh * p.OW; }
+            // A = gy rows: 16 chunks of 8 channels per pixel, this thread takes MN-atom `grp`
+            {
+                const uint32_t dst = a_base + (uint32_t)s * UM_A_STAGE + (uint32_t)grp * (64u * 128u) + (uint32_t)r * 128u;
+                const __nv_bfloat16* src_row = p.gyp + (size_t)(m_ok ? m : 0) * p.Coutp + tile_n * 128 + grp * 64;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bool ok = m_ok && (tile_n * 128 + grp * 64 + j * 8) < p.Coutp;
+                    cp_async_16(dst + ((((uint32_t)j) ^ sw) << 4), ok ? (const void*)(src_row + j * 8) : (const void*)p.gyp,
+                                ok ? 16u : 0u);
+                }
+            }
+            // B = im2col rows: NT/8 chunks per pixel, this thread takes chunks [grp * nchunk/2, +nchunk/2)
+            {
+                const int ih0 = oh * p.stride - p.pad, iw0 = ow * p.stride - p.pad;
+                const __nv_bfloat16* xb = p.xp + (size_t)b * p.H * p.W * p.Cp;
+                const uint32_t dst_row = b_base + (uint32_t)s * b_stage + (uint32_t)r * 128u;
+                const int q0 = grp * (nchunk >> 1), q1 = q0 + (nchunk >> 1);
+                for (int q = q0; q < q1; ++q) {
+                    const int4 t = tab[q];
+                    const int ih = ih0 + t.x, iw = iw0 + t.y;
+                    const bool ok = m_ok && t.w && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
+                    const __nv_bfloat16* src = ok ? xb + ((size_t)ih * p.W + iw) * p.Cp + t.z : p.xp;
+                    cp_async_16(dst_row + (uint32_t)(q >> 3) * (64u * 128u) + ((((uint32_t)(q & 7)) ^ sw) << 4), src,
+                                ok ? 16u : 0u);
+                }
+            }
+            cp_async_mbar_arrive_noinc(full_bar + 8 * s);
+        }
+    } else if (warp == 4) {
+        if (lane == 0) {
+            // MN-major A and B (bits 15, 16), bf16 x bf16 -> f32, M = 128, N = NT
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(UM_BLOCK_M >> 4) << 24);
+            const uint64_t lbo = (uint64_t)((64u * 128u) >> 4) << 16;        // MN-atom stride = 8192 B
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % S;
+                if (!mbar_wait(full_bar + 8 * s, (i / S) & 1)) { *abort_g = 2; break; }
+                fence_proxy_async();
+                tc_fence_after();
+                const uint64_t ad = umma_desc_sw128(a_base + (uint32_t)s * UM_A_STAGE) | lbo;
+                const uint64_t bd = umma_desc_sw128(b_base + (uint32_t)s * b_stage) | lbo;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)                                  // 16 reduction rows = 2048 B = 128 units
+                    umma_bf16(tmem_base, ad + 128 * k, bd + 128 * k, idesc, (i | k) != 0);
+                umma_commit(empty_bar + 8 * s);
+            }
+            umma_commit(tfull_bar);
+        }
+        __syncwarp();
+    }
+
+    bool acc_ok = mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    if (!acc_ok || *abort_g) {
+        if (tid == 0 && p.err_flag) atomicExch(p.err_flag, 200 + (int)*abort_g);
+    } else {
+        const int q = warp & 3, half = warp >> 2;
+        const int n = tile_n * 128 + q * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        float* out = p.partial + ((size_t)split * p.Cout + (n < p.Cout ? n : 0)) * p.ktot_pad + (size_t)tile_k * p.NT;
+        const int nchunks16 = p.NT >> 4;
+        for (int ci = half; ci < nchunks16; ci += 2) {
+            float v[16];
+            if (nkb > 0) tmem_ld16(t_lane + (uint32_t)(ci * 16), v);
+            else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = 0.f;
+            }
+            if (n < p.Cout) {
+                float4* o4 = reinterpret_cast<float4*>(out + ci * 16);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o4[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
+// partial [splits][Cout][ktot_pad] (kcol = tap*Cp + c) -> gw [Cout][Cin][KHW], fixed summation order, scale, STE mask
+__global__ void __launch_bounds__(256)
+k_wgrad_umma_reduce(const float* __restrict__ partial, int splits, int Cout, int Cin, int KHW, int Cp, int ktot_pad,
+                    float scale, float* __restrict__ gw, const float* __restrict__ w_raw, float lo, float hi) {
+    const int64_t total = (int64_t)Cout * Cin * KHW;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int tap = (int)(i % KHW);
+        const int c = (int)((i / KHW) % Cin);
+        const int n = (int)(i / ((int64_t)KHW * Cin));
+        const float* src = partial + (size_t)n * ktot_pad + (size_t)tap * Cp + c;
+        float s = 0.f;
+        for (int z = 0; z < splits; ++z) s += src[(size_t)z * Cout * ktot_pad];
+        s *= scale;
+        if (w_raw) { const float w = __ldg(w_raw + i); if (w > hi || w < lo) s = 0.f; }
+        gw[i] = s;
+    }
+}
 
 // ------------------------------------------------------------------ host-side planning
 struct Plan {
@@ -477,7 +642,7 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st) {
 bool nn_umma_supports(const nn_conv_geom* g, int which) {
     if (which == 0) return true;
     if (which == 1) return g->stride == 1 && g->pad <= g->KH - 1 && g->pad <= g->KW - 1;
-    return false;
+    return true;
 }
 
 int64_t nn_umma_fwd_workspace(const nn_conv_geom* g, int precision) {
@@ -491,7 +656,6 @@ int64_t nn_umma_fwd_workspace(const nn_conv_geom* g, int precision) {
     return (int64_t)((a > b ? a : b) + 2048);
 }
 
-int64_t nn_umma_wgrad_workspace(const nn_conv_geom*, int, int) { return 0; }
 
 int* nn_umma_err_flag(int device) {
     static int* flags[64] = {nullptr};
@@ -595,7 +759,7 @@ int nn_umma_conv_dgrad(const nn_conv_dgrad_args* a, int device, cudaStream_t st)
         pw.w_eff = a->w_eff; pw.w_raw = nullptr; pw.wp = wp;
         pw.Cout = g.Cout; pw.Cin = g.Cin; pw.KHW = g.KH * g.KW; pw.Cp = pl.Cp; pw.n_t = pl.n_t; pw.n_mma = pl.n_mma;
         pw.num_kb = pl.num_kb; pw.n_tiles = pl.n_tiles; pw.main_col = pl.main_col; pw.sig_col = -1; pw.wsum_col = -1;
-        pw.noise_mode = 0; pw.mode = 1; pw.w_code_scale = 0.f;
+        pw.noise_mode = 0; pw.mode = 1; pw.w_code_scale = a->w_code_scale;
         const int64_t total = (int64_t)pl.n_tiles * pl.num_kb * pl.n_mma * 8;
         int grid = (int)((total + 255) / 256);
         if (grid > 8 * nn_num_sms(device)) grid = 8 * nn_num_sms(device);
@@ -608,7 +772,7 @@ int nn_umma_conv_dgrad(const nn_conv_dgrad_args* a, int device, cudaStream_t st)
     p.OH = g.H; p.OW = g.W; p.M = g.B * g.H * g.W; p.Cout = g.Cin; p.n_t = pl.n_t; p.n_mma = pl.n_mma;
     p.num_kb = pl.num_kb; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
     p.main_col = pl.main_col; p.sig_col = -1; p.wsum_col = -1;
-    p.xp = xp; p.wp = wp; p.y_scale = 1.f; p.s_scale = 1.f;
+    p.xp = xp; p.wp = wp; p.y_scale = a->w_code_scale > 0.f ? a->w_code_scale : 1.f; p.s_scale = 1.f;
     p.y = a->gx; p.noise_mode = NN_NOISE_NONE;
     p.mask_x = a->x_pre; p.mask_lo = (float)a->x_lo; p.mask_hi = (float)a->x_hi;
     p.err_flag = nn_umma_err_flag(device);
@@ -617,6 +781,97 @@ int nn_umma_conv_dgrad(const nn_conv_dgrad_args* a, int device, cudaStream_t st)
     return launch_umma(p, pl, st);
 }
 
-int nn_umma_conv_wgrad(const nn_conv_wgrad_args*, int, cudaStream_t) {
-    return nn_fail("nn_noisy_conv_wgrad: tcgen05 wgrad not built yet%s; use NN_PREC_FP32", "");
+namespace {
+struct WgPlan {
+    int Cp, Coutp, Ktot, n_tiles_k, NT, ktot_pad, m_tiles_n, num_kb, splits, kb_per_split, stages, tmem_cols;
+    size_t xp_bytes, gyp_bytes, partial_bytes, smem_bytes;
+};
+WgPlan make_wg_plan(const nn_conv_geom& g, int device) {
+    WgPlan w;
+    int OH, OW;
+    nn_out_hw(g, OH, OW);
+    const int64_t Mpix = (int64_t)g.B * OH * OW;
+    w.Cp = pad_to(g.Cin, 8);
+    w.Coutp = pad_to(g.Cout, 8);
+    w.Ktot = g.KH * g.KW * w.Cp;
+    w.n_tiles_k = (w.Ktot + 255) / 256;
+    w.NT = pad_to((w.Ktot + w.n_tiles_k - 1) / w.n_tiles_k, 64);
+    w.ktot_pad = w.n_tiles_k * w.NT;
+    w.m_tiles_n = (g.Cout + 127) / 128;
+    w.num_kb = (int)((Mpix + 63) / 64);
+    const int tiles = w.n_tiles_k * w.m_tiles_n;
+    int splits = (2 * nn_num_sms(device) + tiles - 1) / tiles;
+    if (splits > w.num_kb) splits = w.num_kb;
+    if (splits < 1) splits = 1;
+    w.kb_per_split = (w.num_kb + splits - 1) / splits;
+    w.splits = (w.num_kb + w.kb_per_split - 1) / w.kb_per_split;
+    const int stage_bytes = UM_A_STAGE + w.NT * 128;
+    w.stages = (100 * 1024 - 3072) / stage_bytes;
+    if (w.stages > 4) w.stages = 4;
+    if (w.stages < 2) w.stages = 2;
+    w.tmem_cols = 32;
+    while (w.tmem_cols < w.NT) w.tmem_cols <<= 1;
+    w.smem_bytes = 1024 + (size_t)w.stages * stage_bytes + 16 * w.stages + 64 + (size_t)(w.NT / 8) * 16 + 16;
+    w.xp_bytes = (size_t)g.B * g.H * g.W * w.Cp * 2;
+    w.gyp_bytes = (size_t)Mpix * w.Coutp * 2;
+    w.partial_bytes = (size_t)w.splits * g.Cout * w.ktot_pad * 4;
+    return w;
+}
+}  // namespace
+
+int64_t nn_umma_wgrad_workspace(const nn_conv_geom* g, int, int device) {
+    WgPlan w = make_wg_plan(*g, device);
+    return (int64_t)(align_up(w.xp_bytes, 1024) + align_up(w.gyp_bytes, 1024) + align_up(w.partial_bytes, 1024) + 2048);
+}
+
+int nn_umma_conv_wgrad(const nn_conv_wgrad_args* a, int device, cudaStream_t st) {
+    if (a->precision != NN_PREC_BF16)
+        return nn_fail("nn_noisy_conv_wgrad: tcgen05 path implements NN_PREC_BF16 only%s", "");
+    const nn_conv_geom& g = a->g;
+    int OH, OW;
+    nn_out_hw(g, OH, OW);
+    WgPlan w = make_wg_plan(g, device);
+    const size_t need = align_up(w.xp_bytes, 1024) + align_up(w.gyp_bytes, 1024) + align_up(w.partial_bytes, 1024) + 1024;
+    if (!a->workspace || (size_t)a->workspace_bytes < need)
+        return nn_fail("nn_noisy_conv_wgrad: workspace too small%s (need %lld bytes)", "", (long long)need);
+    uint8_t* ws = (uint8_t*)align_up((size_t)a->workspace, 1024);
+    __nv_bfloat16* xp = (__nv_bfloat16*)ws;
+    __nv_bfloat16* gyp = (__nv_bfloat16*)(ws + align_up(w.xp_bytes, 1024));
+    float* partial = (float*)(ws + align_up(w.xp_bytes, 1024) + align_up(w.gyp_bytes, 1024));
+    const int sms = nn_num_sms(device);
+    {
+        int64_t total = (int64_t)g.B * g.H * g.W * (w.Cp / 8);
+        int grid = (int)((total + 255) / 256);
+        if (grid > 16 * sms) grid = 16 * sms;
+        k_pack_act<<<grid, 256, 0, st>>>(a->x, xp, g.B, g.Cin, g.H * g.W, w.Cp, a->a_code_scale);
+        NN_LAUNCH_OK();
+        total = (int64_t)g.B * OH * OW * (w.Coutp / 8);
+        grid = (int)((total + 255) / 256);
+        if (grid > 16 * sms) grid = 16 * sms;
+        k_pack_act<<<grid, 256, 0, st>>>(a->gy, gyp, g.B, g.Cout, OH * OW, w.Coutp, 0.f);
+        NN_LAUNCH_OK();
+    }
+    WgUP p;
+    memset(&p, 0, sizeof(p));
+    p.B = g.B; p.H = g.H; p.W = g.W; p.Cp = w.Cp; p.KH = g.KH; p.KW = g.KW; p.stride = g.stride; p.pad = g.pad;
+    p.OH = OH; p.OW = OW; p.Mpix = g.B * OH * OW; p.Cout = g.Cout; p.Coutp = w.Coutp;
+    p.Ktot = w.Ktot; p.NT = w.NT; p.ktot_pad = w.ktot_pad; p.num_kb = w.num_kb; p.kb_per_split = w.kb_per_split;
+    p.stages = w.stages; p.tmem_cols = w.tmem_cols; p.xp = xp; p.gyp = gyp; p.partial = partial;
+    p.err_flag = nn_umma_err_flag(device);
+    static bool attr_set = false;
+    if (!attr_set) {
+        NN_CUDA_OK(cudaFuncSetAttribute(k_wgrad_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(w.n_tiles_k, w.m_tiles_n, w.splits);
+    k_wgrad_umma<<<grid, UM_THREADS, w.smem_bytes, st>>>(p);
+    NN_LAUNCH_OK();
+    const int64_t n = (int64_t)g.Cout * g.Cin * g.KH * g.KW;
+    int rb = (int)((n + 255) / 256);
+    if (rb > 8 * sms) rb = 8 * sms;
+    const float scale = a->a_code_scale > 0.f ? a->a_code_scale : 1.f;
+    k_wgrad_umma_reduce<<<rb, 256, 0, st>>>(partial, w.splits, g.Cout, g.Cin, g.KH * g.KW, w.Cp, w.ktot_pad, scale,
+                                            a->gw, a->w_raw, (float)a->w_lo, (float)a->w_hi);
+    NN_LAUNCH_OK();
+    return 0;
 }

@@ -379,3 +379,87 @@ extern "C" int nn_alt_noise(const float* y, float* out, int64_t n, int kind, flo
     NN_LAUNCH_OK();
     return 0;
 }
+
+// ------------------------------------------------------------------ fused AdamW step + weight clamp + max|W|
+// Replaces, in ONE launch for all parameter tensors, `optimizer.step()` of torch.optim.AdamW
+// (noisynet.py:1163, :1520; decoupled weight decay, bias-corrected moments, no amsgrad) followed by
+// `weight.data.clamp_(-w_max, w_max)` (noisynet.py:1527-1542) and the max|W| reduction the next forward's
+// merged-DAC noise needs (hardware_model.py:47).  `grad_scale` folds the 1/world of the gradient mean.
+struct AdamWP {
+    nn_adamw_tensor t[NN_ADAMW_MAX_TENSORS];
+    int count;
+    float beta1, beta2, eps, grad_scale;
+    const int64_t* step_dev;
+};
+
+__global__ void k_step_inc(int64_t* s) { *s += 1; }
+
+__global__ void __launch_bounds__(256)
+k_adamw(const AdamWP p) {
+    const nn_adamw_tensor t = p.t[blockIdx.y];
+    const int64_t base = (int64_t)blockIdx.x * blockDim.x * 4;
+    if (base >= t.n) return;
+    __shared__ float s_step_size, s_bc2_sqrt;
+    __shared__ float s_red[8];
+    if (threadIdx.x == 0) {
+        const double step = (double)(*p.step_dev);
+        const double bc1 = 1.0 - pow((double)p.beta1, step);
+        const double bc2 = 1.0 - pow((double)p.beta2, step);
+        s_step_size = (float)((double)t.lr / bc1);
+        s_bc2_sqrt = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    const float step_size = s_step_size, bc2s = s_bc2_sqrt;
+    const float decay = 1.0f - t.lr * t.weight_decay;
+    const float om1 = 1.0f - p.beta1, om2 = 1.0f - p.beta2;
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t i = base + (int64_t)j * blockDim.x + threadIdx.x;
+        if (i < t.n) {
+            const float g = t.g[i] * p.grad_scale;
+            float w = t.p[i] * decay;                                  // param.mul_(1 - lr * wd)
+            float m = t.m[i];
+            m = m + om1 * (g - m);                                     // exp_avg.lerp_(grad, 1 - beta1)
+            float v = t.v[i] * p.beta2 + om2 * g * g;                  // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+            const float denom = sqrtf(v) / bc2s + p.eps;
+            w = w - step_size * (m / denom);                           // param.addcdiv_(exp_avg, denom, -step_size)
+            if (t.clamp > 0.f) w = fminf(fmaxf(w, -t.clamp), t.clamp);
+            t.p[i] = w; t.m[i] = m; t.v[i] = v;
+            amax = fmaxf(amax, fabsf(w));
+        }
+    }
+    if (t.absmax_out) {
+        amax = nn_warp_max(amax);
+        const int wi = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (l == 0) s_red[wi] = amax;
+        __syncthreads();
+        if (wi == 0) {
+            amax = (l < 8) ? s_red[l] : 0.f;
+            amax = nn_warp_max(amax);
+            if (l == 0) nn_atomic_max_float(t.absmax_out, amax);
+        }
+    }
+}
+
+extern "C" int nn_adamw_step(const nn_adamw_tensor* tensors, int count, float beta1, float beta2, float eps,
+                             float grad_scale, int64_t* step_dev, int device, void* stream) {
+    if (count <= 0) return 0;
+    if (count > NN_ADAMW_MAX_TENSORS) return nn_fail("nn_adamw_step: too many tensors%s (%lld)", "", count);
+    if (!step_dev) return nn_fail("nn_adamw_step: step_dev missing%s", "");
+    NN_SET_DEVICE(device);
+    AdamWP p;
+    p.count = count; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.grad_scale = grad_scale; p.step_dev = step_dev;
+    int64_t max_n = 0;
+    for (int i = 0; i < count; ++i) {
+        p.t[i] = tensors[i];
+        if (tensors[i].n > max_n) max_n = tensors[i].n;
+        if (tensors[i].absmax_out) NN_CUDA_OK(cudaMemsetAsync(tensors[i].absmax_out, 0, sizeof(float), (cudaStream_t)stream));
+    }
+    k_step_inc<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    NN_LAUNCH_OK();
+    dim3 grid((unsigned)((max_n + 1023) / 1024), (unsigned)count);
+    k_adamw<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    NN_LAUNCH_OK();
+    return 0;
+}

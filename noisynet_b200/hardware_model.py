@@ -171,6 +171,24 @@ class QuantMeasure(nn.Module):
         return out
 
 
+def _f32(v):
+    return torch.tensor(v, dtype=torch.float32).item()
+
+
+def code_scales(x, w):
+    """Integer-code scales for the tcgen05 path from the tags QuantMeasure / _prepare_weight leave on their
+    outputs: activations on the grid k * s (min 0) -> a_code_scale = s; weights on a symmetric grid
+    (2k - qmax) * s/2 -> w_code_scale = s/2.  0.0 = no exact code representation."""
+    a_cs = w_cs = 0.0
+    t = getattr(x, "_nn_quant", None)
+    if t is not None and t[1] == 0.0 and t[2] > 0 and t[0] <= 8:
+        a_cs = _f32(max((t[2] - t[1]) / (2.0 ** t[0] - 1.0), 1e-6))
+    t = getattr(w, "_nn_quant", None)
+    if t is not None and t[1] == -t[2] and t[2] > 0 and t[0] <= 8:
+        w_cs = _f32(max((t[2] - t[1]) / (2.0 ** t[0] - 1.0), 1e-6)) / 2.0
+    return a_cs, w_cs
+
+
 def _prepare_weight(mod, linear):
     """Branch order of hm:343-360 / hm:402-420.  Returns (weight, bias, ste) where ste is None or
     (raw_parameter, lo, hi): the quantized weight is then produced outside autograd and the masked
@@ -229,10 +247,10 @@ class NoisyConv2d(nn.Conv2d):
         else:
             qinput = input
         weight, bias, ste = _prepare_weight(self, linear=False)
-        if ste is None:
-            return ops.ConvFn.apply(qinput, weight, bias, self.stride[0], self.padding[0], self.precision)
-        raw, lo, hi = ste
-        return ops.ConvFn.apply(qinput, weight, bias, self.stride[0], self.padding[0], self.precision, raw, lo, hi)
+        a_cs, w_cs = code_scales(qinput, weight)
+        raw, lo, hi = ste if ste is not None else (None, 0.0, 0.0)
+        return ops.ConvFn.apply(qinput, weight, bias, self.stride[0], self.padding[0], self.precision, raw, lo, hi,
+                                a_cs, w_cs)
 
 
 class NoisyLinear(nn.Linear):
@@ -262,16 +280,17 @@ class NoisyLinear(nn.Linear):
         else:
             qinput = input
         weight, bias, ste = _prepare_weight(self, linear=True)
+        a_cs, w_cs = code_scales(qinput, weight)
         lead = qinput.shape[:-1]
         x4 = qinput.reshape(-1, qinput.shape[-1])
         x4 = x4.view(x4.shape[0], x4.shape[1], 1, 1)
+        w4 = weight.view(weight.shape[0], weight.shape[1], 1, 1)
         if ste is None:
-            w4 = weight.view(weight.shape[0], weight.shape[1], 1, 1)
-            y = ops.ConvFn.apply(x4, w4, bias, 1, 0, self.precision)
+            y = ops.ConvFn.apply(x4, w4, bias, 1, 0, self.precision, None, 0.0, 0.0, a_cs, w_cs)
         else:
             raw, lo, hi = ste
-            w4 = weight.view(weight.shape[0], weight.shape[1], 1, 1)
-            y = ops.ConvFn.apply(x4, w4, bias, 1, 0, self.precision, raw.view(raw.shape[0], raw.shape[1], 1, 1), lo, hi)
+            y = ops.ConvFn.apply(x4, w4, bias, 1, 0, self.precision, raw.view(raw.shape[0], raw.shape[1], 1, 1), lo, hi,
+                                 a_cs, w_cs)
         return y.view(*lead, weight.shape[0])
 
 

@@ -17,7 +17,7 @@ import torch.nn.functional as F
 from . import ops
 from ._lib import NOISE_EXTERNAL, NOISE_MERGED
 from .hardware_model import (NoisyConv2d, NoisyLinear, QuantMeasure, _prepare_weight, _scalar_stats_buffer,
-                             add_noise_calculate_power)
+                             add_noise_calculate_power, code_scales)
 
 
 def default_args(**over):
@@ -96,6 +96,7 @@ class NoisyNet(nn.Module):
             return y
         # ---- fused: one launch
         weight, bias, ste = _prepare_weight(mod, linear=(kind == "linear"))
+        a_cs, w_cs = code_scales(x, weight)          # exact integer operands on the tcgen05 path
         w_raw = mod.weight.detach()
         if kind == "linear":
             x4 = x.reshape(x.shape[0], -1, 1, 1)
@@ -116,12 +117,12 @@ class NoisyNet(nn.Module):
         mode = NOISE_MERGED if merged else NOISE_EXTERNAL
         if ste is None:
             y, yn = ops.FusedNoisyConvFn.apply(x4, weight, bias, w_raw4, 1, 0, mode, float(cur), scale_dev, stats,
-                                               None, self.precision)
+                                               None, self.precision, None, 0.0, 0.0, a_cs, w_cs)
         else:
             raw, lo, hi = ste
             raw4 = raw.view(raw.shape[0], raw.shape[1], 1, 1) if kind == "linear" else raw
             y, yn = ops.FusedNoisyConvFn.apply(x4, weight, bias, w_raw4, 1, 0, mode, float(cur), scale_dev, stats,
-                                               None, self.precision, raw4, lo, hi)
+                                               None, self.precision, raw4, lo, hi, a_cs, w_cs)
         if kind == "linear":
             y, yn = y.view(y.shape[0], -1), yn.view(yn.shape[0], -1)
         if want_stats:
@@ -217,4 +218,36 @@ def train_step(model, opt, x, label, i=0):
     loss.backward()
     opt.step()
     model.clamp_weights_()
+    return loss.detach(), out.detach()
+
+
+def make_fused_optimizer(model, args, grad_scale=1.0):
+    """Same groups as noisynet.py:1135-1169, on the fused AdamW + clamp kernel; the per-layer clamp bounds
+    (noisynet.py:1527-1542) ride along in the groups."""
+    from .optim import FusedAdamW
+    a = args
+    groups = [
+        {'params': model.conv1.parameters(), 'weight_decay': a.L2_1, 'lr': a.LR, 'clamp': a.w_max1},
+        {'params': model.conv2.parameters(), 'weight_decay': a.L2_2, 'lr': a.LR, 'clamp': a.w_max2},
+        {'params': model.linear1.parameters(), 'weight_decay': a.L2_3, 'lr': a.LR, 'clamp': a.w_max3},
+        {'params': model.linear2.parameters(), 'weight_decay': a.L2_4, 'lr': a.LR, 'clamp': a.w_max4},
+        {'params': list(model.bn1.parameters()) + list(model.bn2.parameters()) + list(model.bn3.parameters())
+                   + list(model.bn4.parameters()), 'weight_decay': a.L2_bn, 'lr': a.LR}]
+    return FusedAdamW(groups, lr=a.LR, weight_decay=0.0, grad_scale=grad_scale)
+
+
+def bind_absmax(model, opt):
+    """After the first fused step: the next forwards read max|W| from the optimizer's device scalars."""
+    for idx, mod in enumerate((model.conv1, model.conv2, model.linear1, model.linear2)):
+        model.w_absmax[idx] = (mod.weight._version, opt.absmax_of(mod.weight))
+
+
+def train_step_fused(model, opt, x, label, i=0):
+    """train_step with optimizer.step() + weight clamp + max|W| in one launch (FusedAdamW)."""
+    out = model(x, 0, i)
+    loss = F.cross_entropy(out, label)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    bind_absmax(model, opt)
     return loss.detach(), out.detach()

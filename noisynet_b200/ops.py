@@ -324,7 +324,7 @@ def noisy_conv_fwd(x, w_eff, w_raw=None, bias=None, stride=1, pad=0, noise_mode=
     return out
 
 
-def conv_dgrad(gy, w_eff, x_shape, stride=1, pad=0, x_pre=None, x_lo=0.0, x_hi=0.0, precision=None):
+def conv_dgrad(gy, w_eff, x_shape, stride=1, pad=0, x_pre=None, x_lo=0.0, x_hi=0.0, precision=None, w_code_scale=0.0):
     gy, w_eff = _req(gy, "grad_output"), _req(w_eff, "weight")
     dev = _dev(gy)
     prec = _prec(precision)
@@ -338,6 +338,7 @@ def conv_dgrad(gy, w_eff, x_shape, stride=1, pad=0, x_pre=None, x_lo=0.0, x_hi=0
         x_pre = _req(x_pre, "x_pre")
         a.x_pre, a.x_lo, a.x_hi = _p(x_pre), float(x_lo), float(x_hi)
     a.precision = int(prec)
+    a.w_code_scale = float(w_code_scale)
     lib = _lib.load()
     ws = _workspace(dev, lib.nn_conv_workspace_bytes(C.byref(g), int(prec)), "fwd")
     a.workspace = _p(ws)
@@ -346,7 +347,7 @@ def conv_dgrad(gy, w_eff, x_shape, stride=1, pad=0, x_pre=None, x_lo=0.0, x_hi=0
     return gx
 
 
-def conv_wgrad(gy, x, w_shape, stride=1, pad=0, w_raw=None, w_lo=0.0, w_hi=0.0, precision=None):
+def conv_wgrad(gy, x, w_shape, stride=1, pad=0, w_raw=None, w_lo=0.0, w_hi=0.0, precision=None, a_code_scale=0.0):
     gy, x = _req(gy, "grad_output"), _req(x, "input")
     dev = _dev(gy)
     prec = _prec(precision)
@@ -360,6 +361,7 @@ def conv_wgrad(gy, x, w_shape, stride=1, pad=0, w_raw=None, w_lo=0.0, w_hi=0.0, 
         w_raw = _req(w_raw, "raw weight")
         a.w_raw, a.w_lo, a.w_hi = _p(w_raw), float(w_lo), float(w_hi)
     a.precision = int(prec)
+    a.a_code_scale = float(a_code_scale)
     lib = _lib.load()
     nbytes = lib.nn_conv_wgrad_workspace_bytes(C.byref(g), int(prec), dev)
     ws = _workspace(dev, nbytes, "wgrad")
@@ -435,6 +437,7 @@ class ConvFn(Function):
         w = _req(w, "weight")
         ctx.save_for_backward(x, w, w_raw)
         ctx.cfg = (stride, pad, precision, w_lo, w_hi, bias is not None)
+        ctx.codes = (a_code_scale, w_code_scale)
         return noisy_conv_fwd(x, w, None, bias, stride, pad, precision=precision,
                               a_code_scale=a_code_scale, w_code_scale=w_code_scale)["y"]
 
@@ -444,13 +447,14 @@ class ConvFn(Function):
         x, w, w_raw = ctx.saved_tensors
         stride, pad, precision, w_lo, w_hi, has_bias = ctx.cfg
         gy = gy.contiguous()
+        a_cs, w_cs = ctx.codes
         gx = gw = gb = gwr = None
         if ctx.needs_input_grad[0]:
-            gx = conv_dgrad(gy, w, x.shape, stride, pad, precision=precision)
+            gx = conv_dgrad(gy, w, x.shape, stride, pad, precision=precision, w_code_scale=w_cs)
         if w_raw is not None and ctx.needs_input_grad[6]:
-            gwr = conv_wgrad(gy, x, w.shape, stride, pad, w_raw, w_lo, w_hi, precision=precision)
+            gwr = conv_wgrad(gy, x, w.shape, stride, pad, w_raw, w_lo, w_hi, precision=precision, a_code_scale=a_cs)
         elif ctx.needs_input_grad[1]:
-            gw = conv_wgrad(gy, x, w.shape, stride, pad, precision=precision)
+            gw = conv_wgrad(gy, x, w.shape, stride, pad, precision=precision, a_code_scale=a_cs)
         if has_bias and ctx.needs_input_grad[2]:
             gb = gy.sum((0, 2, 3))
         return gx, gw, gb, None, None, None, gwr, None, None, None, None
@@ -481,6 +485,7 @@ class FusedNoisyConvFn(Function):
         w = _req(w, "weight")
         ctx.save_for_backward(x, w, w_ste_raw)
         ctx.cfg = (stride, pad, precision, w_lo, w_hi, bias is not None)
+        ctx.codes = (a_code_scale, w_code_scale)
         r = noisy_conv_fwd(x, w, w_raw_noise, bias, stride, pad, noise_mode=mode, current=current,
                            scale_dev=scale_dev, z=z, stats=stats, precision=precision,
                            a_code_scale=a_code_scale, w_code_scale=w_code_scale)
@@ -498,13 +503,14 @@ class FusedNoisyConvFn(Function):
         else:
             g = gy + gyn
         g = g.contiguous()
+        a_cs, w_cs = ctx.codes
         gx = gw = gb = gwr = None
         if ctx.needs_input_grad[0]:
-            gx = conv_dgrad(g, w, x.shape, stride, pad, precision=precision)
+            gx = conv_dgrad(g, w, x.shape, stride, pad, precision=precision, w_code_scale=w_cs)
         if w_raw is not None and ctx.needs_input_grad[12]:
-            gwr = conv_wgrad(g, x, w.shape, stride, pad, w_raw, w_lo, w_hi, precision=precision)
+            gwr = conv_wgrad(g, x, w.shape, stride, pad, w_raw, w_lo, w_hi, precision=precision, a_code_scale=a_cs)
         elif ctx.needs_input_grad[1]:
-            gw = conv_wgrad(g, x, w.shape, stride, pad, precision=precision)
+            gw = conv_wgrad(g, x, w.shape, stride, pad, precision=precision, a_code_scale=a_cs)
         if has_bias and ctx.needs_input_grad[2]:
             gb = g.sum((0, 2, 3))
         return (gx, gw, gb) + (None,) * 9 + (gwr,) + (None,) * 4

@@ -143,3 +143,31 @@ def test_training_reduces_loss(dev):
     losses = [train_step(nm, opt, x, lab, i=100 + s)[0].item() for s in range(30)]
     assert losses[-1] < 0.5 * losses[0], losses
     assert all(np.isfinite(losses))
+
+
+def test_fused_adamw_matches_torch(dev):
+    """nn_adamw_step == torch.optim.AdamW + clamp_ over several steps (rtol 1e-5), incl. per-group lr / weight
+    decay, the fused clamp and the max|W| side output."""
+    from noisynet_b200.optim import FusedAdamW
+    torch.manual_seed(0)
+    shapes = [(65, 3, 5, 5), (120, 65, 5, 5), (390, 3000), (10,), (7,)]
+    ps = [torch.nn.Parameter(torch.randn(s, device=dev) * 0.2) for s in shapes]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    groups = lambda xs: [{"params": [xs[0]], "lr": 0.005, "weight_decay": 0.0005, "clamp": 0.3},
+                         {"params": [xs[1], xs[2]], "lr": 0.002, "weight_decay": 0.0, "clamp": 0.0},
+                         {"params": [xs[3], xs[4]], "lr": 0.005, "weight_decay": 0.01, "clamp": 0.0}]
+    ref = torch.optim.AdamW([{k: v for k, v in g.items() if k != "clamp"} for g in groups(qs)], lr=0.005)
+    fus = FusedAdamW(groups(ps), lr=0.005, grad_scale=0.5)
+    for step in range(5):
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(p)
+            p.grad = (g * 2.0).clone() if p.grad is None else p.grad.copy_(g * 2.0)     # grad_scale 0.5 undoes the 2x
+            q.grad = g.clone()
+        fus.step()
+        ref.step()
+        qs[0].data.clamp_(-0.3, 0.3)
+        for p, q in zip(ps, qs):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), (step, (p - q).abs().max())
+    assert fus.absmax_of(ps[0]).item() == pytest.approx(ps[0].abs().max().item())
+    assert fus.absmax_of(ps[2]).item() == pytest.approx(ps[2].abs().max().item())
+    assert fus.step_dev.item() == 5
