@@ -35,6 +35,7 @@ def parse():
     p.add_argument("--variant", default="q4", choices=["q4", "fp"], help="q4: --q_a 4 --q_w 4; fp: README flags")
     p.add_argument("--flow", default="fused", choices=["fused", "dropin"])
     p.add_argument("--precision", default=os.environ.get("NN_BENCH_PRECISION", "auto"))
+    p.add_argument("--optimizer", default="fused", choices=["fused", "torch"])
     p.add_argument("--graph", type=int, default=int(os.environ.get("NN_BENCH_GRAPH", "1")))
     p.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -167,7 +168,7 @@ def workload_config(args, world):
 
 # ------------------------------------------------------------------------------------ our arm
 def build_model(args, dev, precision):
-    from noisynet_b200.net import NoisyNet, default_args, init_like_reference, make_optimizer, with_quant
+    from noisynet_b200.net import NoisyNet, default_args, init_like_reference, make_fused_optimizer, make_optimizer, with_quant
     a = default_args()
     if args.variant == "q4":
         with_quant(a, 4, 4)
@@ -177,6 +178,8 @@ def build_model(args, dev, precision):
         m.quantize4.running_max = torch.tensor(5.0, device=dev)
     m.collect_stats = False       # steady state: i >= 20 (no host-synced side statistics)
     m.train()
+    if args.optimizer == "fused":   # nn_adamw_step: AdamW + clamp + max|W| for all tensors in one launch
+        return m, a, make_fused_optimizer(m, a, grad_scale=1.0 / max(1, int(os.environ.get("WORLD_SIZE", "1"))))
     return m, a, make_optimizer(m, a, capturable=bool(args.graph))
 
 
@@ -204,7 +207,7 @@ def pick_precision(args, dev):
 
 def run_b200(args):
     from noisynet_b200 import _lib, dp, ops
-    from noisynet_b200.net import train_step
+    from noisynet_b200.net import bind_absmax
     import torch.distributed as dist
     import torch.nn.functional as F
     rank, world, local = dp.init_from_env()
@@ -215,6 +218,7 @@ def run_b200(args):
     torch.manual_seed(dp.rank_seed(0, rank))
     precision = pick_precision(args, dev)
     model, a, opt = build_model(args, dev, precision)
+    fused_opt = args.optimizer == "fused"
     red = dp.FlatGradAllReduce(model, world)
     red.broadcast_parameters(model)
     B = args.batch
@@ -231,9 +235,14 @@ def run_b200(args):
         loss = F.cross_entropy(out, y)
         red.zero_()
         loss.backward()
-        red.all_reduce_mean_()
-        opt.step()
-        model.clamp_weights_()
+        if fused_opt:
+            red.all_reduce_sum_()           # the 1/world is folded into the optimizer kernel (grad_scale)
+            opt.step()
+            bind_absmax(model, opt)
+        else:
+            red.all_reduce_mean_()
+            opt.step()
+            model.clamp_weights_()
         loss_out.copy_(loss.detach())
 
     # eager warm-up (allocator, cudnn heuristics, lazy state)

@@ -155,6 +155,9 @@ int nn_conv_supported(const nn_conv_geom* g, int32_t precision, int32_t which);
 /* Test/debug hook: synchronises `device` and returns the tcgen05 pipeline watchdog flag (0 = ok);
  * reset != 0 clears it. */
 int nn_debug_error_flag(int device, int reset);
+/* Measurement hook: enable = 1/0 brackets the main tcgen05 forward kernel (not the operand packs) with CUDA
+ * events on its launch stream; enable < 0 synchronises on them and returns the last elapsed ms (-1: none). */
+float nn_debug_main_kernel_ms(int enable);
 int nn_noisy_conv_fwd(const nn_conv_fwd_args* a, int device, void* stream);
 
 /* ---- a10: backward of a5/a6 with the saturated STE fused --------------------------- */

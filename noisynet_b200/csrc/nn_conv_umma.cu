@@ -19,6 +19,7 @@
 // * Every mbarrier wait is bounded (clock64 watchdog): a protocol bug sets an error flag instead of
 //   hanging the GPU.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "nn_common.cuh"
 
@@ -61,7 +62,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -178,30 +179,43 @@ k_conv_umma(const UmmaP p) {
 
     // ================================================================ main loop roles
     if (warp < 4) {
-        // ---------------- A producers: one tile row per thread, 8 x 16-byte chunks per k-block
-        const int row = tid;
-        const int m = m0 + row;
-        const bool row_ok = m < p.M;
-        int b = 0, oh = 0, ow = 0;
-        if (row_ok) { const int ohw = p.OH * p.OW; b = m / ohw; int r = m - b * ohw; oh = r / p.OW; ow = r - oh * p.OW; }
-        const int ih0 = oh * p.stride - p.pad, iw0 = ow * p.stride - p.pad;
-        const __nv_bfloat16* xb = p.xp + (size_t)b * p.H * p.W * p.Cp;
-        const uint32_t row_off = (uint32_t)row * 128u;
-        const uint32_t sw = (uint32_t)(row & 7);
-        int c0 = 0, kh = 0, kw = 0;                   // incremental decode of k = (kh, kw, c0)
+        // ---------------- A producers.  Lane mapping: 8 consecutive lanes fetch the 8 consecutive 16-byte
+        // chunks of ONE tile row (contiguous channels of one tap, 128 B), so a warp instruction touches 4 rows
+        // = 4-8 cache lines instead of 32 (the gather is L1-wavefront-bound otherwise).  Thread t owns chunk
+        // j = t % 8 of rows (t / 8) + 16 i, i = 0..7.
+        const int j = tid & 7;
+        int rbase[8], rih[8], riw[8];                 // per row: pixel base index (may be negative), ih0, iw0
+        {
+            const int ohw = p.OH * p.OW;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = m0 + (tid >> 3) + 16 * i;
+                if (m < p.M) {
+                    const int b = m / ohw; const int r = m - b * ohw; const int oh = r / p.OW; const int ow = r - oh * p.OW;
+                    rih[i] = oh * p.stride - p.pad; riw[i] = ow * p.stride - p.pad;
+                    rbase[i] = (b * p.H + rih[i]) * p.W + riw[i];
+                } else {
+                    rih[i] = -100000; riw[i] = -100000; rbase[i] = 0;      // fails every bounds check -> zero fill
+                }
+            }
+        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
             const int s = kb % S;
             if (!mbar_wait(empty_bar + 8 * s, ((kb / S) & 1) ^ 1)) { *abort_g = 1; break; }
             if (*abort_g) break;
-            const uint32_t dst_row = a_base + (uint32_t)s * UM_A_STAGE + row_off;
+            const int k = kb * UM_BLOCK_K + j * 8;
+            const int tap = k / p.Cp, c0 = k - tap * p.Cp;
+            const int kh = tap / p.KW, kw = tap - kh * p.KW;
+            const bool tap_ok = kh < p.KH;
+            const int koff = kh * p.W + kw;
+            const uint32_t dst0 = a_base + (uint32_t)s * UM_A_STAGE;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int ih = ih0 + kh, iw = iw0 + kw;
-                const bool ok = row_ok && kh < p.KH && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
-                const __nv_bfloat16* src = ok ? xb + ((size_t)ih * p.W + iw) * p.Cp + c0 : p.xp;
-                cp_async_16(dst_row + ((((uint32_t)j) ^ sw) << 4), src, ok ? 16u : 0u);
-                c0 += 8;
-                if (c0 >= p.Cp) { c0 = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
+            for (int i = 0; i < 8; ++i) {
+                const int row = (tid >> 3) + 16 * i;
+                const int ih = rih[i] + kh, iw = riw[i] + kw;
+                const bool ok = tap_ok && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
+                const __nv_bfloat16* src = ok ? p.xp + (size_t)(rbase[i] + koff) * p.Cp + c0 : p.xp;
+                cp_async_16(dst0 + (uint32_t)row * 128u + ((((uint32_t)j) ^ (uint32_t)(row & 7)) << 4), src, ok ? 16u : 0u);
             }
             cp_async_mbar_arrive_noinc(full_bar + 8 * s);
         }
@@ -473,41 +487,57 @@ k_wgrad_umma(const WgUP p) {
     const uint32_t tmem_base = *tmem_slot_g;
 
     if (warp < 4) {
-        const int r = tid & 63, grp = tid >> 6;
-        const uint32_t sw = (uint32_t)(r & 7);
+        // Lane mapping (as in the forward producer): consecutive lanes fetch consecutive 16-byte chunks of one
+        // pixel row, so a warp instruction touches a few cache lines instead of 32.
+        //   A (gy):     16 chunks per pixel row -> tid & 15 = chunk, rows (tid >> 4) + 8 e,  e < 8
+        //   B (im2col): nchunk (8/16/32) chunks per pixel row -> tid % nchunk = chunk, rows tid/nchunk + rpp e
+        const int ja = tid & 15, rowA0 = tid >> 4;
+        const int qB = tid & (nchunk - 1), rppB = 128 / nchunk, rowB0 = tid / nchunk, passesB = 64 / rppB;
+        const int4 tb = tab[qB];
+        const int koff = tb.x * p.W + tb.y;
+        const bool a_col_ok = (tile_n * 128 + ja * 8) < p.Coutp;
+        const int ohw = p.OH * p.OW;
+        int b0, oh0, ow0;
+        {
+            const int mf = kb0 * 64 + rowB0;
+            b0 = mf / ohw; const int t = mf - b0 * ohw; oh0 = t / p.OW; ow0 = t - oh0 * p.OW;
+        }
+        auto advance = [&](int& b, int& oh, int& ow, int step) {
+            if (ohw == 1) { b += step; return; }
+            ow += step;
+            while (ow >= p.OW) { ow -= p.OW; if (++oh == p.OH) { oh = 0; ++b; } }
+        };
         for (int i = 0; i < nkb; ++i) {
             const int s = i % S;
             if (!mbar_wait(empty_bar + 8 * s, ((i / S) & 1) ^ 1)) { *abort_g = 1; break; }
             if (*abort_g) break;
-            const int m = (kb0 + i) * 64 + r;
-            const bool m_ok = m < p.Mpix;
-            int b = 0, oh = 0, ow = 0;
-            if (m_ok) { const int ohw = p.OH * p.OW; b = m / ohw; int t = m - b * ohw; oh = t / p.OW; ow = t - oh * p.OW; }
-            // A = gy rows: 16 chunks of 8 channels per pixel, this thread takes MN-atom `grp`
+            const int mblk = (kb0 + i) * 64;
             {
-                const uint32_t dst = a_base + (uint32_t)s * UM_A_STAGE + (uint32_t)grp * (64u * 128u) + (uint32_t)r * 128u;
-                const __nv_bfloat16* src_row = p.gyp + (size_t)(m_ok ? m : 0) * p.Coutp + tile_n * 128 + grp * 64;
+                const uint32_t dstA = a_base + (uint32_t)s * UM_A_STAGE + (uint32_t)(ja >> 3) * (64u * 128u);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const bool ok = m_ok && (tile_n * 128 + grp * 64 + j * 8) < p.Coutp;
-                    cp_async_16(dst + ((((uint32_t)j) ^ sw) << 4), ok ? (const void*)(src_row + j * 8) : (const void*)p.gyp,
-                                ok ? 16u : 0u);
+                for (int e = 0; e < 8; ++e) {
+                    const int r = rowA0 + 8 * e;
+                    const int m = mblk + r;
+                    const bool ok = a_col_ok && m < p.Mpix;
+                    const __nv_bfloat16* src = ok ? p.gyp + (size_t)m * p.Coutp + tile_n * 128 + ja * 8 : p.gyp;
+                    cp_async_16(dstA + (uint32_t)r * 128u + ((((uint32_t)(ja & 7)) ^ (uint32_t)(r & 7)) << 4), src, ok ? 16u : 0u);
                 }
             }
-            // B = im2col rows: NT/8 chunks per pixel, this thread takes chunks [grp * nchunk/2, +nchunk/2)
             {
-                const int ih0 = oh * p.stride - p.pad, iw0 = ow * p.stride - p.pad;
-                const __nv_bfloat16* xb = p.xp + (size_t)b * p.H * p.W * p.Cp;
-                const uint32_t dst_row = b_base + (uint32_t)s * b_stage + (uint32_t)r * 128u;
-                const int q0 = grp * (nchunk >> 1), q1 = q0 + (nchunk >> 1);
-                for (int q = q0; q < q1; ++q) {
-                    const int4 t = tab[q];
-                    const int ih = ih0 + t.x, iw = iw0 + t.y;
-                    const bool ok = m_ok && t.w && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
-                    const __nv_bfloat16* src = ok ? xb + ((size_t)ih * p.W + iw) * p.Cp + t.z : p.xp;
-                    cp_async_16(dst_row + (uint32_t)(q >> 3) * (64u * 128u) + ((((uint32_t)(q & 7)) ^ sw) << 4), src,
-                                ok ? 16u : 0u);
+                const uint32_t dstB = b_base + (uint32_t)s * b_stage + (uint32_t)(qB >> 3) * (64u * 128u);
+                int b = b0, oh = oh0, ow = ow0;
+                for (int e = 0; e < passesB; ++e) {
+                    const int r = rowB0 + rppB * e;
+                    const int m = mblk + r;
+                    const int ih = oh * p.stride - p.pad + tb.x, iw = ow * p.stride - p.pad + tb.y;
+                    const bool ok = tb.w && m < p.Mpix && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
+                    const __nv_bfloat16* src =
+                        ok ? p.xp + ((size_t)(b * p.H + oh * p.stride - p.pad) * p.W + (ow * p.stride - p.pad) + koff) * p.Cp + tb.z
+                           : p.xp;
+                    cp_async_16(dstB + (uint32_t)r * 128u + ((((uint32_t)(qB & 7)) ^ (uint32_t)(r & 7)) << 4), src, ok ? 16u : 0u);
+                    advance(b, oh, ow, rppB);
                 }
+                advance(b0, oh0, ow0, 64);
             }
             cp_async_mbar_arrive_noinc(full_bar + 8 * s);
         }
@@ -612,8 +642,10 @@ static Plan make_plan(int Cin_k, int KHW, int n_out, bool has_main, bool has_sig
     pl.tmem_cols = 32;
     while (pl.tmem_cols < need) pl.tmem_cols <<= 1;
     const int stage_bytes = UM_A_STAGE + pl.n_mma * 128;
-    pl.stages = (100 * 1024 - 2048) / stage_bytes;
-    if (pl.stages > 4) pl.stages = 4;
+    static const int budget_kb = getenv("NN_UMMA_SMEM_KB") ? atoi(getenv("NN_UMMA_SMEM_KB")) : 100;   // tuning knob
+    static const int max_stages = getenv("NN_UMMA_MAX_STAGES") ? atoi(getenv("NN_UMMA_MAX_STAGES")) : 4;
+    pl.stages = (budget_kb * 1024 - 2048) / stage_bytes;
+    if (pl.stages > max_stages) pl.stages = max_stages;
     if (pl.stages < 2) pl.stages = 2;
     if (pl.stages > pl.num_kb) pl.stages = pl.num_kb < 1 ? 1 : pl.num_kb;
     pl.smem_bytes = 1024 + (size_t)pl.stages * stage_bytes + 16 * pl.stages + 64;
@@ -624,6 +656,10 @@ static Plan make_plan(int Cin_k, int KHW, int n_out, bool has_main, bool has_sig
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// measurement hook: CUDA events around the main tcgen05 kernel only (excludes the operand packs)
+int g_time_main = 0;
+cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+
 static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -631,7 +667,12 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st) {
         attr_set = true;
     }
     dim3 grid((p.M + UM_BLOCK_M - 1) / UM_BLOCK_M, pl.n_tiles);
+    if (g_time_main) {
+        if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+        cudaEventRecord(g_ev0, st);
+    }
     k_conv_umma<<<grid, UM_THREADS, pl.smem_bytes, st>>>(p);
+    if (g_time_main) cudaEventRecord(g_ev1, st);
     NN_LAUNCH_OK();
     return 0;
 }
@@ -665,6 +706,17 @@ int* nn_umma_err_flag(int device) {
         cudaMemset(flags[device], 0, sizeof(int));
     }
     return flags[device];
+}
+
+extern "C" float nn_debug_main_kernel_ms(int enable) {
+    // enable = 1/0: switch the event pair around k_conv_umma on/off; enable < 0: synchronise and return the
+    // elapsed milliseconds of the last timed main-kernel launch (-1 if none)
+    if (enable >= 0) { g_time_main = enable; return 0.f; }
+    if (!g_ev0 || !g_ev1) return -1.f;
+    if (cudaEventSynchronize(g_ev1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) return -1.f;
+    return ms;
 }
 
 extern "C" int nn_debug_error_flag(int device, int reset) {
@@ -795,7 +847,8 @@ WgPlan make_wg_plan(const nn_conv_geom& g, int device) {
     w.Coutp = pad_to(g.Cout, 8);
     w.Ktot = g.KH * g.KW * w.Cp;
     w.n_tiles_k = (w.Ktot + 255) / 256;
-    w.NT = pad_to((w.Ktot + w.n_tiles_k - 1) / w.n_tiles_k, 64);
+    w.NT = 64;
+    while (w.NT < (w.Ktot + w.n_tiles_k - 1) / w.n_tiles_k) w.NT <<= 1;      // 64 / 128 / 256 (lane mapping needs 2^k chunks)
     w.ktot_pad = w.n_tiles_k * w.NT;
     w.m_tiles_n = (g.Cout + 127) / 128;
     w.num_kb = (int)((Mpix + 63) / 64);

@@ -56,6 +56,11 @@ class FlatGradAllReduce:
             for t in list(model.parameters()) + list(model.buffers()):
                 dist.broadcast(t.data, src)
 
+    def all_reduce_sum_(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        return self.flat
+
     def all_reduce_mean_(self):
         if self.world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
