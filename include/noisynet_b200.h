@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NN_ABI_VERSION 4
+#define NN_ABI_VERSION 5
 
 /* ---- common ---------------------------------------------------------------------- */
 
@@ -146,6 +146,9 @@ typedef struct nn_conv_fwd_args {
     float a_code_scale, w_code_scale;
     void* workspace;         /* device scratch for packed operands (nn_conv_workspace_bytes) */
     int64_t workspace_bytes;
+    const void* x_packed;    /* optional (tcgen05 precisions): the input already packed as NHWC bf16
+                                [B,H,W,ceil8(Cin)] (codes if a_code_scale > 0), e.g. by nn_stage_fwd;
+                                `x` is then ignored and the pack kernel is skipped                    */
 } nn_conv_fwd_args;
 
 int64_t nn_conv_workspace_bytes(const nn_conv_geom* g, int32_t precision);
@@ -173,6 +176,7 @@ typedef struct nn_conv_dgrad_args {
     int32_t precision;
     float w_code_scale;      /* > 0: w_eff holds integer codes * w_code_scale (exact bf16 operand), see fwd */
     void* workspace; int64_t workspace_bytes;
+    const void* gy_packed;   /* optional: grad_output already NHWC bf16 [B,OH,OW,ceil8(Cout)] (nn_stage_bwd) */
 } nn_conv_dgrad_args;
 int nn_noisy_conv_dgrad(const nn_conv_dgrad_args* a, int device, void* stream);
 
@@ -187,9 +191,67 @@ typedef struct nn_conv_wgrad_args {
     int32_t precision;
     float a_code_scale;      /* > 0: x holds integer codes * a_code_scale (exact bf16 operand), see fwd */
     void* workspace; int64_t workspace_bytes;
+    const void* x_packed;    /* optional: layer input already NHWC bf16 [B,H,W,ceil8(Cin)] (codes if a_code_scale > 0) */
+    const void* gy_packed;   /* optional: grad_output already NHWC bf16 [B,OH,OW,ceil8(Cout)] */
 } nn_conv_wgrad_args;
 int64_t nn_conv_wgrad_workspace_bytes(const nn_conv_geom* g, int32_t precision, int device);
 int nn_noisy_conv_wgrad(const nn_conv_wgrad_args* a, int device, void* stream);
+
+/* ---- section 8f.1: the between-layer stages, fused ---------------------------------------------------
+ * conv stage (noisynet.py:419-460, 483-520): MaxPool2d(2,2) -> BatchNorm (batch statistics, running stats
+ * updated) -> ReLU -> clamp(max=act_max) -> k-bit quantize (hardware_model.py:133-173, min 0) -> NHWC bf16
+ * code pack for the next tcgen05 contraction.  fc stage (noisynet.py:540-569): the same with pool = 0,
+ * H = W = 1.  Per-channel reductions use fixed-order partial sums (deterministic). */
+typedef struct nn_stage_args {
+    const float* in;          /* [B,C,H,W] fp32 NCHW: the (noisy) conv / linear output               */
+    int32_t B, C, H, W, pool; /* pool = 1: MaxPool2d(2,2) first (H, W even)                           */
+    float* pooled;            /* out [B,C,H/2,W/2] (pool = 1), saved for the backward                  */
+    uint8_t* argmax;          /* out [B,C,H/2,W/2] window position 0..3 (pool = 1)                    */
+    const float *gamma, *beta;
+    float *running_mean, *running_var;   /* updated with `momentum` (may be NULL)                     */
+    float momentum, eps;
+    float *mean, *invstd;     /* out [C], saved for the backward                                     */
+    float act_max;            /* 0 = no clamp                                                        */
+    int32_t q_bits;           /* 0 = no quantisation (values stored as bf16)                          */
+    double q_hi;              /* quantisation range [0, q_hi]                                         */
+    float stochastic;         /* stochastic-rounding amplitude (training), 0 in eval                 */
+    const float* u_inject;    /* optional uniform draws, shape of the BN input (parity hook)         */
+    nn_rng rng;
+    void* xp; int32_t Cp;     /* out [B,H',W',Cp] bf16 codes, Cp % 8 == 0                            */
+    float* act;               /* optional out: dequantised activation, NCHW fp32                      */
+    float* xmax_out;          /* optional out: max of the activation (device scalar)                  */
+    void* scratch;            /* nn_stage_scratch_bytes(C) bytes                                      */
+} nn_stage_args;
+int64_t nn_stage_scratch_bytes(int C);
+int nn_stage_fwd(const nn_stage_args* a, int device, void* stream);
+
+/* Backward of the stage: masks of the quantizer STE (hardware_model.py:176-183), clamp and ReLU, BatchNorm
+ * backward (dgamma / dbeta are OVERWRITTEN), max-pool routing; emits the gradient w.r.t. the stage input as
+ * NHWC bf16 [B,H,W,Cp] -- the operand the tcgen05 wgrad / dgrad kernels read -- and optionally NCHW fp32. */
+typedef struct nn_stage_bwd_args {
+    const float* g;           /* grad w.r.t. the stage output, NCHW fp32 (pooled shape)               */
+    const float* x;           /* the BN input saved by the forward (pooled if pool = 1, else `in`)    */
+    const uint8_t* argmax;
+    int32_t B, C, H, W, pool; /* H, W of the stage INPUT (pre-pool)                                   */
+    const float *mean, *invstd, *gamma, *beta;
+    float act_max; int32_t q_bits; double q_hi;
+    float *dgamma, *dbeta;
+    void* gyp; int32_t Cp;
+    float* gy_f32;
+    void* scratch;
+} nn_stage_bwd_args;
+int nn_stage_bwd(const nn_stage_bwd_args* a, int device, void* stream);
+
+/* Input quantizer (quantize1, noisynet.py:344, :390-393) + NHWC bf16 code pack of the network input. */
+int nn_input_quant_pack(const float* x, void* xp, float* act, int B, int C, int HW, int Cp, int q_bits,
+                        double q_hi, float stochastic, const float* u_inject, nn_rng rng, int device, void* stream);
+
+/* Head (noisynet.py:594, :1278): BatchNorm1d(C <= 32, batch statistics) -> mean cross-entropy, and the
+ * gradient back through both: g [B,C] fp32 (+ optional bf16 [B,Cp] pack), dgamma / dbeta (overwritten). */
+int nn_head_fwd_bwd(const float* logits, const int64_t* labels, int B, int C, const float* gamma,
+                    const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                    float* loss_out, float* out, float* g, void* g_packed, int Cp, float* dgamma, float* dbeta,
+                    int device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libnoisynet_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 NOISE_NONE, NOISE_MERGED, NOISE_EXTERNAL = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
@@ -37,7 +37,7 @@ class ConvFwdArgs(C.Structure):
                 ("stats", C.c_void_p),
                 ("precision", C.c_int32),
                 ("a_code_scale", C.c_float), ("w_code_scale", C.c_float),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("x_packed", C.c_void_p)]
 
 
 class ConvDgradArgs(C.Structure):
@@ -45,7 +45,7 @@ class ConvDgradArgs(C.Structure):
                 ("gy", C.c_void_p), ("w_eff", C.c_void_p), ("gx", C.c_void_p),
                 ("x_pre", C.c_void_p), ("x_lo", C.c_double), ("x_hi", C.c_double),
                 ("precision", C.c_int32), ("w_code_scale", C.c_float),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("gy_packed", C.c_void_p)]
 
 
 class ConvWgradArgs(C.Structure):
@@ -53,13 +53,33 @@ class ConvWgradArgs(C.Structure):
                 ("gy", C.c_void_p), ("x", C.c_void_p), ("gw", C.c_void_p),
                 ("w_raw", C.c_void_p), ("w_lo", C.c_double), ("w_hi", C.c_double),
                 ("precision", C.c_int32), ("a_code_scale", C.c_float),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("x_packed", C.c_void_p),
+                ("gy_packed", C.c_void_p)]
 
 
 class AdamWTensor(C.Structure):
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
                 ("n", C.c_int64), ("lr", C.c_float), ("weight_decay", C.c_float), ("clamp", C.c_float),
                 ("absmax_out", C.c_void_p)]
+
+
+class StageArgs(C.Structure):
+    _fields_ = [("in_", C.c_void_p), ("B", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("pool", C.c_int32), ("pooled", C.c_void_p), ("argmax", C.c_void_p),
+                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
+                ("momentum", C.c_float), ("eps", C.c_float), ("mean", C.c_void_p), ("invstd", C.c_void_p),
+                ("act_max", C.c_float), ("q_bits", C.c_int32), ("q_hi", C.c_double), ("stochastic", C.c_float),
+                ("u_inject", C.c_void_p), ("rng", Rng), ("xp", C.c_void_p), ("Cp", C.c_int32),
+                ("act", C.c_void_p), ("xmax_out", C.c_void_p), ("scratch", C.c_void_p)]
+
+
+class StageBwdArgs(C.Structure):
+    _fields_ = [("g", C.c_void_p), ("x", C.c_void_p), ("argmax", C.c_void_p),
+                ("B", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("pool", C.c_int32),
+                ("mean", C.c_void_p), ("invstd", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("act_max", C.c_float), ("q_bits", C.c_int32), ("q_hi", C.c_double),
+                ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("gyp", C.c_void_p), ("Cp", C.c_int32),
+                ("gy_f32", C.c_void_p), ("scratch", C.c_void_p)]
 
 
 # name -> (restype, argtypes); mirrors include/noisynet_b200.h one to one
@@ -77,6 +97,14 @@ SIGNATURES = {
                                       C.c_int, C.c_void_p]),
     "nn_adamw_step": (C.c_int, [C.POINTER(AdamWTensor), C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_void_p, C.c_int, C.c_void_p]),
+    "nn_stage_scratch_bytes": (C.c_int64, [C.c_int]),
+    "nn_stage_fwd": (C.c_int, [C.POINTER(StageArgs), C.c_int, C.c_void_p]),
+    "nn_stage_bwd": (C.c_int, [C.POINTER(StageBwdArgs), C.c_int, C.c_void_p]),
+    "nn_input_quant_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_double, C.c_float, C.c_void_p, Rng, C.c_int, C.c_void_p]),
+    "nn_head_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "nn_tensor_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
     "nn_clamp_absmax": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "nn_noise_epilogue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,

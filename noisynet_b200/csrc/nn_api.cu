@@ -43,7 +43,7 @@ extern "C" int64_t nn_conv_workspace_bytes(const nn_conv_geom* g, int32_t precis
 extern "C" int nn_noisy_conv_fwd(const nn_conv_fwd_args* a, int device, void* stream) {
     if (!a) return nn_fail("nn_noisy_conv_fwd: null args%s", "");
     if (int e = check_geom(a->g, "nn_noisy_conv_fwd")) return e;
-    if (!a->x) return nn_fail("nn_noisy_conv_fwd: x missing%s", "");
+    if (!a->x && !(a->x_packed && a->precision != NN_PREC_FP32)) return nn_fail("nn_noisy_conv_fwd: x missing%s", "");
     if (!a->w_eff && (a->noise_mode == NN_NOISE_NONE || !a->y))
         return nn_fail("nn_noisy_conv_fwd: w_eff missing%s (noise-only mode needs noise_mode > 0 and y as input)", "");
     if (a->noise_mode < 0 || a->noise_mode > 2) return nn_fail("nn_noisy_conv_fwd: bad noise_mode%s", "");
@@ -67,7 +67,8 @@ extern "C" int nn_noisy_conv_fwd(const nn_conv_fwd_args* a, int device, void* st
 extern "C" int nn_noisy_conv_dgrad(const nn_conv_dgrad_args* a, int device, void* stream) {
     if (!a) return nn_fail("nn_noisy_conv_dgrad: null args%s", "");
     if (int e = check_geom(a->g, "nn_noisy_conv_dgrad")) return e;
-    if (!a->gy || !a->w_eff || !a->gx) return nn_fail("nn_noisy_conv_dgrad: null tensor%s", "");
+    if ((!a->gy && !(a->gy_packed && a->precision != NN_PREC_FP32)) || !a->w_eff || !a->gx)
+        return nn_fail("nn_noisy_conv_dgrad: null tensor%s", "");
     NN_SET_DEVICE(device);
     if (a->precision == NN_PREC_FP32) return nn_simt_conv_dgrad(a, device, (cudaStream_t)stream);
     if (!nn_umma_supports(&a->g, 1))
@@ -83,7 +84,9 @@ extern "C" int64_t nn_conv_wgrad_workspace_bytes(const nn_conv_geom* g, int32_t 
 extern "C" int nn_noisy_conv_wgrad(const nn_conv_wgrad_args* a, int device, void* stream) {
     if (!a) return nn_fail("nn_noisy_conv_wgrad: null args%s", "");
     if (int e = check_geom(a->g, "nn_noisy_conv_wgrad")) return e;
-    if (!a->gy || !a->x || !a->gw) return nn_fail("nn_noisy_conv_wgrad: null tensor%s", "");
+    const bool packed_ok = a->precision != NN_PREC_FP32;
+    if ((!a->gy && !(a->gy_packed && packed_ok)) || (!a->x && !(a->x_packed && packed_ok)) || !a->gw)
+        return nn_fail("nn_noisy_conv_wgrad: null tensor%s", "");
     NN_SET_DEVICE(device);
     if (a->precision == NN_PREC_FP32) return nn_simt_conv_wgrad(a, device, (cudaStream_t)stream);
     if (!nn_umma_supports(&a->g, 2))

@@ -748,7 +748,9 @@ int nn_umma_conv_fwd(const nn_conv_fwd_args* a, int device, cudaStream_t st) {
     __nv_bfloat16* wp = (__nv_bfloat16*)(ws + align_up(pl.xp_bytes, 1024));
     int* err = nn_umma_err_flag(device);
 
-    {   // activations -> NHWC bf16 (integer codes when a_code_scale > 0)
+    if (a->x_packed) {
+        xp = (__nv_bfloat16*)a->x_packed;
+    } else {   // activations -> NHWC bf16 (integer codes when a_code_scale > 0)
         const int64_t total = (int64_t)g.B * g.H * g.W * (pl.Cp / 8);
         int grid = (int)((total + 255) / 256);
         if (grid > 16 * nn_num_sms(device)) grid = 16 * nn_num_sms(device);
@@ -799,7 +801,9 @@ int nn_umma_conv_dgrad(const nn_conv_dgrad_args* a, int device, cudaStream_t st)
     uint8_t* ws = (uint8_t*)align_up((size_t)a->workspace, 1024);
     __nv_bfloat16* xp = (__nv_bfloat16*)ws;
     __nv_bfloat16* wp = (__nv_bfloat16*)(ws + align_up(pl.xp_bytes, 1024));
-    {
+    if (a->gy_packed) {
+        xp = (__nv_bfloat16*)a->gy_packed;
+    } else {
         const int64_t total = (int64_t)g.B * OH * OW * (pl.Cp / 8);
         int grid = (int)((total + 255) / 256);
         if (grid > 16 * nn_num_sms(device)) grid = 16 * nn_num_sms(device);
@@ -892,14 +896,20 @@ int nn_umma_conv_wgrad(const nn_conv_wgrad_args* a, int device, cudaStream_t st)
     __nv_bfloat16* gyp = (__nv_bfloat16*)(ws + align_up(w.xp_bytes, 1024));
     float* partial = (float*)(ws + align_up(w.xp_bytes, 1024) + align_up(w.gyp_bytes, 1024));
     const int sms = nn_num_sms(device);
-    {
+    if (a->x_packed) {
+        xp = (__nv_bfloat16*)a->x_packed;
+    } else {
         int64_t total = (int64_t)g.B * g.H * g.W * (w.Cp / 8);
         int grid = (int)((total + 255) / 256);
         if (grid > 16 * sms) grid = 16 * sms;
         k_pack_act<<<grid, 256, 0, st>>>(a->x, xp, g.B, g.Cin, g.H * g.W, w.Cp, a->a_code_scale);
         NN_LAUNCH_OK();
-        total = (int64_t)g.B * OH * OW * (w.Coutp / 8);
-        grid = (int)((total + 255) / 256);
+    }
+    if (a->gy_packed) {
+        gyp = (__nv_bfloat16*)a->gy_packed;
+    } else {
+        int64_t total = (int64_t)g.B * OH * OW * (w.Coutp / 8);
+        int grid = (int)((total + 255) / 256);
         if (grid > 16 * sms) grid = 16 * sms;
         k_pack_act<<<grid, 256, 0, st>>>(a->gy, gyp, g.B, g.Cout, OH * OW, w.Coutp, 0.f);
         NN_LAUNCH_OK();

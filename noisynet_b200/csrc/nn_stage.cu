@@ -1,0 +1,479 @@
+// Between-layer stages of the NoisyNet step, fused:
+//   conv stage : MaxPool2d(2,2) -> BatchNorm2d (batch statistics) -> ReLU -> clamp(max=act_max) -> 4-bit
+//                quantize (stochastic rounding) -> NHWC bf16 code pack for the next tensor-core contraction
+//                (noisynet.py:419-460, 483-520), and its backward (STE + clamp + ReLU masks, BN backward,
+//                max-pool routing) emitting the NHWC bf16 gradient the wgrad/dgrad kernels consume.
+//   fc stage   : BatchNorm1d -> ReLU -> clamp -> quantize -> pack (noisynet.py:540-569) and backward.
+//   head       : BatchNorm1d(10) -> cross-entropy (mean) -> gradient (noisynet.py:594, :1278).
+// All HBM-bound elementwise/reduction work; per-channel reductions use fixed-order partials (deterministic).
+#include <cuda_bf16.h>
+
+#include "nn_common.cuh"
+
+namespace {
+
+constexpr int ST_SPLITS = 16;   // batch slices per channel for the deterministic partial sums
+
+__device__ __forceinline__ float quant_code(float v, float s, float qmax, float u) {
+    // hardware_model.py:154-166 with min_value = 0: rne(clamp(v / s + u, 0, qmax))
+    float t = __fadd_rn(__fdiv_rn(v, s), u);
+    return rintf(fminf(fmaxf(t, 0.f), qmax));
+}
+
+// ------------------------------------------------------------------ F1: 2x2 max pool + per-channel partial sums
+// grid (C, ST_SPLITS); block 256.  y [B,C,OH,OW] -> pooled [B,C,PH,PW], argmax (0..3), partial [C][SPLITS][2] (double)
+__global__ void __launch_bounds__(256)
+k_pool_stats(const float* __restrict__ y, float* __restrict__ pooled, uint8_t* __restrict__ amax, double* __restrict__ partial,
+             int B, int C, int OH, int OW) {
+    const int c = blockIdx.x, sp = blockIdx.y;
+    const int PH = OH >> 1, PW = OW >> 1, PHW = PH * PW;
+    const int b0 = (int)((int64_t)B * sp / ST_SPLITS), b1 = (int)((int64_t)B * (sp + 1) / ST_SPLITS);
+    const int n = (b1 - b0) * PHW;
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int b = b0 + i / PHW, r = i % PHW, ph = r / PW, pw = r - ph * PW;
+        const float* src = y + (((int64_t)b * C + c) * OH + 2 * ph) * OW + 2 * pw;
+        const float2 t0 = *reinterpret_cast<const float2*>(src);
+        const float2 t1 = *reinterpret_cast<const float2*>(src + OW);
+        float m = t0.x; int a = 0;
+        if (t0.y > m) { m = t0.y; a = 1; }
+        if (t1.x > m) { m = t1.x; a = 2; }
+        if (t1.y > m) { m = t1.y; a = 3; }
+        const int64_t o = ((int64_t)b * C + c) * PHW + r;
+        pooled[o] = m;
+        amax[o] = (uint8_t)a;
+        s1 += m; s2 += (double)m * m;
+    }
+    __shared__ double sh[2][8];
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s1; sh[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
+        partial[((int64_t)c * ST_SPLITS + sp) * 2 + 0] = a;
+        partial[((int64_t)c * ST_SPLITS + sp) * 2 + 1] = b;
+    }
+}
+
+// statistics only (fc stages / no pooling): x [B,C,HW]
+__global__ void __launch_bounds__(256)
+k_chan_stats(const float* __restrict__ x, double* __restrict__ partial, int B, int C, int HW) {
+    const int c = blockIdx.x, sp = blockIdx.y;
+    const int b0 = (int)((int64_t)B * sp / ST_SPLITS), b1 = (int)((int64_t)B * (sp + 1) / ST_SPLITS);
+    const int n = (b1 - b0) * HW;
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int b = b0 + i / HW, r = i % HW;
+        const float m = __ldg(x + ((int64_t)b * C + c) * HW + r);
+        s1 += m; s2 += (double)m * m;
+    }
+    __shared__ double sh[2][8];
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s1; sh[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
+        partial[((int64_t)c * ST_SPLITS + sp) * 2 + 0] = a;
+        partial[((int64_t)c * ST_SPLITS + sp) * 2 + 1] = b;
+    }
+}
+
+// finalize BN statistics: mean / invstd (biased var) + running stats update (momentum, unbiased var)
+__global__ void k_bn_finalize(const double* __restrict__ partial, int C, double count, float eps, float momentum,
+                              float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
+                              float* __restrict__ running_var, float* __restrict__ xmax_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && xmax_out) *xmax_out = 0.f;
+    if (c >= C) return;
+    double s1 = 0, s2 = 0;
+    for (int s = 0; s < ST_SPLITS; ++s) { s1 += partial[((int64_t)c * ST_SPLITS + s) * 2]; s2 += partial[((int64_t)c * ST_SPLITS + s) * 2 + 1]; }
+    const double m = s1 / count;
+    double var = s2 / count - m * m;
+    if (var < 0) var = 0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        const double unb = count > 1 ? var * count / (count - 1) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+    }
+}
+
+// ------------------------------------------------------------------ F2: BN + ReLU + clamp + quantize + NHWC pack
+// one thread = (pixel, 8-channel chunk).  pooled [B,C,PH,PW] fp32 -> xp [B,PH,PW,Cp] bf16 codes; optional act
+// (dequantised fp32, NCHW) for callers that want the reference-layout tensor; xmax_out = max value (for the
+// external-DAC sigma of the next layer, hardware_model.py:45).
+struct BnActP {
+    const float *x, *mean, *invstd, *gamma, *beta, *u_inject;
+    __nv_bfloat16* xp;
+    float* act;
+    float* xmax_out;
+    int B, C, HW, Cp;
+    float act_max, q_scale, q_max, stoch;
+    int quant;
+    nn_rng rng;
+};
+
+__global__ void __launch_bounds__(256)
+k_bn_act_pack(const BnActP p) {
+    const NnRng rs = nn_rng_load(p.rng);
+    const int chunks = p.Cp >> 3;
+    const int64_t npix = (int64_t)p.B * p.HW, total = npix * chunks;
+    float vmax = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pixel = i % npix;
+        const int chunk = (int)(i / npix);
+        const int b = (int)(pixel / p.HW), r = (int)(pixel - (int64_t)b * p.HW);
+        __align__(16) __nv_bfloat16 out[8];
+        uint4 rnd[2];
+        if (p.quant && p.stoch > 0.f && !p.u_inject) {
+            // Philox group = (NCHW element index of channel c) / 4 is not chunk aligned; use one group per
+            // (pixel, chunk, half): 8 uniforms for 8 channels
+            rnd[0] = nn_philox(rs, (uint64_t)i * 2);
+            rnd[1] = nn_philox(rs, (uint64_t)i * 2 + 1);
+        }
+        const uint32_t* rr = reinterpret_cast<const uint32_t*>(rnd);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = chunk * 8 + j;
+            float code = 0.f;
+            if (c < p.C) {
+                const int64_t o = ((int64_t)b * p.C + c) * p.HW + r;
+                float v = (__ldg(p.x + o) - __ldg(p.mean + c)) * __ldg(p.invstd + c) * __ldg(p.gamma + c) + __ldg(p.beta + c);
+                v = fmaxf(v, 0.f);                                          // ReLU
+                if (p.act_max > 0.f) v = fminf(v, p.act_max);               // clamp(max=act_max)
+                float val = v;
+                if (p.quant) {
+                    const float u = p.stoch > 0.f ? (p.u_inject ? __ldg(p.u_inject + o) : nn_usym(rr[j], p.stoch)) : 0.f;
+                    code = quant_code(v, p.q_scale, p.q_max, u);
+                    val = __fmul_rn(code, p.q_scale);
+                } else {
+                    code = v;
+                }
+                if (p.act) p.act[o] = val;
+                vmax = fmaxf(vmax, val);
+            }
+            out[j] = __float2bfloat16_rn(code);
+        }
+        *reinterpret_cast<uint4*>(p.xp + (pixel * p.Cp + chunk * 8)) = *reinterpret_cast<const uint4*>(out);
+    }
+    if (p.xmax_out) {
+        vmax = nn_warp_max(vmax);
+        if ((threadIdx.x & 31) == 0 && vmax > 0.f) nn_atomic_max_float(p.xmax_out, vmax);
+    }
+}
+
+// ------------------------------------------------------------------ B1: masks + per-channel sums of dv, dv*xhat
+struct BnBwdP {
+    const float *g, *x, *mean, *invstd, *gamma, *beta;
+    double* partial;              // [C][SPLITS][2]
+    int B, C, HW;
+    float act_max, q_hi;
+};
+
+__device__ __forceinline__ float stage_dv(float g, float x, float mean, float invstd, float gamma, float beta,
+                                          float act_max, float q_hi, float& xhat) {
+    xhat = (x - mean) * invstd;
+    const float v = xhat * gamma + beta;
+    // ReLU: v > 0; clamp(max): v <= act_max; quantizer STE (hardware_model.py:176-183): 0 <= clamped <= q_hi
+    bool pass = v > 0.f;
+    if (act_max > 0.f) pass = pass && (v <= act_max);
+    if (q_hi > 0.f) pass = pass && (fminf(v, act_max > 0.f ? act_max : v) <= q_hi);
+    return pass ? g : 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_bwd_stats(const BnBwdP p) {
+    const int c = blockIdx.x, sp = blockIdx.y;
+    const int b0 = (int)((int64_t)p.B * sp / ST_SPLITS), b1 = (int)((int64_t)p.B * (sp + 1) / ST_SPLITS);
+    const int n = (b1 - b0) * p.HW;
+    const float mean = p.mean[c], invstd = p.invstd[c], gamma = p.gamma[c], beta = p.beta[c];
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int b = b0 + i / p.HW, r = i % p.HW;
+        const int64_t o = ((int64_t)b * p.C + c) * p.HW + r;
+        float xhat;
+        const float dv = stage_dv(__ldg(p.g + o), __ldg(p.x + o), mean, invstd, gamma, beta, p.act_max, p.q_hi, xhat);
+        s1 += dv; s2 += (double)dv * xhat;
+    }
+    __shared__ double sh[2][8];
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s1; sh[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
+        p.partial[((int64_t)c * ST_SPLITS + sp) * 2 + 0] = a;
+        p.partial[((int64_t)c * ST_SPLITS + sp) * 2 + 1] = b;
+    }
+}
+
+__global__ void k_bn_bwd_finalize(const double* __restrict__ partial, int C, float* __restrict__ dbeta, float* __restrict__ dgamma) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0, s2 = 0;
+    for (int s = 0; s < ST_SPLITS; ++s) { s1 += partial[((int64_t)c * ST_SPLITS + s) * 2]; s2 += partial[((int64_t)c * ST_SPLITS + s) * 2 + 1]; }
+    dbeta[c] = (float)s1;        // grads are OVERWRITTEN (the step zeroes them anyway)
+    dgamma[c] = (float)s2;
+}
+
+// ------------------------------------------------------------------ B2: BN backward + max-pool routing -> NHWC bf16
+// one thread = (output pixel (b, oh, ow), 8-channel chunk) of gyp [B,OH,OW,Cp]; pool = 0 -> no pooling (HW = OH*OW)
+struct BnBwdApplyP {
+    const float *g, *x, *mean, *invstd, *gamma, *beta, *dbeta, *dgamma;
+    const uint8_t* amax;
+    __nv_bfloat16* gyp;
+    float* gy_f32;                // optional NCHW fp32 copy of the same gradient [B,C,OH,OW]
+    int B, C, OH, OW, Cp, pool;
+    float act_max, q_hi, inv_count;
+};
+
+__global__ void __launch_bounds__(256)
+k_bn_bwd_apply(const BnBwdApplyP p) {
+    const int chunks = p.Cp >> 3;
+    const int64_t npix = (int64_t)p.B * p.OH * p.OW, total = npix * chunks;
+    const int PH = p.pool ? p.OH >> 1 : p.OH, PW = p.pool ? p.OW >> 1 : p.OW, PHW = PH * PW;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pixel = i % npix;
+        const int chunk = (int)(i / npix);
+        const int b = (int)(pixel / (p.OH * p.OW)), r = (int)(pixel - (int64_t)b * p.OH * p.OW);
+        const int oh = r / p.OW, ow = r - oh * p.OW;
+        const int ph = p.pool ? oh >> 1 : oh, pw = p.pool ? ow >> 1 : ow;
+        const int my = p.pool ? ((oh & 1) * 2 + (ow & 1)) : 0;
+        __align__(16) __nv_bfloat16 out[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = chunk * 8 + j;
+            float d = 0.f;
+            if (c < p.C) {
+                const int64_t o = ((int64_t)b * p.C + c) * PHW + ph * PW + pw;
+                if (!p.pool || __ldg(p.amax + o) == my) {
+                    float xhat;
+                    const float invstd = __ldg(p.invstd + c), gamma = __ldg(p.gamma + c);
+                    const float dv = stage_dv(__ldg(p.g + o), __ldg(p.x + o), __ldg(p.mean + c), invstd, gamma,
+                                              __ldg(p.beta + c), p.act_max, p.q_hi, xhat);
+                    d = gamma * invstd * (dv - __ldg(p.dbeta + c) * p.inv_count - xhat * __ldg(p.dgamma + c) * p.inv_count);
+                }
+                if (p.gy_f32) p.gy_f32[((int64_t)b * p.C + c) * p.OH * p.OW + r] = d;
+            }
+            out[j] = __float2bfloat16_rn(d);
+        }
+        *reinterpret_cast<uint4*>(p.gyp + (pixel * p.Cp + chunk * 8)) = *reinterpret_cast<const uint4*>(out);
+    }
+}
+
+// ------------------------------------------------------------------ input quantize + pack (noisynet.py:390-393)
+__global__ void __launch_bounds__(256)
+k_quant_pack_input(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, float* __restrict__ act, int B, int C, int HW,
+                   int Cp, int quant, float q_scale, float q_max, float stoch, const float* __restrict__ u_inject, nn_rng rng) {
+    const NnRng rs = nn_rng_load(rng);
+    const int chunks = Cp >> 3;
+    const int64_t npix = (int64_t)B * HW, total = npix * chunks;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pixel = i % npix;
+        const int chunk = (int)(i / npix);
+        const int b = (int)(pixel / HW), r = (int)(pixel - (int64_t)b * HW);
+        uint4 rnd[2];
+        if (quant && stoch > 0.f && !u_inject) { rnd[0] = nn_philox(rs, (uint64_t)i * 2); rnd[1] = nn_philox(rs, (uint64_t)i * 2 + 1); }
+        const uint32_t* rr = reinterpret_cast<const uint32_t*>(rnd);
+        __align__(16) __nv_bfloat16 out[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = chunk * 8 + j;
+            float code = 0.f;
+            if (c < C) {
+                const int64_t o = ((int64_t)b * C + c) * HW + r;
+                const float v = __ldg(x + o);
+                if (quant) {
+                    code = quant_code(v, q_scale, q_max, stoch > 0.f ? (u_inject ? __ldg(u_inject + o) : nn_usym(rr[j], stoch)) : 0.f);
+                    if (act) act[o] = __fmul_rn(code, q_scale);
+                } else {
+                    code = v;
+                    if (act) act[o] = v;
+                }
+            }
+            out[j] = __float2bfloat16_rn(code);
+        }
+        *reinterpret_cast<uint4*>(xp + (pixel * Cp + chunk * 8)) = *reinterpret_cast<const uint4*>(out);
+    }
+}
+
+// ------------------------------------------------------------------ head: BatchNorm1d(C<=32) + cross entropy + backward
+// single block; logits [B,C] -> loss (mean CE), out (bn output, optional), g [B,C] = d loss / d logits (through BN),
+// dgamma/dbeta, running stats.  thread = row.
+__global__ void __launch_bounds__(1024)
+k_head(const float* __restrict__ z, const int64_t* __restrict__ label, int B, int C, const float* __restrict__ gamma,
+       const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+       float eps, float* __restrict__ loss_out, float* __restrict__ out, float* __restrict__ g, __nv_bfloat16* __restrict__ gp,
+       int Cp, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ double red[32][2];
+    __shared__ float s_mean[32], s_invstd[32], s_dg[32], s_db[32];
+    __shared__ double s_loss;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    // channel statistics (fixed order: thread c sums column c sequentially in double; B is small)
+    if (tid < C) {
+        double s1 = 0, s2 = 0;
+        for (int b = 0; b < B; ++b) { const double v = z[(int64_t)b * C + tid]; s1 += v; s2 += v * v; }
+        const double m = s1 / B;
+        double var = s2 / B - m * m;
+        if (var < 0) var = 0;
+        s_mean[tid] = (float)m;
+        s_invstd[tid] = (float)(1.0 / sqrt(var + (double)eps));
+        if (running_mean) {
+            const double unb = B > 1 ? var * B / (B - 1) : var;
+            running_mean[tid] = (float)((1.0 - momentum) * running_mean[tid] + momentum * m);
+            running_var[tid] = (float)((1.0 - momentum) * running_var[tid] + momentum * unb);
+        }
+    }
+    if (tid == 0) s_loss = 0.0;
+    __syncthreads();
+    // per-row softmax / CE; dv = (softmax - onehot) / B stored to g temporarily
+    double my_loss = 0.0;
+    for (int b = tid; b < B; b += nthr) {
+        float v[32];
+        float mx = -3.4e38f;
+        for (int c = 0; c < C; ++c) {
+            v[c] = (z[(int64_t)b * C + c] - s_mean[c]) * s_invstd[c] * gamma[c] + beta[c];
+            if (out) out[(int64_t)b * C + c] = v[c];
+            mx = fmaxf(mx, v[c]);
+        }
+        float se = 0.f;
+        for (int c = 0; c < C; ++c) se += expf(v[c] - mx);
+        const int lab = (int)label[b];
+        my_loss += (double)(logf(se) + mx - v[lab]);
+        for (int c = 0; c < C; ++c) g[(int64_t)b * C + c] = (expf(v[c] - mx) / se - (c == lab ? 1.f : 0.f)) / (float)B;
+    }
+    atomicAdd(&s_loss, my_loss);   // double atomics in smem: order varies, loss is a report value only
+    __syncthreads();
+    if (tid == 0) *loss_out = (float)(s_loss / B);
+    // BN backward sums (fixed order)
+    if (tid < C) {
+        double s1 = 0, s2 = 0;
+        for (int b = 0; b < B; ++b) {
+            const float dv = g[(int64_t)b * C + tid];
+            const float xhat = (z[(int64_t)b * C + tid] - s_mean[tid]) * s_invstd[tid];
+            s1 += dv; s2 += (double)dv * xhat;
+        }
+        s_db[tid] = (float)s1; s_dg[tid] = (float)s2;
+        dbeta[tid] = (float)s1; dgamma[tid] = (float)s2;
+    }
+    __syncthreads();
+    const float invB = 1.f / (float)B;
+    for (int b = tid; b < B; b += nthr) {
+        for (int c = 0; c < Cp; ++c) {
+            float d = 0.f;
+            if (c < C) {
+                const float xhat = (z[(int64_t)b * C + c] - s_mean[c]) * s_invstd[c];
+                d = gamma[c] * s_invstd[c] * (g[(int64_t)b * C + c] - s_db[c] * invB - xhat * s_dg[c] * invB);
+                g[(int64_t)b * C + c] = d;
+            }
+            if (gp) gp[(int64_t)b * Cp + c] = __float2bfloat16_rn(d);
+        }
+    }
+    (void)red;
+}
+
+static inline int grid_cap(int64_t items, int device, int waves = 8) {
+    int64_t blocks = (items + 255) / 256, cap = (int64_t)nn_num_sms(device) * waves;
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace
+
+extern "C" int64_t nn_stage_scratch_bytes(int C) { return (int64_t)C * ST_SPLITS * 2 * sizeof(double); }
+
+extern "C" int nn_stage_fwd(const nn_stage_args* a, int device, void* stream) {
+    if (!a || !a->in || !a->xp || !a->scratch || !a->mean || !a->invstd)
+        return nn_fail("nn_stage_fwd: null argument%s", "");
+    if (a->pool && ((a->H | a->W) & 1)) return nn_fail("nn_stage_fwd: pooling needs even H, W%s", "");
+    if (a->Cp % 8 || a->Cp < a->C) return nn_fail("nn_stage_fwd: bad Cp%s", "");
+    NN_SET_DEVICE(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* bn_in = a->in;
+    int HW = a->H * a->W;
+    double* partial = (double*)a->scratch;
+    if (a->pool) {
+        if (!a->pooled || !a->argmax) return nn_fail("nn_stage_fwd: pooled/argmax buffers missing%s", "");
+        dim3 grid(a->C, ST_SPLITS);
+        k_pool_stats<<<grid, 256, 0, st>>>(a->in, a->pooled, a->argmax, partial, a->B, a->C, a->H, a->W);
+        NN_LAUNCH_OK();
+        bn_in = a->pooled;
+        HW = (a->H / 2) * (a->W / 2);
+    } else {
+        dim3 grid(a->C, ST_SPLITS);
+        k_chan_stats<<<grid, 256, 0, st>>>(a->in, partial, a->B, a->C, HW);
+        NN_LAUNCH_OK();
+    }
+    k_bn_finalize<<<(a->C + 127) / 128, 128, 0, st>>>(partial, a->C, (double)a->B * HW, a->eps, a->momentum, a->mean,
+                                                      a->invstd, a->running_mean, a->running_var, a->xmax_out);
+    NN_LAUNCH_OK();
+    BnActP p;
+    p.x = bn_in; p.mean = a->mean; p.invstd = a->invstd; p.gamma = a->gamma; p.beta = a->beta; p.u_inject = a->u_inject;
+    p.xp = (__nv_bfloat16*)a->xp; p.act = a->act; p.xmax_out = a->xmax_out;
+    p.B = a->B; p.C = a->C; p.HW = HW; p.Cp = a->Cp; p.act_max = a->act_max;
+    p.quant = a->q_bits > 0;
+    double qmax = a->q_bits > 0 ? (double)((1u << a->q_bits) - 1u) : 0.0;
+    double scale = a->q_bits > 0 ? a->q_hi / qmax : 1.0;
+    if (scale < 1e-6) scale = 1e-6;
+    p.q_scale = (float)scale; p.q_max = (float)qmax; p.stoch = a->stochastic; p.rng = a->rng;
+    k_bn_act_pack<<<grid_cap((int64_t)a->B * HW * (a->Cp / 8), device), 256, 0, st>>>(p);
+    NN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int nn_stage_bwd(const nn_stage_bwd_args* a, int device, void* stream) {
+    if (!a || !a->g || !a->x || !a->gyp || !a->scratch) return nn_fail("nn_stage_bwd: null argument%s", "");
+    NN_SET_DEVICE(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int PH = a->pool ? a->H / 2 : a->H, PW = a->pool ? a->W / 2 : a->W;
+    BnBwdP q;
+    q.g = a->g; q.x = a->x; q.mean = a->mean; q.invstd = a->invstd; q.gamma = a->gamma; q.beta = a->beta;
+    q.partial = (double*)a->scratch; q.B = a->B; q.C = a->C; q.HW = PH * PW; q.act_max = a->act_max;
+    q.q_hi = a->q_bits > 0 ? (float)a->q_hi : 0.f;
+    dim3 grid(a->C, ST_SPLITS);
+    k_bn_bwd_stats<<<grid, 256, 0, st>>>(q);
+    NN_LAUNCH_OK();
+    k_bn_bwd_finalize<<<(a->C + 127) / 128, 128, 0, st>>>(q.partial, a->C, a->dbeta, a->dgamma);
+    NN_LAUNCH_OK();
+    BnBwdApplyP p;
+    p.g = a->g; p.x = a->x; p.mean = a->mean; p.invstd = a->invstd; p.gamma = a->gamma; p.beta = a->beta;
+    p.dbeta = a->dbeta; p.dgamma = a->dgamma; p.amax = a->argmax; p.gyp = (__nv_bfloat16*)a->gyp; p.gy_f32 = a->gy_f32;
+    p.B = a->B; p.C = a->C; p.OH = a->H; p.OW = a->W; p.Cp = a->Cp; p.pool = a->pool;
+    p.act_max = a->act_max; p.q_hi = q.q_hi; p.inv_count = 1.f / ((float)a->B * PH * PW);
+    if (a->pool && !a->argmax) return nn_fail("nn_stage_bwd: argmax missing%s", "");
+    k_bn_bwd_apply<<<grid_cap((int64_t)a->B * a->H * a->W * (a->Cp / 8), device), 256, 0, st>>>(p);
+    NN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int nn_input_quant_pack(const float* x, void* xp, float* act, int B, int C, int HW, int Cp, int q_bits,
+                                   double q_hi, float stochastic, const float* u_inject, nn_rng rng, int device,
+                                   void* stream) {
+    if (!x || !xp || Cp % 8 || Cp < C) return nn_fail("nn_input_quant_pack: bad argument%s", "");
+    NN_SET_DEVICE(device);
+    double qmax = q_bits > 0 ? (double)((1u << q_bits) - 1u) : 0.0;
+    double scale = q_bits > 0 ? q_hi / qmax : 1.0;
+    if (scale < 1e-6) scale = 1e-6;
+    k_quant_pack_input<<<grid_cap((int64_t)B * HW * (Cp / 8), device), 256, 0, (cudaStream_t)stream>>>(
+        x, (__nv_bfloat16*)xp, act, B, C, HW, Cp, q_bits > 0, (float)scale, (float)qmax, stochastic, u_inject, rng);
+    NN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int nn_head_fwd_bwd(const float* logits, const int64_t* labels, int B, int C, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                               float* loss_out, float* out, float* g, void* g_packed, int Cp, float* dgamma,
+                               float* dbeta, int device, void* stream) {
+    if (C > 32 || C < 1) return nn_fail("nn_head_fwd_bwd: C must be <= 32%s", "");
+    if (!logits || !labels || !loss_out || !g || !dgamma || !dbeta) return nn_fail("nn_head_fwd_bwd: null argument%s", "");
+    NN_SET_DEVICE(device);
+    int threads = B >= 1024 ? 1024 : ((B + 31) / 32) * 32;
+    if (threads < 32) threads = 32;
+    k_head<<<1, threads, 0, (cudaStream_t)stream>>>(logits, labels, B, C, gamma, beta, running_mean, running_var, momentum,
+                                                    eps, loss_out, out, g, (__nv_bfloat16*)g_packed, Cp, dgamma, dbeta);
+    NN_LAUNCH_OK();
+    return 0;
+}

@@ -1,0 +1,242 @@
+"""NoisyNetEngine -- the whole CIFAR NoisyNet training step (noisynet.py:1276-1542) as an explicit schedule
+of this library's kernels, with static buffers (CUDA-graph capturable, no autograd, no torch kernels):
+
+  forward : input quantize+pack -> [tcgen05 fused noisy conv -> pool+BN+ReLU+clamp+quantize+pack stage] x 2
+            -> [tcgen05 fused noisy linear -> BN+ReLU+clamp+quantize+pack stage] -> fused noisy linear -> BN + CE head
+  backward: head -> wgrad/dgrad (tcgen05) -> stage backward (STE/clamp/ReLU masks, BN backward, pool routing,
+            emitted as NHWC bf16 for the next wgrad/dgrad) ... -> conv1 wgrad
+  update  : [flat-gradient all-reduce] -> fused AdamW + weight clamp + max|W|
+
+Activations travel between layers as NHWC bf16 integer codes (exact 4-bit operands for the tensor cores);
+fp32 NCHW tensors exist only where the maths needs them (noisy conv outputs, pooled BN inputs, gradients).
+Parameters, BN buffers and quantizer ranges are those of a `NoisyNet` module (state_dict compatible).
+Requires q_a > 0 and q_w > 0 (the 4-bit configuration); steady-state semantics (no i < 20 side statistics).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib, ops
+from ._lib import (NOISE_EXTERNAL, NOISE_MERGED, PREC_BF16, ConvDgradArgs, ConvFwdArgs, ConvGeom, ConvWgradArgs,
+                   Rng, StageArgs, StageBwdArgs)
+from .hardware_model import _f32
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class _Layer:
+    pass
+
+
+class NoisyNetEngine:
+    def __init__(self, model, batch, opt=None, reducer=None):
+        a = model.args
+        if not (a.q_a1 > 0 and a.q_a2 > 0 and a.q_a3 > 0 and a.q_a4 > 0 and a.q_w1 > 0):
+            raise ValueError("NoisyNetEngine implements the quantized configuration (q_a > 0, q_w > 0)")
+        if a.use_bias or a.dropout > 0 or a.dropout_conv > 0:
+            raise NotImplementedError("NoisyNetEngine: bias / dropout are not on the benchmark path")
+        self.m, self.a, self.B = model, a, int(batch)
+        self.opt, self.red = opt, reducer
+        self.dev = model.conv1.weight.device
+        self.di = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
+        self.lib = _lib.load()
+        B, dev = self.B, self.dev
+        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        bf16 = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
+        C1, C2, FC = a.fm1 * a.width, a.fm2 * a.width, a.fc * a.width
+        fs = a.fs
+        H1 = 32 - fs + 1                  # 28
+        P1 = H1 // 2                      # 14
+        H2 = P1 - fs + 1                  # 10
+        P2 = H2 // 2                      # 5
+        self.dims = (C1, C2, FC, H1, P1, H2, P2)
+        c8 = lambda c: (c + 7) // 8 * 8
+        # activations
+        self.xp1 = bf16(B, 32, 32, 8)
+        self.y1n = f32(B, C1, H1, H1); self.pool1 = f32(B, C1, P1, P1); self.amax1 = torch.empty(B, C1, P1, P1, dtype=torch.uint8, device=dev)
+        self.xp2 = bf16(B, P1, P1, c8(C1)); self.xmax2 = f32(1)
+        self.y2n = f32(B, C2, H2, H2); self.pool2 = f32(B, C2, P2, P2); self.amax2 = torch.empty(B, C2, P2, P2, dtype=torch.uint8, device=dev)
+        self.xp3 = bf16(B, P2, P2, c8(C2))
+        self.l1n = f32(B, FC); self.xp4 = bf16(B, c8(FC)); self.xmax4 = f32(1)
+        self.l2n = f32(B, 10)
+        self.stat = {k: (f32(c), f32(c)) for k, c in (("bn1", C1), ("bn2", C2), ("bn3", FC))}
+        # gradients of activations
+        self.g4 = f32(B, 10); self.gyp4 = bf16(B, 16)
+        self.gx4 = f32(B, FC); self.gyp3 = bf16(B, c8(FC))
+        self.gx3 = f32(B, C2, P2, P2); self.gyp2 = bf16(B, H2, H2, c8(C2))
+        self.gx2 = f32(B, C1, P1, P1); self.gyp1 = bf16(B, H1, H1, c8(C1))
+        self.loss = f32(1)
+        self.scratch = torch.empty(int(self.lib.nn_stage_scratch_bytes(max(C1, C2, FC))) + 64, dtype=torch.uint8, device=dev)
+        self.wq = [torch.empty_like(w) for w in self._weights()]
+        self.absmax_fallback = f32(4)
+        # geometry of the four contractions (fc1 forward / wgrad run as a 5x5 conv over the NHWC pooled map)
+        self.geom = [ConvGeom(B, 3, 32, 32, C1, fs, fs, 1, 0), ConvGeom(B, C1, P1, P1, C2, fs, fs, 1, 0),
+                     ConvGeom(B, C2, P2, P2, FC, P2, P2, 1, 0), ConvGeom(B, FC, 1, 1, 10, 1, 1, 1, 0)]
+        self.geom_fc1_lin = ConvGeom(B, C2 * P2 * P2, 1, 1, FC, 1, 1, 1, 0)
+        need = 0
+        for g in self.geom + [self.geom_fc1_lin]:
+            need = max(need, self.lib.nn_conv_workspace_bytes(C.byref(g), PREC_BF16),
+                       self.lib.nn_conv_wgrad_workspace_bytes(C.byref(g), PREC_BF16, self.di))
+        self.ws = torch.empty(int(need) + 4096, dtype=torch.uint8, device=dev)
+        for p in model.parameters():
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        self.inject = None          # parity hook: dict(u=[...], z=[...]) consumed in the reference's draw order
+
+    # ------------------------------------------------------------------ helpers
+    def _weights(self):
+        m = self.m
+        return [m.conv1.weight, m.conv2.weight, m.linear1.weight, m.linear2.weight]
+
+    def _rng(self):
+        return ops.next_rng(self.di)
+
+    def _st(self):
+        return torch.cuda.current_stream(self.di).cuda_stream
+
+    def _take(self, kind):
+        if self.inject is None or not self.inject[kind]:
+            return None
+        return self.inject[kind].pop(0)
+
+    def _absmax(self, idx, w):
+        hit = self.m.w_absmax.get(idx)
+        if hit is not None and hit[0] == w._version:
+            return hit[1]
+        return ops.tensor_stats(w.detach())[1:2]
+
+    def _fwd_gemm(self, idx, xp, a_cs, w_raw, wq, y_noisy, mode, scale_dev, z=None):
+        a = ConvFwdArgs()
+        a.g = self.geom[idx]
+        a.x = None
+        a.x_packed = _p(xp)
+        a.w_eff, a.w_raw = _p(wq), _p(w_raw)
+        cur = float(self.a.layer_currents[idx])
+        if cur > 0:
+            a.y, a.y_noisy = None, _p(y_noisy)
+            a.noise_mode, a.current = mode, cur
+            a.scale_dev = _p(scale_dev)
+            a.z_inject = _p(z)
+            a.rng = Rng(0, 0, None) if z is not None else self._rng()
+        else:                                   # currentN == 0: no analog noise on this layer (noisynet.py:414)
+            a.y, a.y_noisy, a.noise_mode = _p(y_noisy), None, 0
+        a.precision = PREC_BF16
+        a.a_code_scale, a.w_code_scale = a_cs, self.w_cs
+        a.workspace, a.workspace_bytes = _p(self.ws), self.ws.numel()
+        _lib.check(self.lib.nn_noisy_conv_fwd(C.byref(a), self.di, self._st()), "nn_noisy_conv_fwd")
+
+    def _wgrad(self, idx, gyp, xp, a_cs, w_raw, gw):
+        a = ConvWgradArgs()
+        a.g = self.geom[idx]
+        a.gy, a.x, a.gw = None, None, _p(gw)
+        a.gy_packed, a.x_packed = _p(gyp), _p(xp)
+        a.w_raw, a.w_lo, a.w_hi = _p(w_raw), -1.0, 1.0            # STE of the weight quantizer (hardware_model.py:323)
+        a.precision, a.a_code_scale = PREC_BF16, a_cs
+        a.workspace, a.workspace_bytes = _p(self.ws), self.ws.numel()
+        _lib.check(self.lib.nn_noisy_conv_wgrad(C.byref(a), self.di, self._st()), "nn_noisy_conv_wgrad")
+
+    def _dgrad(self, geom, gyp, wq, gx):
+        a = ConvDgradArgs()
+        a.g = geom
+        a.gy, a.gy_packed, a.w_eff, a.gx = None, _p(gyp), _p(wq), _p(gx)
+        a.precision, a.w_code_scale = PREC_BF16, self.w_cs
+        a.workspace, a.workspace_bytes = _p(self.ws), self.ws.numel()
+        _lib.check(self.lib.nn_noisy_conv_dgrad(C.byref(a), self.di, self._st()), "nn_noisy_conv_dgrad")
+
+    def _stage_fwd(self, x_in, C_, H, pool, pooled, amax, bn, key, q_bits, q_hi, xp, xmax, u=None):
+        a = StageArgs()
+        a.in_ = _p(x_in)
+        a.B, a.C, a.H, a.W, a.pool = self.B, C_, H, H, pool
+        a.pooled, a.argmax = _p(pooled), _p(amax)
+        a.gamma, a.beta = _p(bn.weight), _p(bn.bias)
+        a.running_mean, a.running_var = _p(bn.running_mean), _p(bn.running_var)
+        a.momentum, a.eps = float(bn.momentum), float(bn.eps)
+        a.mean, a.invstd = _p(self.stat[key][0]), _p(self.stat[key][1])
+        a.act_max = float(self.a.act_max)
+        a.q_bits, a.q_hi = int(q_bits), float(q_hi)
+        a.stochastic = float(self.a.stochastic) if self.m.training else 0.0
+        a.u_inject = _p(u)
+        a.rng = Rng(0, 0, None) if u is not None else self._rng()
+        a.xp, a.Cp = _p(xp), xp.shape[-1]
+        a.act, a.xmax_out = None, _p(xmax)
+        a.scratch = _p(self.scratch)
+        _lib.check(self.lib.nn_stage_fwd(C.byref(a), self.di, self._st()), "nn_stage_fwd")
+
+    def _stage_bwd(self, g, x, amax, C_, H, pool, bn, key, q_bits, q_hi, gyp):
+        a = StageBwdArgs()
+        a.g, a.x, a.argmax = _p(g), _p(x), _p(amax)
+        a.B, a.C, a.H, a.W, a.pool = self.B, C_, H, H, pool
+        a.mean, a.invstd = _p(self.stat[key][0]), _p(self.stat[key][1])
+        a.gamma, a.beta = _p(bn.weight), _p(bn.bias)
+        a.act_max, a.q_bits, a.q_hi = float(self.a.act_max), int(q_bits), float(q_hi)
+        a.dgamma, a.dbeta = _p(bn.weight.grad), _p(bn.bias.grad)
+        a.gyp, a.Cp, a.gy_f32 = _p(gyp), gyp.shape[-1], None
+        a.scratch = _p(self.scratch)
+        _lib.check(self.lib.nn_stage_bwd(C.byref(a), self.di, self._st()), "nn_stage_bwd")
+
+    def _qhi(self, qm):
+        """Fixed quantisation range of a QuantMeasure (hardware_model.py:265-271, host values cached)."""
+        if qm.max_value > 0:
+            return float(qm.max_value)
+        v = qm._host('running_max')
+        if v <= 0:
+            raise RuntimeError("NoisyNetEngine needs calibrated activation ranges (running_max > 0)")
+        return v
+
+    # ------------------------------------------------------------------ one training step
+    @torch.no_grad()
+    def train_step(self, x, labels):
+        m, a, B, lib, di = self.m, self.a, self.B, self.lib, self.di
+        C1, C2, FC, H1, P1, H2, P2 = self.dims
+        st = self._st()
+        W = self._weights()
+        stoch = float(a.stochastic) if m.training else 0.0
+        qh1, qh2, qh3, qh4 = (self._qhi(q) for q in (m.quantize1, m.quantize2, m.quantize3, m.quantize4))
+        s1, s2, s3, s4 = (_f32(max(h / (2.0 ** b - 1.0), 1e-6))
+                          for h, b in ((qh1, a.q_a1), (qh2, a.q_a2), (qh3, a.q_a3), (qh4, a.q_a4)))
+        self.w_cs = _f32(max(2.0 / (2.0 ** a.q_w1 - 1.0), 1e-6)) / 2.0
+        # ---- forward.  Draw order = the reference's (quantize1, w1, z1, quantize2, w2, z2, ...)
+        u = self._take("u")
+        _lib.check(lib.nn_input_quant_pack(_p(x), _p(self.xp1), None, B, 3, 32 * 32, 8, int(a.q_a1), qh1, stoch, _p(u),
+                                           Rng(0, 0, None) if u is not None else self._rng(), di, st), "nn_input_quant_pack")
+
+        def wquant(i):
+            ops.quantize_fwd(W[i].detach(), a.q_w1, -1.0, 1.0, stoch, u=self._take("u"), out=self.wq[i])
+
+        wquant(0)
+        self._fwd_gemm(0, self.xp1, s1, W[0], self.wq[0], self.y1n, NOISE_MERGED, self._absmax(0, W[0]), self._take("z"))
+        self._stage_fwd(self.y1n, C1, H1, 1, self.pool1, self.amax1, m.bn1, "bn1", a.q_a2, qh2, self.xp2, self.xmax2, self._take("u"))
+        wquant(1)
+        self._fwd_gemm(1, self.xp2, s2, W[1], self.wq[1], self.y2n, NOISE_EXTERNAL, self.xmax2, self._take("z"))
+        self._stage_fwd(self.y2n, C2, H2, 1, self.pool2, self.amax2, m.bn2, "bn2", a.q_a3, qh3, self.xp3, None, self._take("u"))
+        wquant(2)
+        self._fwd_gemm(2, self.xp3, s3, W[2], self.wq[2], self.l1n, NOISE_MERGED, self._absmax(2, W[2]), self._take("z"))
+        self._stage_fwd(self.l1n, FC, 1, 0, None, None, m.bn3, "bn3", a.q_a4, qh4, self.xp4, self.xmax4, self._take("u"))
+        wquant(3)
+        self._fwd_gemm(3, self.xp4, s4, W[3], self.wq[3], self.l2n, NOISE_EXTERNAL, self.xmax4, self._take("z"))
+        bn4 = m.bn4
+        _lib.check(lib.nn_head_fwd_bwd(_p(self.l2n), _p(labels), B, 10, _p(bn4.weight), _p(bn4.bias), _p(bn4.running_mean),
+                                       _p(bn4.running_var), float(bn4.momentum), float(bn4.eps), _p(self.loss), None,
+                                       _p(self.g4), _p(self.gyp4), 16, _p(bn4.weight.grad), _p(bn4.bias.grad), di, st),
+                   "nn_head_fwd_bwd")
+        # ---- backward
+        self._wgrad(3, self.gyp4, self.xp4, s4, W[3], W[3].grad)
+        self._dgrad(self.geom[3], self.gyp4, self.wq[3], self.gx4)
+        self._stage_bwd(self.gx4, self.l1n, None, FC, 1, 0, m.bn3, "bn3", a.q_a4, qh4, self.gyp3)
+        self._wgrad(2, self.gyp3, self.xp3, s3, W[2], W[2].grad)
+        self._dgrad(self.geom_fc1_lin, self.gyp3, self.wq[2], self.gx3)
+        self._stage_bwd(self.gx3, self.pool2, self.amax2, C2, H2, 1, m.bn2, "bn2", a.q_a3, qh3, self.gyp2)
+        self._wgrad(1, self.gyp2, self.xp2, s2, W[1], W[1].grad)
+        self._dgrad(self.geom[1], self.gyp2, self.wq[1], self.gx2)
+        self._stage_bwd(self.gx2, self.pool1, self.amax1, C1, H1, 1, m.bn1, "bn1", a.q_a2, qh2, self.gyp1)
+        self._wgrad(0, self.gyp1, self.xp1, s1, W[0], W[0].grad)
+        # ---- exchange + update
+        if self.red is not None:
+            self.red.all_reduce_sum_()
+        if self.opt is not None:
+            self.opt.step()
+            for idx, w in enumerate(W):
+                m.w_absmax[idx] = (w._version, self.opt.absmax_of(w))
+        return self.loss

@@ -1,0 +1,245 @@
+"""Fused between-layer stages and the NoisyNetEngine training step.
+
+Stage kernels are compared with the torch ops the reference script composes (MaxPool2d, BatchNorm, ReLU,
+clamp, the oracle quantizer) -- fp32, tolerance 1e-5; quantisation codes may flip where the BN output sits
+within rounding of a code boundary, hence a mismatch-fraction criterion (<= 2e-4) for codes.
+The whole engine step (bf16 tensor-core contractions, bf16 gradients) is compared with the CPU oracle's step:
+forward loss within 2e-3, gradients within 2e-2 of each tensor's max (bf16 training tolerance).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import noisynet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    import __graft_entry__ as entry
+    entry.build()
+    return torch.device("cuda:0")
+
+
+def _stage_call(dev, x, gamma, beta, rm, rv, pool, act_max, bits, q_hi, u):
+    from noisynet_b200 import _lib
+    lib = _lib.load()
+    B, Cc, H, W = x.shape
+    PH, PW = (H // 2, W // 2) if pool else (H, W)
+    Cp = (Cc + 7) // 8 * 8
+    pooled = torch.empty(B, Cc, PH, PW, device=dev)
+    amax = torch.empty(B, Cc, PH, PW, dtype=torch.uint8, device=dev)
+    mean, invstd = torch.empty(Cc, device=dev), torch.empty(Cc, device=dev)
+    xp = torch.zeros(B, PH, PW, Cp, dtype=torch.bfloat16, device=dev)
+    act = torch.empty(B, Cc, PH, PW, device=dev)
+    xmax = torch.zeros(1, device=dev)
+    scratch = torch.empty(int(lib.nn_stage_scratch_bytes(Cc)) + 64, dtype=torch.uint8, device=dev)
+    a = _lib.StageArgs()
+    a.in_ = x.data_ptr(); a.B, a.C, a.H, a.W, a.pool = B, Cc, H, W, pool
+    a.pooled, a.argmax = pooled.data_ptr(), amax.data_ptr()
+    a.gamma, a.beta, a.running_mean, a.running_var = gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr()
+    a.momentum, a.eps = 0.1, 1e-5
+    a.mean, a.invstd = mean.data_ptr(), invstd.data_ptr()
+    a.act_max, a.q_bits, a.q_hi, a.stochastic = act_max, bits, q_hi, 0.5
+    a.u_inject = u.data_ptr()
+    a.rng = _lib.Rng(0, 0, None)
+    a.xp, a.Cp, a.act, a.xmax_out, a.scratch = xp.data_ptr(), Cp, act.data_ptr(), xmax.data_ptr(), scratch.data_ptr()
+    _lib.check(lib.nn_stage_fwd(C.byref(a), 0, torch.cuda.current_stream().cuda_stream), "nn_stage_fwd")
+    return dict(pooled=pooled, amax=amax, mean=mean, invstd=invstd, xp=xp, act=act, xmax=xmax, scratch=scratch)
+
+
+@pytest.mark.parametrize("shape,pool", [((6, 65, 28, 28), 1), ((5, 120, 10, 10), 1), ((33, 390, 1, 1), 0), ((4, 7, 6, 6), 1)])
+def test_stage_fwd_bwd_vs_torch(dev, shape, pool):
+    from noisynet_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(sum(shape))
+    B, Cc, H, W = shape
+    x = torch.randn(shape, generator=g) * 1.5 + 0.3
+    gamma, beta = torch.rand(Cc, generator=g) + 0.5, torch.randn(Cc, generator=g) * 0.5 + 0.5
+    act_max, bits, q_hi = 5.0, 4, 4.0
+    PH, PW = (H // 2, W // 2) if pool else (H, W)
+    u = torch.rand(B, Cc, PH, PW, generator=g) - 0.5
+    gout = torch.randn(B, Cc, PH, PW, generator=g)
+    # ---- torch / oracle reference
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm, rv = torch.zeros(Cc), torch.ones(Cc)
+    pooled = F.max_pool2d(xr, 2, 2) if pool else xr
+    bn = F.batch_norm(pooled, rm, rv, gr, br, True, 0.1, 1e-5)
+    h = torch.clamp(F.relu(bn), max=act_max)
+    q = O.OracleNet._STEQuant.apply(h, bits, 0.0, q_hi, 0.5, u)
+    q.backward(gout)
+    codes_ref = O.uniform_quantize_codes(h.detach(), bits, 0.0, q_hi, 0.5, u)
+    # ---- kernels
+    xd = x.to(dev)
+    rmd, rvd = torch.zeros(Cc, device=dev), torch.ones(Cc, device=dev)
+    r = _stage_call(dev, xd, gamma.to(dev), beta.to(dev), rmd, rvd, pool, act_max, bits, q_hi, u.to(dev))
+    if pool:
+        assert torch.equal(r["pooled"].cpu(), pooled.detach())
+    assert torch.allclose(rmd.cpu(), rm, rtol=1e-5, atol=1e-6) and torch.allclose(rvd.cpu(), rv, rtol=1e-4, atol=1e-6)
+    codes = r["xp"].float().cpu()[..., :Cc].permute(0, 3, 1, 2)
+    bad = (codes != codes_ref).float().mean().item()
+    assert bad <= 2e-4, bad
+    assert torch.all(r["xp"].float().cpu()[..., Cc:] == 0)
+    assert (r["act"].cpu() - q.detach()).abs().max().item() <= (q_hi / 15) + 1e-5 and \
+        ((r["act"].cpu() - q.detach()).abs() > 1e-5).float().mean().item() <= 2e-4
+    assert r["xmax"].item() == pytest.approx(r["act"].max().item())
+    # ---- backward
+    Cp = (Cc + 7) // 8 * 8
+    gyp = torch.zeros(B, H, W, Cp, dtype=torch.bfloat16, device=dev)
+    gyf = torch.empty(B, Cc, H, W, device=dev)
+    dg, db = torch.empty(Cc, device=dev), torch.empty(Cc, device=dev)
+    b = _lib.StageBwdArgs()
+    b.g = gout.to(dev).data_ptr()
+    gkeep = gout.to(dev)
+    b.g = gkeep.data_ptr()
+    b.x = (r["pooled"] if pool else xd).data_ptr(); b.argmax = r["amax"].data_ptr()
+    b.B, b.C, b.H, b.W, b.pool = B, Cc, H, W, pool
+    gd, bd = gamma.to(dev), beta.to(dev)
+    b.mean, b.invstd, b.gamma, b.beta = r["mean"].data_ptr(), r["invstd"].data_ptr(), gd.data_ptr(), bd.data_ptr()
+    b.act_max, b.q_bits, b.q_hi = act_max, bits, q_hi
+    b.dgamma, b.dbeta = dg.data_ptr(), db.data_ptr()
+    b.gyp, b.Cp, b.gy_f32, b.scratch = gyp.data_ptr(), Cp, gyf.data_ptr(), r["scratch"].data_ptr()
+    _lib.check(lib.nn_stage_bwd(C.byref(b), 0, torch.cuda.current_stream().cuda_stream), "nn_stage_bwd")
+    ref = xr.grad
+    tol = 2e-5 * max(1.0, ref.abs().max().item())
+    assert (gyf.cpu() - ref).abs().max().item() <= tol, (gyf.cpu() - ref).abs().max()
+    assert torch.allclose(dg.cpu(), gr.grad, rtol=1e-4, atol=1e-4) and torch.allclose(db.cpu(), br.grad, rtol=1e-4, atol=1e-4)
+    packed = gyp.float().cpu()[..., :Cc].permute(0, 3, 1, 2)
+    assert (packed - ref).abs().max().item() <= 4e-3 * ref.abs().max().item() + 1e-6       # bf16 rounding of the pack
+
+
+def test_head_vs_torch(dev):
+    from noisynet_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    B, Cc = 200, 10
+    z = torch.randn(B, Cc, generator=g) * 2
+    lab = torch.randint(0, Cc, (B,), generator=g)
+    gamma, beta = torch.rand(Cc, generator=g) + 0.5, torch.randn(Cc, generator=g) * 0.1
+    zr = z.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm, rv = torch.zeros(Cc), torch.ones(Cc)
+    out = F.batch_norm(zr, rm, rv, gr, br, True, 0.1, 1e-5)
+    loss = F.cross_entropy(out, lab)
+    loss.backward()
+    zd, ld = z.to(dev), lab.to(dev)
+    gd, bd, rmd, rvd = gamma.to(dev), beta.to(dev), torch.zeros(Cc, device=dev), torch.ones(Cc, device=dev)
+    lo, o, gg = torch.zeros(1, device=dev), torch.empty(B, Cc, device=dev), torch.empty(B, Cc, device=dev)
+    gp = torch.zeros(B, 16, dtype=torch.bfloat16, device=dev)
+    dg, db = torch.empty(Cc, device=dev), torch.empty(Cc, device=dev)
+    _lib.check(lib.nn_head_fwd_bwd(zd.data_ptr(), ld.data_ptr(), B, Cc, gd.data_ptr(), bd.data_ptr(), rmd.data_ptr(),
+                                   rvd.data_ptr(), 0.1, 1e-5, lo.data_ptr(), o.data_ptr(), gg.data_ptr(), gp.data_ptr(), 16,
+                                   dg.data_ptr(), db.data_ptr(), 0, torch.cuda.current_stream().cuda_stream))
+    assert abs(lo.item() - loss.item()) < 1e-5
+    assert torch.allclose(o.cpu(), out.detach(), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(gg.cpu(), zr.grad, rtol=1e-4, atol=1e-7)
+    assert torch.allclose(dg.cpu(), gr.grad, rtol=1e-4, atol=1e-6) and torch.allclose(db.cpu(), br.grad, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(rmd.cpu(), rm, rtol=1e-5, atol=1e-6) and torch.allclose(rvd.cpu(), rv, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(gp.float().cpu()[:, :Cc], zr.grad, rtol=1e-2, atol=1e-6)
+
+
+def _engine_pair(dev, widths, B, current):
+    from noisynet_b200.engine import NoisyNetEngine
+    from noisynet_b200.net import NoisyNet, default_args, make_fused_optimizer, with_quant
+    from test_gpu_net import _make_rnd
+    q = 4
+    oa = O.default_args(q_a=q, q_w=q, quant_max2=4.0, quant_max4=4.5, current=current, **widths)
+    torch.manual_seed(1)
+    om = O.OracleNet(oa).init_like_reference()
+    na = with_quant(default_args(layer_currents=[current] * 4, **widths), q, q)
+    nm = NoisyNet(na, fused=True, precision="bf16").to(dev)
+    nm.load_state_dict(om.state_dict(), strict=False)
+    nm.quantize2.running_max = torch.tensor(4.0, device=dev)
+    nm.quantize4.running_max = torch.tensor(4.5, device=dev)
+    om.train(), nm.train()
+    oopt = O.make_optimizer(om, oa)
+    eng = NoisyNetEngine(nm, B, opt=make_fused_optimizer(nm, na))
+    x, lab = O.synthetic_cifar(B, seed=10)
+    rnd = _make_rnd(oa, B, q, 100)
+    oloss, _ = O.train_step(om, oopt, x, lab, i=100, rnd=rnd)
+    eng.inject = dict(u=[rnd[k].to(dev) for k in ("ua1", "uw0", "ua2", "uw1", "ua3", "uw2", "ua4", "uw3")],
+                      z=[rnd[k].to(dev) for k in ("z0", "z1", "z2", "z3")] if current > 0 else [])
+    loss = eng.train_step(x.to(dev), lab.to(dev))
+    return om, nm, eng, oloss, loss, x, lab
+
+
+def test_engine_forward_exact_vs_oracle(dev):
+    """I = 0 (no analog noise): the tensor-core forward is exact integer arithmetic, the engine's 4-bit codes
+    equal the oracle's and the loss agrees to 1e-5.  (Gradients are NOT compared here: noise-free conv outputs
+    sit on a discrete grid, 2x2 pooling windows tie, and tie-breaking under 1e-7 rounding differences routes
+    the gradient differently -- both valid.)"""
+    from noisynet_b200 import ops
+    om, nm, eng, oloss, loss, x, lab = _engine_pair(dev, dict(fm1=9, fm2=12, fc=24), 8, 0.0)
+    assert ops.error_flag() == 0 and not eng.inject["u"]
+    assert abs(loss.item() - oloss.item()) < 1e-5, (loss.item(), oloss.item())
+    for k in ("bn1", "bn2", "bn3", "bn4"):
+        assert torch.allclose(getattr(nm, k).running_mean.cpu(), getattr(om, k).running_mean, rtol=1e-4, atol=1e-5), k
+        assert torch.allclose(getattr(nm, k).running_var.cpu(), getattr(om, k).running_var, rtol=1e-3, atol=1e-5), k
+    assert nm.conv1.weight.abs().max().item() <= torch.tensor(0.3).item()
+
+
+@pytest.mark.parametrize("widths,B", [(dict(fm1=9, fm2=12, fc=24), 8), ({}, 16)])
+def test_engine_step_vs_module_path(dev, widths, B):
+    """Wiring check at I = 1 nA: the engine (stage kernels, packed operands, explicit backward) against the
+    autograd module path (NoisyNet(fused=True, precision='bf16'): same tcgen05 contractions, torch pool / BN /
+    ReLU / clamp, nn_quantize kernels) with identical injected draws.  The module path itself is pinned to the
+    oracle in test_gpu_net.py (fp32) and its bf16 kernels to the fp32 ones in test_gpu_umma*.py.
+    Tolerance: loss 2e-3, gradients rel-L2 2e-2 (rare 4-bit code flips from 1e-7 BatchNorm rounding differences)."""
+    from noisynet_b200 import ops
+    from noisynet_b200.engine import NoisyNetEngine
+    from noisynet_b200.net import NoisyNet, default_args, with_quant
+    from test_gpu_net import _make_rnd
+    q = 4
+    torch.manual_seed(2)
+    na = with_quant(default_args(**widths), q, q)
+    ref = NoisyNet(na, fused=True, precision="bf16").to(dev)
+    eng_m = NoisyNet(na, fused=True, precision="bf16").to(dev)
+    eng_m.load_state_dict(ref.state_dict())
+    for mdl in (ref, eng_m):
+        mdl.quantize2.running_max = torch.tensor(4.0, device=dev)
+        mdl.quantize4.running_max = torch.tensor(4.5, device=dev)
+        mdl.collect_stats = False
+        mdl.train()
+    oa = O.default_args(q_a=q, q_w=q, **widths)
+    x, lab = O.synthetic_cifar(B, seed=11)
+    x, lab = x.to(dev), lab.to(dev)
+    rnd = _make_rnd(oa, B, q, 200)
+    us = [rnd[k].to(dev) for k in ("ua1", "uw0", "ua2", "uw1", "ua3", "uw2", "ua4", "uw3")]
+    zs = [rnd[k].to(dev) for k in ("z0", "z1", "z2", "z3")]
+    with ops.inject_random(list(us), list(zs)):
+        out = ref(x, 0, 100)
+        rloss = F.cross_entropy(out, lab)
+        rloss.backward()
+    eng = NoisyNetEngine(eng_m, B, opt=None)
+    eng.inject = dict(u=list(us), z=list(zs))
+    loss = eng.train_step(x, lab)
+    assert ops.error_flag() == 0 and not eng.inject["u"] and not eng.inject["z"]
+    assert abs(loss.item() - rloss.item()) < 2e-3, (loss.item(), rloss.item())
+    rg = dict(ref.named_parameters())
+    for k, p in eng_m.named_parameters():
+        g_ref = rg[k].grad
+        rel = ((p.grad - g_ref).norm() / (g_ref.norm() + 1e-12)).item()
+        assert rel < 2e-2, (k, rel)
+    for k in ("bn1", "bn2", "bn3", "bn4"):
+        assert torch.allclose(getattr(eng_m, k).running_mean, getattr(ref, k).running_mean, rtol=1e-3, atol=1e-4), k
+        assert torch.allclose(getattr(eng_m, k).running_var, getattr(ref, k).running_var, rtol=2e-3, atol=1e-4), k
+
+
+def test_engine_step_with_noise(dev):
+    """I = 1 nA: sigma is computed from bf16 weights (3e-3 relative), which flips a few 4-bit codes downstream
+    (discrete, chaotic amplification) -- the per-layer noise maths is pinned in test_gpu_umma.py; here the whole
+    step must stay close in loss and keep training."""
+    from noisynet_b200 import ops
+    om, nm, eng, oloss, loss, x, lab = _engine_pair(dev, dict(fm1=9, fm2=12, fc=24), 8, 1.0)
+    assert ops.error_flag() == 0 and not eng.inject["u"] and not eng.inject["z"]
+    assert abs(loss.item() - oloss.item()) < 0.1, (loss.item(), oloss.item())
+    eng.inject = None
+    losses = [eng.train_step(x.to(dev), lab.to(dev)).item() for _ in range(25)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    assert ops.error_flag() == 0
