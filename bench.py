@@ -33,7 +33,8 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--batch", type=int, default=512, help="per-GPU batch")
     p.add_argument("--variant", default="q4", choices=["q4", "fp"], help="q4: --q_a 4 --q_w 4; fp: README flags")
-    p.add_argument("--flow", default="fused", choices=["fused", "dropin"])
+    p.add_argument("--flow", default="engine", choices=["engine", "fused", "dropin"],
+                   help="engine: explicit kernel schedule (NoisyNetEngine); fused/dropin: autograd module paths")
     p.add_argument("--precision", default=os.environ.get("NN_BENCH_PRECISION", "auto"))
     p.add_argument("--optimizer", default="fused", choices=["fused", "torch"])
     p.add_argument("--graph", type=int, default=int(os.environ.get("NN_BENCH_GRAPH", "1")))
@@ -172,7 +173,7 @@ def build_model(args, dev, precision):
     a = default_args()
     if args.variant == "q4":
         with_quant(a, 4, 4)
-    m = init_like_reference(NoisyNet(a, fused=(args.flow == "fused"), precision=precision)).to(dev)
+    m = init_like_reference(NoisyNet(a, fused=(args.flow != "dropin"), precision=precision)).to(dev)
     if args.variant == "q4":      # ranges as after the 5-batch calibration (noisynet.py:1251-1259): fixed running_max
         m.quantize2.running_max = torch.tensor(5.0, device=dev)
         m.quantize4.running_max = torch.tensor(5.0, device=dev)
@@ -230,7 +231,17 @@ def run_b200(args):
     sx, sy = torch.empty_like(dev_x[0]), torch.empty_like(dev_y[0])   # static inputs for the captured graph
     loss_out = torch.zeros((), device=dev)
 
+    engine = None
+    if args.flow == "engine":
+        if not (fused_opt and args.variant == "q4" and precision == "bf16"):
+            raise SystemExit("--flow engine needs --variant q4, the tcgen05 path and --optimizer fused")
+        from noisynet_b200.engine import NoisyNetEngine
+        engine = NoisyNetEngine(model, B, opt=opt, reducer=red if world > 1 else None)
+
     def step_body(x, y):
+        if engine is not None:
+            loss_out.copy_(engine.train_step(x, y)[0])
+            return
         out = model(x, 0, 100)
         loss = F.cross_entropy(out, y)
         red.zero_()

@@ -246,7 +246,7 @@ int nn_stage_bwd(const nn_stage_bwd_args* a, int device, void* stream);
 int nn_input_quant_pack(const float* x, void* xp, float* act, int B, int C, int HW, int Cp, int q_bits,
                         double q_hi, float stochastic, const float* u_inject, nn_rng rng, int device, void* stream);
 
-/* Head (noisynet.py:594, :1278): BatchNorm1d(C <= 32, batch statistics) -> mean cross-entropy, and the
+/* Head (noisynet.py:594, :1278): BatchNorm1d(C <= 16, batch statistics) -> mean cross-entropy, and the
  * gradient back through both: g [B,C] fp32 (+ optional bf16 [B,Cp] pack), dgamma / dbeta (overwritten). */
 int nn_head_fwd_bwd(const float* logits, const int64_t* labels, int B, int C, const float* gamma,
                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,

@@ -593,21 +593,23 @@ k_wgrad_umma(const WgUP p) {
     if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
 
-// partial [splits][Cout][ktot_pad] (kcol = tap*Cp + c) -> gw [Cout][Cin][KHW], fixed summation order, scale, STE mask
+// partial [splits][Cout][ktot_pad] (kcol = tap*Cp + c) -> gw [Cout][Cin][KHW], fixed summation order, scale, STE mask.
+// Thread = (n, kcol): reads of the partials are coalesced along kcol (the scattered 4-byte write is tiny).
 __global__ void __launch_bounds__(256)
 k_wgrad_umma_reduce(const float* __restrict__ partial, int splits, int Cout, int Cin, int KHW, int Cp, int ktot_pad,
                     float scale, float* __restrict__ gw, const float* __restrict__ w_raw, float lo, float hi) {
-    const int64_t total = (int64_t)Cout * Cin * KHW;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int tap = (int)(i % KHW);
-        const int c = (int)((i / KHW) % Cin);
-        const int n = (int)(i / ((int64_t)KHW * Cin));
-        const float* src = partial + (size_t)n * ktot_pad + (size_t)tap * Cp + c;
+    const unsigned total = (unsigned)Cout * ktot_pad;
+    const size_t zstride = (size_t)Cout * ktot_pad;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int n = (int)(i / ktot_pad), kcol = (int)(i - (unsigned)n * ktot_pad);
+        const int tap = kcol / Cp, c = kcol - tap * Cp;
+        if (tap >= KHW || c >= Cin) continue;
         float s = 0.f;
-        for (int z = 0; z < splits; ++z) s += src[(size_t)z * Cout * ktot_pad];
+        for (int z = 0; z < splits; ++z) s += partial[(size_t)z * zstride + i];
         s *= scale;
-        if (w_raw) { const float w = __ldg(w_raw + i); if (w > hi || w < lo) s = 0.f; }
-        gw[i] = s;
+        const size_t o = ((size_t)n * Cin + c) * KHW + tap;
+        if (w_raw) { const float w = __ldg(w_raw + o); if (w > hi || w < lo) s = 0.f; }
+        gw[o] = s;
     }
 }
 
@@ -929,7 +931,7 @@ int nn_umma_conv_wgrad(const nn_conv_wgrad_args* a, int device, cudaStream_t st)
     dim3 grid(w.n_tiles_k, w.m_tiles_n, w.splits);
     k_wgrad_umma<<<grid, UM_THREADS, w.smem_bytes, st>>>(p);
     NN_LAUNCH_OK();
-    const int64_t n = (int64_t)g.Cout * g.Cin * g.KH * g.KW;
+    const int64_t n = (int64_t)g.Cout * w.ktot_pad;
     int rb = (int)((n + 255) / 256);
     if (rb > 8 * sms) rb = 8 * sms;
     const float scale = a->a_code_scale > 0.f ? a->a_code_scale : 1.f;

@@ -120,12 +120,12 @@ __global__ void __launch_bounds__(256)
 k_bn_act_pack(const BnActP p) {
     const NnRng rs = nn_rng_load(p.rng);
     const int chunks = p.Cp >> 3;
-    const int64_t npix = (int64_t)p.B * p.HW, total = npix * chunks;
+    const unsigned npix = (unsigned)p.B * p.HW, total = npix * chunks;      // 32-bit index arithmetic
     float vmax = 0.f;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pixel = i % npix;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned pixel = i % npix;
         const int chunk = (int)(i / npix);
-        const int b = (int)(pixel / p.HW), r = (int)(pixel - (int64_t)b * p.HW);
+        const int b = (int)(pixel / p.HW), r = (int)(pixel - (unsigned)b * p.HW);
         __align__(16) __nv_bfloat16 out[8];
         uint4 rnd[2];
         if (p.quant && p.stoch > 0.f && !p.u_inject) {
@@ -157,7 +157,7 @@ k_bn_act_pack(const BnActP p) {
             }
             out[j] = __float2bfloat16_rn(code);
         }
-        *reinterpret_cast<uint4*>(p.xp + (pixel * p.Cp + chunk * 8)) = *reinterpret_cast<const uint4*>(out);
+        *reinterpret_cast<uint4*>(p.xp + ((size_t)pixel * p.Cp + chunk * 8)) = *reinterpret_cast<const uint4*>(out);
     }
     if (p.xmax_out) {
         vmax = nn_warp_max(vmax);
@@ -232,35 +232,49 @@ struct BnBwdApplyP {
 
 __global__ void __launch_bounds__(256)
 k_bn_bwd_apply(const BnBwdApplyP p) {
+    // one thread = (pooled pixel, 8-channel chunk): the BN-backward value of each channel is computed ONCE and
+    // written to its arg-max window position (zeros to the other three) -- 4x fewer loads than a thread per
+    // output pixel.  32-bit index arithmetic (sizes are < 2^31 by the API checks).
     const int chunks = p.Cp >> 3;
-    const int64_t npix = (int64_t)p.B * p.OH * p.OW, total = npix * chunks;
     const int PH = p.pool ? p.OH >> 1 : p.OH, PW = p.pool ? p.OW >> 1 : p.OW, PHW = PH * PW;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pixel = i % npix;
-        const int chunk = (int)(i / npix);
-        const int b = (int)(pixel / (p.OH * p.OW)), r = (int)(pixel - (int64_t)b * p.OH * p.OW);
-        const int oh = r / p.OW, ow = r - oh * p.OW;
-        const int ph = p.pool ? oh >> 1 : oh, pw = p.pool ? ow >> 1 : ow;
-        const int my = p.pool ? ((oh & 1) * 2 + (ow & 1)) : 0;
-        __align__(16) __nv_bfloat16 out[8];
+    const unsigned npp = (unsigned)p.B * PHW, total = npp * chunks;
+    const int npos = p.pool ? 4 : 1;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned pp = i % npp;
+        const int chunk = (int)(i / npp);
+        const int b = (int)(pp / PHW), r = (int)(pp - (unsigned)b * PHW);
+        const int ph = r / PW, pw = r - ph * PW;
+        float d[8];
+        int pos[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = chunk * 8 + j;
-            float d = 0.f;
+            d[j] = 0.f; pos[j] = -1;
             if (c < p.C) {
-                const int64_t o = ((int64_t)b * p.C + c) * PHW + ph * PW + pw;
-                if (!p.pool || __ldg(p.amax + o) == my) {
-                    float xhat;
-                    const float invstd = __ldg(p.invstd + c), gamma = __ldg(p.gamma + c);
-                    const float dv = stage_dv(__ldg(p.g + o), __ldg(p.x + o), __ldg(p.mean + c), invstd, gamma,
-                                              __ldg(p.beta + c), p.act_max, p.q_hi, xhat);
-                    d = gamma * invstd * (dv - __ldg(p.dbeta + c) * p.inv_count - xhat * __ldg(p.dgamma + c) * p.inv_count);
-                }
-                if (p.gy_f32) p.gy_f32[((int64_t)b * p.C + c) * p.OH * p.OW + r] = d;
+                const size_t o = ((size_t)b * p.C + c) * PHW + r;
+                float xhat;
+                const float invstd = __ldg(p.invstd + c), gamma = __ldg(p.gamma + c);
+                const float dv = stage_dv(__ldg(p.g + o), __ldg(p.x + o), __ldg(p.mean + c), invstd, gamma,
+                                          __ldg(p.beta + c), p.act_max, p.q_hi, xhat);
+                d[j] = gamma * invstd * (dv - __ldg(p.dbeta + c) * p.inv_count - xhat * __ldg(p.dgamma + c) * p.inv_count);
+                pos[j] = p.pool ? (int)__ldg(p.amax + o) : 0;
             }
-            out[j] = __float2bfloat16_rn(d);
         }
-        *reinterpret_cast<uint4*>(p.gyp + (pixel * p.Cp + chunk * 8)) = *reinterpret_cast<const uint4*>(out);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (q >= npos) break;
+            const int oh = p.pool ? 2 * ph + (q >> 1) : ph, ow = p.pool ? 2 * pw + (q & 1) : pw;
+            __align__(16) __nv_bfloat16 out[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float v = (pos[j] == q) ? d[j] : 0.f;
+                out[j] = __float2bfloat16_rn(v);
+                if (p.gy_f32 && pos[j] >= 0)
+                    p.gy_f32[(((size_t)b * p.C + chunk * 8 + j) * p.OH + oh) * p.OW + ow] = v;
+            }
+            *reinterpret_cast<uint4*>(p.gyp + ((((size_t)b * p.OH + oh) * p.OW + ow) * p.Cp + chunk * 8)) =
+                *reinterpret_cast<const uint4*>(out);
+        }
     }
 }
 
@@ -270,11 +284,11 @@ k_quant_pack_input(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, 
                    int Cp, int quant, float q_scale, float q_max, float stoch, const float* __restrict__ u_inject, nn_rng rng) {
     const NnRng rs = nn_rng_load(rng);
     const int chunks = Cp >> 3;
-    const int64_t npix = (int64_t)B * HW, total = npix * chunks;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pixel = i % npix;
+    const unsigned npix = (unsigned)B * HW, total = npix * chunks;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned pixel = i % npix;
         const int chunk = (int)(i / npix);
-        const int b = (int)(pixel / HW), r = (int)(pixel - (int64_t)b * HW);
+        const int b = (int)(pixel / HW), r = (int)(pixel - (unsigned)b * HW);
         uint4 rnd[2];
         if (quant && stoch > 0.f && !u_inject) { rnd[0] = nn_philox(rs, (uint64_t)i * 2); rnd[1] = nn_philox(rs, (uint64_t)i * 2 + 1); }
         const uint32_t* rr = reinterpret_cast<const uint32_t*>(rnd);
@@ -296,83 +310,118 @@ k_quant_pack_input(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, 
             }
             out[j] = __float2bfloat16_rn(code);
         }
-        *reinterpret_cast<uint4*>(xp + (pixel * Cp + chunk * 8)) = *reinterpret_cast<const uint4*>(out);
+        *reinterpret_cast<uint4*>(xp + ((size_t)pixel * Cp + chunk * 8)) = *reinterpret_cast<const uint4*>(out);
     }
 }
 
-// ------------------------------------------------------------------ head: BatchNorm1d(C<=32) + cross entropy + backward
-// single block; logits [B,C] -> loss (mean CE), out (bn output, optional), g [B,C] = d loss / d logits (through BN),
-// dgamma/dbeta, running stats.  thread = row.
+// ------------------------------------------------------------------ head: BatchNorm1d(C<=16) + cross entropy + backward
+// single block, thread = row (rows strided by blockDim when B > blockDim).  Per-channel sums: registers ->
+// warp shuffle tree -> fixed-order sum over warps in shared memory (deterministic).
+constexpr int HEAD_MAXC = 16;
+
+__device__ __forceinline__ void head_block_sum(double (&v)[HEAD_MAXC], int C, double (*sh)[HEAD_MAXC], double* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c) {
+        if (c < C) {
+            double x = v[c];
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) sh[warp][c] = x;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+        double t = 0;
+        for (int w = 0; w < nwarp; ++w) t += sh[w][threadIdx.x];
+        out[threadIdx.x] = t;
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(1024)
 k_head(const float* __restrict__ z, const int64_t* __restrict__ label, int B, int C, const float* __restrict__ gamma,
        const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
        float eps, float* __restrict__ loss_out, float* __restrict__ out, float* __restrict__ g, __nv_bfloat16* __restrict__ gp,
        int Cp, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    __shared__ double red[32][2];
-    __shared__ float s_mean[32], s_invstd[32], s_dg[32], s_db[32];
-    __shared__ double s_loss;
+    __shared__ double sh[32][HEAD_MAXC];
+    __shared__ double tot1[HEAD_MAXC], tot2[HEAD_MAXC];
+    __shared__ float s_mean[HEAD_MAXC], s_invstd[HEAD_MAXC], s_g[HEAD_MAXC], s_b[HEAD_MAXC];
     const int tid = threadIdx.x, nthr = blockDim.x;
-    // channel statistics (fixed order: thread c sums column c sequentially in double; B is small)
+    double a1[HEAD_MAXC], a2[HEAD_MAXC];
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c) { a1[c] = 0; a2[c] = 0; }
+    for (int b = tid; b < B; b += nthr) {
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c)
+            if (c < C) { const double v = z[(size_t)b * C + c]; a1[c] += v; a2[c] += v * v; }
+    }
+    head_block_sum(a1, C, sh, tot1);
+    head_block_sum(a2, C, sh, tot2);
     if (tid < C) {
-        double s1 = 0, s2 = 0;
-        for (int b = 0; b < B; ++b) { const double v = z[(int64_t)b * C + tid]; s1 += v; s2 += v * v; }
-        const double m = s1 / B;
-        double var = s2 / B - m * m;
+        const double m = tot1[tid] / B;
+        double var = tot2[tid] / B - m * m;
         if (var < 0) var = 0;
         s_mean[tid] = (float)m;
         s_invstd[tid] = (float)(1.0 / sqrt(var + (double)eps));
+        s_g[tid] = gamma[tid]; s_b[tid] = beta[tid];
         if (running_mean) {
             const double unb = B > 1 ? var * B / (B - 1) : var;
             running_mean[tid] = (float)((1.0 - momentum) * running_mean[tid] + momentum * m);
             running_var[tid] = (float)((1.0 - momentum) * running_var[tid] + momentum * unb);
         }
     }
-    if (tid == 0) s_loss = 0.0;
     __syncthreads();
-    // per-row softmax / CE; dv = (softmax - onehot) / B stored to g temporarily
-    double my_loss = 0.0;
+    // softmax / CE per row; dv = (softmax - onehot) / B kept in g; per-channel sums of dv and dv * xhat
+    double lsum[HEAD_MAXC];
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c) { a1[c] = 0; a2[c] = 0; lsum[c] = 0; }
     for (int b = tid; b < B; b += nthr) {
-        float v[32];
+        float v[HEAD_MAXC], xh[HEAD_MAXC];
         float mx = -3.4e38f;
-        for (int c = 0; c < C; ++c) {
-            v[c] = (z[(int64_t)b * C + c] - s_mean[c]) * s_invstd[c] * gamma[c] + beta[c];
-            if (out) out[(int64_t)b * C + c] = v[c];
-            mx = fmaxf(mx, v[c]);
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c) {
+            if (c < C) {
+                xh[c] = (z[(size_t)b * C + c] - s_mean[c]) * s_invstd[c];
+                v[c] = xh[c] * s_g[c] + s_b[c];
+                if (out) out[(size_t)b * C + c] = v[c];
+                mx = fmaxf(mx, v[c]);
+            }
         }
         float se = 0.f;
-        for (int c = 0; c < C; ++c) se += expf(v[c] - mx);
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c) if (c < C) se += expf(v[c] - mx);
         const int lab = (int)label[b];
-        my_loss += (double)(logf(se) + mx - v[lab]);
-        for (int c = 0; c < C; ++c) g[(int64_t)b * C + c] = (expf(v[c] - mx) / se - (c == lab ? 1.f : 0.f)) / (float)B;
-    }
-    atomicAdd(&s_loss, my_loss);   // double atomics in smem: order varies, loss is a report value only
-    __syncthreads();
-    if (tid == 0) *loss_out = (float)(s_loss / B);
-    // BN backward sums (fixed order)
-    if (tid < C) {
-        double s1 = 0, s2 = 0;
-        for (int b = 0; b < B; ++b) {
-            const float dv = g[(int64_t)b * C + tid];
-            const float xhat = (z[(int64_t)b * C + tid] - s_mean[tid]) * s_invstd[tid];
-            s1 += dv; s2 += (double)dv * xhat;
+        float vl = 0.f;
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c) if (c == lab) vl = v[c];
+        lsum[0] += (double)(logf(se) + mx - vl);
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c) {
+            if (c < C) {
+                const float dv = (expf(v[c] - mx) / se - (c == lab ? 1.f : 0.f)) / (float)B;
+                g[(size_t)b * C + c] = dv;
+                a1[c] += dv; a2[c] += (double)dv * xh[c];
+            }
         }
-        s_db[tid] = (float)s1; s_dg[tid] = (float)s2;
-        dbeta[tid] = (float)s1; dgamma[tid] = (float)s2;
     }
+    head_block_sum(lsum, 1, sh, tot1);
+    if (tid == 0) *loss_out = (float)(tot1[0] / B);
     __syncthreads();
+    head_block_sum(a1, C, sh, tot1);
+    head_block_sum(a2, C, sh, tot2);
+    if (tid < C) { dbeta[tid] = (float)tot1[tid]; dgamma[tid] = (float)tot2[tid]; }
     const float invB = 1.f / (float)B;
     for (int b = tid; b < B; b += nthr) {
         for (int c = 0; c < Cp; ++c) {
             float d = 0.f;
             if (c < C) {
-                const float xhat = (z[(int64_t)b * C + c] - s_mean[c]) * s_invstd[c];
-                d = gamma[c] * s_invstd[c] * (g[(int64_t)b * C + c] - s_db[c] * invB - xhat * s_dg[c] * invB);
-                g[(int64_t)b * C + c] = d;
+                const float xhat = (z[(size_t)b * C + c] - s_mean[c]) * s_invstd[c];
+                d = s_g[c] * s_invstd[c] * (g[(size_t)b * C + c] - (float)tot1[c] * invB - xhat * (float)tot2[c] * invB);
+                g[(size_t)b * C + c] = d;
             }
-            if (gp) gp[(int64_t)b * Cp + c] = __float2bfloat16_rn(d);
+            if (gp) gp[(size_t)b * Cp + c] = __float2bfloat16_rn(d);
         }
     }
-    (void)red;
 }
 
 static inline int grid_cap(int64_t items, int device, int waves = 8) {
@@ -444,7 +493,7 @@ extern "C" int nn_stage_bwd(const nn_stage_bwd_args* a, int device, void* stream
     p.B = a->B; p.C = a->C; p.OH = a->H; p.OW = a->W; p.Cp = a->Cp; p.pool = a->pool;
     p.act_max = a->act_max; p.q_hi = q.q_hi; p.inv_count = 1.f / ((float)a->B * PH * PW);
     if (a->pool && !a->argmax) return nn_fail("nn_stage_bwd: argmax missing%s", "");
-    k_bn_bwd_apply<<<grid_cap((int64_t)a->B * a->H * a->W * (a->Cp / 8), device), 256, 0, st>>>(p);
+    k_bn_bwd_apply<<<grid_cap((int64_t)a->B * PH * PW * (a->Cp / 8), device), 256, 0, st>>>(p);
     NN_LAUNCH_OK();
     return 0;
 }
@@ -467,7 +516,7 @@ extern "C" int nn_head_fwd_bwd(const float* logits, const int64_t* labels, int B
                                const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                                float* loss_out, float* out, float* g, void* g_packed, int Cp, float* dgamma,
                                float* dbeta, int device, void* stream) {
-    if (C > 32 || C < 1) return nn_fail("nn_head_fwd_bwd: C must be <= 32%s", "");
+    if (C > HEAD_MAXC || C < 1) return nn_fail("nn_head_fwd_bwd: C must be <= 16%s", "");
     if (!logits || !labels || !loss_out || !g || !dgamma || !dbeta) return nn_fail("nn_head_fwd_bwd: null argument%s", "");
     NN_SET_DEVICE(device);
     int threads = B >= 1024 ? 1024 : ((B + 31) / 32) * 32;

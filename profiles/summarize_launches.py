@@ -11,7 +11,8 @@ for row in csv.DictReader(lines):
     except Exception:
         pass
 names = [r[0] for r in rows]
-idx = [i for i, n in enumerate(names) if 'nll_loss_forward' in n]
+marker = sys.argv[4] if len(sys.argv) > 4 else 'nll_loss_forward'
+idx = [i for i, n in enumerate(names) if marker in n]
 seg = rows[idx[which]:idx[which + 1]]
 def short(n):
     n = n.replace('<unnamed>::', '').replace('void ', '')
