@@ -161,6 +161,8 @@ int nn_debug_error_flag(int device, int reset);
 /* Measurement hook: enable = 1/0 brackets the main tcgen05 forward kernel (not the operand packs) with CUDA
  * events on its launch stream; enable < 0 synchronises on them and returns the last elapsed ms (-1: none). */
 float nn_debug_main_kernel_ms(int enable);
+/* Debug (env NN_UMMA_DEBUG=1): per-CTA clock64 phase stamps [cta][8] of the last tcgen05 forward launch. */
+int nn_debug_cta_timeline(long long* host_out, int max_ctas);
 int nn_noisy_conv_fwd(const nn_conv_fwd_args* a, int device, void* stream);
 
 /* ---- a10: backward of a5/a6 with the saturated STE fused --------------------------- */

@@ -115,6 +115,7 @@ SIGNATURES = {
     "nn_conv_supported": (C.c_int, [C.POINTER(ConvGeom), C.c_int32, C.c_int32]),
     "nn_debug_error_flag": (C.c_int, [C.c_int, C.c_int]),
     "nn_debug_main_kernel_ms": (C.c_float, [C.c_int]),
+    "nn_debug_cta_timeline": (C.c_int, [C.c_void_p, C.c_int]),
     "nn_noisy_conv_fwd": (C.c_int, [C.POINTER(ConvFwdArgs), C.c_int, C.c_void_p]),
     "nn_noisy_conv_dgrad": (C.c_int, [C.POINTER(ConvDgradArgs), C.c_int, C.c_void_p]),
     "nn_conv_wgrad_workspace_bytes": (C.c_int64, [C.POINTER(ConvGeom), C.c_int32, C.c_int]),

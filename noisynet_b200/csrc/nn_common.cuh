@@ -83,16 +83,22 @@ __device__ __forceinline__ float nn_usym(uint32_t r, float s) {
     return __fadd_rn(__fmul_rn(nn_u01(r), __fmul_rn(2.0f, s)), -s);
 }
 
-// Box-Muller on one pair.  u1 = fl(fl(r*2^-32) + 2^-33) in (0,1]; theta = pi*(2*u2-1).
+// Box-Muller on one pair, MUFU-only transcendentals (the conv epilogues are instruction-bound on the noise:
+// ~32.5 M normals per NoisyNet step at batch 512).  u1 = fma(r, 2^-32, 2^-33) in (0,1];
+// rad = sqrt(-2 ln u1) via lg2.approx / sqrt.approx; theta = fma(u2, 2pi, -pi), sin/cos.approx.
+// Absolute error vs an exact evaluation: ~1e-6 typical, <= ~2e-3 for the rare rad < 1e-3 (P ~ 5e-7).
+__device__ __forceinline__ float nn_sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ void nn_box_muller(uint32_t ra, uint32_t rb, float& z0, float& z1) {
-    float u1 = __fadd_rn(__fmul_rn(__uint2float_rn(ra), 2.3283064365386963e-10f), 1.1641532182693481e-10f);
-    float u2 = nn_u01(rb);
-    float rad = sqrtf(-2.0f * logf(u1));
-    float th = __fmul_rn(3.14159274101257324f, __fadd_rn(__fmul_rn(2.0f, u2), -1.0f));
-    float sn, cs;
-    __sincosf(th, &sn, &cs);
-    z0 = rad * cs;
-    z1 = rad * sn;
+    const float u1 = fmaf(__uint2float_rn(ra), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float u2 = nn_u01(rb);
+    const float rad = nn_sqrt_approx(-1.3862943611198906f * __log2f(u1));
+    const float th = fmaf(u2, 6.2831853071795865f, -3.14159265358979324f);
+    z0 = rad * __cosf(th);
+    z1 = rad * __sinf(th);
 }
 
 __device__ __forceinline__ void nn_normal4(const NnRng& s, uint64_t group, float z[4]) {
@@ -124,7 +130,7 @@ __device__ __forceinline__ float nn_warp_max(float v) {
 __device__ __forceinline__ float nn_noise_coef(float scale, float current) {
     return __fmul_rn(0.1f, __fdiv_rn(scale, current));
 }
-__device__ __forceinline__ float nn_sigma(float coef, float S) { return sqrtf(__fmul_rn(coef, S)); }
+__device__ __forceinline__ float nn_sigma(float coef, float S) { return nn_sqrt_approx(__fmul_rn(coef, S)); }
 
 static inline void nn_out_hw(const nn_conv_geom& g, int& OH, int& OW) {
     OH = (g.H + 2 * g.pad - g.KH) / g.stride + 1;

@@ -139,8 +139,14 @@ struct UmmaP {
     const float* mask_x;           // optional STE mask source, same NCHW shape as the output
     float mask_lo, mask_hi;
     int* err_flag;
+    long long* dbg;                // optional per-CTA phase timestamps (clock64): [cta][8]
 };
 
+// EPI selects the epilogue at compile time: 0 = generic (every option), 1 = lean noisy (main + sigma, Philox z,
+// y_noisy [+ y], no bias / mask / inject / export / stats) -- the training hot path, 2 = lean plain (y only).
+// The epilogue is issue-bound (Philox + Box-Muller per output), so the hot variants carry no per-element
+// option checks.
+template <int EPI>
 __global__ void __launch_bounds__(UM_THREADS, 2)
 k_conv_umma(const UmmaP p) {
     extern __shared__ uint8_t smem_raw[];
@@ -161,6 +167,8 @@ k_conv_umma(const UmmaP p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * UM_BLOCK_M;
     const int tile_n = blockIdx.y;
+    long long* dbg = p.dbg ? p.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    if (dbg && tid == 0) dbg[0] = clock64();
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -176,6 +184,7 @@ k_conv_umma(const UmmaP p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_g;
+    if (dbg && tid == 0) dbg[1] = clock64();
 
     // ================================================================ main loop roles
     if (warp < 4) {
@@ -219,6 +228,7 @@ k_conv_umma(const UmmaP p) {
             }
             cp_async_mbar_arrive_noinc(full_bar + 8 * s);
         }
+        if (dbg && tid == 0) dbg[6] = clock64();
     } else if (warp == 4) {
         // ---------------- MMA issuer (single thread)
         if (lane == 0) {
@@ -238,6 +248,7 @@ k_conv_umma(const UmmaP p) {
                 umma_commit(empty_bar + 8 * s);           // frees the smem stage when these MMAs retire
             }
             umma_commit(tfull_bar);                        // accumulators complete
+            if (dbg) dbg[2] = clock64();
         }
         __syncwarp();
     } else if (warp == 5) {
@@ -258,6 +269,7 @@ k_conv_umma(const UmmaP p) {
     // ================================================================ epilogue (all 8 warps)
     bool acc_ok = mbar_wait(tfull_bar, 0);
     tc_fence_after();
+    if (dbg && tid == 0) dbg[3] = clock64();
     if (!acc_ok || *abort_g) {
         if (tid == 0 && p.err_flag) atomicExch(p.err_flag, 100 + (int)*abort_g);
     } else {
@@ -277,7 +289,46 @@ k_conv_umma(const UmmaP p) {
         const int ngrp = (p.Cout + 3) >> 2;
         const int n_base = tile_n * p.n_t;
         float s_plain = 0.f, s_abs = 0.f, s_max = __int_as_float(0xff800000);
+        const bool want_stats = p.stats != nullptr;
         const int nchunks = (p.n_t + 15) >> 4;
+        if (EPI == 1 || EPI == 2) {
+            const float y_scale = p.y_scale, s_scale = p.s_scale;
+            const uint64_t grp_row = (uint64_t)m * ngrp;
+            float* const out_main = (EPI == 1 ? p.y_noisy : p.y) + out_row;
+            float* const out_y = (EPI == 1 && p.y) ? p.y + out_row : nullptr;
+            for (int ci = half; ci < nchunks; ci += 2) {
+                const int cc = ci * 16;
+                float am[16], as[16];
+                tmem_ld16(t_lane + (uint32_t)(p.main_col + cc), am);
+                if (EPI == 1) tmem_ld16(t_lane + (uint32_t)(p.sig_col + cc), as);
+                if (!row_ok) continue;
+                const int nb = n_base + cc;
+                const int nvalid = min(16, min(p.n_t - cc, p.Cout - nb));
+                float* o = out_main + (size_t)nb * ohw;
+                float* oy = out_y ? out_y + (size_t)nb * ohw : nullptr;
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    if (g4 * 4 < nvalid) {
+                        float z[4];
+                        if (EPI == 1) nn_normal4(rs, grp_row + (uint64_t)((nb + g4 * 4) >> 2), z);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int e = g4 * 4 + j;
+                            if (e < nvalid) {
+                                const float yv = am[e] * y_scale;
+                                if (EPI == 1) {
+                                    const float sg = nn_sigma(coef, as[e] * s_scale);
+                                    o[(size_t)e * ohw] = __fadd_rn(yv, __fmul_rn(z[j], sg));
+                                    if (oy) oy[(size_t)e * ohw] = yv;
+                                } else {
+                                    o[(size_t)e * ohw] = yv;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        } else
         for (int ci = half; ci < nchunks; ci += 2) {
             const int cc = ci * 16;
             float am[16], as[16];
@@ -312,14 +363,16 @@ k_conv_umma(const UmmaP p) {
                         p.y_noisy[o] = __fadd_rn(yv, nz);
                         if (p.z_export) p.z_export[o] = zz;
                         if (p.sigma_export) p.sigma_export[o] = sg;
-                        if (p.noise_mode == NN_NOISE_MERGED) s_plain += Sv;
-                        s_abs += fabsf(nz);
-                        s_max = fmaxf(s_max, yv);
+                        if (want_stats) {
+                            if (p.noise_mode == NN_NOISE_MERGED) s_plain += Sv;
+                            s_abs += fabsf(nz);
+                            s_max = fmaxf(s_max, yv);
+                        }
                     }
                 }
             }
         }
-        if (noise && p.stats) {
+        if (EPI == 0 && noise && p.stats) {
             if (p.wsum_col >= 0 && half == 0) {      // external DAC: row sum of x (*) |w| from the colsum row
                 float ws[16];
                 tmem_ld16(t_lane + (uint32_t)p.wsum_col, ws);
@@ -333,9 +386,11 @@ k_conv_umma(const UmmaP p) {
             }
         }
     }
+    if (dbg && tid == 0) dbg[4] = clock64();
     tc_fence_before();
     __syncthreads();
     if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+    if (dbg && tid == 128) { dbg[5] = clock64(); unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); dbg[7] = smid; }
 }
 
 // ------------------------------------------------------------------ operand packing
@@ -658,6 +713,10 @@ static Plan make_plan(int Cin_k, int KHW, int n_out, bool has_main, bool has_sig
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// debug hook: per-CTA phase timestamps of the next forward launches (NN_UMMA_DEBUG=1)
+long long* g_dbg_buf = nullptr;
+size_t g_dbg_ctas = 0;
+
 // measurement hook: CUDA events around the main tcgen05 kernel only (excludes the operand packs)
 int g_time_main = 0;
 cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
@@ -665,15 +724,37 @@ cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
+    const bool extras = p.bias || p.mask_x || p.z_inject || p.z_export || p.sigma_export || p.stats;
+    int epi = 0;
+    if (!extras && p.main_col >= 0 && p.noise_mode != NN_NOISE_NONE && p.y_noisy) epi = 1;
+    else if (!extras && p.main_col >= 0 && p.noise_mode == NN_NOISE_NONE && p.y) epi = 2;
+    static const bool force_generic = getenv("NN_UMMA_GENERIC_EPI") != nullptr;
+    if (force_generic) epi = 0;
     dim3 grid((p.M + UM_BLOCK_M - 1) / UM_BLOCK_M, pl.n_tiles);
+    UmmaP pd = p;
+    static const bool want_dbg = getenv("NN_UMMA_DEBUG") != nullptr;
+    if (want_dbg) {
+        const size_t ctas = (size_t)grid.x * grid.y;
+        if (ctas > g_dbg_ctas) {
+            if (g_dbg_buf) cudaFree(g_dbg_buf);
+            cudaMalloc(&g_dbg_buf, ctas * 8 * sizeof(long long));
+            g_dbg_ctas = ctas;
+        }
+        cudaMemsetAsync(g_dbg_buf, 0, ctas * 8 * sizeof(long long), st);
+        pd.dbg = g_dbg_buf;
+    }
     if (g_time_main) {
         if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
         cudaEventRecord(g_ev0, st);
     }
-    k_conv_umma<<<grid, UM_THREADS, pl.smem_bytes, st>>>(p);
+    if (epi == 1) k_conv_umma<1><<<grid, UM_THREADS, pl.smem_bytes, st>>>(pd);
+    else if (epi == 2) k_conv_umma<2><<<grid, UM_THREADS, pl.smem_bytes, st>>>(pd);
+    else k_conv_umma<0><<<grid, UM_THREADS, pl.smem_bytes, st>>>(pd);
     if (g_time_main) cudaEventRecord(g_ev1, st);
     NN_LAUNCH_OK();
     return 0;
@@ -708,6 +789,16 @@ int* nn_umma_err_flag(int device) {
         cudaMemset(flags[device], 0, sizeof(int));
     }
     return flags[device];
+}
+
+extern "C" int nn_debug_cta_timeline(long long* host_out, int max_ctas) {
+    // copies [cta][8] clock64 stamps of the last forward launch (NN_UMMA_DEBUG=1): 0 start, 1 setup done,
+    // 2 last MMA issued, 3 accumulators ready, 4 epilogue done, 5 teardown, 6 producers done, 7 smid
+    if (!g_dbg_buf) return 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    const size_t n = g_dbg_ctas < (size_t)max_ctas ? g_dbg_ctas : (size_t)max_ctas;
+    if (cudaMemcpy(host_out, g_dbg_buf, n * 8 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int)n;
 }
 
 extern "C" float nn_debug_main_kernel_ms(int enable) {
