@@ -226,6 +226,8 @@ class NoisyNetEngine:
         self._dgrad(self.geom[3], self.gyp4, self.wq[3], self.gx4)
         self._stage_bwd(self.gx4, self.l1n, None, FC, 1, 0, m.bn3, "bn3", a.q_a4, qh4, self.gyp3)
         self._wgrad(2, self.gyp3, self.xp3, s3, W[2], W[2].grad)
+        if self.red is not None:
+            self.red.start_early()      # fc gradients (85 % of the payload) travel while the conv backward runs
         self._dgrad(self.geom_fc1_lin, self.gyp3, self.wq[2], self.gx3)
         self._stage_bwd(self.gx3, self.pool2, self.amax2, C2, H2, 1, m.bn2, "bn2", a.q_a3, qh3, self.gyp2)
         self._wgrad(1, self.gyp2, self.xp2, s2, W[1], W[1].grad)

@@ -28,7 +28,8 @@ def _worker(rank, world, port, out_dir):
     assert (r, w) == (rank, world)
     torch.manual_seed(dp.rank_seed(0, rank))                       # different init per rank on purpose
     model = torch.nn.Sequential(torch.nn.Linear(12, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
-    red = dp.FlatGradAllReduce(model, world)
+    red = dp.FlatGradAllReduce(model, world, early=[model[2].weight])      # early bucket: last layer's weight
+    assert red.params[0] is model[2].weight and red.n_early == 21
     red.broadcast_parameters(model)                                 # now identical to rank 0
     g = torch.Generator().manual_seed(123)
     X, Y = torch.randn(16, 12, generator=g), torch.randint(0, 3, (16,), generator=g)
@@ -37,7 +38,9 @@ def _worker(rank, world, port, out_dir):
     loss = torch.nn.functional.cross_entropy(model(X[lo:hi]), Y[lo:hi])
     loss.backward()
     assert all(p.grad.data_ptr() >= red.flat.data_ptr() for p in model.parameters())   # grads are views
+    red.start_early()                                            # async bucket, joined by all_reduce_mean_
     red.all_reduce_mean_()
+    assert red._work is None
     torch.save({"flat": red.flat.clone(), "params": [p.detach().clone() for p in model.parameters()]},
                os.path.join(out_dir, "rank%d.pt" % rank))
     dist.barrier()
@@ -61,7 +64,8 @@ def test_flat_grad_allreduce_world2(tmp_path):
     g = torch.Generator().manual_seed(123)
     X, Y = torch.randn(16, 12, generator=g), torch.randint(0, 3, (16,), generator=g)
     torch.nn.functional.cross_entropy(model(X), Y).backward()
-    full = torch.cat([p.grad.flatten() for p in model.parameters()])
+    order = [model[2].weight] + [p for p in model.parameters() if p is not model[2].weight]   # early bucket first
+    full = torch.cat([p.grad.flatten() for p in order])
     assert torch.allclose(a["flat"], full, atol=1e-6)
 
 
