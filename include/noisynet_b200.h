@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NN_ABI_VERSION 5
+#define NN_ABI_VERSION 6
 
 /* ---- common ---------------------------------------------------------------------- */
 
@@ -149,6 +149,9 @@ typedef struct nn_conv_fwd_args {
     const void* x_packed;    /* optional (tcgen05 precisions): the input already packed as NHWC bf16
                                 [B,H,W,ceil8(Cin)] (codes if a_code_scale > 0), e.g. by nn_stage_fwd;
                                 `x` is then ignored and the pack kernel is skipped                    */
+    const void* w_packed;    /* optional: weights already packed by nn_prepare_weights (mode 0, same
+                                noise_mode / stats choice); w_eff may then be NULL, w_code_scale must be
+                                the quantizer's s/2                                                   */
 } nn_conv_fwd_args;
 
 int64_t nn_conv_workspace_bytes(const nn_conv_geom* g, int32_t precision);
@@ -179,6 +182,7 @@ typedef struct nn_conv_dgrad_args {
     float w_code_scale;      /* > 0: w_eff holds integer codes * w_code_scale (exact bf16 operand), see fwd */
     void* workspace; int64_t workspace_bytes;
     const void* gy_packed;   /* optional: grad_output already NHWC bf16 [B,OH,OW,ceil8(Cout)] (nn_stage_bwd) */
+    const void* w_packed;    /* optional: weights already packed by nn_prepare_weights (mode 1)        */
 } nn_conv_dgrad_args;
 int nn_noisy_conv_dgrad(const nn_conv_dgrad_args* a, int device, void* stream);
 
@@ -198,6 +202,23 @@ typedef struct nn_conv_wgrad_args {
 } nn_conv_wgrad_args;
 int64_t nn_conv_wgrad_workspace_bytes(const nn_conv_geom* g, int32_t precision, int device);
 int nn_noisy_conv_wgrad(const nn_conv_wgrad_args* a, int device, void* stream);
+
+/* ---- weight preparation for a whole step in one launch ------------------------------------------------
+ * Each job packs one layer's weights into the tcgen05 operand image: mode 0 = forward rows
+ * [quantized main | g(|w_raw|) | colsum |w_raw|], mode 1 = transposed, tap-flipped rows for dgrad.  With
+ * q_bits > 0 the weight quantizer (hardware_model.py:323, :343: range [-q_hi, q_hi], stochastic rounding)
+ * runs in registers; jobs sharing `rng` (or u_inject) quantize identically.  `jobs` is a HOST array (<= 8). */
+typedef struct nn_wprep_job {
+    const float* w_raw;      /* [Cout,Cin,KH,KW] fp32 parameter                                       */
+    int32_t Cout, Cin, KHW;
+    int32_t mode;            /* 0 forward, 1 dgrad                                                    */
+    int32_t noise_mode;      /* mode 0: NN_NOISE_* (which sigma rows to add)                          */
+    int32_t want_wsum;       /* mode 0, external DAC: add the colsum row (power statistic)            */
+    int32_t q_bits; double q_hi; float stochastic; const float* u_inject; nn_rng rng;
+    void* packed_out;        /* nn_weight_pack_bytes(job) bytes                                       */
+} nn_wprep_job;
+int64_t nn_weight_pack_bytes(const nn_wprep_job* job);
+int nn_prepare_weights(const nn_wprep_job* jobs, int count, int device, void* stream);
 
 /* ---- section 8f.1: the between-layer stages, fused ---------------------------------------------------
  * conv stage (noisynet.py:419-460, 483-520): MaxPool2d(2,2) -> BatchNorm (batch statistics, running stats
@@ -222,7 +243,8 @@ typedef struct nn_stage_args {
     void* xp; int32_t Cp;     /* out [B,H',W',Cp] bf16 codes, Cp % 8 == 0                            */
     float* act;               /* optional out: dequantised activation, NCHW fp32                      */
     float* xmax_out;          /* optional out: max of the activation (device scalar)                  */
-    void* scratch;            /* nn_stage_scratch_bytes(C) bytes                                      */
+    void* scratch;            /* nn_stage_scratch_bytes(C) bytes, ZEROED once by the caller (kernels keep it
+                                 consistent); shared by the forward and backward of all stages          */
 } nn_stage_args;
 int64_t nn_stage_scratch_bytes(int C);
 int nn_stage_fwd(const nn_stage_args* a, int device, void* stream);

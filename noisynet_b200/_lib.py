@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libnoisynet_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 NOISE_NONE, NOISE_MERGED, NOISE_EXTERNAL = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
@@ -37,7 +37,8 @@ class ConvFwdArgs(C.Structure):
                 ("stats", C.c_void_p),
                 ("precision", C.c_int32),
                 ("a_code_scale", C.c_float), ("w_code_scale", C.c_float),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("x_packed", C.c_void_p)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("x_packed", C.c_void_p),
+                ("w_packed", C.c_void_p)]
 
 
 class ConvDgradArgs(C.Structure):
@@ -45,7 +46,8 @@ class ConvDgradArgs(C.Structure):
                 ("gy", C.c_void_p), ("w_eff", C.c_void_p), ("gx", C.c_void_p),
                 ("x_pre", C.c_void_p), ("x_lo", C.c_double), ("x_hi", C.c_double),
                 ("precision", C.c_int32), ("w_code_scale", C.c_float),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("gy_packed", C.c_void_p)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("gy_packed", C.c_void_p),
+                ("w_packed", C.c_void_p)]
 
 
 class ConvWgradArgs(C.Structure):
@@ -61,6 +63,13 @@ class AdamWTensor(C.Structure):
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
                 ("n", C.c_int64), ("lr", C.c_float), ("weight_decay", C.c_float), ("clamp", C.c_float),
                 ("absmax_out", C.c_void_p)]
+
+
+class WPrepJob(C.Structure):
+    _fields_ = [("w_raw", C.c_void_p), ("Cout", C.c_int32), ("Cin", C.c_int32), ("KHW", C.c_int32),
+                ("mode", C.c_int32), ("noise_mode", C.c_int32), ("want_wsum", C.c_int32),
+                ("q_bits", C.c_int32), ("q_hi", C.c_double), ("stochastic", C.c_float), ("u_inject", C.c_void_p),
+                ("rng", Rng), ("packed_out", C.c_void_p)]
 
 
 class StageArgs(C.Structure):
@@ -97,6 +106,8 @@ SIGNATURES = {
                                       C.c_int, C.c_void_p]),
     "nn_adamw_step": (C.c_int, [C.POINTER(AdamWTensor), C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_void_p, C.c_int, C.c_void_p]),
+    "nn_weight_pack_bytes": (C.c_int64, [C.POINTER(WPrepJob)]),
+    "nn_prepare_weights": (C.c_int, [C.POINTER(WPrepJob), C.c_int, C.c_int, C.c_void_p]),
     "nn_stage_scratch_bytes": (C.c_int64, [C.c_int]),
     "nn_stage_fwd": (C.c_int, [C.POINTER(StageArgs), C.c_int, C.c_void_p]),
     "nn_stage_bwd": (C.c_int, [C.POINTER(StageBwdArgs), C.c_int, C.c_void_p]),

@@ -44,11 +44,11 @@ extern "C" int nn_noisy_conv_fwd(const nn_conv_fwd_args* a, int device, void* st
     if (!a) return nn_fail("nn_noisy_conv_fwd: null args%s", "");
     if (int e = check_geom(a->g, "nn_noisy_conv_fwd")) return e;
     if (!a->x && !(a->x_packed && a->precision != NN_PREC_FP32)) return nn_fail("nn_noisy_conv_fwd: x missing%s", "");
-    if (!a->w_eff && (a->noise_mode == NN_NOISE_NONE || !a->y))
+    if (!a->w_eff && !a->w_packed && (a->noise_mode == NN_NOISE_NONE || !a->y))
         return nn_fail("nn_noisy_conv_fwd: w_eff missing%s (noise-only mode needs noise_mode > 0 and y as input)", "");
     if (a->noise_mode < 0 || a->noise_mode > 2) return nn_fail("nn_noisy_conv_fwd: bad noise_mode%s", "");
     if (a->noise_mode != NN_NOISE_NONE) {
-        if (!a->w_raw || !a->y_noisy || !a->scale_dev)
+        if ((!a->w_raw && !a->w_packed) || !a->y_noisy || !a->scale_dev)
             return nn_fail("nn_noisy_conv_fwd: noise needs w_raw, y_noisy and scale_dev%s", "");
         if (!(a->current > 0.f)) return nn_fail("nn_noisy_conv_fwd: current must be > 0%s", "");
     } else if (!a->y) {
@@ -67,7 +67,8 @@ extern "C" int nn_noisy_conv_fwd(const nn_conv_fwd_args* a, int device, void* st
 extern "C" int nn_noisy_conv_dgrad(const nn_conv_dgrad_args* a, int device, void* stream) {
     if (!a) return nn_fail("nn_noisy_conv_dgrad: null args%s", "");
     if (int e = check_geom(a->g, "nn_noisy_conv_dgrad")) return e;
-    if ((!a->gy && !(a->gy_packed && a->precision != NN_PREC_FP32)) || !a->w_eff || !a->gx)
+    if ((!a->gy && !(a->gy_packed && a->precision != NN_PREC_FP32)) ||
+        (!a->w_eff && !(a->w_packed && a->precision != NN_PREC_FP32)) || !a->gx)
         return nn_fail("nn_noisy_conv_dgrad: null tensor%s", "");
     NN_SET_DEVICE(device);
     if (a->precision == NN_PREC_FP32) return nn_simt_conv_dgrad(a, device, (cudaStream_t)stream);

@@ -428,12 +428,41 @@ struct PackWP {
     int Cout, Cin, KHW, Cp, n_t, n_mma, num_kb, n_tiles;
     int main_col, sig_col, wsum_col, noise_mode, mode;
     float w_code_scale;
+    // optional in-register weight quantizer (hardware_model.py:323, :343; range [-q_hi, q_hi] symmetric): the
+    // main rows are then produced from w_raw directly -- k = rne(clamp((w + q_hi)/s + u, 0, qmax)), stored as the
+    // odd-integer code 2k - qmax (exact in bf16; epilogue scale s/2).  u: Philox word (idx/4, idx%4), i.e. the
+    // same draw nn_quantize_fwd would make for element idx with the same rng, or u_inject[idx].
+    int q_bits;
+    float q_hi, q_scale, q_max, q_stoch;
+    const float* u_inject;
+    nn_rng rng;
 };
 
-__global__ void __launch_bounds__(256)
-k_pack_w(const PackWP p) {
+__device__ __forceinline__ float pack_main_value(const PackWP& p, const NnRng& rs, int64_t idx) {
+    if (p.q_bits > 0) {
+        const float w = __ldg(p.w_raw + idx);
+        float u = 0.f;
+        if (p.q_stoch > 0.f) {
+            if (p.u_inject) u = __ldg(p.u_inject + idx);
+            else {
+                const uint4 r = nn_philox(rs, (uint64_t)(idx >> 2));
+                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+                u = nn_usym(rr[idx & 3], p.q_stoch);
+            }
+        }
+        float t = __fadd_rn(__fdiv_rn(__fadd_rn(w, p.q_hi), p.q_scale), u);
+        t = rintf(fminf(fmaxf(t, 0.f), p.q_max));
+        return 2.f * t - p.q_max;
+    }
+    float f = __ldg(p.w_eff + idx);
+    if (p.w_code_scale > 0.f) f = rintf(__fdiv_rn(f, p.w_code_scale));
+    return f;
+}
+
+__device__ __forceinline__ void pack_w_job(const PackWP& p, int64_t start, int64_t stride) {
+    const NnRng rs = nn_rng_load(p.rng);
     const int64_t total = (int64_t)p.n_tiles * p.num_kb * p.n_mma * 8;     // one thread per 16-byte chunk
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = start; i < total; i += stride) {
         const int j = (int)(i & 7);
         int64_t t = i >> 3;
         const int r = (int)(t % p.n_mma); t /= p.n_mma;
@@ -461,16 +490,14 @@ k_pack_w(const PackWP p) {
                         if (p.mode == 0) {
                             const int64_t idx = ((int64_t)n * p.Cin + c) * p.KHW + tap;
                             if (kind == 0) {
-                                f = __ldg(p.w_eff + idx);
-                                if (p.w_code_scale > 0.f) f = rintf(__fdiv_rn(f, p.w_code_scale));
+                                f = pack_main_value(p, rs, idx);
                             } else {
                                 const float a = fabsf(__ldg(p.w_raw + idx));
                                 f = (p.noise_mode == NN_NOISE_MERGED) ? a : __fadd_rn(__fmul_rn(a, a), a);
                             }
                         } else {
                             const int64_t idx = ((int64_t)c * p.Cin + n) * p.KHW + (p.KHW - 1 - tap);
-                            f = __ldg(p.w_eff + idx);
-                            if (p.w_code_scale > 0.f) f = rintf(__fdiv_rn(f, p.w_code_scale));
+                            f = pack_main_value(p, rs, idx);
                         }
                     }
                 }
@@ -481,6 +508,20 @@ k_pack_w(const PackWP p) {
         const int64_t off = blk + (int64_t)r * 64 + (((j ^ (r & 7))) << 3);           // 128B swizzle
         *reinterpret_cast<uint4*>(p.wp + off) = *reinterpret_cast<const uint4*>(v);
     }
+}
+
+__global__ void __launch_bounds__(256)
+k_pack_w(const PackWP p) {
+    pack_w_job(p, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+}
+
+// all weight packs of a training step (forward x layers, dgrad x layers) in ONE launch: blockIdx.y = job
+constexpr int UM_MAX_PACK_JOBS = 8;
+struct PackJobs { PackWP j[UM_MAX_PACK_JOBS]; };
+
+__global__ void __launch_bounds__(256)
+k_pack_w_batch(const PackJobs jobs) {
+    pack_w_job(jobs.j[blockIdx.y], blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
 // ------------------------------------------------------------------ wgrad on tcgen05 (MN-major operands)
@@ -829,7 +870,7 @@ int nn_umma_conv_fwd(const nn_conv_fwd_args* a, int device, cudaStream_t st) {
     const nn_conv_geom& g = a->g;
     int OH, OW;
     nn_out_hw(g, OH, OW);
-    const bool has_main = a->w_eff != nullptr;
+    const bool has_main = a->w_eff != nullptr || a->w_packed != nullptr;
     const bool noise = a->noise_mode != NN_NOISE_NONE;
     const bool has_wsum = noise && a->noise_mode == NN_NOISE_EXTERNAL && a->stats != nullptr;
     Plan pl = make_plan(g.Cin, g.KH * g.KW, g.Cout, has_main, noise, has_wsum, (int64_t)g.B * g.H * g.W);
@@ -850,8 +891,11 @@ int nn_umma_conv_fwd(const nn_conv_fwd_args* a, int device, cudaStream_t st) {
         k_pack_act<<<grid, 256, 0, st>>>(a->x, xp, g.B, g.Cin, g.H * g.W, pl.Cp, a->a_code_scale);
         NN_LAUNCH_OK();
     }
-    {
+    if (a->w_packed) {
+        wp = (__nv_bfloat16*)a->w_packed;
+    } else {
         PackWP pw;
+        memset(&pw, 0, sizeof(pw));
         pw.w_eff = a->w_eff; pw.w_raw = a->w_raw; pw.wp = wp;
         pw.Cout = g.Cout; pw.Cin = g.Cin; pw.KHW = g.KH * g.KW; pw.Cp = pl.Cp; pw.n_t = pl.n_t; pw.n_mma = pl.n_mma;
         pw.num_kb = pl.num_kb; pw.n_tiles = pl.n_tiles; pw.main_col = pl.main_col; pw.sig_col = pl.sig_col;
@@ -879,6 +923,54 @@ int nn_umma_conv_fwd(const nn_conv_fwd_args* a, int device, cudaStream_t st) {
     return launch_umma(p, pl, st);
 }
 
+static Plan plan_for_job(const nn_wprep_job& jb) {
+    if (jb.mode == 0)
+        return make_plan(jb.Cin, jb.KHW, jb.Cout, true, jb.noise_mode != NN_NOISE_NONE,
+                         jb.noise_mode == NN_NOISE_EXTERNAL && jb.want_wsum, 0);
+    return make_plan(jb.Cout, jb.KHW, jb.Cin, true, false, false, 0);
+}
+
+extern "C" int64_t nn_weight_pack_bytes(const nn_wprep_job* jb) {
+    if (!jb) return 0;
+    return (int64_t)align_up(plan_for_job(*jb).wp_bytes, 1024);
+}
+
+extern "C" int nn_prepare_weights(const nn_wprep_job* jobs, int count, int device, void* stream) {
+    if (count <= 0) return 0;
+    if (count > UM_MAX_PACK_JOBS) return nn_fail("nn_prepare_weights: too many jobs%s (%lld)", "", count);
+    NN_SET_DEVICE(device);
+    PackJobs pj;
+    memset(&pj, 0, sizeof(pj));
+    int64_t max_total = 0;
+    for (int i = 0; i < count; ++i) {
+        const nn_wprep_job& jb = jobs[i];
+        if (!jb.w_raw || !jb.packed_out) return nn_fail("nn_prepare_weights: null pointer%s", "");
+        if (jb.q_bits > 0 && !(jb.q_hi > 0)) return nn_fail("nn_prepare_weights: symmetric range needs q_hi > 0%s", "");
+        const Plan pl = plan_for_job(jb);
+        PackWP& pw = pj.j[i];
+        pw.w_eff = jb.w_raw; pw.w_raw = jb.w_raw; pw.wp = (__nv_bfloat16*)jb.packed_out;
+        pw.Cout = jb.Cout; pw.Cin = jb.Cin; pw.KHW = jb.KHW; pw.Cp = pl.Cp; pw.n_t = pl.n_t; pw.n_mma = pl.n_mma;
+        pw.num_kb = pl.num_kb; pw.n_tiles = pl.n_tiles; pw.main_col = pl.main_col; pw.sig_col = pl.sig_col;
+        pw.wsum_col = pl.wsum_col; pw.noise_mode = jb.noise_mode; pw.mode = jb.mode; pw.w_code_scale = 0.f;
+        pw.q_bits = jb.q_bits;
+        if (jb.q_bits > 0) {
+            const double qmax = (double)((1u << jb.q_bits) - 1u);
+            double sc = 2.0 * jb.q_hi / qmax;
+            if (sc < 1e-6) sc = 1e-6;
+            pw.q_hi = (float)jb.q_hi; pw.q_scale = (float)sc; pw.q_max = (float)qmax; pw.q_stoch = jb.stochastic;
+            pw.u_inject = jb.u_inject; pw.rng = jb.rng;
+        }
+        const int64_t total = (int64_t)pl.n_tiles * pl.num_kb * pl.n_mma * 8;
+        if (total > max_total) max_total = total;
+    }
+    int gx = (int)((max_total + 255) / 256);
+    if (gx > 4 * nn_num_sms(device)) gx = 4 * nn_num_sms(device);
+    dim3 grid(gx, count);
+    k_pack_w_batch<<<grid, 256, 0, (cudaStream_t)stream>>>(pj);
+    NN_LAUNCH_OK();
+    return 0;
+}
+
 int nn_umma_conv_dgrad(const nn_conv_dgrad_args* a, int device, cudaStream_t st) {
     if (a->precision != NN_PREC_BF16)
         return nn_fail("nn_noisy_conv_dgrad: tcgen05 path implements NN_PREC_BF16 only%s", "");
@@ -903,8 +995,11 @@ int nn_umma_conv_dgrad(const nn_conv_dgrad_args* a, int device, cudaStream_t st)
         k_pack_act<<<grid, 256, 0, st>>>(a->gy, xp, g.B, g.Cout, OH * OW, pl.Cp, 0.f);
         NN_LAUNCH_OK();
     }
-    {
+    if (a->w_packed) {
+        wp = (__nv_bfloat16*)a->w_packed;
+    } else {
         PackWP pw;
+        memset(&pw, 0, sizeof(pw));
         pw.w_eff = a->w_eff; pw.w_raw = nullptr; pw.wp = wp;
         pw.Cout = g.Cout; pw.Cin = g.Cin; pw.KHW = g.KH * g.KW; pw.Cp = pl.Cp; pw.n_t = pl.n_t; pw.n_mma = pl.n_mma;
         pw.num_kb = pl.num_kb; pw.n_tiles = pl.n_tiles; pw.main_col = pl.main_col; pw.sig_col = -1; pw.wsum_col = -1;

@@ -18,7 +18,7 @@ import torch
 
 from . import _lib, ops
 from ._lib import (NOISE_EXTERNAL, NOISE_MERGED, PREC_BF16, ConvDgradArgs, ConvFwdArgs, ConvGeom, ConvWgradArgs,
-                   Rng, StageArgs, StageBwdArgs)
+                   Rng, StageArgs, StageBwdArgs, WPrepJob)
 from .hardware_model import _f32
 
 
@@ -68,9 +68,30 @@ class NoisyNetEngine:
         self.gx3 = f32(B, C2, P2, P2); self.gyp2 = bf16(B, H2, H2, c8(C2))
         self.gx2 = f32(B, C1, P1, P1); self.gyp1 = bf16(B, H1, H1, c8(C1))
         self.loss = f32(1)
-        self.scratch = torch.empty(int(self.lib.nn_stage_scratch_bytes(max(C1, C2, FC))) + 64, dtype=torch.uint8, device=dev)
-        self.wq = [torch.empty_like(w) for w in self._weights()]
-        self.absmax_fallback = f32(4)
+        self.scratch = torch.zeros(int(self.lib.nn_stage_scratch_bytes(max(C1, C2, FC))) + 64, dtype=torch.uint8, device=dev)
+        # weight packs of the step: forward (4 layers) + dgrad (fc2, fc1 as a linear, conv2), one launch
+        modes = [NOISE_MERGED if a.merged_dac else NOISE_EXTERNAL, NOISE_EXTERNAL,
+                 NOISE_MERGED if a.merged_dac else NOISE_EXTERNAL, NOISE_EXTERNAL]
+        self.noise_modes = [m if a.layer_currents[i] > 0 else 0 for i, m in enumerate(modes)]
+        W = self._weights()
+        shapes = [(C1, 3, fs * fs), (C2, C1, fs * fs), (FC, C2, P2 * P2), (10, FC, 1)]
+        self.jobs = (WPrepJob * 7)()
+        self.job_layer = [0, 1, 2, 3, 3, 2, 1]
+        specs = [(0, shapes[0], 0), (1, shapes[1], 0), (2, shapes[2], 0), (3, shapes[3], 0),
+                 (3, shapes[3], 1), (2, (FC, C2 * P2 * P2, 1), 1), (1, shapes[1], 1)]
+        self.wpack = []
+        for j, (li, (co, ci, khw), mode) in enumerate(specs):
+            jb = self.jobs[j]
+            jb.w_raw = W[li].data_ptr()
+            jb.Cout, jb.Cin, jb.KHW, jb.mode = co, ci, khw, mode
+            jb.noise_mode = self.noise_modes[li] if mode == 0 else 0
+            jb.want_wsum = 0
+            jb.q_bits, jb.q_hi = int(a.q_w1), 1.0
+            buf = torch.zeros(int(self.lib.nn_weight_pack_bytes(C.byref(jb))) + 1024, dtype=torch.uint8, device=dev)
+            jb.packed_out = (buf.data_ptr() + 1023) // 1024 * 1024
+            self.wpack.append(buf)
+        self.wp_fwd = [self.jobs[i].packed_out for i in range(4)]
+        self.wp_dgrad = {3: self.jobs[4].packed_out, 2: self.jobs[5].packed_out, 1: self.jobs[6].packed_out}
         # geometry of the four contractions (fc1 forward / wgrad run as a 5x5 conv over the NHWC pooled map)
         self.geom = [ConvGeom(B, 3, 32, 32, C1, fs, fs, 1, 0), ConvGeom(B, C1, P1, P1, C2, fs, fs, 1, 0),
                      ConvGeom(B, C2, P2, P2, FC, P2, P2, 1, 0), ConvGeom(B, FC, 1, 1, 10, 1, 1, 1, 0)]
@@ -107,12 +128,12 @@ class NoisyNetEngine:
             return hit[1]
         return ops.tensor_stats(w.detach())[1:2]
 
-    def _fwd_gemm(self, idx, xp, a_cs, w_raw, wq, y_noisy, mode, scale_dev, z=None):
+    def _fwd_gemm(self, idx, xp, a_cs, y_noisy, mode, scale_dev, z=None):
         a = ConvFwdArgs()
         a.g = self.geom[idx]
         a.x = None
         a.x_packed = _p(xp)
-        a.w_eff, a.w_raw = _p(wq), _p(w_raw)
+        a.w_eff, a.w_raw, a.w_packed = None, None, self.wp_fwd[idx]
         cur = float(self.a.layer_currents[idx])
         if cur > 0:
             a.y, a.y_noisy = None, _p(y_noisy)
@@ -137,10 +158,10 @@ class NoisyNetEngine:
         a.workspace, a.workspace_bytes = _p(self.ws), self.ws.numel()
         _lib.check(self.lib.nn_noisy_conv_wgrad(C.byref(a), self.di, self._st()), "nn_noisy_conv_wgrad")
 
-    def _dgrad(self, geom, gyp, wq, gx):
+    def _dgrad(self, geom, gyp, layer, gx):
         a = ConvDgradArgs()
         a.g = geom
-        a.gy, a.gy_packed, a.w_eff, a.gx = None, _p(gyp), _p(wq), _p(gx)
+        a.gy, a.gy_packed, a.w_eff, a.w_packed, a.gx = None, _p(gyp), None, self.wp_dgrad[layer], _p(gx)
         a.precision, a.w_code_scale = PREC_BF16, self.w_cs
         a.workspace, a.workspace_bytes = _p(self.ws), self.ws.numel()
         _lib.check(self.lib.nn_noisy_conv_dgrad(C.byref(a), self.di, self._st()), "nn_noisy_conv_dgrad")
@@ -197,25 +218,30 @@ class NoisyNetEngine:
         s1, s2, s3, s4 = (_f32(max(h / (2.0 ** b - 1.0), 1e-6))
                           for h, b in ((qh1, a.q_a1), (qh2, a.q_a2), (qh3, a.q_a3), (qh4, a.q_a4)))
         self.w_cs = _f32(max(2.0 / (2.0 ** a.q_w1 - 1.0), 1e-6)) / 2.0
-        # ---- forward.  Draw order = the reference's (quantize1, w1, z1, quantize2, w2, z2, ...)
+        # ---- weights: quantize (stochastic rounding) + pack for forward and dgrad, all layers, ONE launch
+        self._uw_keep = []
+        for li in range(4):
+            uw = self._take("uw")
+            self._uw_keep.append(uw)             # keep injected tensors alive until the launch below has run
+            rng = Rng(0, 0, None) if uw is not None else self._rng()
+            for j in range(7):
+                if self.job_layer[j] == li:
+                    self.jobs[j].stochastic = stoch
+                    self.jobs[j].u_inject = _p(uw)
+                    self.jobs[j].rng = rng
+        _lib.check(lib.nn_prepare_weights(self.jobs, 7, di, st), "nn_prepare_weights")
+        # ---- forward
         u = self._take("u")
         _lib.check(lib.nn_input_quant_pack(_p(x), _p(self.xp1), None, B, 3, 32 * 32, 8, int(a.q_a1), qh1, stoch, _p(u),
                                            Rng(0, 0, None) if u is not None else self._rng(), di, st), "nn_input_quant_pack")
 
-        def wquant(i):
-            ops.quantize_fwd(W[i].detach(), a.q_w1, -1.0, 1.0, stoch, u=self._take("u"), out=self.wq[i])
-
-        wquant(0)
-        self._fwd_gemm(0, self.xp1, s1, W[0], self.wq[0], self.y1n, NOISE_MERGED, self._absmax(0, W[0]), self._take("z"))
+        self._fwd_gemm(0, self.xp1, s1, self.y1n, self.noise_modes[0], self._absmax(0, W[0]), self._take("z"))
         self._stage_fwd(self.y1n, C1, H1, 1, self.pool1, self.amax1, m.bn1, "bn1", a.q_a2, qh2, self.xp2, self.xmax2, self._take("u"))
-        wquant(1)
-        self._fwd_gemm(1, self.xp2, s2, W[1], self.wq[1], self.y2n, NOISE_EXTERNAL, self.xmax2, self._take("z"))
+        self._fwd_gemm(1, self.xp2, s2, self.y2n, self.noise_modes[1], self.xmax2, self._take("z"))
         self._stage_fwd(self.y2n, C2, H2, 1, self.pool2, self.amax2, m.bn2, "bn2", a.q_a3, qh3, self.xp3, None, self._take("u"))
-        wquant(2)
-        self._fwd_gemm(2, self.xp3, s3, W[2], self.wq[2], self.l1n, NOISE_MERGED, self._absmax(2, W[2]), self._take("z"))
+        self._fwd_gemm(2, self.xp3, s3, self.l1n, self.noise_modes[2], self._absmax(2, W[2]), self._take("z"))
         self._stage_fwd(self.l1n, FC, 1, 0, None, None, m.bn3, "bn3", a.q_a4, qh4, self.xp4, self.xmax4, self._take("u"))
-        wquant(3)
-        self._fwd_gemm(3, self.xp4, s4, W[3], self.wq[3], self.l2n, NOISE_EXTERNAL, self.xmax4, self._take("z"))
+        self._fwd_gemm(3, self.xp4, s4, self.l2n, self.noise_modes[3], self.xmax4, self._take("z"))
         bn4 = m.bn4
         _lib.check(lib.nn_head_fwd_bwd(_p(self.l2n), _p(labels), B, 10, _p(bn4.weight), _p(bn4.bias), _p(bn4.running_mean),
                                        _p(bn4.running_var), float(bn4.momentum), float(bn4.eps), _p(self.loss), None,
@@ -223,15 +249,15 @@ class NoisyNetEngine:
                    "nn_head_fwd_bwd")
         # ---- backward
         self._wgrad(3, self.gyp4, self.xp4, s4, W[3], W[3].grad)
-        self._dgrad(self.geom[3], self.gyp4, self.wq[3], self.gx4)
+        self._dgrad(self.geom[3], self.gyp4, 3, self.gx4)
         self._stage_bwd(self.gx4, self.l1n, None, FC, 1, 0, m.bn3, "bn3", a.q_a4, qh4, self.gyp3)
         self._wgrad(2, self.gyp3, self.xp3, s3, W[2], W[2].grad)
         if self.red is not None:
             self.red.start_early()      # fc gradients (85 % of the payload) travel while the conv backward runs
-        self._dgrad(self.geom_fc1_lin, self.gyp3, self.wq[2], self.gx3)
+        self._dgrad(self.geom_fc1_lin, self.gyp3, 2, self.gx3)
         self._stage_bwd(self.gx3, self.pool2, self.amax2, C2, H2, 1, m.bn2, "bn2", a.q_a3, qh3, self.gyp2)
         self._wgrad(1, self.gyp2, self.xp2, s2, W[1], W[1].grad)
-        self._dgrad(self.geom[1], self.gyp2, self.wq[1], self.gx2)
+        self._dgrad(self.geom[1], self.gyp2, 1, self.gx2)
         self._stage_bwd(self.gx2, self.pool1, self.amax1, C1, H1, 1, m.bn1, "bn1", a.q_a2, qh2, self.gyp1)
         self._wgrad(0, self.gyp1, self.xp1, s1, W[0], W[0].grad)
         # ---- exchange + update

@@ -38,7 +38,7 @@ def _stage_call(dev, x, gamma, beta, rm, rv, pool, act_max, bits, q_hi, u):
     xp = torch.zeros(B, PH, PW, Cp, dtype=torch.bfloat16, device=dev)
     act = torch.empty(B, Cc, PH, PW, device=dev)
     xmax = torch.zeros(1, device=dev)
-    scratch = torch.empty(int(lib.nn_stage_scratch_bytes(Cc)) + 64, dtype=torch.uint8, device=dev)
+    scratch = torch.zeros(int(lib.nn_stage_scratch_bytes(Cc)) + 64, dtype=torch.uint8, device=dev)
     a = _lib.StageArgs()
     a.in_ = x.data_ptr(); a.B, a.C, a.H, a.W, a.pool = B, Cc, H, W, pool
     a.pooled, a.argmax = pooled.data_ptr(), amax.data_ptr()
@@ -163,7 +163,8 @@ def _engine_pair(dev, widths, B, current):
     x, lab = O.synthetic_cifar(B, seed=10)
     rnd = _make_rnd(oa, B, q, 100)
     oloss, _ = O.train_step(om, oopt, x, lab, i=100, rnd=rnd)
-    eng.inject = dict(u=[rnd[k].to(dev) for k in ("ua1", "uw0", "ua2", "uw1", "ua3", "uw2", "ua4", "uw3")],
+    eng.inject = dict(u=[rnd[k].to(dev) for k in ("ua1", "ua2", "ua3", "ua4")],
+                      uw=[rnd[k].to(dev) for k in ("uw0", "uw1", "uw2", "uw3")],
                       z=[rnd[k].to(dev) for k in ("z0", "z1", "z2", "z3")] if current > 0 else [])
     loss = eng.train_step(x.to(dev), lab.to(dev))
     return om, nm, eng, oloss, loss, x, lab
@@ -217,7 +218,7 @@ def test_engine_step_vs_module_path(dev, widths, B):
         rloss = F.cross_entropy(out, lab)
         rloss.backward()
     eng = NoisyNetEngine(eng_m, B, opt=None)
-    eng.inject = dict(u=list(us), z=list(zs))
+    eng.inject = dict(u=[us[0], us[2], us[4], us[6]], uw=[us[1], us[3], us[5], us[7]], z=list(zs))
     loss = eng.train_step(x, lab)
     assert ops.error_flag() == 0 and not eng.inject["u"] and not eng.inject["z"]
     assert abs(loss.item() - rloss.item()) < 2e-3, (loss.item(), rloss.item())

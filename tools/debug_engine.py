@@ -55,7 +55,7 @@ with torch.no_grad():
     w3 = O.uniform_quantize_fwd(om.linear2.weight, 4, -1.0, 1.0, 0.5, rnd["uw3"])
     l2 = F.linear(q4, w3)
 
-eng.inject = dict(u=[rnd[k].to(dev) for k in ("ua1", "uw0", "ua2", "uw1", "ua3", "uw2", "ua4", "uw3")],
+eng.inject = dict(u=[rnd[k].to(dev) for k in ("ua1", "ua2", "ua3", "ua4")], uw=[rnd[k].to(dev) for k in ("uw0", "uw1", "uw2", "uw3")],
                   z=[rnd[k].to(dev) for k in ("z0", "z1", "z2", "z3")] if CUR > 0 else [])
 loss = eng.train_step(x.to(dev), lab.to(dev))
 torch.cuda.synchronize()
