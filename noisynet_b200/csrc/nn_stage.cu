@@ -20,54 +20,11 @@ __device__ __forceinline__ float quant_code(float v, float s, float qmax, float 
     return rintf(fminf(fmaxf(t, 0.f), qmax));
 }
 
-// "last block finalizes": after writing its partial sums every block takes a ticket; the block that draws the
-// last one reduces all partials (fixed order -> deterministic) and resets the counter -- no separate launch.
-__device__ __forceinline__ bool stage_is_last_block(unsigned int* counter, unsigned int nblocks) {
-    __shared__ unsigned int s_ticket;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1u);
-    __syncthreads();
-    const bool last = (s_ticket == nblocks - 1);
-    if (last) __threadfence();
-    return last;
-}
-
-struct BnFinP {
-    unsigned int* counter;
-    int C;
-    double count;
-    float eps, momentum;
-    float *mean, *invstd, *running_mean, *running_var, *xmax_out;
-};
-
-__device__ __forceinline__ void bn_finalize_all(const double* partial, const BnFinP f) {
-    if (threadIdx.x == 0 && f.xmax_out) *f.xmax_out = 0.f;
-    for (int c = threadIdx.x; c < f.C; c += blockDim.x) {
-        double s1 = 0, s2 = 0;
-        for (int s = 0; s < ST_SPLITS; ++s) {
-            s1 += __ldcg(partial + ((size_t)c * ST_SPLITS + s) * 2);
-            s2 += __ldcg(partial + ((size_t)c * ST_SPLITS + s) * 2 + 1);
-        }
-        const double m = s1 / f.count;
-        double var = s2 / f.count - m * m;
-        if (var < 0) var = 0;
-        f.mean[c] = (float)m;
-        f.invstd[c] = (float)(1.0 / sqrt(var + (double)f.eps));
-        if (f.running_mean) {
-            const double unb = f.count > 1 ? var * f.count / (f.count - 1) : var;
-            f.running_mean[c] = (float)((1.0 - f.momentum) * f.running_mean[c] + f.momentum * m);
-            f.running_var[c] = (float)((1.0 - f.momentum) * f.running_var[c] + f.momentum * unb);
-        }
-    }
-    if (threadIdx.x == 0) *f.counter = 0u;
-}
-
 // ------------------------------------------------------------------ F1: 2x2 max pool + per-channel partial sums
 // grid (C, ST_SPLITS); block 256.  y [B,C,OH,OW] -> pooled [B,C,PH,PW], argmax (0..3), partial [C][SPLITS][2] (double)
 __global__ void __launch_bounds__(256)
 k_pool_stats(const float* __restrict__ y, float* __restrict__ pooled, uint8_t* __restrict__ amax, double* __restrict__ partial,
-             int B, int C, int OH, int OW, const BnFinP fin) {
+             int B, int C, int OH, int OW) {
     const int c = blockIdx.x, sp = blockIdx.y;
     const int PH = OH >> 1, PW = OW >> 1, PHW = PH * PW;
     const int b0 = (int)((int64_t)B * sp / ST_SPLITS), b1 = (int)((int64_t)B * (sp + 1) / ST_SPLITS);
@@ -97,12 +54,11 @@ k_pool_stats(const float* __restrict__ y, float* __restrict__ pooled, uint8_t* _
         partial[((int64_t)c * ST_SPLITS + sp) * 2 + 0] = a;
         partial[((int64_t)c * ST_SPLITS + sp) * 2 + 1] = b;
     }
-    if (stage_is_last_block(fin.counter, gridDim.x * gridDim.y)) bn_finalize_all(partial, fin);
 }
 
 // statistics only (fc stages / no pooling): x [B,C,HW]
 __global__ void __launch_bounds__(256)
-k_chan_stats(const float* __restrict__ x, double* __restrict__ partial, int B, int C, int HW, const BnFinP fin) {
+k_chan_stats(const float* __restrict__ x, double* __restrict__ partial, int B, int C, int HW) {
     const int c = blockIdx.x, sp = blockIdx.y;
     const int b0 = (int)((int64_t)B * sp / ST_SPLITS), b1 = (int)((int64_t)B * (sp + 1) / ST_SPLITS);
     const int n = (b1 - b0) * HW;
@@ -122,7 +78,27 @@ k_chan_stats(const float* __restrict__ x, double* __restrict__ partial, int B, i
         partial[((int64_t)c * ST_SPLITS + sp) * 2 + 0] = a;
         partial[((int64_t)c * ST_SPLITS + sp) * 2 + 1] = b;
     }
-    if (stage_is_last_block(fin.counter, gridDim.x * gridDim.y)) bn_finalize_all(partial, fin);
+}
+
+// finalize BN statistics: mean / invstd (biased var) + running stats update (momentum, unbiased var)
+__global__ void k_bn_finalize(const double* __restrict__ partial, int C, double count, float eps, float momentum,
+                              float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
+                              float* __restrict__ running_var, float* __restrict__ xmax_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && xmax_out) *xmax_out = 0.f;
+    if (c >= C) return;
+    double s1 = 0, s2 = 0;
+    for (int s = 0; s < ST_SPLITS; ++s) { s1 += partial[((int64_t)c * ST_SPLITS + s) * 2]; s2 += partial[((int64_t)c * ST_SPLITS + s) * 2 + 1]; }
+    const double m = s1 / count;
+    double var = s2 / count - m * m;
+    if (var < 0) var = 0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        const double unb = count > 1 ? var * count / (count - 1) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+    }
 }
 
 // ------------------------------------------------------------------ F2: BN + ReLU + clamp + quantize + NHWC pack
@@ -195,8 +171,6 @@ struct BnBwdP {
     double* partial;              // [C][SPLITS][2]
     int B, C, HW;
     float act_max, q_hi;
-    unsigned int* counter;
-    float *dbeta, *dgamma;
 };
 
 __device__ __forceinline__ float stage_dv(float g, float x, float mean, float invstd, float gamma, float beta,
@@ -234,18 +208,15 @@ k_bn_bwd_stats(const BnBwdP p) {
         p.partial[((int64_t)c * ST_SPLITS + sp) * 2 + 0] = a;
         p.partial[((int64_t)c * ST_SPLITS + sp) * 2 + 1] = b;
     }
-    if (stage_is_last_block(p.counter, gridDim.x * gridDim.y)) {
-        for (int cc = threadIdx.x; cc < p.C; cc += blockDim.x) {
-            double t1 = 0, t2 = 0;
-            for (int s = 0; s < ST_SPLITS; ++s) {
-                t1 += __ldcg(p.partial + ((size_t)cc * ST_SPLITS + s) * 2);
-                t2 += __ldcg(p.partial + ((size_t)cc * ST_SPLITS + s) * 2 + 1);
-            }
-            p.dbeta[cc] = (float)t1;          // grads are OVERWRITTEN (the step zeroes them anyway)
-            p.dgamma[cc] = (float)t2;
-        }
-        if (threadIdx.x == 0) *p.counter = 0u;
-    }
+}
+
+__global__ void k_bn_bwd_finalize(const double* __restrict__ partial, int C, float* __restrict__ dbeta, float* __restrict__ dgamma) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0, s2 = 0;
+    for (int s = 0; s < ST_SPLITS; ++s) { s1 += partial[((int64_t)c * ST_SPLITS + s) * 2]; s2 += partial[((int64_t)c * ST_SPLITS + s) * 2 + 1]; }
+    dbeta[c] = (float)s1;        // grads are OVERWRITTEN (the step zeroes them anyway)
+    dgamma[c] = (float)s2;
 }
 
 // ------------------------------------------------------------------ B2: BN backward + max-pool routing -> NHWC bf16
@@ -461,9 +432,7 @@ static inline int grid_cap(int64_t items, int device, int waves = 8) {
 
 }  // namespace
 
-// scratch = [ticket counter, 16 bytes][partials C x SPLITS x 2 doubles]; must be zero-initialised ONCE by the
-// caller (the kernels leave the counter at zero).
-extern "C" int64_t nn_stage_scratch_bytes(int C) { return 16 + (int64_t)C * ST_SPLITS * 2 * sizeof(double); }
+extern "C" int64_t nn_stage_scratch_bytes(int C) { return (int64_t)C * ST_SPLITS * 2 * sizeof(double); }
 
 extern "C" int nn_stage_fwd(const nn_stage_args* a, int device, void* stream) {
     if (!a || !a->in || !a->xp || !a->scratch || !a->mean || !a->invstd)
@@ -474,24 +443,22 @@ extern "C" int nn_stage_fwd(const nn_stage_args* a, int device, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const float* bn_in = a->in;
     int HW = a->H * a->W;
-    double* partial = (double*)((char*)a->scratch + 16);
-    BnFinP fin;
-    fin.counter = (unsigned int*)a->scratch; fin.C = a->C; fin.eps = a->eps; fin.momentum = a->momentum;
-    fin.mean = a->mean; fin.invstd = a->invstd; fin.running_mean = a->running_mean; fin.running_var = a->running_var;
-    fin.xmax_out = a->xmax_out;
-    fin.count = (double)a->B * (a->pool ? (a->H / 2) * (a->W / 2) : a->H * a->W);
+    double* partial = (double*)a->scratch;
     if (a->pool) {
         if (!a->pooled || !a->argmax) return nn_fail("nn_stage_fwd: pooled/argmax buffers missing%s", "");
         dim3 grid(a->C, ST_SPLITS);
-        k_pool_stats<<<grid, 256, 0, st>>>(a->in, a->pooled, a->argmax, partial, a->B, a->C, a->H, a->W, fin);
+        k_pool_stats<<<grid, 256, 0, st>>>(a->in, a->pooled, a->argmax, partial, a->B, a->C, a->H, a->W);
         NN_LAUNCH_OK();
         bn_in = a->pooled;
         HW = (a->H / 2) * (a->W / 2);
     } else {
         dim3 grid(a->C, ST_SPLITS);
-        k_chan_stats<<<grid, 256, 0, st>>>(a->in, partial, a->B, a->C, HW, fin);
+        k_chan_stats<<<grid, 256, 0, st>>>(a->in, partial, a->B, a->C, HW);
         NN_LAUNCH_OK();
     }
+    k_bn_finalize<<<(a->C + 127) / 128, 128, 0, st>>>(partial, a->C, (double)a->B * HW, a->eps, a->momentum, a->mean,
+                                                      a->invstd, a->running_mean, a->running_var, a->xmax_out);
+    NN_LAUNCH_OK();
     BnActP p;
     p.x = bn_in; p.mean = a->mean; p.invstd = a->invstd; p.gamma = a->gamma; p.beta = a->beta; p.u_inject = a->u_inject;
     p.xp = (__nv_bfloat16*)a->xp; p.act = a->act; p.xmax_out = a->xmax_out;
@@ -513,11 +480,12 @@ extern "C" int nn_stage_bwd(const nn_stage_bwd_args* a, int device, void* stream
     const int PH = a->pool ? a->H / 2 : a->H, PW = a->pool ? a->W / 2 : a->W;
     BnBwdP q;
     q.g = a->g; q.x = a->x; q.mean = a->mean; q.invstd = a->invstd; q.gamma = a->gamma; q.beta = a->beta;
-    q.partial = (double*)((char*)a->scratch + 16); q.counter = (unsigned int*)a->scratch;
-    q.dbeta = a->dbeta; q.dgamma = a->dgamma; q.B = a->B; q.C = a->C; q.HW = PH * PW; q.act_max = a->act_max;
+    q.partial = (double*)a->scratch; q.B = a->B; q.C = a->C; q.HW = PH * PW; q.act_max = a->act_max;
     q.q_hi = a->q_bits > 0 ? (float)a->q_hi : 0.f;
     dim3 grid(a->C, ST_SPLITS);
     k_bn_bwd_stats<<<grid, 256, 0, st>>>(q);
+    NN_LAUNCH_OK();
+    k_bn_bwd_finalize<<<(a->C + 127) / 128, 128, 0, st>>>(q.partial, a->C, a->dbeta, a->dgamma);
     NN_LAUNCH_OK();
     BnBwdApplyP p;
     p.g = a->g; p.x = a->x; p.mean = a->mean; p.invstd = a->invstd; p.gamma = a->gamma; p.beta = a->beta;
