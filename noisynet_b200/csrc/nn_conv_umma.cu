@@ -147,7 +147,7 @@ struct UmmaP {
 // The epilogue is issue-bound (Philox + Box-Muller per output), so the hot variants carry no per-element
 // option checks.
 template <int EPI>
-__global__ void __launch_bounds__(UM_THREADS, 2)
+__global__ void __launch_bounds__(UM_THREADS, EPI == 2 ? 3 : 2)
 k_conv_umma(const UmmaP p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -296,6 +296,8 @@ k_conv_umma(const UmmaP p) {
             const uint64_t grp_row = (uint64_t)m * ngrp;
             float* const out_main = (EPI == 1 ? p.y_noisy : p.y) + out_row;
             float* const out_y = (EPI == 1 && p.y) ? p.y + out_row : nullptr;
+            // linear layers (one output pixel per sample): a thread's channels are contiguous in memory -> vector stores
+            const bool vec4 = (ohw == 1) && ((p.Cout & 3) == 0) && (out_y == nullptr);
             for (int ci = half; ci < nchunks; ci += 2) {
                 const int cc = ci * 16;
                 float am[16], as[16];
@@ -311,6 +313,17 @@ k_conv_umma(const UmmaP p) {
                     if (g4 * 4 < nvalid) {
                         float z[4];
                         if (EPI == 1) nn_normal4(rs, grp_row + (uint64_t)((nb + g4 * 4) >> 2), z);
+                        if (vec4 && g4 * 4 + 4 <= nvalid) {
+                            float r4[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int e = g4 * 4 + j;
+                                const float yv = am[e] * y_scale;
+                                r4[j] = (EPI == 1) ? __fadd_rn(yv, __fmul_rn(z[j], nn_sigma(coef, as[e] * s_scale))) : yv;
+                            }
+                            *reinterpret_cast<float4*>(o + g4 * 4) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+                            continue;
+                        }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int e = g4 * 4 + j;
@@ -689,8 +702,41 @@ k_wgrad_umma(const WgUP p) {
     if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
 
-// partial [splits][Cout][ktot_pad] (kcol = tap*Cp + c) -> gw [Cout][Cin][KHW], fixed summation order, scale, STE mask.
-// Thread = (n, kcol): reads of the partials are coalesced along kcol (the scattered 4-byte write is tiny).
+// partial [splits][Cout][ktot_pad] (kcol = tap*Cp + c) -> gw [Cout][Cin][KHW], scale, STE mask.  Block = 32 columns
+// x 8 split groups: group g sums splits g, g+8, ... (coalesced along kcol), then the 8 group sums are added in a
+// fixed order through shared memory -- deterministic, and the serial chain over splits is 8x shorter.
+__global__ void __launch_bounds__(256)
+k_wgrad_umma_reduce2(const float* __restrict__ partial, int splits, int Cout, int Cin, int KHW, int Cp, int ktot_pad,
+                     float scale, float* __restrict__ gw, const float* __restrict__ w_raw, float lo, float hi) {
+    __shared__ float sh[8][32];
+    const unsigned total = (unsigned)Cout * ktot_pad;
+    const size_t zstride = (size_t)Cout * ktot_pad;
+    const int col = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    for (unsigned base = blockIdx.x * 32u; base < total; base += gridDim.x * 32u) {
+        const unsigned i = base + col;
+        float s = 0.f;
+        if (i < total)
+            for (int z = grp; z < splits; z += 8) s += partial[(size_t)z * zstride + i];
+        sh[grp][col] = s;
+        __syncthreads();
+        if (grp == 0 && i < total) {
+            float t = sh[0][col];
+#pragma unroll
+            for (int g = 1; g < 8; ++g) t += sh[g][col];
+            const int n = (int)(i / ktot_pad), kcol = (int)(i - (unsigned)n * ktot_pad);
+            const int tap = kcol / Cp, c = kcol - tap * Cp;
+            if (tap < KHW && c < Cin) {
+                t *= scale;
+                const size_t o = ((size_t)n * Cin + c) * KHW + tap;
+                if (w_raw) { const float w = __ldg(w_raw + o); if (w > hi || w < lo) t = 0.f; }
+                gw[o] = t;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// few splits / many columns: one thread per (n, kcol), splits summed sequentially (coalesced along kcol)
 __global__ void __launch_bounds__(256)
 k_wgrad_umma_reduce(const float* __restrict__ partial, int splits, int Cout, int Cin, int KHW, int Cp, int ktot_pad,
                     float scale, float* __restrict__ gw, const float* __restrict__ w_raw, float lo, float hi) {
@@ -742,7 +788,10 @@ static Plan make_plan(int Cin_k, int KHW, int n_out, bool has_main, bool has_sig
     const int stage_bytes = UM_A_STAGE + pl.n_mma * 128;
     static const int budget_kb = getenv("NN_UMMA_SMEM_KB") ? atoi(getenv("NN_UMMA_SMEM_KB")) : 100;   // tuning knob
     static const int max_stages = getenv("NN_UMMA_MAX_STAGES") ? atoi(getenv("NN_UMMA_MAX_STAGES")) : 4;
-    pl.stages = (budget_kb * 1024 - 2048) / stage_bytes;
+    // kernels whose accumulators fit 128 TMEM columns (dgrad, narrow layers) run 3 CTAs/SM: more resident CTAs hide
+    // the load / barrier round-trip latency better than deeper per-CTA pipelines (measured: conv2 dgrad 144 -> 121 us)
+    const int budget = (pl.tmem_cols <= 128 && !has_sigma && budget_kb > 72) ? 72 : budget_kb;
+    pl.stages = (budget * 1024 - 2048) / stage_bytes;
     if (pl.stages > max_stages) pl.stages = max_stages;
     if (pl.stages < 2) pl.stages = 2;
     if (pl.stages > pl.num_kb) pl.stages = pl.num_kb < 1 ? 1 : pl.num_kb;
@@ -1118,11 +1167,18 @@ int nn_umma_conv_wgrad(const nn_conv_wgrad_args* a, int device, cudaStream_t st)
     k_wgrad_umma<<<grid, UM_THREADS, w.smem_bytes, st>>>(p);
     NN_LAUNCH_OK();
     const int64_t n = (int64_t)g.Cout * w.ktot_pad;
-    int rb = (int)((n + 255) / 256);
-    if (rb > 8 * sms) rb = 8 * sms;
     const float scale = a->a_code_scale > 0.f ? a->a_code_scale : 1.f;
-    k_wgrad_umma_reduce<<<rb, 256, 0, st>>>(partial, w.splits, g.Cout, g.Cin, g.KH * g.KW, w.Cp, w.ktot_pad, scale,
-                                            a->gw, a->w_raw, (float)a->w_lo, (float)a->w_hi);
+    if (w.splits >= 64) {       // many splits, few columns (conv1): shorten the serial chain over splits 8x
+        int rb = (int)((n + 31) / 32);
+        if (rb > 16 * sms) rb = 16 * sms;
+        k_wgrad_umma_reduce2<<<rb, 256, 0, st>>>(partial, w.splits, g.Cout, g.Cin, g.KH * g.KW, w.Cp, w.ktot_pad, scale,
+                                                 a->gw, a->w_raw, (float)a->w_lo, (float)a->w_hi);
+    } else {
+        int rb = (int)((n + 255) / 256);
+        if (rb > 8 * sms) rb = 8 * sms;
+        k_wgrad_umma_reduce<<<rb, 256, 0, st>>>(partial, w.splits, g.Cout, g.Cin, g.KH * g.KW, w.Cp, w.ktot_pad, scale,
+                                                a->gw, a->w_raw, (float)a->w_lo, (float)a->w_hi);
+    }
     NN_LAUNCH_OK();
     return 0;
 }
