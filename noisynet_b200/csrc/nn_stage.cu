@@ -12,6 +12,9 @@
 
 namespace {
 
+#ifndef ST_CHUNK_FAST
+#define ST_CHUNK_FAST 1   // thread index: 16-byte channel chunk fastest (coalesced NHWC stores) vs pixel fastest
+#endif
 constexpr int ST_SPLITS = 16;   // batch slices per channel for the deterministic partial sums
 
 __device__ __forceinline__ float quant_code(float v, float s, float qmax, float u) {
@@ -123,8 +126,8 @@ k_bn_act_pack(const BnActP p) {
     const unsigned npix = (unsigned)p.B * p.HW, total = npix * chunks;      // 32-bit index arithmetic
     float vmax = 0.f;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const unsigned pixel = i % npix;
-        const int chunk = (int)(i / npix);
+        const unsigned pixel = ST_CHUNK_FAST ? i / chunks : i % npix;
+        const int chunk = (int)(ST_CHUNK_FAST ? i % chunks : i / npix);
         const int b = (int)(pixel / p.HW), r = (int)(pixel - (unsigned)b * p.HW);
         __align__(16) __nv_bfloat16 out[8];
         uint4 rnd[2];
@@ -240,8 +243,8 @@ k_bn_bwd_apply(const BnBwdApplyP p) {
     const unsigned npp = (unsigned)p.B * PHW, total = npp * chunks;
     const int npos = p.pool ? 4 : 1;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const unsigned pp = i % npp;
-        const int chunk = (int)(i / npp);
+        const unsigned pp = ST_CHUNK_FAST ? i / chunks : i % npp;
+        const int chunk = (int)(ST_CHUNK_FAST ? i % chunks : i / npp);
         const int b = (int)(pp / PHW), r = (int)(pp - (unsigned)b * PHW);
         const int ph = r / PW, pw = r - ph * PW;
         float d[8];
