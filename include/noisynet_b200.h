@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NN_ABI_VERSION 6
+#define NN_ABI_VERSION 7
 
 /* ---- common ---------------------------------------------------------------------- */
 
@@ -211,6 +211,8 @@ int nn_noisy_conv_wgrad(const nn_conv_wgrad_args* a, int device, void* stream);
 typedef struct nn_wprep_job {
     const float* w_raw;      /* [Cout,Cin,KH,KW] fp32 parameter                                       */
     int32_t Cout, Cin, KHW;
+    int32_t m_rows;          /* rows of the GEMM that will consume the pack: B*OH*OW (mode 0) / B*H*W (mode 1);
+                                the n-tiling is chosen from it and must match the consumer's             */
     int32_t mode;            /* 0 forward, 1 dgrad                                                    */
     int32_t noise_mode;      /* mode 0: NN_NOISE_* (which sigma rows to add)                          */
     int32_t want_wsum;       /* mode 0, external DAC: add the colsum row (power statistic)            */

@@ -146,8 +146,11 @@ struct UmmaP {
 // y_noisy [+ y], no bias / mask / inject / export / stats) -- the training hot path, 2 = lean plain (y only).
 // The epilogue is issue-bound (Philox + Box-Muller per output), so the hot variants carry no per-element
 // option checks.
+#ifndef NN_EPI1_MINBLOCKS
+#define NN_EPI1_MINBLOCKS 2
+#endif
 template <int EPI>
-__global__ void __launch_bounds__(UM_THREADS, EPI == 2 ? 3 : 2)
+__global__ void __launch_bounds__(UM_THREADS, EPI == 2 ? 3 : (EPI == 1 ? NN_EPI1_MINBLOCKS : 2))
 k_conv_umma(const UmmaP p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -763,14 +766,22 @@ struct Plan {
 
 static inline int pad_to(int v, int a) { return (v + a - 1) / a * a; }
 
-static Plan make_plan(int Cin_k, int KHW, int n_out, bool has_main, bool has_sigma, bool has_wsum, int64_t pixels_in) {
+static Plan make_plan(int Cin_k, int KHW, int n_out, bool has_main, bool has_sigma, bool has_wsum, int64_t pixels_in,
+                      int m_tiles_hint = 0) {
     Plan pl;
     pl.Cp = pad_to(Cin_k, 8);
     pl.K_total = KHW * pl.Cp;
     pl.num_kb = (pl.K_total + UM_BLOCK_K - 1) / UM_BLOCK_K;
-    const int max_nt = has_sigma ? (has_main ? UM_MAX_NT : 248) : 256;
+    static const int env_max_nt = getenv("NN_UMMA_MAX_NT") ? atoi(getenv("NN_UMMA_MAX_NT")) : UM_MAX_NT;   // tuning knob
+    const int max_nt = has_sigma ? (has_main ? env_max_nt : 248) : 256;
     pl.n_tiles = (n_out + max_nt - 1) / max_nt;
+    // skinny problems (few 128-row m-tiles, e.g. the fully connected layers at batch 512) are latency-bound:
+    // trade operand re-reads for more CTAs by narrowing the n-tile until ~100 CTAs exist (measured: fc1 fwd 55 -> 45 us)
+    if (m_tiles_hint > 0) {
+        while (m_tiles_hint * pl.n_tiles < 96 && (n_out + pl.n_tiles - 1) / pl.n_tiles > 48) pl.n_tiles *= 2;
+    }
     pl.n_t = pad_to((n_out + pl.n_tiles - 1) / pl.n_tiles, 8);
+    pl.n_tiles = (n_out + pl.n_t - 1) / pl.n_t;
     int col = 0;
     pl.main_col = pl.sig_col = pl.wsum_col = -1;
     if (has_main) { pl.main_col = col; col += pl.n_t; }
@@ -863,8 +874,10 @@ int64_t nn_umma_fwd_workspace(const nn_conv_geom* g, int precision) {
     // sized for the larger of forward (input packed) and dgrad (grad_output packed)
     int OH, OW;
     nn_out_hw(*g, OH, OW);
-    Plan f = make_plan(g->Cin, g->KH * g->KW, g->Cout, true, true, true, (int64_t)g->B * g->H * g->W);
-    Plan d = make_plan(g->Cout, g->KH * g->KW, g->Cin, true, false, false, (int64_t)g->B * OH * OW);
+    Plan f = make_plan(g->Cin, g->KH * g->KW, g->Cout, true, true, true, (int64_t)g->B * g->H * g->W,
+                       (g->B * OH * OW + 127) / 128);
+    Plan d = make_plan(g->Cout, g->KH * g->KW, g->Cin, true, false, false, (int64_t)g->B * OH * OW,
+                       (g->B * g->H * g->W + 127) / 128);
     size_t a = align_up(f.xp_bytes, 1024) + align_up(f.wp_bytes, 1024);
     size_t b = align_up(d.xp_bytes, 1024) + align_up(d.wp_bytes, 1024);
     return (int64_t)((a > b ? a : b) + 2048);
@@ -922,7 +935,8 @@ int nn_umma_conv_fwd(const nn_conv_fwd_args* a, int device, cudaStream_t st) {
     const bool has_main = a->w_eff != nullptr || a->w_packed != nullptr;
     const bool noise = a->noise_mode != NN_NOISE_NONE;
     const bool has_wsum = noise && a->noise_mode == NN_NOISE_EXTERNAL && a->stats != nullptr;
-    Plan pl = make_plan(g.Cin, g.KH * g.KW, g.Cout, has_main, noise, has_wsum, (int64_t)g.B * g.H * g.W);
+    Plan pl = make_plan(g.Cin, g.KH * g.KW, g.Cout, has_main, noise, has_wsum, (int64_t)g.B * g.H * g.W,
+                        (g.B * OH * OW + 127) / 128);
     const size_t need = align_up(pl.xp_bytes, 1024) + align_up(pl.wp_bytes, 1024) + 1024;
     if (!a->workspace || (size_t)a->workspace_bytes < need)
         return nn_fail("nn_noisy_conv_fwd: workspace too small%s (need %lld bytes)", "", (long long)need);
@@ -975,8 +989,8 @@ int nn_umma_conv_fwd(const nn_conv_fwd_args* a, int device, cudaStream_t st) {
 static Plan plan_for_job(const nn_wprep_job& jb) {
     if (jb.mode == 0)
         return make_plan(jb.Cin, jb.KHW, jb.Cout, true, jb.noise_mode != NN_NOISE_NONE,
-                         jb.noise_mode == NN_NOISE_EXTERNAL && jb.want_wsum, 0);
-    return make_plan(jb.Cout, jb.KHW, jb.Cin, true, false, false, 0);
+                         jb.noise_mode == NN_NOISE_EXTERNAL && jb.want_wsum, 0, (jb.m_rows + 127) / 128);
+    return make_plan(jb.Cout, jb.KHW, jb.Cin, true, false, false, 0, (jb.m_rows + 127) / 128);
 }
 
 extern "C" int64_t nn_weight_pack_bytes(const nn_wprep_job* jb) {
@@ -1028,7 +1042,8 @@ int nn_umma_conv_dgrad(const nn_conv_dgrad_args* a, int device, cudaStream_t st)
     nn_out_hw(g, OH, OW);
     // dgrad(stride 1) == forward conv of gy [B,Cout,OH,OW] with the transposed, tap-flipped weights and
     // padding K-1-pad, producing [B,Cin,H,W]
-    Plan pl = make_plan(g.Cout, g.KH * g.KW, g.Cin, true, false, false, (int64_t)g.B * OH * OW);
+    Plan pl = make_plan(g.Cout, g.KH * g.KW, g.Cin, true, false, false, (int64_t)g.B * OH * OW,
+                        (g.B * g.H * g.W + 127) / 128);
     const size_t need = align_up(pl.xp_bytes, 1024) + align_up(pl.wp_bytes, 1024) + 1024;
     if (!a->workspace || (size_t)a->workspace_bytes < need)
         return nn_fail("nn_noisy_conv_dgrad: workspace too small%s (need %lld bytes)", "", (long long)need);

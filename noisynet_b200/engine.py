@@ -77,13 +77,14 @@ class NoisyNetEngine:
         shapes = [(C1, 3, fs * fs), (C2, C1, fs * fs), (FC, C2, P2 * P2), (10, FC, 1)]
         self.jobs = (WPrepJob * 7)()
         self.job_layer = [0, 1, 2, 3, 3, 2, 1]
-        specs = [(0, shapes[0], 0), (1, shapes[1], 0), (2, shapes[2], 0), (3, shapes[3], 0),
-                 (3, shapes[3], 1), (2, (FC, C2 * P2 * P2, 1), 1), (1, shapes[1], 1)]
+        # (layer, (Cout, Cin, KHW), mode, rows of the consuming GEMM)
+        specs = [(0, shapes[0], 0, B * H1 * H1), (1, shapes[1], 0, B * H2 * H2), (2, shapes[2], 0, B), (3, shapes[3], 0, B),
+                 (3, shapes[3], 1, B), (2, (FC, C2 * P2 * P2, 1), 1, B), (1, shapes[1], 1, B * P1 * P1)]
         self.wpack = []
-        for j, (li, (co, ci, khw), mode) in enumerate(specs):
+        for j, (li, (co, ci, khw), mode, m_rows) in enumerate(specs):
             jb = self.jobs[j]
             jb.w_raw = W[li].data_ptr()
-            jb.Cout, jb.Cin, jb.KHW, jb.mode = co, ci, khw, mode
+            jb.Cout, jb.Cin, jb.KHW, jb.mode, jb.m_rows = co, ci, khw, mode, m_rows
             jb.noise_mode = self.noise_modes[li] if mode == 0 else 0
             jb.want_wsum = 0
             jb.q_bits, jb.q_hi = int(a.q_w1), 1.0
