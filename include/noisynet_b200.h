@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NN_ABI_VERSION 7
+#define NN_ABI_VERSION 8
 
 /* ---- common ---------------------------------------------------------------------- */
 
@@ -152,7 +152,19 @@ typedef struct nn_conv_fwd_args {
     const void* w_packed;    /* optional: weights already packed by nn_prepare_weights (mode 0, same
                                 noise_mode / stats choice); w_eff may then be NULL, w_code_scale must be
                                 the quantizer's s/2                                                   */
+    int32_t w_packed_layout; /* NN_PACK_*: the layout `w_packed` was prepared in (nn_wprep_job.layout)      */
 } nn_conv_fwd_args;
+
+/* Packed-weight layouts.  NN_PACK_TILED: 128B-swizzled [n-tile][k-block] shared-memory images (every geometry).
+ * NN_PACK_SHIFT: [tap][row][8] image of the persistent shift-GEMM forward kernel, served for stride-1 unpadded
+ * layers with Cin <= 8 (the first layer, noisynet.py:344): ask nn_conv_pack_layout which one the forward of a
+ * geometry prefers; nn_noisy_conv_fwd rejects a layout it cannot serve (bias / stats / export requests need
+ * NN_PACK_TILED). */
+#define NN_PACK_TILED 0
+#define NN_PACK_SHIFT 1
+int nn_conv_pack_layout(const nn_conv_geom* g, int32_t noise_mode, int32_t precision);
+/* Test hook: enable = 0/1 switches the shift-GEMM path off/on (< 0: query); returns the previous setting. */
+int nn_debug_shift_enable(int enable);
 
 int64_t nn_conv_workspace_bytes(const nn_conv_geom* g, int32_t precision);
 /* 1 if (geometry, precision) is served for which = 0 forward / 1 dgrad / 2 wgrad.  NN_PREC_FP32 serves
@@ -218,6 +230,7 @@ typedef struct nn_wprep_job {
     int32_t want_wsum;       /* mode 0, external DAC: add the colsum row (power statistic)            */
     int32_t q_bits; double q_hi; float stochastic; const float* u_inject; nn_rng rng;
     void* packed_out;        /* nn_weight_pack_bytes(job) bytes                                       */
+    int32_t layout;          /* NN_PACK_* (mode 0 only; see nn_conv_pack_layout)                       */
 } nn_wprep_job;
 int64_t nn_weight_pack_bytes(const nn_wprep_job* job);
 int nn_prepare_weights(const nn_wprep_job* jobs, int count, int device, void* stream);

@@ -8,10 +8,11 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libnoisynet_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 NOISE_NONE, NOISE_MERGED, NOISE_EXTERNAL = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
+PACK_TILED, PACK_SHIFT = 0, 1
 
 c_f32p = C.c_void_p      # device pointers travel as void* (int addresses from tensor.data_ptr())
 
@@ -38,7 +39,7 @@ class ConvFwdArgs(C.Structure):
                 ("precision", C.c_int32),
                 ("a_code_scale", C.c_float), ("w_code_scale", C.c_float),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("x_packed", C.c_void_p),
-                ("w_packed", C.c_void_p)]
+                ("w_packed", C.c_void_p), ("w_packed_layout", C.c_int32)]
 
 
 class ConvDgradArgs(C.Structure):
@@ -69,7 +70,7 @@ class WPrepJob(C.Structure):
     _fields_ = [("w_raw", C.c_void_p), ("Cout", C.c_int32), ("Cin", C.c_int32), ("KHW", C.c_int32),
                 ("m_rows", C.c_int32), ("mode", C.c_int32), ("noise_mode", C.c_int32), ("want_wsum", C.c_int32),
                 ("q_bits", C.c_int32), ("q_hi", C.c_double), ("stochastic", C.c_float), ("u_inject", C.c_void_p),
-                ("rng", Rng), ("packed_out", C.c_void_p)]
+                ("rng", Rng), ("packed_out", C.c_void_p), ("layout", C.c_int32)]
 
 
 class StageArgs(C.Structure):
@@ -127,6 +128,8 @@ SIGNATURES = {
     "nn_debug_error_flag": (C.c_int, [C.c_int, C.c_int]),
     "nn_debug_main_kernel_ms": (C.c_float, [C.c_int]),
     "nn_debug_cta_timeline": (C.c_int, [C.c_void_p, C.c_int]),
+    "nn_conv_pack_layout": (C.c_int, [C.POINTER(ConvGeom), C.c_int32, C.c_int32]),
+    "nn_debug_shift_enable": (C.c_int, [C.c_int]),
     "nn_noisy_conv_fwd": (C.c_int, [C.POINTER(ConvFwdArgs), C.c_int, C.c_void_p]),
     "nn_noisy_conv_dgrad": (C.c_int, [C.POINTER(ConvDgradArgs), C.c_int, C.c_void_p]),
     "nn_conv_wgrad_workspace_bytes": (C.c_int64, [C.POINTER(ConvGeom), C.c_int32, C.c_int]),

@@ -409,6 +409,253 @@ k_conv_umma(const UmmaP p) {
     if (dbg && tid == 128) { dbg[5] = clock64(); unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); dbg[7] = smid; }
 }
 
+
+// ================================================================== shift-GEMM forward (narrow-input layers)
+// For a stride-1, unpadded conv whose input has <= 8 channels (the first layer: 3 -> Cp = 8, ONE 16-byte
+// chunk per pixel), the im2col rows of tap (kh, kw) are the packed pixels themselves, shifted by kh*W + kw:
+// with the SWIZZLE_NONE ("interleave") K-major descriptor a core matrix is 8 rows x 16 B = 8 CONSECUTIVE
+// PIXELS of the NHWC pack, so the A operand of every tap is the same shared-memory tile read through a
+// shifted start address -- nothing is gathered.  An m-tile is 128 consecutive positions of the INPUT pixel
+// grid ("virtual" outputs: positions with ow >= OW or oh >= OH are computed and dropped, 12.5 % for 32 -> 28),
+// staged by ONE cp.async.bulk of (128 + (KH-1) W + KW-1) pixels = 4 KB instead of 64 KB of gathered im2col.
+// The whole weight image (taps x rows, 60 KB) stays resident in shared memory, so the CTA is persistent:
+//   warp 0   : bulk-copy issuer (weights once, then the A ring)
+//   warp 1   : tcgen05.mma issuer, one K = 16 MMA per PAIR of taps (LBO = pixel distance of the two taps),
+//              accumulators double-buffered in TMEM (2 x 256 columns)
+//   warps 2+ : epilogue (tcgen05.ld -> scale, Philox/Box-Muller noise -> NCHW stores), overlapping the next
+//              tile's MMAs.  The kernel is bound by the epilogue's instruction issue, not by data movement.
+constexpr int SH_EPI_WARPS = 12;
+constexpr int SH_THREADS = (2 + SH_EPI_WARPS) * 32;
+constexpr int SH_STAGES = 4;
+constexpr int SH_ACC_STRIDE = 256;                  // TMEM columns between the two accumulator buffers
+
+struct ShiftP {
+    int H, W, OH, OW, KH, KW, Cout;
+    int n_mma, main_col, sig_col, n_pairs;
+    int a_pixels, a_stage, b_bytes, n_tiles;        // pixels / bytes per A stage, weight image bytes, m-tiles
+    long long total_pixels;
+    const __nv_bfloat16 *xp, *wp;
+    float y_scale, s_scale;
+    float *y, *y_noisy;
+    const float* z_inject;
+    float current;
+    const float* scale_dev;
+    nn_rng rng;
+    int* err_flag;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// two 8-column loads and the wait in ONE asm statement (the registers are only defined after the wait)
+__device__ __forceinline__ void tmem_ld8x2(uint32_t ta, uint32_t tb, float a[8], float b[8]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%17];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(ta), "r"(tb)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[8 + i]); }
+}
+
+// K-major SWIZZLE_NONE descriptor: core matrix = 8 rows x 16 B contiguous; lbo = distance between the two
+// K chunks of one MMA, sbo = distance between 8-row groups (both in 16-byte units).
+__device__ __forceinline__ uint64_t umma_desc_none(uint32_t smem_addr, uint32_t lbo_units, uint32_t sbo_units) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(lbo_units & 0x3FFF) << 16;
+    d |= (uint64_t)(sbo_units & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// a tile is skipped when none of its 128 positions can be a real output (whole rows oh >= OH of one image)
+__device__ __forceinline__ bool shift_tile_live(const ShiftP& p, int t) {
+    const long long v0 = (long long)t * UM_BLOCK_M;
+    long long v1 = v0 + UM_BLOCK_M - 1;
+    if (v1 >= p.total_pixels) v1 = p.total_pixels - 1;
+    const int hw = p.H * p.W;
+    const long long b0 = v0 / hw, b1 = v1 / hw;
+    if (b0 != b1) return true;
+    return (int)((v0 - b0 * hw) / p.W) < p.OH;
+}
+
+template <int MODE>      // 0 plain, 1 noisy (Philox z), 2 noisy with injected z (parity hook)
+__global__ void __launch_bounds__(SH_THREADS, 1)
+k_conv_shift(const ShiftP p) {
+    constexpr bool NOISY = MODE != 0;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t b_base = base;
+    const uint32_t a_base = b_base + (uint32_t)p.b_bytes;
+    const uint32_t bar_base = a_base + (uint32_t)SH_STAGES * (uint32_t)p.a_stage;
+    const uint32_t a_full = bar_base, a_empty = bar_base + 8u * SH_STAGES;
+    const uint32_t acc_full = bar_base + 16u * SH_STAGES, acc_empty = acc_full + 16u, b_full = acc_empty + 16u;
+    const uint32_t tmem_slot = b_full + 8u, abort_slot = tmem_slot + 4u;
+    uint8_t* gen0 = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gen0 + (tmem_slot - base));
+    volatile uint32_t* abort_g = reinterpret_cast<volatile uint32_t*>(gen0 + (abort_slot - base));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < SH_STAGES; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full + 8 * b, 1); mbar_init(acc_empty + 8 * b, SH_EPI_WARPS); }
+        mbar_init(b_full, 1);
+        *abort_g = 0;
+        fence_mbar_init();
+    }
+    {   // the A ring starts as zeros: positions past the end of the pack are never loaded, and the padding tap of an
+        // odd tap count multiplies whatever lies there by a zero weight row -- it has to be finite
+        uint4* az = reinterpret_cast<uint4*>(gen0 + (a_base - base));
+        const int n16 = SH_STAGES * p.a_stage / 16;
+        for (int i = tid; i < n16; i += SH_THREADS) az[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_g;
+    const int hw = p.H * p.W;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(b_full, (uint32_t)p.b_bytes);
+            bulk_g2s(b_base, p.wp, (uint32_t)p.b_bytes, b_full);
+            int i = 0;
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+                if (!shift_tile_live(p, t)) continue;
+                const int s = i % SH_STAGES;
+                if (!mbar_wait(a_empty + 8 * s, ((i / SH_STAGES) & 1) ^ 1)) { *abort_g = 1; break; }
+                if (*abort_g) break;
+                const long long v0 = (long long)t * UM_BLOCK_M;
+                long long px = p.total_pixels - v0;
+                if (px > p.a_pixels) px = p.a_pixels;
+                const uint32_t bytes = (uint32_t)px * 16u;
+                mbar_arrive_expect_tx(a_full + 8 * s, bytes);
+                bulk_g2s(a_base + (uint32_t)s * p.a_stage, p.xp + v0 * 8, bytes, a_full + 8 * s);
+                ++i;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) |
+                                   ((uint32_t)(UM_BLOCK_M >> 4) << 24);
+            const int khw = p.KH * p.KW;
+            bool ok = mbar_wait(b_full, 0);
+            if (!ok) *abort_g = 2;
+            int i = 0;
+            for (int t = blockIdx.x; t < p.n_tiles && ok; t += gridDim.x) {
+                if (!shift_tile_live(p, t)) continue;
+                const int s = i % SH_STAGES, buf = i & 1;
+                if (!mbar_wait(acc_empty + 8 * buf, ((i >> 1) & 1) ^ 1)) { *abort_g = 3; break; }
+                if (!mbar_wait(a_full + 8 * s, (i / SH_STAGES) & 1)) { *abort_g = 4; break; }
+                if (*abort_g) break;
+                tc_fence_after();
+                const uint32_t a_s = a_base + (uint32_t)s * p.a_stage;
+                const uint32_t d = tmem_base + (uint32_t)(buf * SH_ACC_STRIDE);
+                for (int j = 0; j < p.n_pairs; ++j) {
+                    const int t0 = 2 * j, t1 = 2 * j + 1;
+                    const int sh0 = (t0 / p.KW) * p.W + (t0 % p.KW);
+                    const int sh1 = t1 < khw ? (t1 / p.KW) * p.W + (t1 % p.KW) : sh0 + 1;   // padding tap: zero weights
+                    const uint64_t ad = umma_desc_none(a_s + (uint32_t)sh0 * 16u, (uint32_t)(sh1 - sh0), 8u);
+                    const uint64_t bd = umma_desc_none(b_base + (uint32_t)(t0 * p.n_mma) * 16u, (uint32_t)p.n_mma, 8u);
+                    umma_bf16(d, ad, bd, idesc, j != 0);
+                }
+                umma_commit(a_empty + 8 * s);
+                umma_commit(acc_full + 8 * buf);
+                ++i;
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3, jq = (warp - 2) >> 2;
+        constexpr int per_q = SH_EPI_WARPS / 4;
+        const int ohw = p.OH * p.OW;
+        const int ngrp = (p.Cout + 3) >> 2;
+        const int ng8 = (p.Cout + 7) >> 3;
+        float coef = 0.f;
+        NnRng rs = {0, 0, 0, 0};
+        if (NOISY) coef = nn_noise_coef(*p.scale_dev, p.current);
+        if (MODE == 1) rs = nn_rng_load(p.rng);
+        const float y_scale = p.y_scale, s_scale = p.s_scale;
+        int i = 0;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+            if (!shift_tile_live(p, t)) continue;
+            const int buf = i & 1;
+            if (!mbar_wait(acc_full + 8 * buf, (i >> 1) & 1)) { *abort_g = 5; break; }
+            if (*abort_g) break;
+            tc_fence_after();
+            const long long v = (long long)t * UM_BLOCK_M + q * 32 + lane;
+            const int b = (int)(v / hw);
+            const int rem = (int)(v - (long long)b * hw);
+            const int ih = rem / p.W, iw = rem - ih * p.W;
+            const bool row_ok = v < p.total_pixels && ih < p.OH && iw < p.OW;
+            const int pix = ih * p.OW + iw;
+            const uint64_t grp_row = (uint64_t)((long long)b * ohw + pix) * ngrp;
+            const size_t out_row = (size_t)b * p.Cout * ohw + pix;
+            float* const out_main = (NOISY ? p.y_noisy : p.y) + out_row;
+            float* const out_y = (NOISY && p.y) ? p.y + out_row : nullptr;
+            const uint32_t t_lane = tmem_base + (uint32_t)(buf * SH_ACC_STRIDE) + ((uint32_t)(q * 32) << 16);
+            for (int g8 = jq; g8 < ng8; g8 += per_q) {
+                float am[8], as[8];
+                if (NOISY) tmem_ld8x2(t_lane + (uint32_t)(p.main_col + g8 * 8), t_lane + (uint32_t)(p.sig_col + g8 * 8), am, as);
+                else { tmem_ld8(t_lane + (uint32_t)(p.main_col + g8 * 8), am); tmem_ld_wait(); }
+                if (!row_ok) continue;
+                const int nb = g8 * 8;
+                const int nvalid = min(8, p.Cout - nb);
+                float* o = out_main + (size_t)nb * ohw;
+                float* oy = out_y ? out_y + (size_t)nb * ohw : nullptr;
+#pragma unroll
+                for (int g4 = 0; g4 < 2; ++g4) {
+                    if (g4 * 4 < nvalid) {
+                        float z[4];
+                        if (MODE == 1) nn_normal4(rs, grp_row + (uint64_t)((nb + g4 * 4) >> 2), z);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int e = g4 * 4 + j;
+                            if (e < nvalid) {
+                                const float yv = am[e] * y_scale;
+                                if (NOISY) {
+                                    const float sg = nn_sigma(coef, as[e] * s_scale);
+                                    const float zz = MODE == 2 ? __ldg(p.z_inject + out_row + (size_t)(nb + e) * ohw) : z[j];
+                                    o[(size_t)e * ohw] = __fadd_rn(yv, __fmul_rn(zz, sg));
+                                    if (oy) oy[(size_t)e * ohw] = yv;
+                                } else {
+                                    o[(size_t)e * ohw] = yv;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+            ++i;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (*abort_g && tid == 0 && p.err_flag) atomicExch(p.err_flag, 200 + (int)*abort_g);
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // ------------------------------------------------------------------ operand packing
 // NCHW fp32 -> NHWC bf16 with Cp (multiple of 8) channels.  inv_scale > 0: integer-code mode, the value
 // written is rne(x * ... ) -- the activation's quantisation code recovered in registers (exact in bf16).
@@ -443,6 +690,7 @@ struct PackWP {
     __nv_bfloat16* wp;
     int Cout, Cin, KHW, Cp, n_t, n_mma, num_kb, n_tiles;
     int main_col, sig_col, wsum_col, noise_mode, mode;
+    int layout;                    // 0: swizzled [tile][k-block] images, 1: shift-GEMM [k chunk][row][8] (num_kb = chunks)
     float w_code_scale;
     // optional in-register weight quantizer (hardware_model.py:323, :343; range [-q_hi, q_hi] symmetric): the
     // main rows are then produced from w_raw directly -- k = rne(clamp((w + q_hi)/s + u, 0, qmax)), stored as the
@@ -477,13 +725,21 @@ __device__ __forceinline__ float pack_main_value(const PackWP& p, const NnRng& r
 
 __device__ __forceinline__ void pack_w_job(const PackWP& p, int64_t start, int64_t stride) {
     const NnRng rs = nn_rng_load(p.rng);
-    const int64_t total = (int64_t)p.n_tiles * p.num_kb * p.n_mma * 8;     // one thread per 16-byte chunk
+    const bool shift = p.layout == 1;
+    const int64_t total = shift ? (int64_t)p.num_kb * p.n_mma
+                                : (int64_t)p.n_tiles * p.num_kb * p.n_mma * 8;     // one thread per 16-byte chunk
     for (int64_t i = start; i < total; i += stride) {
-        const int j = (int)(i & 7);
-        int64_t t = i >> 3;
-        const int r = (int)(t % p.n_mma); t /= p.n_mma;
-        const int kb = (int)(t % p.num_kb);
-        const int tile = (int)(t / p.num_kb);
+        int j, r, kb, tile, kbase;
+        if (shift) {
+            r = (int)(i % p.n_mma); kb = (int)(i / p.n_mma); j = 0; tile = 0; kbase = kb * 8;
+        } else {
+            j = (int)(i & 7);
+            int64_t t = i >> 3;
+            r = (int)(t % p.n_mma); t /= p.n_mma;
+            kb = (int)(t % p.num_kb);
+            tile = (int)(t / p.num_kb);
+            kbase = kb * 64 + j * 8;
+        }
         __align__(16) __nv_bfloat16 v[8];
         int kind = -1, rr = 0;                       // 0 main, 1 sigma, 2 wsum
         if (p.main_col >= 0 && r >= p.main_col && r < p.main_col + p.n_t) { kind = 0; rr = r - p.main_col; }
@@ -493,7 +749,7 @@ __device__ __forceinline__ void pack_w_job(const PackWP& p, int64_t start, int64
         const int kdim = p.mode == 0 ? p.Cin : p.Cout;    // real channels inside a tap
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int k = kb * 64 + j * 8 + e;
+            const int k = kbase + e;
             const int tap = k / p.Cp, c = k - tap * p.Cp;
             float f = 0.f;
             if (tap < p.KHW && c < kdim && kind >= 0) {
@@ -521,7 +777,7 @@ __device__ __forceinline__ void pack_w_job(const PackWP& p, int64_t start, int64
             v[e] = __float2bfloat16_rn(f);
         }
         const int64_t blk = ((int64_t)tile * p.num_kb + kb) * p.n_mma * 64;          // elements
-        const int64_t off = blk + (int64_t)r * 64 + (((j ^ (r & 7))) << 3);           // 128B swizzle
+        const int64_t off = shift ? i * 8 : blk + (int64_t)r * 64 + (((j ^ (r & 7))) << 3);   // 128B swizzle
         *reinterpret_cast<uint4*>(p.wp + off) = *reinterpret_cast<const uint4*>(v);
     }
 }
@@ -814,9 +1070,39 @@ static Plan make_plan(int Cin_k, int KHW, int n_out, bool has_main, bool has_sig
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ---- shift-GEMM forward (k_conv_shift): eligibility and sizes
+struct ShiftPlan {
+    int n_t, n_mma, main_col, sig_col, n_chunks, n_pairs, a_pixels, a_stage, b_bytes, n_tiles;
+    size_t smem_bytes, wp_bytes;
+};
+int g_shift_enable = getenv("NN_SHIFT_OFF") ? 0 : 1;
+
+static bool make_shift_plan(const nn_conv_geom& g, bool noisy, ShiftPlan* out) {
+    if (!g_shift_enable) return false;
+    if (g.Cin > 8 || g.stride != 1 || g.pad != 0 || g.KH > g.H || g.KW > g.W || g.W >= 4096) return false;
+    ShiftPlan sp;
+    sp.n_t = pad_to(g.Cout, 8);
+    sp.main_col = 0;
+    sp.sig_col = noisy ? sp.n_t : -1;
+    sp.n_mma = pad_to(noisy ? 2 * sp.n_t : sp.n_t, 16);
+    if (sp.n_mma > SH_ACC_STRIDE) return false;
+    const int khw = g.KH * g.KW;
+    sp.n_pairs = (khw + 1) / 2;
+    sp.n_chunks = 2 * sp.n_pairs;
+    sp.a_pixels = UM_BLOCK_M + (g.KH - 1) * g.W + (g.KW - 1) + 8;
+    sp.a_stage = pad_to(sp.a_pixels * 16, 128);
+    sp.b_bytes = sp.n_chunks * sp.n_mma * 16;
+    sp.n_tiles = (int)(((int64_t)g.B * g.H * g.W + UM_BLOCK_M - 1) / UM_BLOCK_M);
+    sp.smem_bytes = 128 + (size_t)sp.b_bytes + (size_t)SH_STAGES * sp.a_stage + 16 * SH_STAGES + 64;
+    sp.wp_bytes = (size_t)sp.b_bytes;
+    if (sp.smem_bytes > 200 * 1024) return false;
+    if (out) *out = sp;
+    return true;
+}
+
 // debug hook: per-CTA phase timestamps of the next forward launches (NN_UMMA_DEBUG=1)
 long long* g_dbg_buf = nullptr;
-size_t g_dbg_ctas = 0;
+size_t g_dbg_ctas = 0, g_dbg_last = 0;
 
 // measurement hook: CUDA events around the main tcgen05 kernel only (excludes the operand packs)
 int g_time_main = 0;
@@ -848,6 +1134,7 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st) {
         }
         cudaMemsetAsync(g_dbg_buf, 0, ctas * 8 * sizeof(long long), st);
         pd.dbg = g_dbg_buf;
+        g_dbg_last = ctas;
     }
     if (g_time_main) {
         if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
@@ -899,7 +1186,7 @@ extern "C" int nn_debug_cta_timeline(long long* host_out, int max_ctas) {
     // 2 last MMA issued, 3 accumulators ready, 4 epilogue done, 5 teardown, 6 producers done, 7 smid
     if (!g_dbg_buf) return 0;
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
-    const size_t n = g_dbg_ctas < (size_t)max_ctas ? g_dbg_ctas : (size_t)max_ctas;
+    const size_t n = g_dbg_last < (size_t)max_ctas ? g_dbg_last : (size_t)max_ctas;
     if (cudaMemcpy(host_out, g_dbg_buf, n * 8 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return (int)n;
 }
@@ -926,6 +1213,83 @@ extern "C" int nn_debug_error_flag(int device, int reset) {
     return v;
 }
 
+static int shift_conv_fwd(const nn_conv_fwd_args* a, const ShiftPlan& sp, int device, cudaStream_t st) {
+    const nn_conv_geom& g = a->g;
+    int OH, OW;
+    nn_out_hw(g, OH, OW);
+    const bool noise = a->noise_mode != NN_NOISE_NONE;
+    const size_t xp_bytes = (size_t)g.B * g.H * g.W * 16;
+    uint8_t* ws = (uint8_t*)align_up((size_t)a->workspace, 1024);
+    const size_t need = (a->x_packed ? 0 : align_up(xp_bytes, 1024)) + (a->w_packed ? 0 : align_up(sp.wp_bytes, 1024)) + 1024;
+    if ((!a->x_packed || !a->w_packed) && (!a->workspace || (size_t)a->workspace_bytes < need))
+        return nn_fail("nn_noisy_conv_fwd: workspace too small%s (need %lld bytes)", "", (long long)need);
+    const __nv_bfloat16* xp = (const __nv_bfloat16*)a->x_packed;
+    const __nv_bfloat16* wp = (const __nv_bfloat16*)a->w_packed;
+    if (!xp) {
+        const int64_t total = (int64_t)g.B * g.H * g.W;
+        int grid = (int)((total + 255) / 256);
+        if (grid > 16 * nn_num_sms(device)) grid = 16 * nn_num_sms(device);
+        k_pack_act<<<grid, 256, 0, st>>>(a->x, (__nv_bfloat16*)ws, g.B, g.Cin, g.H * g.W, 8, a->a_code_scale);
+        NN_LAUNCH_OK();
+        xp = (const __nv_bfloat16*)ws;
+        ws += align_up(xp_bytes, 1024);
+    }
+    if (!wp) {
+        PackWP pw;
+        memset(&pw, 0, sizeof(pw));
+        pw.w_eff = a->w_eff; pw.w_raw = a->w_raw; pw.wp = (__nv_bfloat16*)ws;
+        pw.Cout = g.Cout; pw.Cin = g.Cin; pw.KHW = g.KH * g.KW; pw.Cp = 8; pw.n_t = sp.n_t; pw.n_mma = sp.n_mma;
+        pw.num_kb = sp.n_chunks; pw.n_tiles = 1; pw.main_col = sp.main_col; pw.sig_col = sp.sig_col; pw.wsum_col = -1;
+        pw.noise_mode = a->noise_mode; pw.mode = 0; pw.layout = NN_PACK_SHIFT; pw.w_code_scale = a->w_code_scale;
+        const int64_t total = (int64_t)sp.n_chunks * sp.n_mma;
+        k_pack_w<<<(int)((total + 255) / 256), 256, 0, st>>>(pw);
+        NN_LAUNCH_OK();
+        wp = (const __nv_bfloat16*)ws;
+    }
+    ShiftP p;
+    memset(&p, 0, sizeof(p));
+    p.H = g.H; p.W = g.W; p.OH = OH; p.OW = OW; p.KH = g.KH; p.KW = g.KW; p.Cout = g.Cout;
+    p.n_mma = sp.n_mma; p.main_col = sp.main_col; p.sig_col = sp.sig_col; p.n_pairs = sp.n_pairs;
+    p.a_pixels = sp.a_pixels; p.a_stage = sp.a_stage; p.b_bytes = sp.b_bytes; p.n_tiles = sp.n_tiles;
+    p.total_pixels = (long long)g.B * g.H * g.W;
+    p.xp = xp; p.wp = wp;
+    const float as = a->a_code_scale > 0.f ? a->a_code_scale : 1.f;
+    const float wsc = a->w_code_scale > 0.f ? a->w_code_scale : 1.f;
+    p.y_scale = as * wsc; p.s_scale = as;
+    p.y = a->y; p.y_noisy = a->y_noisy; p.z_inject = a->z_inject;
+    p.current = a->current; p.scale_dev = a->scale_dev; p.rng = a->rng;
+    p.err_flag = nn_umma_err_flag(device);
+    static bool attr_set = false;
+    if (!attr_set) {
+        NN_CUDA_OK(cudaFuncSetAttribute(k_conv_shift<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        NN_CUDA_OK(cudaFuncSetAttribute(k_conv_shift<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        NN_CUDA_OK(cudaFuncSetAttribute(k_conv_shift<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    int grid = nn_num_sms(device);
+    if (grid > sp.n_tiles) grid = sp.n_tiles;
+    if (g_time_main) {
+        if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+        cudaEventRecord(g_ev0, st);
+    }
+    if (!noise) k_conv_shift<0><<<grid, SH_THREADS, sp.smem_bytes, st>>>(p);
+    else if (a->z_inject) k_conv_shift<2><<<grid, SH_THREADS, sp.smem_bytes, st>>>(p);
+    else k_conv_shift<1><<<grid, SH_THREADS, sp.smem_bytes, st>>>(p);
+    if (g_time_main) cudaEventRecord(g_ev1, st);
+    NN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int nn_conv_pack_layout(const nn_conv_geom* g, int32_t noise_mode, int32_t precision) {
+    if (!g || precision != NN_PREC_BF16) return NN_PACK_TILED;
+    return make_shift_plan(*g, noise_mode != NN_NOISE_NONE, nullptr) ? NN_PACK_SHIFT : NN_PACK_TILED;
+}
+extern "C" int nn_debug_shift_enable(int enable) {
+    const int prev = g_shift_enable;
+    if (enable >= 0) g_shift_enable = enable;
+    return prev;
+}
+
 int nn_umma_conv_fwd(const nn_conv_fwd_args* a, int device, cudaStream_t st) {
     if (a->precision != NN_PREC_BF16)
         return nn_fail("nn_noisy_conv_fwd: tcgen05 path implements NN_PREC_BF16 only%s", "");
@@ -935,6 +1299,16 @@ int nn_umma_conv_fwd(const nn_conv_fwd_args* a, int device, cudaStream_t st) {
     const bool has_main = a->w_eff != nullptr || a->w_packed != nullptr;
     const bool noise = a->noise_mode != NN_NOISE_NONE;
     const bool has_wsum = noise && a->noise_mode == NN_NOISE_EXTERNAL && a->stats != nullptr;
+    {   // narrow-input layers: persistent shift-GEMM kernel (weights resident, no im2col gather)
+        const bool extras = a->bias || a->z_export || a->sigma_export || a->stats;
+        ShiftPlan sp;
+        const bool can = has_main && !extras && make_shift_plan(g, noise, &sp);
+        const int layout = a->w_packed ? a->w_packed_layout : (can ? NN_PACK_SHIFT : NN_PACK_TILED);
+        if (layout == NN_PACK_SHIFT) {
+            if (!can) return nn_fail("nn_noisy_conv_fwd: w_packed_layout = NN_PACK_SHIFT is not served for this call%s", "");
+            return shift_conv_fwd(a, sp, device, st);
+        }
+    }
     Plan pl = make_plan(g.Cin, g.KH * g.KW, g.Cout, has_main, noise, has_wsum, (int64_t)g.B * g.H * g.W,
                         (g.B * OH * OW + 127) / 128);
     const size_t need = align_up(pl.xp_bytes, 1024) + align_up(pl.wp_bytes, 1024) + 1024;
@@ -993,8 +1367,18 @@ static Plan plan_for_job(const nn_wprep_job& jb) {
     return make_plan(jb.Cout, jb.KHW, jb.Cin, true, false, false, 0, (jb.m_rows + 127) / 128);
 }
 
+// shift-layout jobs carry the conv geometry implicitly: Cin <= 8, one chunk per tap
+static void shift_plan_for_job(const nn_wprep_job& jb, ShiftPlan* sp) {
+    const bool noisy = jb.noise_mode != NN_NOISE_NONE;
+    sp->n_t = pad_to(jb.Cout, 8); sp->main_col = 0; sp->sig_col = noisy ? sp->n_t : -1;
+    sp->n_mma = pad_to(noisy ? 2 * sp->n_t : sp->n_t, 16);
+    sp->n_pairs = (jb.KHW + 1) / 2; sp->n_chunks = 2 * sp->n_pairs;
+    sp->b_bytes = sp->n_chunks * sp->n_mma * 16; sp->wp_bytes = (size_t)sp->b_bytes;
+}
+
 extern "C" int64_t nn_weight_pack_bytes(const nn_wprep_job* jb) {
     if (!jb) return 0;
+    if (jb->layout == NN_PACK_SHIFT) { ShiftPlan sp; shift_plan_for_job(*jb, &sp); return (int64_t)align_up(sp.wp_bytes, 1024); }
     return (int64_t)align_up(plan_for_job(*jb).wp_bytes, 1024);
 }
 
@@ -1009,12 +1393,21 @@ extern "C" int nn_prepare_weights(const nn_wprep_job* jobs, int count, int devic
         const nn_wprep_job& jb = jobs[i];
         if (!jb.w_raw || !jb.packed_out) return nn_fail("nn_prepare_weights: null pointer%s", "");
         if (jb.q_bits > 0 && !(jb.q_hi > 0)) return nn_fail("nn_prepare_weights: symmetric range needs q_hi > 0%s", "");
-        const Plan pl = plan_for_job(jb);
+        Plan pl = plan_for_job(jb);
+        if (jb.layout == NN_PACK_SHIFT) {
+            if (jb.mode != 0 || jb.Cin > 8 || jb.want_wsum)
+                return nn_fail("nn_prepare_weights: NN_PACK_SHIFT needs a forward job with Cin <= 8 and no colsum row%s", "");
+            ShiftPlan sp;
+            shift_plan_for_job(jb, &sp);
+            pl.Cp = 8; pl.n_t = sp.n_t; pl.n_mma = sp.n_mma; pl.num_kb = sp.n_chunks; pl.n_tiles = 1;
+            pl.main_col = sp.main_col; pl.sig_col = sp.sig_col; pl.wsum_col = -1;
+        }
         PackWP& pw = pj.j[i];
         pw.w_eff = jb.w_raw; pw.w_raw = jb.w_raw; pw.wp = (__nv_bfloat16*)jb.packed_out;
         pw.Cout = jb.Cout; pw.Cin = jb.Cin; pw.KHW = jb.KHW; pw.Cp = pl.Cp; pw.n_t = pl.n_t; pw.n_mma = pl.n_mma;
         pw.num_kb = pl.num_kb; pw.n_tiles = pl.n_tiles; pw.main_col = pl.main_col; pw.sig_col = pl.sig_col;
         pw.wsum_col = pl.wsum_col; pw.noise_mode = jb.noise_mode; pw.mode = jb.mode; pw.w_code_scale = 0.f;
+        pw.layout = jb.layout;
         pw.q_bits = jb.q_bits;
         if (jb.q_bits > 0) {
             const double qmax = (double)((1u << jb.q_bits) - 1u);
@@ -1023,7 +1416,8 @@ extern "C" int nn_prepare_weights(const nn_wprep_job* jobs, int count, int devic
             pw.q_hi = (float)jb.q_hi; pw.q_scale = (float)sc; pw.q_max = (float)qmax; pw.q_stoch = jb.stochastic;
             pw.u_inject = jb.u_inject; pw.rng = jb.rng;
         }
-        const int64_t total = (int64_t)pl.n_tiles * pl.num_kb * pl.n_mma * 8;
+        const int64_t total = jb.layout == NN_PACK_SHIFT ? (int64_t)pl.num_kb * pl.n_mma
+                                                         : (int64_t)pl.n_tiles * pl.num_kb * pl.n_mma * 8;
         if (total > max_total) max_total = total;
     }
     int gx = (int)((max_total + 255) / 256);

@@ -80,6 +80,10 @@ class NoisyNetEngine:
         # (layer, (Cout, Cin, KHW), mode, rows of the consuming GEMM)
         specs = [(0, shapes[0], 0, B * H1 * H1), (1, shapes[1], 0, B * H2 * H2), (2, shapes[2], 0, B), (3, shapes[3], 0, B),
                  (3, shapes[3], 1, B), (2, (FC, C2 * P2 * P2, 1), 1, B), (1, shapes[1], 1, B * P1 * P1)]
+        # geometry of the four contractions (fc1 forward / wgrad run as a 5x5 conv over the NHWC pooled map)
+        self.geom = [ConvGeom(B, 3, 32, 32, C1, fs, fs, 1, 0), ConvGeom(B, C1, P1, P1, C2, fs, fs, 1, 0),
+                     ConvGeom(B, C2, P2, P2, FC, P2, P2, 1, 0), ConvGeom(B, FC, 1, 1, 10, 1, 1, 1, 0)]
+        self.geom_fc1_lin = ConvGeom(B, C2 * P2 * P2, 1, 1, FC, 1, 1, 1, 0)
         self.wpack = []
         for j, (li, (co, ci, khw), mode, m_rows) in enumerate(specs):
             jb = self.jobs[j]
@@ -87,16 +91,13 @@ class NoisyNetEngine:
             jb.Cout, jb.Cin, jb.KHW, jb.mode, jb.m_rows = co, ci, khw, mode, m_rows
             jb.noise_mode = self.noise_modes[li] if mode == 0 else 0
             jb.want_wsum = 0
+            jb.layout = self.lib.nn_conv_pack_layout(C.byref(self.geom[li]), jb.noise_mode, PREC_BF16) if mode == 0 else 0
             jb.q_bits, jb.q_hi = int(a.q_w1), 1.0
             buf = torch.zeros(int(self.lib.nn_weight_pack_bytes(C.byref(jb))) + 1024, dtype=torch.uint8, device=dev)
             jb.packed_out = (buf.data_ptr() + 1023) // 1024 * 1024
             self.wpack.append(buf)
         self.wp_fwd = [self.jobs[i].packed_out for i in range(4)]
         self.wp_dgrad = {3: self.jobs[4].packed_out, 2: self.jobs[5].packed_out, 1: self.jobs[6].packed_out}
-        # geometry of the four contractions (fc1 forward / wgrad run as a 5x5 conv over the NHWC pooled map)
-        self.geom = [ConvGeom(B, 3, 32, 32, C1, fs, fs, 1, 0), ConvGeom(B, C1, P1, P1, C2, fs, fs, 1, 0),
-                     ConvGeom(B, C2, P2, P2, FC, P2, P2, 1, 0), ConvGeom(B, FC, 1, 1, 10, 1, 1, 1, 0)]
-        self.geom_fc1_lin = ConvGeom(B, C2 * P2 * P2, 1, 1, FC, 1, 1, 1, 0)
         need = 0
         for g in self.geom + [self.geom_fc1_lin]:
             need = max(need, self.lib.nn_conv_workspace_bytes(C.byref(g), PREC_BF16),
@@ -135,6 +136,7 @@ class NoisyNetEngine:
         a.x = None
         a.x_packed = _p(xp)
         a.w_eff, a.w_raw, a.w_packed = None, None, self.wp_fwd[idx]
+        a.w_packed_layout = self.jobs[idx].layout
         cur = float(self.a.layer_currents[idx])
         if cur > 0:
             a.y, a.y_noisy = None, _p(y_noisy)

@@ -28,11 +28,17 @@ for name, (Cin, H, Cout, k, mode, a_cs) in {"conv1": (3, 32, 65, 5, NOISE_MERGED
     t = buf[:got].astype(np.float64)
     t0 = t[:, 0].min()
     d = lambda a, b: (t[:, a] - t[:, b])
-    print("%s: %d CTAs; kernel span %.1f us (@1.9GHz)" % (name, got, (t[:, 5].max() - t0) / 1900.0))
+    print("%s: %d CTAs" % (name, got))
     for lab, a, b in (("setup (start->tmem/barriers ready)", 1, 0), ("mainloop (setup->last MMA issued)", 2, 1),
                       ("producers done - setup", 6, 1), ("MMA drain (issued->acc ready)", 3, 2), ("epilogue", 4, 3),
                       ("teardown", 5, 4), ("total CTA", 5, 0)):
         v = d(a, b) / 1900.0
         print("   %-38s mean %6.2f us  p10 %6.2f  p90 %6.2f" % (lab, v.mean(), np.percentile(v, 10), np.percentile(v, 90)))
-    starts = np.sort(t[:, 0] - t0) / 1900.0
-    print("   CTA start times: p50 %.1f us, p90 %.1f us, last %.1f us" % (starts[len(starts) // 2], starts[int(len(starts) * .9)], starts[-1]))
+    # per-SM view (clock64 is per SM): busy span and number of CTAs
+    sm = t[:, 7].astype(int)
+    spans = []
+    for sid in np.unique(sm):
+        sel = t[sm == sid]
+        spans.append(((sel[:, 5].max() - sel[:, 0].min()) / 1900.0, len(sel)))
+    spans = np.array(spans)
+    print("   per SM: span mean %.1f us max %.1f us, CTAs per SM mean %.2f max %d" % (spans[:, 0].mean(), spans[:, 0].max(), spans[:, 1].mean(), spans[:, 1].max()))
