@@ -92,10 +92,15 @@ __device__ __forceinline__ float nn_sqrt_approx(float x) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ float nn_lg2_approx(float x) {      // x is never subnormal here: no range fix-up code
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ void nn_box_muller(uint32_t ra, uint32_t rb, float& z0, float& z1) {
     const float u1 = fmaf(__uint2float_rn(ra), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
     const float u2 = nn_u01(rb);
-    const float rad = nn_sqrt_approx(-1.3862943611198906f * __log2f(u1));
+    const float rad = nn_sqrt_approx(-1.3862943611198906f * nn_lg2_approx(u1));
     const float th = fmaf(u2, 6.2831853071795865f, -3.14159265358979324f);
     z0 = rad * __cosf(th);
     z1 = rad * __sinf(th);

@@ -424,8 +424,7 @@ k_conv_umma(const UmmaP p) {
 //              accumulators double-buffered in TMEM (2 x 256 columns)
 //   warps 2+ : epilogue (tcgen05.ld -> scale, Philox/Box-Muller noise -> NCHW stores), overlapping the next
 //              tile's MMAs.  The kernel is bound by the epilogue's instruction issue, not by data movement.
-constexpr int SH_EPI_WARPS = 12;
-constexpr int SH_THREADS = (2 + SH_EPI_WARPS) * 32;
+constexpr int SH_MAX_PAIRS = 64;
 constexpr int SH_STAGES = 4;
 constexpr int SH_ACC_STRIDE = 256;                  // TMEM columns between the two accumulator buffers
 
@@ -442,36 +441,33 @@ struct ShiftP {
     const float* scale_dev;
     nn_rng rng;
     int* err_flag;
+    long long* dbg;          // optional [cta][32 tiles][4] clock64 stamps: MMA ready / issued, accumulator seen / epilogue done
 };
 
+__device__ __forceinline__ void st_global_f32(float* ptr, float v) {
+    asm volatile("st.global.f32 [%0], %1;" ::"l"(ptr), "f"(v) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float v[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld4x2(uint32_t ta, uint32_t tb, float a[4], float b[4]) {
     uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// two 8-column loads and the wait in ONE asm statement (the registers are only defined after the wait)
-__device__ __forceinline__ void tmem_ld8x2(uint32_t ta, uint32_t tb, float a[8], float b[8]) {
-    uint32_t r[16];
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%17];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%8];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4,%5,%6,%7}, [%9];\n\t"
         "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(ta), "r"(tb)
-        : "memory");
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(ta), "r"(tb) : "memory");
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[8 + i]); }
+    for (int i = 0; i < 4; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[4 + i]); }
 }
-
 // K-major SWIZZLE_NONE descriptor: core matrix = 8 rows x 16 B contiguous; lbo = distance between the two
 // K chunks of one MMA, sbo = distance between 8-row groups (both in 16-byte units).
 __device__ __forceinline__ uint64_t umma_desc_none(uint32_t smem_addr, uint32_t lbo_units, uint32_t sbo_units) {
@@ -494,10 +490,13 @@ __device__ __forceinline__ bool shift_tile_live(const ShiftP& p, int t) {
     return (int)((v0 - b0 * hw) / p.W) < p.OH;
 }
 
-template <int MODE>      // 0 plain, 1 noisy (Philox z), 2 noisy with injected z (parity hook)
-__global__ void __launch_bounds__(SH_THREADS, 1)
+// MODE: 0 plain, 1 noisy (Philox z), 2 noisy with injected z (parity hook); SH_EPI_WARPS: epilogue warps, a
+// multiple of 4 (one TMEM lane quarter per warp % 4)
+template <int MODE, int SH_EPI_WARPS>
+__global__ void __launch_bounds__((2 + SH_EPI_WARPS) * 32, 1)
 k_conv_shift(const ShiftP p) {
     constexpr bool NOISY = MODE != 0;
+    constexpr int SH_THREADS = (2 + SH_EPI_WARPS) * 32;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     const uint32_t b_base = base;
@@ -505,12 +504,19 @@ k_conv_shift(const ShiftP p) {
     const uint32_t bar_base = a_base + (uint32_t)SH_STAGES * (uint32_t)p.a_stage;
     const uint32_t a_full = bar_base, a_empty = bar_base + 8u * SH_STAGES;
     const uint32_t acc_full = bar_base + 16u * SH_STAGES, acc_empty = acc_full + 16u, b_full = acc_empty + 16u;
-    const uint32_t tmem_slot = b_full + 8u, abort_slot = tmem_slot + 4u;
+    const uint32_t tmem_slot = b_full + 8u, abort_slot = tmem_slot + 4u, tab_slot = abort_slot + 4u;
     uint8_t* gen0 = smem_raw + (base - smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gen0 + (tmem_slot - base));
     volatile uint32_t* abort_g = reinterpret_cast<volatile uint32_t*>(gen0 + (abort_slot - base));
+    uint32_t* tap_tab = reinterpret_cast<uint32_t*>(gen0 + (tab_slot - base));   // per tap pair: shift | lbo << 16
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < p.n_pairs) {       // descriptor increments of every tap pair (no divisions in the issue loop)
+        const int khw = p.KH * p.KW, t0 = 2 * tid, t1 = 2 * tid + 1;
+        const int sh0 = (t0 / p.KW) * p.W + (t0 % p.KW);
+        const int sh1 = t1 < khw ? (t1 / p.KW) * p.W + (t1 % p.KW) : sh0 + 1;          // padding tap: zero weights
+        tap_tab[tid] = (uint32_t)sh0 | ((uint32_t)(sh1 - sh0) << 16);
+    }
     if (tid == 0) {
         for (int s = 0; s < SH_STAGES; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(acc_full + 8 * b, 1); mbar_init(acc_empty + 8 * b, SH_EPI_WARPS); }
@@ -556,7 +562,6 @@ k_conv_shift(const ShiftP p) {
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) |
                                    ((uint32_t)(UM_BLOCK_M >> 4) << 24);
-            const int khw = p.KH * p.KW;
             bool ok = mbar_wait(b_full, 0);
             if (!ok) *abort_g = 2;
             int i = 0;
@@ -567,18 +572,18 @@ k_conv_shift(const ShiftP p) {
                 if (!mbar_wait(a_full + 8 * s, (i / SH_STAGES) & 1)) { *abort_g = 4; break; }
                 if (*abort_g) break;
                 tc_fence_after();
+                if (p.dbg && i < 32) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 0] = clock64();
                 const uint32_t a_s = a_base + (uint32_t)s * p.a_stage;
                 const uint32_t d = tmem_base + (uint32_t)(buf * SH_ACC_STRIDE);
+                const uint64_t bd0 = umma_desc_none(b_base, (uint32_t)p.n_mma, 8u);
                 for (int j = 0; j < p.n_pairs; ++j) {
-                    const int t0 = 2 * j, t1 = 2 * j + 1;
-                    const int sh0 = (t0 / p.KW) * p.W + (t0 % p.KW);
-                    const int sh1 = t1 < khw ? (t1 / p.KW) * p.W + (t1 % p.KW) : sh0 + 1;   // padding tap: zero weights
-                    const uint64_t ad = umma_desc_none(a_s + (uint32_t)sh0 * 16u, (uint32_t)(sh1 - sh0), 8u);
-                    const uint64_t bd = umma_desc_none(b_base + (uint32_t)(t0 * p.n_mma) * 16u, (uint32_t)p.n_mma, 8u);
-                    umma_bf16(d, ad, bd, idesc, j != 0);
+                    const uint32_t e = tap_tab[j];
+                    const uint64_t ad = umma_desc_none(a_s + (e & 0xFFFFu) * 16u, e >> 16, 8u);
+                    umma_bf16(d, ad, bd0 + (uint64_t)(2 * j * p.n_mma), idesc, j != 0);
                 }
                 umma_commit(a_empty + 8 * s);
                 umma_commit(acc_full + 8 * buf);
+                if (p.dbg && i < 32) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 1] = clock64();
                 ++i;
             }
         }
@@ -588,7 +593,6 @@ k_conv_shift(const ShiftP p) {
         constexpr int per_q = SH_EPI_WARPS / 4;
         const int ohw = p.OH * p.OW;
         const int ngrp = (p.Cout + 3) >> 2;
-        const int ng8 = (p.Cout + 7) >> 3;
         float coef = 0.f;
         NnRng rs = {0, 0, 0, 0};
         if (NOISY) coef = nn_noise_coef(*p.scale_dev, p.current);
@@ -601,6 +605,7 @@ k_conv_shift(const ShiftP p) {
             if (!mbar_wait(acc_full + 8 * buf, (i >> 1) & 1)) { *abort_g = 5; break; }
             if (*abort_g) break;
             tc_fence_after();
+            if (p.dbg && i < 32 && warp == 2 && lane == 0) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 2] = clock64();
             const long long v = (long long)t * UM_BLOCK_M + q * 32 + lane;
             const int b = (int)(v / hw);
             const int rem = (int)(v - (long long)b * hw);
@@ -612,34 +617,42 @@ k_conv_shift(const ShiftP p) {
             float* const out_main = (NOISY ? p.y_noisy : p.y) + out_row;
             float* const out_y = (NOISY && p.y) ? p.y + out_row : nullptr;
             const uint32_t t_lane = tmem_base + (uint32_t)(buf * SH_ACC_STRIDE) + ((uint32_t)(q * 32) << 16);
-            for (int g8 = jq; g8 < ng8; g8 += per_q) {
-                float am[8], as[8];
-                if (NOISY) tmem_ld8x2(t_lane + (uint32_t)(p.main_col + g8 * 8), t_lane + (uint32_t)(p.sig_col + g8 * 8), am, as);
-                else { tmem_ld8(t_lane + (uint32_t)(p.main_col + g8 * 8), am); tmem_ld_wait(); }
+            // 4-channel groups (one Philox call each), dealt round-robin to the warps of this lane quarter; the deal
+            // rotates with the tile so that an uneven group count (17 for 65 channels) averages out across tiles
+            for (int g4 = (jq + i) % per_q; g4 < ngrp; g4 += per_q) {
+                float am[4], as[4];
+                if (NOISY) tmem_ld4x2(t_lane + (uint32_t)(p.main_col + g4 * 4), t_lane + (uint32_t)(p.sig_col + g4 * 4), am, as);
+                else tmem_ld4(t_lane + (uint32_t)(p.main_col + g4 * 4), am);
                 if (!row_ok) continue;
-                const int nb = g8 * 8;
-                const int nvalid = min(8, p.Cout - nb);
+                const int nb = g4 * 4;
+                float z[4];
+                if (MODE == 1) nn_normal4(rs, grp_row + (uint64_t)g4, z);
                 float* o = out_main + (size_t)nb * ohw;
+                if (nb + 4 <= p.Cout && (!NOISY || out_y == nullptr) && MODE != 2) {
+                    float* o_run = o;
+                    asm volatile("" : "+l"(o_run));      // one live 64-bit pointer per group, bumped per store
+                    // hot path: full group, no clean-output copy -- straight-line code, no per-element predicates
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float yv = am[j] * y_scale;
+                        st_global_f32(o_run, NOISY ? __fadd_rn(yv, __fmul_rn(z[j], nn_sigma(coef, as[j] * s_scale))) : yv);
+                        o_run += ohw;
+                    }
+                    continue;
+                }
+                const int nvalid = min(4, p.Cout - nb);
                 float* oy = out_y ? out_y + (size_t)nb * ohw : nullptr;
 #pragma unroll
-                for (int g4 = 0; g4 < 2; ++g4) {
-                    if (g4 * 4 < nvalid) {
-                        float z[4];
-                        if (MODE == 1) nn_normal4(rs, grp_row + (uint64_t)((nb + g4 * 4) >> 2), z);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int e = g4 * 4 + j;
-                            if (e < nvalid) {
-                                const float yv = am[e] * y_scale;
-                                if (NOISY) {
-                                    const float sg = nn_sigma(coef, as[e] * s_scale);
-                                    const float zz = MODE == 2 ? __ldg(p.z_inject + out_row + (size_t)(nb + e) * ohw) : z[j];
-                                    o[(size_t)e * ohw] = __fadd_rn(yv, __fmul_rn(zz, sg));
-                                    if (oy) oy[(size_t)e * ohw] = yv;
-                                } else {
-                                    o[(size_t)e * ohw] = yv;
-                                }
-                            }
+                for (int j = 0; j < 4; ++j) {
+                    if (j < nvalid) {
+                        const float yv = am[j] * y_scale;
+                        if (NOISY) {
+                            const float sg = nn_sigma(coef, as[j] * s_scale);
+                            const float zz = MODE == 2 ? __ldg(p.z_inject + out_row + (size_t)(nb + j) * ohw) : z[j];
+                            o[(size_t)j * ohw] = __fadd_rn(yv, __fmul_rn(zz, sg));
+                            if (oy) oy[(size_t)j * ohw] = yv;
+                        } else {
+                            o[(size_t)j * ohw] = yv;
                         }
                     }
                 }
@@ -647,6 +660,7 @@ k_conv_shift(const ShiftP p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+            if (p.dbg && i < 32 && warp == 2 && lane == 0) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 3] = clock64();
             ++i;
         }
     }
@@ -1093,7 +1107,8 @@ static bool make_shift_plan(const nn_conv_geom& g, bool noisy, ShiftPlan* out) {
     sp.a_stage = pad_to(sp.a_pixels * 16, 128);
     sp.b_bytes = sp.n_chunks * sp.n_mma * 16;
     sp.n_tiles = (int)(((int64_t)g.B * g.H * g.W + UM_BLOCK_M - 1) / UM_BLOCK_M);
-    sp.smem_bytes = 128 + (size_t)sp.b_bytes + (size_t)SH_STAGES * sp.a_stage + 16 * SH_STAGES + 64;
+    sp.smem_bytes = 128 + (size_t)sp.b_bytes + (size_t)SH_STAGES * sp.a_stage + 16 * SH_STAGES + 64 + 4 * SH_MAX_PAIRS;
+    if (sp.n_pairs > SH_MAX_PAIRS) return false;
     sp.wp_bytes = (size_t)sp.b_bytes;
     if (sp.smem_bytes > 200 * 1024) return false;
     if (out) *out = sp;
@@ -1259,22 +1274,45 @@ static int shift_conv_fwd(const nn_conv_fwd_args* a, const ShiftPlan& sp, int de
     p.y = a->y; p.y_noisy = a->y_noisy; p.z_inject = a->z_inject;
     p.current = a->current; p.scale_dev = a->scale_dev; p.rng = a->rng;
     p.err_flag = nn_umma_err_flag(device);
-    static bool attr_set = false;
-    if (!attr_set) {
-        NN_CUDA_OK(cudaFuncSetAttribute(k_conv_shift<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        NN_CUDA_OK(cudaFuncSetAttribute(k_conv_shift<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        NN_CUDA_OK(cudaFuncSetAttribute(k_conv_shift<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
     int grid = nn_num_sms(device);
     if (grid > sp.n_tiles) grid = sp.n_tiles;
+    static const bool want_dbg = getenv("NN_UMMA_DEBUG") != nullptr;
+    if (want_dbg) {
+        const size_t rows = (size_t)grid * 16;           // 32 tiles x 4 stamps = 16 rows of 8
+        if (rows > g_dbg_ctas) {
+            if (g_dbg_buf) cudaFree(g_dbg_buf);
+            cudaMalloc(&g_dbg_buf, rows * 8 * sizeof(long long));
+            g_dbg_ctas = rows;
+        }
+        cudaMemsetAsync(g_dbg_buf, 0, rows * 8 * sizeof(long long), st);
+        p.dbg = g_dbg_buf;
+        g_dbg_last = rows;
+    }
     if (g_time_main) {
         if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
         cudaEventRecord(g_ev0, st);
     }
-    if (!noise) k_conv_shift<0><<<grid, SH_THREADS, sp.smem_bytes, st>>>(p);
-    else if (a->z_inject) k_conv_shift<2><<<grid, SH_THREADS, sp.smem_bytes, st>>>(p);
-    else k_conv_shift<1><<<grid, SH_THREADS, sp.smem_bytes, st>>>(p);
+    static const int env_ew = getenv("NN_SH_EPI_WARPS") ? atoi(getenv("NN_SH_EPI_WARPS")) : 16;   // tuning knob
+    const int mode = !noise ? 0 : (a->z_inject ? 2 : 1);
+#define NN_SHIFT_LAUNCH(MODE, EW)                                                                                      \
+    do {                                                                                                               \
+        static bool attr = false;                                                                                      \
+        if (!attr) {                                                                                                   \
+            NN_CUDA_OK(cudaFuncSetAttribute(k_conv_shift<MODE, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+            attr = true;                                                                                               \
+        }                                                                                                              \
+        k_conv_shift<MODE, EW><<<grid, (2 + EW) * 32, sp.smem_bytes, st>>>(p);                                          \
+    } while (0)
+#define NN_SHIFT_MODES(EW)                                                                                             \
+    do {                                                                                                               \
+        if (mode == 0) NN_SHIFT_LAUNCH(0, EW); else if (mode == 1) NN_SHIFT_LAUNCH(1, EW); else NN_SHIFT_LAUNCH(2, EW);  \
+    } while (0)
+    if (env_ew == 12) NN_SHIFT_MODES(12);
+    else if (env_ew == 20) NN_SHIFT_MODES(20);
+    else if (env_ew == 24) NN_SHIFT_MODES(24);
+    else NN_SHIFT_MODES(16);
+#undef NN_SHIFT_MODES
+#undef NN_SHIFT_LAUNCH
     if (g_time_main) cudaEventRecord(g_ev1, st);
     NN_LAUNCH_OK();
     return 0;
