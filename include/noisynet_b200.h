@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NN_ABI_VERSION 8
+#define NN_ABI_VERSION 9
 
 /* ---- common ---------------------------------------------------------------------- */
 
@@ -210,9 +210,18 @@ typedef struct nn_conv_wgrad_args {
     float a_code_scale;      /* > 0: x holds integer codes * a_code_scale (exact bf16 operand), see fwd */
     void* workspace; int64_t workspace_bytes;
     const void* x_packed;    /* optional: layer input already NHWC bf16 [B,H,W,ceil8(Cin)] (codes if a_code_scale > 0) */
-    const void* gy_packed;   /* optional: grad_output already NHWC bf16 [B,OH,OW,ceil8(Cout)] */
+    const void* gy_packed;   /* optional: grad_output already packed, in the layout named below           */
+    int32_t gy_packed_layout;/* NN_PACK_TILED: NHWC bf16 [B,OH,OW,ceil8(Cout)].  NN_PACK_SHIFT: the planes
+                                layout [ceil(Cout/8)][P][8] bf16 on the INPUT pixel grid -- element (b,n,oh,ow)
+                                at plane n/8, pixel (b*H + oh)*W + ow, zeros at every other pixel; P = B*H*W
+                                rounded up to 128 (nn_conv_gy_planes_bytes).  nn_stage_bwd writes it directly */
 } nn_conv_wgrad_args;
 int64_t nn_conv_wgrad_workspace_bytes(const nn_conv_geom* g, int32_t precision, int device);
+/* NN_PACK_SHIFT if the weight gradient of this geometry is served by the shift-GEMM kernel (stride 1, no
+ * padding, Cin <= 8, Cout <= 128: both operands are read in place through shifted descriptors, nothing is
+ * gathered), else NN_PACK_TILED.  Un-packed callers (gy fp32) are routed automatically. */
+int nn_conv_wgrad_pack_layout(const nn_conv_geom* g, int32_t precision, int device);
+int64_t nn_conv_gy_planes_bytes(const nn_conv_geom* g);
 int nn_noisy_conv_wgrad(const nn_conv_wgrad_args* a, int device, void* stream);
 
 /* ---- weight preparation for a whole step in one launch ------------------------------------------------
@@ -275,9 +284,13 @@ typedef struct nn_stage_bwd_args {
     const float *mean, *invstd, *gamma, *beta;
     float act_max; int32_t q_bits; double q_hi;
     float *dgamma, *dbeta;
-    void* gyp; int32_t Cp;
+    void* gyp; int32_t Cp;    /* out: grad w.r.t. the stage input as the bf16 pack the next wgrad / dgrad reads */
     float* gy_f32;
     void* scratch;
+    int32_t gy_layout;        /* NN_PACK_TILED: NHWC [B,H,W,Cp].  NN_PACK_SHIFT: planes layout on a virt_H x virt_W
+                                 pixel grid (the producing conv's INPUT grid, see nn_conv_wgrad_args); the buffer
+                                 must have been zeroed once -- only output positions are ever written            */
+    int32_t virt_H, virt_W;
 } nn_stage_bwd_args;
 int nn_stage_bwd(const nn_stage_bwd_args* a, int device, void* stream);
 

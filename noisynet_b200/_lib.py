@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libnoisynet_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 NOISE_NONE, NOISE_MERGED, NOISE_EXTERNAL = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
@@ -57,7 +57,7 @@ class ConvWgradArgs(C.Structure):
                 ("w_raw", C.c_void_p), ("w_lo", C.c_double), ("w_hi", C.c_double),
                 ("precision", C.c_int32), ("a_code_scale", C.c_float),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("x_packed", C.c_void_p),
-                ("gy_packed", C.c_void_p)]
+                ("gy_packed", C.c_void_p), ("gy_packed_layout", C.c_int32)]
 
 
 class AdamWTensor(C.Structure):
@@ -89,7 +89,8 @@ class StageBwdArgs(C.Structure):
                 ("mean", C.c_void_p), ("invstd", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
                 ("act_max", C.c_float), ("q_bits", C.c_int32), ("q_hi", C.c_double),
                 ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("gyp", C.c_void_p), ("Cp", C.c_int32),
-                ("gy_f32", C.c_void_p), ("scratch", C.c_void_p)]
+                ("gy_f32", C.c_void_p), ("scratch", C.c_void_p),
+                ("gy_layout", C.c_int32), ("virt_H", C.c_int32), ("virt_W", C.c_int32)]
 
 
 # name -> (restype, argtypes); mirrors include/noisynet_b200.h one to one
@@ -130,6 +131,8 @@ SIGNATURES = {
     "nn_debug_cta_timeline": (C.c_int, [C.c_void_p, C.c_int]),
     "nn_conv_pack_layout": (C.c_int, [C.POINTER(ConvGeom), C.c_int32, C.c_int32]),
     "nn_debug_shift_enable": (C.c_int, [C.c_int]),
+    "nn_conv_wgrad_pack_layout": (C.c_int, [C.POINTER(ConvGeom), C.c_int32, C.c_int]),
+    "nn_conv_gy_planes_bytes": (C.c_int64, [C.POINTER(ConvGeom)]),
     "nn_noisy_conv_fwd": (C.c_int, [C.POINTER(ConvFwdArgs), C.c_int, C.c_void_p]),
     "nn_noisy_conv_dgrad": (C.c_int, [C.POINTER(ConvDgradArgs), C.c_int, C.c_void_p]),
     "nn_conv_wgrad_workspace_bytes": (C.c_int64, [C.POINTER(ConvGeom), C.c_int32, C.c_int]),

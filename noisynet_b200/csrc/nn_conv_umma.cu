@@ -975,6 +975,193 @@ k_wgrad_umma(const WgUP p) {
     if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
 
+// ================================================================== shift-GEMM wgrad (narrow-input layers)
+//   gw[n][c][kh][kw] = sum over pixels  gy[pixel][n] * x[pixel + kh*W + kw][c]
+// with BOTH operands read in place through SWIZZLE_NONE MN-major descriptors (core matrix = 8 reduction rows x
+// 16 B, the rows 16 B apart = consecutive pixels):
+//   * x is the layer's NHWC pack with 8 channels = 16 B per pixel; the five taps of one kernel row are five
+//     "MN atoms" ONE PIXEL (16 B) apart, so one MMA per kernel row covers (kw, c) = N = 48 columns (the sixth
+//     atom is a harmless extra tap) from a start address shifted by kh*W pixels;
+//   * grad_output comes in the PLANES layout [channel chunk][virtual pixel][8] on the INPUT pixel grid (zeros at
+//     positions that are not outputs; written once per step by the stage backward, NN_PACK_SHIFT), so a chunk
+//     of 128 pixels is one contiguous 2 KB slab per channel chunk and the M atoms are the planes.
+// Nothing is gathered: per 128-pixel reduction chunk the loader issues 9 + 1 bulk copies (23 KB), the MMA
+// thread 8 x KH MMAs, and the CTA (persistent, split over the reduction) keeps its accumulators in TMEM until the
+// end: HBM-bound (gy 75 MB at batch 512) instead of gather-bound.
+constexpr int WS_KP = 128;                 // reduction pixels per stage
+constexpr int WS_MAX_STAGES = 6;
+constexpr int WS_THREADS = 192;            // warp 0 loader, warp 1 MMA, warps 2-5 epilogue
+
+struct WgShiftP {
+    int H, W, OH, OW, KH, KW, Cout;
+    int n_planes, n_row, n_chunks;          // gy channel chunks, accumulator columns per kernel row, reduction chunks
+    int b_pixels, a_stage, b_stage, stages, tmem_cols;
+    long long total_pixels, plane_stride;   // plane_stride = total_pixels rounded up to WS_KP (zeros in the padding)
+    const __nv_bfloat16 *xp, *gyv;
+    float* partial;                         // [gridDim.x][Cout][KH*KW*8]
+    int* err_flag;
+};
+
+// SWIZZLE_NONE MN-major descriptor: sbo = distance between 8-element MN atoms, lbo = distance between 8-row
+// reduction groups (16-byte units)
+__device__ __forceinline__ uint64_t umma_desc_none_mn(uint32_t smem_addr, uint32_t lbo_units, uint32_t sbo_units) {
+    return umma_desc_none(smem_addr, lbo_units, sbo_units);
+}
+
+__device__ __forceinline__ bool wgshift_chunk_live(const WgShiftP& p, int t) {
+    const long long v0 = (long long)t * WS_KP;
+    long long v1 = v0 + WS_KP - 1;
+    if (v1 >= p.total_pixels) v1 = p.total_pixels - 1;
+    const int hw = p.H * p.W;
+    const long long b0 = v0 / hw, b1 = v1 / hw;
+    if (b0 != b1) return true;
+    return (int)((v0 - b0 * hw) / p.W) < p.OH;
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+k_wgrad_shift(const WgShiftP p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    const int WS_STAGES = p.stages;
+    const uint32_t b_base = base;
+    const uint32_t a_base = b_base + (uint32_t)WS_STAGES * (uint32_t)p.b_stage;
+    const uint32_t bar_base = a_base + (uint32_t)WS_STAGES * (uint32_t)p.a_stage + 16u * WS_KP * 16u;   // + phantom planes
+    const uint32_t full_bar = bar_base, empty_bar = bar_base + 8u * WS_MAX_STAGES, acc_bar = bar_base + 16u * WS_MAX_STAGES;
+    const uint32_t tmem_slot = acc_bar + 8u, abort_slot = tmem_slot + 4u, work_slot = abort_slot + 4u;
+    uint8_t* gen0 = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gen0 + (tmem_slot - base));
+    volatile uint32_t* abort_g = reinterpret_cast<volatile uint32_t*>(gen0 + (abort_slot - base));
+    volatile uint32_t* work_g = reinterpret_cast<volatile uint32_t*>(gen0 + (work_slot - base));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < WS_STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        mbar_init(acc_bar, 1);
+        *abort_g = 0;
+        *work_g = 0;
+        fence_mbar_init();
+    }
+    {   // zero both rings once: x pixels past the end of the pack are never loaded but are multiplied by zero
+        // grad_output entries, and the phantom planes beyond the real channel chunks feed unused accumulator rows
+        uint4* z = reinterpret_cast<uint4*>(gen0);
+        const int n16 = (int)((bar_base - base) / 16);
+        for (int i = tid; i < n16; i += WS_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_g;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int i = 0;
+            for (int t = blockIdx.x; t < p.n_chunks; t += gridDim.x) {
+                if (!wgshift_chunk_live(p, t)) continue;
+                const int s = i % WS_STAGES;
+                if (!mbar_wait(empty_bar + 8 * s, ((i / WS_STAGES) & 1) ^ 1)) { *abort_g = 1; break; }
+                if (*abort_g) break;
+                const long long v0 = (long long)t * WS_KP;
+                const long long pa = WS_KP;              // planes are padded to a multiple of WS_KP pixels
+                long long pb = p.total_pixels - v0;
+                if (pb > p.b_pixels) pb = p.b_pixels;
+                mbar_arrive_expect_tx(full_bar + 8 * s, (uint32_t)(pa * 16 * p.n_planes + pb * 16));
+                bulk_g2s(b_base + (uint32_t)s * p.b_stage, p.xp + v0 * 8, (uint32_t)pb * 16u, full_bar + 8 * s);
+                for (int c = 0; c < p.n_planes; ++c)
+                    bulk_g2s(a_base + (uint32_t)s * p.a_stage + (uint32_t)c * (WS_KP * 16u),
+                             p.gyv + ((long long)c * p.plane_stride + v0) * 8, (uint32_t)pa * 16u, full_bar + 8 * s);
+                ++i;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // MN-major A and B (bits 15, 16), bf16 x bf16 -> fp32, M = 128, N = n_row
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.n_row >> 3) << 17) | ((uint32_t)(UM_BLOCK_M >> 4) << 24);
+            int i = 0;
+            for (int t = blockIdx.x; t < p.n_chunks; t += gridDim.x) {
+                if (!wgshift_chunk_live(p, t)) continue;
+                const int s = i % WS_STAGES;
+                if (!mbar_wait(full_bar + 8 * s, (i / WS_STAGES) & 1)) { *abort_g = 2; break; }
+                if (*abort_g) break;
+                tc_fence_after();
+                const uint64_t ad0 = umma_desc_none_mn(a_base + (uint32_t)s * p.a_stage, 8u, (uint32_t)WS_KP);
+                const uint64_t bd0 = umma_desc_none_mn(b_base + (uint32_t)s * p.b_stage, 8u, 1u);
+#pragma unroll 1
+                for (int k = 0; k < WS_KP / 16; ++k) {
+                    for (int kh = 0; kh < p.KH; ++kh)
+                        umma_bf16(tmem_base + (uint32_t)(kh * p.n_row), ad0 + (uint64_t)(k * 16),
+                                  bd0 + (uint64_t)(k * 16 + kh * p.W), idesc, (i | k) != 0);
+                }
+                umma_commit(empty_bar + 8 * s);
+                ++i;
+            }
+            *work_g = (uint32_t)i;
+            umma_commit(acc_bar);
+        }
+        __syncwarp();
+    }
+    if (warp >= 2) {
+        // epilogue: accumulator rows = output channels; columns (kh, kw, c) -> partial[cta][n][tap * 8 + c]
+        const bool ok = mbar_wait(acc_bar, 0);
+        tc_fence_after();
+        if (!ok) *abort_g = 3;
+        const int q = warp & 3;
+        const int n = q * 32 + lane;
+        const int kcols = p.KH * p.KW * 8;
+        float* dst = p.partial + ((size_t)blockIdx.x * p.Cout + n) * kcols;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (ok && !*abort_g) {
+            for (int kh = 0; kh < p.KH; ++kh)
+                for (int kw = 0; kw < p.KW; kw += 2) {
+                    float v[16];
+                    tmem_ld16(t_lane + (uint32_t)(kh * p.n_row + kw * 8), v);     // two taps (the second may be the extra one)
+                    if (*work_g == 0) {                                            // a CTA without live chunks contributes zeros
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] = 0.f;
+                    }
+                    if (n < p.Cout) {
+                        float4* d4 = reinterpret_cast<float4*>(dst + (kh * p.KW + kw) * 8);
+                        d4[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        d4[1] = make_float4(v[4], v[5], v[6], v[7]);
+                        if (kw + 1 < p.KW) {
+                            d4[2] = make_float4(v[8], v[9], v[10], v[11]);
+                            d4[3] = make_float4(v[12], v[13], v[14], v[15]);
+                        }
+                    }
+                }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (*abort_g && tid == 0 && p.err_flag) atomicExch(p.err_flag, 300 + (int)*abort_g);
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
+// grad_output NCHW fp32 -> planes layout on the input pixel grid (zeros elsewhere), for callers that did not
+// get it from nn_stage_bwd
+__global__ void __launch_bounds__(256)
+k_pack_gy_planes(const float* __restrict__ gy, __nv_bfloat16* __restrict__ gyv, int B, int C, int H, int W, int OH, int OW,
+                 int n_planes, int64_t plane_stride) {
+    const int64_t npix = (int64_t)B * H * W, total = plane_stride * n_planes;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pixel = i % plane_stride;
+        const int chunk = (int)(i / plane_stride);
+        const int b = (int)(pixel / (H * W)), r = (int)(pixel - (int64_t)b * H * W);
+        const int ih = r / W, iw = r - ih * W;
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = chunk * 8 + j;
+            float f = 0.f;
+            if (pixel < npix && c < C && ih < OH && iw < OW) f = __ldg(gy + (((int64_t)b * C + c) * OH + ih) * OW + iw);
+            v[j] = __float2bfloat16_rn(f);
+        }
+        *reinterpret_cast<uint4*>(gyv + i * 8) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
 // partial [splits][Cout][ktot_pad] (kcol = tap*Cp + c) -> gw [Cout][Cin][KHW], scale, STE mask.  Block = 32 columns
 // x 8 split groups: group g sums splits g, g+8, ... (coalesced along kcol), then the 8 group sums are added in a
 // fixed order through shared memory -- deterministic, and the serial chain over splits is 8x shorter.
@@ -1560,9 +1747,122 @@ WgPlan make_wg_plan(const nn_conv_geom& g, int device) {
 }
 }  // namespace
 
+
+
+namespace {
+struct WgShiftPlan {
+    int n_planes, n_row, n_chunks, b_pixels, a_stage, b_stage, stages, tmem_cols, grid;
+    int64_t plane_stride;
+    size_t smem_bytes, xp_bytes, gyv_bytes, partial_bytes;
+};
+bool make_wg_shift_plan(const nn_conv_geom& g, int device, WgShiftPlan* out) {
+    if (!g_shift_enable) return false;
+    if (g.Cin > 8 || g.stride != 1 || g.pad != 0 || g.KH > g.H || g.KW > g.W || g.W >= 2048 || g.Cout > 128) return false;
+    WgShiftPlan w;
+    w.n_planes = (g.Cout + 7) / 8;
+    w.n_row = pad_to(g.KW * 8, 16);
+    const int need = g.KH * w.n_row;
+    if (need > 512 || w.n_row > 256) return false;
+    w.tmem_cols = 32;
+    while (w.tmem_cols < need) w.tmem_cols <<= 1;
+    const int64_t total = (int64_t)g.B * g.H * g.W;
+    w.plane_stride = (total + WS_KP - 1) / WS_KP * WS_KP;
+    w.n_chunks = (int)(w.plane_stride / WS_KP);
+    w.b_pixels = pad_to(WS_KP + (g.KH - 1) * g.W + w.n_row / 8, 8);
+    w.a_stage = w.n_planes * WS_KP * 16;
+    w.b_stage = pad_to(w.b_pixels * 16, 128);
+    const int fixed = 128 + 16 * WS_KP * 16 + 16 * WS_MAX_STAGES + 64;
+    w.stages = (190 * 1024 - fixed) / (w.a_stage + w.b_stage);
+    if (w.stages > WS_MAX_STAGES) w.stages = WS_MAX_STAGES;
+    if (w.stages < 2) return false;
+    w.smem_bytes = (size_t)fixed + (size_t)w.stages * (w.a_stage + w.b_stage);
+    w.grid = nn_num_sms(device);
+    if (w.grid > w.n_chunks) w.grid = w.n_chunks;
+    w.xp_bytes = (size_t)total * 16;
+    w.gyv_bytes = (size_t)w.n_planes * w.plane_stride * 16;
+    w.partial_bytes = (size_t)w.grid * g.Cout * g.KH * g.KW * 8 * sizeof(float);
+    if (out) *out = w;
+    return true;
+}
+}  // namespace
+
 int64_t nn_umma_wgrad_workspace(const nn_conv_geom* g, int, int device) {
     WgPlan w = make_wg_plan(*g, device);
-    return (int64_t)(align_up(w.xp_bytes, 1024) + align_up(w.gyp_bytes, 1024) + align_up(w.partial_bytes, 1024) + 2048);
+    size_t need = align_up(w.xp_bytes, 1024) + align_up(w.gyp_bytes, 1024) + align_up(w.partial_bytes, 1024) + 2048;
+    WgShiftPlan sw;
+    if (make_wg_shift_plan(*g, device, &sw)) {
+        const size_t ns = align_up(sw.xp_bytes, 1024) + align_up(sw.gyv_bytes, 1024) + align_up(sw.partial_bytes, 1024) + 2048;
+        if (ns > need) need = ns;
+    }
+    return (int64_t)need;
+}
+
+extern "C" int nn_conv_wgrad_pack_layout(const nn_conv_geom* g, int32_t precision, int device) {
+    if (!g || precision != NN_PREC_BF16) return NN_PACK_TILED;
+    return make_wg_shift_plan(*g, device, nullptr) ? NN_PACK_SHIFT : NN_PACK_TILED;
+}
+extern "C" int64_t nn_conv_gy_planes_bytes(const nn_conv_geom* g) {
+    if (!g) return 0;
+    const int64_t total = (int64_t)g->B * g->H * g->W;
+    return (int64_t)((g->Cout + 7) / 8) * ((total + WS_KP - 1) / WS_KP * WS_KP) * 16;
+}
+
+static int shift_conv_wgrad(const nn_conv_wgrad_args* a, const WgShiftPlan& w, int device, cudaStream_t st) {
+    const nn_conv_geom& g = a->g;
+    int OH, OW;
+    nn_out_hw(g, OH, OW);
+    const bool gy_ready = a->gy_packed && a->gy_packed_layout == NN_PACK_SHIFT;
+    const size_t need = (a->x_packed ? 0 : align_up(w.xp_bytes, 1024)) + (gy_ready ? 0 : align_up(w.gyv_bytes, 1024)) +
+                        align_up(w.partial_bytes, 1024) + 1024;
+    if (!a->workspace || (size_t)a->workspace_bytes < need)
+        return nn_fail("nn_noisy_conv_wgrad: workspace too small%s (need %lld bytes)", "", (long long)need);
+    uint8_t* ws = (uint8_t*)align_up((size_t)a->workspace, 1024);
+    const int sms = nn_num_sms(device);
+    const __nv_bfloat16* xp = (const __nv_bfloat16*)a->x_packed;
+    if (!xp) {
+        const int64_t total = (int64_t)g.B * g.H * g.W;
+        int grid = (int)((total + 255) / 256);
+        if (grid > 16 * sms) grid = 16 * sms;
+        k_pack_act<<<grid, 256, 0, st>>>(a->x, (__nv_bfloat16*)ws, g.B, g.Cin, g.H * g.W, 8, a->a_code_scale);
+        NN_LAUNCH_OK();
+        xp = (const __nv_bfloat16*)ws;
+        ws += align_up(w.xp_bytes, 1024);
+    }
+    const __nv_bfloat16* gyv = (const __nv_bfloat16*)a->gy_packed;
+    if (!gy_ready) {
+        if (!a->gy) return nn_fail("nn_noisy_conv_wgrad: the shift path needs gy (fp32) or a NN_PACK_SHIFT gy_packed%s", "");
+        const int64_t total = w.plane_stride * w.n_planes;
+        int grid = (int)((total + 255) / 256);
+        if (grid > 16 * sms) grid = 16 * sms;
+        k_pack_gy_planes<<<grid, 256, 0, st>>>(a->gy, (__nv_bfloat16*)ws, g.B, g.Cout, g.H, g.W, OH, OW, w.n_planes, w.plane_stride);
+        NN_LAUNCH_OK();
+        gyv = (const __nv_bfloat16*)ws;
+        ws += align_up(w.gyv_bytes, 1024);
+    }
+    float* partial = (float*)ws;
+    WgShiftP p;
+    memset(&p, 0, sizeof(p));
+    p.H = g.H; p.W = g.W; p.OH = OH; p.OW = OW; p.KH = g.KH; p.KW = g.KW; p.Cout = g.Cout;
+    p.n_planes = w.n_planes; p.n_row = w.n_row; p.n_chunks = w.n_chunks; p.b_pixels = w.b_pixels;
+    p.a_stage = w.a_stage; p.b_stage = w.b_stage; p.stages = w.stages; p.tmem_cols = w.tmem_cols;
+    p.total_pixels = (long long)g.B * g.H * g.W; p.plane_stride = w.plane_stride;
+    p.xp = xp; p.gyv = gyv; p.partial = partial; p.err_flag = nn_umma_err_flag(device);
+    static bool attr_set = false;
+    if (!attr_set) {
+        NN_CUDA_OK(cudaFuncSetAttribute(k_wgrad_shift, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    k_wgrad_shift<<<w.grid, WS_THREADS, w.smem_bytes, st>>>(p);
+    NN_LAUNCH_OK();
+    const int kcols = g.KH * g.KW * 8;
+    const int64_t n = (int64_t)g.Cout * kcols;
+    const float scale = a->a_code_scale > 0.f ? a->a_code_scale : 1.f;
+    int rb = (int)((n + 31) / 32);
+    if (rb > 16 * sms) rb = 16 * sms;
+    k_wgrad_umma_reduce2<<<rb, 256, 0, st>>>(partial, w.grid, g.Cout, g.Cin, g.KH * g.KW, 8, kcols, scale, a->gw, a->w_raw,
+                                             (float)a->w_lo, (float)a->w_hi);
+    NN_LAUNCH_OK();
+    return 0;
 }
 
 int nn_umma_conv_wgrad(const nn_conv_wgrad_args* a, int device, cudaStream_t st) {
@@ -1571,6 +1871,15 @@ int nn_umma_conv_wgrad(const nn_conv_wgrad_args* a, int device, cudaStream_t st)
     const nn_conv_geom& g = a->g;
     int OH, OW;
     nn_out_hw(g, OH, OW);
+    {   // narrow-input layers: both operands read in place (no im2col gather)
+        WgShiftPlan sw;
+        const bool can = make_wg_shift_plan(g, device, &sw);
+        const bool want = a->gy_packed ? a->gy_packed_layout == NN_PACK_SHIFT : can;
+        if (want) {
+            if (!can) return nn_fail("nn_noisy_conv_wgrad: gy_packed_layout = NN_PACK_SHIFT is not served for this geometry%s", "");
+            return shift_conv_wgrad(a, sw, device, st);
+        }
+    }
     WgPlan w = make_wg_plan(g, device);
     const size_t need = align_up(w.xp_bytes, 1024) + align_up(w.gyp_bytes, 1024) + align_up(w.partial_bytes, 1024) + 1024;
     if (!a->workspace || (size_t)a->workspace_bytes < need)

@@ -231,6 +231,8 @@ struct BnBwdApplyP {
     float* gy_f32;                // optional NCHW fp32 copy of the same gradient [B,C,OH,OW]
     int B, C, OH, OW, Cp, pool;
     float act_max, q_hi, inv_count;
+    int planes, vH, vW;           // planes = 1: output in the planes layout [chunk][plane_stride][8] on a vH x vW grid
+    long long plane_stride;
 };
 
 __global__ void __launch_bounds__(256)
@@ -243,8 +245,10 @@ k_bn_bwd_apply(const BnBwdApplyP p) {
     const unsigned npp = (unsigned)p.B * PHW, total = npp * chunks;
     const int npos = p.pool ? 4 : 1;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const unsigned pp = ST_CHUNK_FAST ? i / chunks : i % npp;
-        const int chunk = (int)(ST_CHUNK_FAST ? i % chunks : i / npp);
+        // NHWC output: chunk fastest (a warp writes whole pixels); planes output: pixel fastest (a warp writes one plane)
+        const bool chunk_fast = ST_CHUNK_FAST && !p.planes;
+        const unsigned pp = chunk_fast ? i / chunks : i % npp;
+        const int chunk = (int)(chunk_fast ? i % chunks : i / npp);
         const int b = (int)(pp / PHW), r = (int)(pp - (unsigned)b * PHW);
         const int ph = r / PW, pw = r - ph * PW;
         float d[8];
@@ -275,8 +279,9 @@ k_bn_bwd_apply(const BnBwdApplyP p) {
                 if (p.gy_f32 && pos[j] >= 0)
                     p.gy_f32[(((size_t)b * p.C + chunk * 8 + j) * p.OH + oh) * p.OW + ow] = v;
             }
-            *reinterpret_cast<uint4*>(p.gyp + ((((size_t)b * p.OH + oh) * p.OW + ow) * p.Cp + chunk * 8)) =
-                *reinterpret_cast<const uint4*>(out);
+            const size_t off = p.planes ? ((size_t)chunk * p.plane_stride + ((size_t)b * p.vH + oh) * p.vW + ow) * 8
+                                        : (((size_t)b * p.OH + oh) * p.OW + ow) * p.Cp + chunk * 8;
+            *reinterpret_cast<uint4*>(p.gyp + off) = *reinterpret_cast<const uint4*>(out);
         }
     }
 }
@@ -496,6 +501,14 @@ extern "C" int nn_stage_bwd(const nn_stage_bwd_args* a, int device, void* stream
     p.B = a->B; p.C = a->C; p.OH = a->H; p.OW = a->W; p.Cp = a->Cp; p.pool = a->pool;
     p.act_max = a->act_max; p.q_hi = q.q_hi; p.inv_count = 1.f / ((float)a->B * PH * PW);
     if (a->pool && !a->argmax) return nn_fail("nn_stage_bwd: argmax missing%s", "");
+    p.planes = a->gy_layout == NN_PACK_SHIFT ? 1 : 0;
+    p.vH = p.vW = 0; p.plane_stride = 0;
+    if (p.planes) {
+        if (a->virt_H < a->H || a->virt_W < a->W) return nn_fail("nn_stage_bwd: virtual grid smaller than the stage input%s", "");
+        p.vH = a->virt_H; p.vW = a->virt_W;
+        const long long total = (long long)a->B * a->virt_H * a->virt_W;
+        p.plane_stride = (total + 127) / 128 * 128;
+    }
     k_bn_bwd_apply<<<grid_cap((int64_t)a->B * PH * PW * (a->Cp / 8), device), 256, 0, st>>>(p);
     NN_LAUNCH_OK();
     return 0;

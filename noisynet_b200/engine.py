@@ -17,7 +17,7 @@ import ctypes as C
 import torch
 
 from . import _lib, ops
-from ._lib import (NOISE_EXTERNAL, NOISE_MERGED, PREC_BF16, ConvDgradArgs, ConvFwdArgs, ConvGeom, ConvWgradArgs,
+from ._lib import (NOISE_EXTERNAL, NOISE_MERGED, PACK_SHIFT, PREC_BF16, ConvDgradArgs, ConvFwdArgs, ConvGeom, ConvWgradArgs,
                    Rng, StageArgs, StageBwdArgs, WPrepJob)
 from .hardware_model import _f32
 
@@ -66,7 +66,7 @@ class NoisyNetEngine:
         self.g4 = f32(B, 10); self.gyp4 = bf16(B, 16)
         self.gx4 = f32(B, FC); self.gyp3 = bf16(B, c8(FC))
         self.gx3 = f32(B, C2, P2, P2); self.gyp2 = bf16(B, H2, H2, c8(C2))
-        self.gx2 = f32(B, C1, P1, P1); self.gyp1 = bf16(B, H1, H1, c8(C1))
+        self.gx2 = f32(B, C1, P1, P1); self.gyp1 = bf16(B, H1, H1, c8(C1))     # re-laid out below if conv1's wgrad is in-place
         self.loss = f32(1)
         self.scratch = torch.zeros(int(self.lib.nn_stage_scratch_bytes(max(C1, C2, FC))) + 64, dtype=torch.uint8, device=dev)
         # weight packs of the step: forward (4 layers) + dgrad (fc2, fc1 as a linear, conv2), one launch
@@ -84,6 +84,12 @@ class NoisyNetEngine:
         self.geom = [ConvGeom(B, 3, 32, 32, C1, fs, fs, 1, 0), ConvGeom(B, C1, P1, P1, C2, fs, fs, 1, 0),
                      ConvGeom(B, C2, P2, P2, FC, P2, P2, 1, 0), ConvGeom(B, FC, 1, 1, 10, 1, 1, 1, 0)]
         self.geom_fc1_lin = ConvGeom(B, C2 * P2 * P2, 1, 1, FC, 1, 1, 1, 0)
+        # conv1 weight gradient through the in-place (shift) kernel: its grad_output lives in the planes layout on the
+        # 32x32 input grid, zeroed once here -- nn_stage_bwd only ever writes the 28x28 output positions
+        self.gy1_layout = self.lib.nn_conv_wgrad_pack_layout(C.byref(self.geom[0]), PREC_BF16, self.di)
+        if self.gy1_layout:
+            nbytes = int(self.lib.nn_conv_gy_planes_bytes(C.byref(self.geom[0])))
+            self.gyp1 = torch.zeros(nbytes // 16, 8, dtype=torch.bfloat16, device=dev)
         self.wpack = []
         for j, (li, (co, ci, khw), mode, m_rows) in enumerate(specs):
             jb = self.jobs[j]
@@ -151,11 +157,11 @@ class NoisyNetEngine:
         a.workspace, a.workspace_bytes = _p(self.ws), self.ws.numel()
         _lib.check(self.lib.nn_noisy_conv_fwd(C.byref(a), self.di, self._st()), "nn_noisy_conv_fwd")
 
-    def _wgrad(self, idx, gyp, xp, a_cs, w_raw, gw):
+    def _wgrad(self, idx, gyp, xp, a_cs, w_raw, gw, gy_layout=0):
         a = ConvWgradArgs()
         a.g = self.geom[idx]
         a.gy, a.x, a.gw = None, None, _p(gw)
-        a.gy_packed, a.x_packed = _p(gyp), _p(xp)
+        a.gy_packed, a.x_packed, a.gy_packed_layout = _p(gyp), _p(xp), gy_layout
         a.w_raw, a.w_lo, a.w_hi = _p(w_raw), -1.0, 1.0            # STE of the weight quantizer (hardware_model.py:323)
         a.precision, a.a_code_scale = PREC_BF16, a_cs
         a.workspace, a.workspace_bytes = _p(self.ws), self.ws.numel()
@@ -188,7 +194,7 @@ class NoisyNetEngine:
         a.scratch = _p(self.scratch)
         _lib.check(self.lib.nn_stage_fwd(C.byref(a), self.di, self._st()), "nn_stage_fwd")
 
-    def _stage_bwd(self, g, x, amax, C_, H, pool, bn, key, q_bits, q_hi, gyp):
+    def _stage_bwd(self, g, x, amax, C_, H, pool, bn, key, q_bits, q_hi, gyp, planes_grid=None):
         a = StageBwdArgs()
         a.g, a.x, a.argmax = _p(g), _p(x), _p(amax)
         a.B, a.C, a.H, a.W, a.pool = self.B, C_, H, H, pool
@@ -196,7 +202,9 @@ class NoisyNetEngine:
         a.gamma, a.beta = _p(bn.weight), _p(bn.bias)
         a.act_max, a.q_bits, a.q_hi = float(self.a.act_max), int(q_bits), float(q_hi)
         a.dgamma, a.dbeta = _p(bn.weight.grad), _p(bn.bias.grad)
-        a.gyp, a.Cp, a.gy_f32 = _p(gyp), gyp.shape[-1], None
+        a.gyp, a.Cp, a.gy_f32 = _p(gyp), (C_ + 7) // 8 * 8, None
+        if planes_grid is not None:
+            a.gy_layout, a.virt_H, a.virt_W = PACK_SHIFT, planes_grid[0], planes_grid[1]
         a.scratch = _p(self.scratch)
         _lib.check(self.lib.nn_stage_bwd(C.byref(a), self.di, self._st()), "nn_stage_bwd")
 
@@ -261,8 +269,9 @@ class NoisyNetEngine:
         self._stage_bwd(self.gx3, self.pool2, self.amax2, C2, H2, 1, m.bn2, "bn2", a.q_a3, qh3, self.gyp2)
         self._wgrad(1, self.gyp2, self.xp2, s2, W[1], W[1].grad)
         self._dgrad(self.geom[1], self.gyp2, 1, self.gx2)
-        self._stage_bwd(self.gx2, self.pool1, self.amax1, C1, H1, 1, m.bn1, "bn1", a.q_a2, qh2, self.gyp1)
-        self._wgrad(0, self.gyp1, self.xp1, s1, W[0], W[0].grad)
+        self._stage_bwd(self.gx2, self.pool1, self.amax1, C1, H1, 1, m.bn1, "bn1", a.q_a2, qh2, self.gyp1,
+                        planes_grid=(32, 32) if self.gy1_layout else None)
+        self._wgrad(0, self.gyp1, self.xp1, s1, W[0], W[0].grad, self.gy1_layout)
         # ---- exchange + update
         if self.red is not None:
             self.red.all_reduce_sum_()

@@ -101,3 +101,106 @@ def test_shift_layout_rejected_when_not_served(dev):
         assert lib.nn_conv_pack_layout(C.byref(g), NOISE_MERGED, PREC_BF16) == PACK_TILED
     g = ConvGeom(4, 3, 32, 32, 200, 5, 5, 1, 0)
     assert lib.nn_conv_pack_layout(C.byref(g), 0, PREC_BF16) == PACK_SHIFT      # 200 plain columns fit, 400 do not
+
+
+WG_SHAPES = [  # B, Cin, H, W, Cout, k
+    (4, 3, 32, 32, 65, 5),        # NoisyNet conv1
+    (3, 1, 28, 28, 16, 4),        # even kernel, 784 pixels per image (chunks straddle images)
+    (5, 8, 9, 11, 120, 3),        # 495 pixels: the last reduction chunk is padding; 15 channel planes
+    (2, 3, 12, 12, 7, 1),         # 1x1
+    (40, 2, 16, 16, 33, 7),       # 7x7 (KH * 64 = 448 accumulator columns), more chunks than one per CTA
+]
+
+
+@pytest.mark.parametrize("shape", WG_SHAPES)
+def test_shift_wgrad_matches_tiled_and_fp64(dev, shape):
+    """Weight gradient through the in-place (shift) kernel: integer activation codes x bf16 grad_output, fp32
+    accumulation.  Against float64 on the SAME bf16-rounded grad_output the only error is the fp32 summation
+    (rtol 2e-5 of the largest entry); against the tiled tcgen05 kernel (same operands, different summation order)
+    likewise."""
+    from noisynet_b200 import _lib, ops
+    from noisynet_b200._lib import PACK_SHIFT, PREC_BF16, ConvGeom
+    import ctypes as C
+    lib = _lib.load()
+    B, Cin, H, W, Cout, k = shape
+    g = ConvGeom(B, Cin, H, W, Cout, k, k, 1, 0)
+    assert lib.nn_conv_wgrad_pack_layout(C.byref(g), PREC_BF16, 0) == PACK_SHIFT
+    gen = torch.Generator().manual_seed(sum(shape) + 1)
+    s_a = 5.0 / 15.0
+    ka = torch.randint(0, 16, (B, Cin, H, W), generator=gen).float()
+    x = (ka * s_a).float()
+    OH, OW = H - k + 1, W - k + 1
+    gy = torch.randn(B, Cout, OH, OW, generator=gen) * 0.01
+    w_raw = torch.randn(Cout, Cin, k, k, generator=gen) * 0.6          # some |w| > 1: STE mask zeros those entries
+    gyb = gy.bfloat16().double()
+    ref = torch.nn.grad.conv2d_weight(ka.double(), (Cout, Cin, k, k), gyb) * float(np.float32(s_a))
+    ref = ref * ((w_raw >= -1) & (w_raw <= 1)).double()
+    xd, gyd, wrd = x.to(dev), gy.to(dev), w_raw.to(dev)
+    try:
+        lib.nn_debug_shift_enable(1)
+        a = ops.conv_wgrad(gyd, xd, w_raw.shape, 1, 0, w_raw=wrd, w_lo=-1.0, w_hi=1.0, precision="bf16", a_code_scale=s_a)
+        assert ops.error_flag() == 0
+        lib.nn_debug_shift_enable(0)
+        b = ops.conv_wgrad(gyd, xd, w_raw.shape, 1, 0, w_raw=wrd, w_lo=-1.0, w_hi=1.0, precision="bf16", a_code_scale=s_a)
+        assert ops.error_flag() == 0
+    finally:
+        lib.nn_debug_shift_enable(1)
+    tol = 2e-5 * float(ref.abs().max())
+    assert (a.cpu().double() - ref).abs().max().item() <= tol
+    assert (a - b).abs().max().item() <= tol
+
+
+def test_stage_bwd_planes_layout(dev):
+    """nn_stage_bwd with gy_layout = NN_PACK_SHIFT writes the same values as the NHWC pack, at the planes-layout
+    addresses of the (larger) virtual grid, and nothing else."""
+    from noisynet_b200 import _lib, ops
+    from noisynet_b200._lib import PACK_SHIFT, StageArgs, StageBwdArgs
+    import ctypes as C
+    lib = _lib.load()
+    B, Cc, H, W, vH, vW = 3, 13, 8, 8, 12, 12
+    gen = torch.Generator().manual_seed(5)
+    x_in = torch.randn(B, Cc, H, W, generator=gen).to(dev)
+    gamma, beta = (torch.rand(Cc, generator=gen) + 0.5).to(dev), (torch.randn(Cc, generator=gen) * 0.1).to(dev)
+    PH, PW = H // 2, W // 2
+    f32 = lambda *s: torch.empty(*s, device=dev)
+    pooled, amax = f32(B, Cc, PH, PW), torch.empty(B, Cc, PH, PW, dtype=torch.uint8, device=dev)
+    mean, invstd, xmax = f32(Cc), f32(Cc), f32(1)
+    Cp = 16
+    xp = torch.empty(B, PH, PW, Cp, dtype=torch.bfloat16, device=dev)
+    scratch = torch.zeros(int(lib.nn_stage_scratch_bytes(Cc)) + 64, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    a = StageArgs()
+    a.in_, a.B, a.C, a.H, a.W, a.pool = x_in.data_ptr(), B, Cc, H, W, 1
+    a.pooled, a.argmax, a.gamma, a.beta = pooled.data_ptr(), amax.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+    a.running_mean, a.running_var, a.momentum, a.eps = None, None, 0.1, 1e-5
+    a.mean, a.invstd, a.act_max, a.q_bits, a.q_hi, a.stochastic = mean.data_ptr(), invstd.data_ptr(), 5.0, 4, 5.0, 0.0
+    a.u_inject, a.rng, a.xp, a.Cp, a.act, a.xmax_out, a.scratch = None, ops._fixed_rng(1, 1), xp.data_ptr(), Cp, None, xmax.data_ptr(), scratch.data_ptr()
+    _lib.check(lib.nn_stage_fwd(C.byref(a), 0, st), "nn_stage_fwd")
+    gup = torch.randn(B, Cc, PH, PW, generator=gen).to(dev)
+    outs = []
+    for layout in (0, PACK_SHIFT):
+        b = StageBwdArgs()
+        b.g, b.x, b.argmax = gup.data_ptr(), pooled.data_ptr(), amax.data_ptr()
+        b.B, b.C, b.H, b.W, b.pool = B, Cc, H, W, 1
+        b.mean, b.invstd, b.gamma, b.beta = mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+        b.act_max, b.q_bits, b.q_hi = 5.0, 4, 5.0
+        dg, db = f32(Cc), f32(Cc)
+        b.dgamma, b.dbeta = dg.data_ptr(), db.data_ptr()
+        if layout == 0:
+            buf = torch.zeros(B, H, W, Cp, dtype=torch.bfloat16, device=dev)
+        else:
+            P = (B * vH * vW + 127) // 128 * 128
+            buf = torch.zeros(Cp // 8, P, 8, dtype=torch.bfloat16, device=dev)
+            b.gy_layout, b.virt_H, b.virt_W = PACK_SHIFT, vH, vW
+        b.gyp, b.Cp, b.gy_f32, b.scratch = buf.data_ptr(), Cp, None, scratch.data_ptr()
+        _lib.check(lib.nn_stage_bwd(C.byref(b), 0, st), "nn_stage_bwd")
+        outs.append(buf)
+    torch.cuda.synchronize()
+    nhwc, planes = outs[0].float().cpu(), outs[1].float().cpu()
+    P = planes.shape[1]
+    grid = planes[:, :B * vH * vW].reshape(Cp // 8, B, vH, vW, 8)
+    got = grid[:, :, :H, :W].permute(1, 2, 3, 0, 4).reshape(B, H, W, Cp)
+    assert torch.equal(got, nhwc)
+    mask = torch.ones(Cp // 8, B, vH, vW, 8, dtype=torch.bool)
+    mask[:, :, :H, :W] = False
+    assert float(grid[mask].abs().max()) == 0.0 and float(planes[:, B * vH * vW:].abs().max() if P > B * vH * vW else 0.0) == 0.0
