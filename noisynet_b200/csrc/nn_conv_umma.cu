@@ -995,11 +995,12 @@ constexpr int WS_THREADS = 192;            // warp 0 loader, warp 1 MMA, warps 2
 struct WgShiftP {
     int H, W, OH, OW, KH, KW, Cout;
     int n_planes, n_row, n_chunks;          // gy channel chunks, accumulator columns per kernel row, reduction chunks
-    int b_pixels, a_stage, b_stage, stages, tmem_cols;
+    int b_pixels, a_stage, b_stage, stages, tmem_cols, order;
     long long total_pixels, plane_stride;   // plane_stride = total_pixels rounded up to WS_KP (zeros in the padding)
     const __nv_bfloat16 *xp, *gyv;
     float* partial;                         // [gridDim.x][Cout][KH*KW*8]
     int* err_flag;
+    long long* dbg;                         // optional [cta][32 chunks][4]: before wait, operands landed, MMAs issued
 };
 
 // SWIZZLE_NONE MN-major descriptor: sbo = distance between 8-element MN atoms, lbo = distance between 8-row
@@ -1018,7 +1019,7 @@ __device__ __forceinline__ bool wgshift_chunk_live(const WgShiftP& p, int t) {
     return (int)((v0 - b0 * hw) / p.W) < p.OH;
 }
 
-__global__ void __launch_bounds__(WS_THREADS, 1)
+__global__ void __launch_bounds__(WS_THREADS, 2)
 k_wgrad_shift(const WgShiftP p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -1083,18 +1084,29 @@ k_wgrad_shift(const WgShiftP p) {
             for (int t = blockIdx.x; t < p.n_chunks; t += gridDim.x) {
                 if (!wgshift_chunk_live(p, t)) continue;
                 const int s = i % WS_STAGES;
+                if (p.dbg && i < 32) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 0] = clock64();
                 if (!mbar_wait(full_bar + 8 * s, (i / WS_STAGES) & 1)) { *abort_g = 2; break; }
                 if (*abort_g) break;
                 tc_fence_after();
+                if (p.dbg && i < 32) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 1] = clock64();
                 const uint64_t ad0 = umma_desc_none_mn(a_base + (uint32_t)s * p.a_stage, 8u, (uint32_t)WS_KP);
                 const uint64_t bd0 = umma_desc_none_mn(b_base + (uint32_t)s * p.b_stage, 8u, 1u);
+                if (p.order) {
 #pragma unroll 1
-                for (int k = 0; k < WS_KP / 16; ++k) {
                     for (int kh = 0; kh < p.KH; ++kh)
-                        umma_bf16(tmem_base + (uint32_t)(kh * p.n_row), ad0 + (uint64_t)(k * 16),
-                                  bd0 + (uint64_t)(k * 16 + kh * p.W), idesc, (i | k) != 0);
+                        for (int k = 0; k < WS_KP / 16; ++k)
+                            umma_bf16(tmem_base + (uint32_t)(kh * p.n_row), ad0 + (uint64_t)(k * 16),
+                                      bd0 + (uint64_t)(k * 16 + kh * p.W), idesc, (i | k) != 0);
+                } else {
+#pragma unroll 1
+                    for (int k = 0; k < WS_KP / 16; ++k) {
+                        for (int kh = 0; kh < p.KH; ++kh)
+                            umma_bf16(tmem_base + (uint32_t)(kh * p.n_row), ad0 + (uint64_t)(k * 16),
+                                      bd0 + (uint64_t)(k * 16 + kh * p.W), idesc, (i | k) != 0);
+                    }
                 }
                 umma_commit(empty_bar + 8 * s);
+                if (p.dbg && i < 32) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 2] = clock64();
                 ++i;
             }
             *work_g = (uint32_t)i;
@@ -1772,11 +1784,15 @@ bool make_wg_shift_plan(const nn_conv_geom& g, int device, WgShiftPlan* out) {
     w.a_stage = w.n_planes * WS_KP * 16;
     w.b_stage = pad_to(w.b_pixels * 16, 128);
     const int fixed = 128 + 16 * WS_KP * 16 + 16 * WS_MAX_STAGES + 64;
-    w.stages = (190 * 1024 - fixed) / (w.a_stage + w.b_stage);
+    // two CTAs per SM when the accumulators leave room in TMEM: one CTA's MMA stream has issue gaps (barrier waits,
+    // commits, accumulator switches) that a second stream fills -- measured at batch 512: CTA span 70 -> 35 us
+    static const int env_ctas = getenv("NN_WS_CTAS") ? atoi(getenv("NN_WS_CTAS")) : 2;      // tuning knob: CTAs per SM
+    const int ctas = (env_ctas == 2 && w.tmem_cols <= 256) ? 2 : 1;
+    w.stages = ((ctas == 2 ? 100 : 190) * 1024 - fixed) / (w.a_stage + w.b_stage);
     if (w.stages > WS_MAX_STAGES) w.stages = WS_MAX_STAGES;
     if (w.stages < 2) return false;
     w.smem_bytes = (size_t)fixed + (size_t)w.stages * (w.a_stage + w.b_stage);
-    w.grid = nn_num_sms(device);
+    w.grid = ctas * nn_num_sms(device);
     if (w.grid > w.n_chunks) w.grid = w.n_chunks;
     w.xp_bytes = (size_t)total * 16;
     w.gyv_bytes = (size_t)w.n_planes * w.plane_stride * 16;
@@ -1846,11 +1862,25 @@ static int shift_conv_wgrad(const nn_conv_wgrad_args* a, const WgShiftPlan& w, i
     p.n_planes = w.n_planes; p.n_row = w.n_row; p.n_chunks = w.n_chunks; p.b_pixels = w.b_pixels;
     p.a_stage = w.a_stage; p.b_stage = w.b_stage; p.stages = w.stages; p.tmem_cols = w.tmem_cols;
     p.total_pixels = (long long)g.B * g.H * g.W; p.plane_stride = w.plane_stride;
+    static const int env_order = getenv("NN_WS_ORDER") ? atoi(getenv("NN_WS_ORDER")) : 1;   // 1: kernel row outermost (8 MMAs per accumulator in a row: 56 -> 40 ns per MMA)
+    p.order = env_order;
     p.xp = xp; p.gyv = gyv; p.partial = partial; p.err_flag = nn_umma_err_flag(device);
     static bool attr_set = false;
     if (!attr_set) {
         NN_CUDA_OK(cudaFuncSetAttribute(k_wgrad_shift, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
+    }
+    static const bool want_dbg = getenv("NN_UMMA_DEBUG") != nullptr;
+    if (want_dbg) {
+        const size_t rows = (size_t)w.grid * 16;
+        if (rows > g_dbg_ctas) {
+            if (g_dbg_buf) cudaFree(g_dbg_buf);
+            cudaMalloc(&g_dbg_buf, rows * 8 * sizeof(long long));
+            g_dbg_ctas = rows;
+        }
+        cudaMemsetAsync(g_dbg_buf, 0, rows * 8 * sizeof(long long), st);
+        p.dbg = g_dbg_buf;
+        g_dbg_last = rows;
     }
     k_wgrad_shift<<<w.grid, WS_THREADS, w.smem_bytes, st>>>(p);
     NN_LAUNCH_OK();
