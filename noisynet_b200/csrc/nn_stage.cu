@@ -432,6 +432,112 @@ k_head(const float* __restrict__ z, const int64_t* __restrict__ label, int B, in
     }
 }
 
+// Faster formulation for B <= blockDim (one thread per row, the training batch): the per-channel reductions run
+// one WARP PER CHANNEL over shared-memory columns (lane-strided fp64 partials, then one shuffle tree) instead of 16
+// fp64 shuffle trees per warp -- fp64 issue is the scarce resource here.  Same arithmetic and summation order
+// independent of the launch; results differ from k_head only in the (fixed) order of the fp64 sums.
+__device__ __forceinline__ double head_col_sum(const float* col, int B) {
+    const int lane = threadIdx.x & 31;
+    double s = 0;
+    for (int b = lane; b < B; b += 32) s += (double)col[b];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
+__global__ void __launch_bounds__(1024)
+k_head_rows(const float* __restrict__ z, const int64_t* __restrict__ label, int B, int C, const float* __restrict__ gamma,
+            const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+            float eps, float* __restrict__ loss_out, float* __restrict__ out, float* __restrict__ g, __nv_bfloat16* __restrict__ gp,
+            int Cp, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    extern __shared__ float hsm[];
+    float* colA = hsm;                       // [C][B]: z, then dv
+    float* colB = hsm + (size_t)C * B;       // [C][B]: z^2, then dv * xhat
+    float* lrow = colB + (size_t)C * B;      // [B] loss terms
+    __shared__ float s_mean[HEAD_MAXC], s_invstd[HEAD_MAXC], s_g[HEAD_MAXC], s_b[HEAD_MAXC], s_db[HEAD_MAXC], s_dg[HEAD_MAXC];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+    const bool row = tid < B;
+    float zr[HEAD_MAXC];
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c) {
+        zr[c] = 0.f;
+        if (c < C && row) {
+            zr[c] = z[(size_t)tid * C + c];
+            colA[(size_t)c * B + tid] = zr[c];
+            colB[(size_t)c * B + tid] = zr[c] * zr[c];
+        }
+    }
+    __syncthreads();
+    for (int c = warp; c < C; c += nwarp) {
+        const double t1 = head_col_sum(colA + (size_t)c * B, B), t2 = head_col_sum(colB + (size_t)c * B, B);
+        if (lane == 0) {
+            const double m = t1 / B;
+            double var = t2 / B - m * m;
+            if (var < 0) var = 0;
+            s_mean[c] = (float)m;
+            s_invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+            s_g[c] = gamma[c]; s_b[c] = beta[c];
+            if (running_mean) {
+                const double unb = B > 1 ? var * B / (B - 1) : var;
+                running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+                running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+            }
+        }
+    }
+    __syncthreads();
+    float xh[HEAD_MAXC], dvr[HEAD_MAXC];
+    if (row) {
+        float vv[HEAD_MAXC];
+        float mx = -3.4e38f;
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c) {
+            if (c < C) {
+                xh[c] = (zr[c] - s_mean[c]) * s_invstd[c];
+                vv[c] = xh[c] * s_g[c] + s_b[c];
+                if (out) out[(size_t)tid * C + c] = vv[c];
+                mx = fmaxf(mx, vv[c]);
+            }
+        }
+        float se = 0.f;
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c) if (c < C) se += expf(vv[c] - mx);
+        const int lab = (int)label[tid];
+        float vl = 0.f;
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c) if (c == lab) vl = vv[c];
+        lrow[tid] = logf(se) + mx - vl;
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c) {
+            if (c < C) {
+                dvr[c] = (expf(vv[c] - mx) / se - (c == lab ? 1.f : 0.f)) / (float)B;
+                colA[(size_t)c * B + tid] = dvr[c];
+                colB[(size_t)c * B + tid] = dvr[c] * xh[c];
+            }
+        }
+    }
+    __syncthreads();
+    for (int c = warp; c <= C; c += nwarp) {
+        if (c == C) {
+            const double t = head_col_sum(lrow, B);
+            if (lane == 0) *loss_out = (float)(t / B);
+        } else {
+            const double t1 = head_col_sum(colA + (size_t)c * B, B), t2 = head_col_sum(colB + (size_t)c * B, B);
+            if (lane == 0) { s_db[c] = (float)t1; s_dg[c] = (float)t2; dbeta[c] = (float)t1; dgamma[c] = (float)t2; }
+        }
+    }
+    __syncthreads();
+    if (row) {
+        const float invB = 1.f / (float)B;
+        for (int c = 0; c < Cp; ++c) {
+            float d = 0.f;
+            if (c < C) {
+                d = s_g[c] * s_invstd[c] * (dvr[c] - s_db[c] * invB - xh[c] * s_dg[c] * invB);
+                g[(size_t)tid * C + c] = d;
+            }
+            if (gp) gp[(size_t)tid * Cp + c] = __float2bfloat16_rn(d);
+        }
+    }
+}
+
 static inline int grid_cap(int64_t items, int device, int waves = 8) {
     int64_t blocks = (items + 255) / 256, cap = (int64_t)nn_num_sms(device) * waves;
     if (blocks > cap) blocks = cap;
@@ -537,6 +643,18 @@ extern "C" int nn_head_fwd_bwd(const float* logits, const int64_t* labels, int B
     NN_SET_DEVICE(device);
     int threads = B >= 1024 ? 1024 : ((B + 31) / 32) * 32;
     if (threads < 32) threads = 32;
+    const size_t hsm = ((size_t)2 * C * B + B) * sizeof(float);
+    if (B <= 1024 && hsm <= 160 * 1024) {        // one thread per row, warp-per-channel reductions
+        static bool attr_set = false;
+        if (!attr_set) {
+            NN_CUDA_OK(cudaFuncSetAttribute(k_head_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attr_set = true;
+        }
+        if (threads < 32 * (C + 1) && 32 * (C + 1) <= 1024) threads = 32 * (C + 1);      // a warp per channel + the loss
+        k_head_rows<<<1, threads, hsm, (cudaStream_t)stream>>>(logits, labels, B, C, gamma, beta, running_mean, running_var,
+                                                              momentum, eps, loss_out, out, g, (__nv_bfloat16*)g_packed, Cp,
+                                                              dgamma, dbeta);
+    } else
     k_head<<<1, threads, 0, (cudaStream_t)stream>>>(logits, labels, B, C, gamma, beta, running_mean, running_var, momentum,
                                                     eps, loss_out, out, g, (__nv_bfloat16*)g_packed, Cp, dgamma, dbeta);
     NN_LAUNCH_OK();

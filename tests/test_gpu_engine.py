@@ -114,11 +114,12 @@ def test_stage_fwd_bwd_vs_torch(dev, shape, pool):
     assert (packed - ref).abs().max().item() <= 4e-3 * ref.abs().max().item() + 1e-6       # bf16 rounding of the pack
 
 
-def test_head_vs_torch(dev):
+@pytest.mark.parametrize("B", [200, 512, 37, 1500])      # 1500 > 1024 rows: the strided single-block kernel
+def test_head_vs_torch(dev, B):
     from noisynet_b200 import _lib
     lib = _lib.load()
     g = torch.Generator().manual_seed(3)
-    B, Cc = 200, 10
+    Cc = 10
     z = torch.randn(B, Cc, generator=g) * 2
     lab = torch.randint(0, Cc, (B,), generator=g)
     gamma, beta = torch.rand(Cc, generator=g) + 0.5, torch.randn(Cc, generator=g) * 0.1
