@@ -479,15 +479,16 @@ __device__ __forceinline__ uint64_t umma_desc_none(uint32_t smem_addr, uint32_t 
     return d;
 }
 
-// a tile is skipped when none of its 128 positions can be a real output (whole rows oh >= OH of one image)
+// a tile is skipped when none of its 128 positions can be a real output (whole rows oh >= OH of one image).
+// 32-bit arithmetic: the host rejects inputs with 2^31 pixels or more.
 __device__ __forceinline__ bool shift_tile_live(const ShiftP& p, int t) {
-    const long long v0 = (long long)t * UM_BLOCK_M;
-    long long v1 = v0 + UM_BLOCK_M - 1;
-    if (v1 >= p.total_pixels) v1 = p.total_pixels - 1;
-    const int hw = p.H * p.W;
-    const long long b0 = v0 / hw, b1 = v1 / hw;
+    const unsigned v0 = (unsigned)t * UM_BLOCK_M, total = (unsigned)p.total_pixels;
+    unsigned v1 = v0 + UM_BLOCK_M - 1;
+    if (v1 >= total) v1 = total - 1;
+    const unsigned hw = (unsigned)(p.H * p.W);
+    const unsigned b0 = v0 / hw, b1 = v1 / hw;
     if (b0 != b1) return true;
-    return (int)((v0 - b0 * hw) / p.W) < p.OH;
+    return (int)((v0 - b0 * hw) / (unsigned)p.W) < p.OH;
 }
 
 // MODE: 0 plain, 1 noisy (Philox z), 2 noisy with injected z (parity hook); SH_EPI_WARPS: epilogue warps, a
@@ -606,11 +607,11 @@ k_conv_shift(const ShiftP p) {
             if (*abort_g) break;
             tc_fence_after();
             if (p.dbg && i < 32 && warp == 2 && lane == 0) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 2] = clock64();
-            const long long v = (long long)t * UM_BLOCK_M + q * 32 + lane;
-            const int b = (int)(v / hw);
-            const int rem = (int)(v - (long long)b * hw);
-            const int ih = rem / p.W, iw = rem - ih * p.W;
-            const bool row_ok = v < p.total_pixels && ih < p.OH && iw < p.OW;
+            const unsigned v = (unsigned)t * UM_BLOCK_M + q * 32 + lane;
+            const int b = (int)(v / (unsigned)hw);
+            const int rem = (int)(v - (unsigned)b * (unsigned)hw);
+            const int ih = (int)((unsigned)rem / (unsigned)p.W), iw = rem - ih * p.W;
+            const bool row_ok = v < (unsigned)p.total_pixels && ih < p.OH && iw < p.OW;
             const int pix = ih * p.OW + iw;
             const uint64_t grp_row = (uint64_t)((long long)b * ohw + pix) * ngrp;
             const size_t out_row = (size_t)b * p.Cout * ohw + pix;
@@ -1293,6 +1294,7 @@ int g_shift_enable = getenv("NN_SHIFT_OFF") ? 0 : 1;
 static bool make_shift_plan(const nn_conv_geom& g, bool noisy, ShiftPlan* out) {
     if (!g_shift_enable) return false;
     if (g.Cin > 8 || g.stride != 1 || g.pad != 0 || g.KH > g.H || g.KW > g.W || g.W >= 4096) return false;
+    if ((int64_t)g.B * g.H * g.W >= (int64_t)1 << 31) return false;
     ShiftPlan sp;
     sp.n_t = pad_to(g.Cout, 8);
     sp.main_col = 0;
