@@ -168,6 +168,47 @@ k_bn_act_pack(const BnActP p) {
     }
 }
 
+// Hot-path variant of k_bn_act_pack (training: k-bit quantisation, stochastic rounding from Philox, no injected draws,
+// no fp32 copy): same thread mapping and arithmetic, but the run-time option checks are compiled out and the index
+// arithmetic is 32-bit.  Registers are capped for 6 blocks/SM: the kernel is latency-bound, occupancy matters more
+// than instruction count (variants that kept parameters in registers were slower).
+__global__ void __launch_bounds__(256, 6)
+k_bn_act_pack_lean(const BnActP p) {
+    const NnRng rs = nn_rng_load(p.rng);
+    const unsigned chunks = (unsigned)(p.Cp >> 3), HW = (unsigned)p.HW, C = (unsigned)p.C;
+    const unsigned npix = (unsigned)p.B * HW, total = npix * chunks;
+    const float act_hi = p.act_max > 0.f ? p.act_max : __int_as_float(0x7f800000);
+    const float two_s = __fmul_rn(2.0f, p.stoch), q_scale = p.q_scale, q_max = p.q_max, stoch = p.stoch;
+    float vmax = 0.f;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned pixel = i / chunks, chunk = i - pixel * chunks;
+        const unsigned b = pixel / HW, r = pixel - b * HW;
+        const unsigned c0 = chunk * 8;
+        const float* src = p.x + (b * C + c0) * HW + r;           // element index < 2^31 (host check)
+        const uint4 r0 = nn_philox(rs, (uint64_t)i * 2), r1 = nn_philox(rs, (uint64_t)i * 2 + 1);
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        __align__(16) __nv_bfloat16 out[8];
+#pragma unroll
+        for (unsigned j = 0; j < 8; ++j) {
+            float code = 0.f;
+            const unsigned c = c0 + j;
+            if (c < C) {
+                float v = (__ldg(src + j * HW) - __ldg(p.mean + c)) * __ldg(p.invstd + c) * __ldg(p.gamma + c) + __ldg(p.beta + c);
+                v = fminf(fmaxf(v, 0.f), act_hi);                                   // ReLU, clamp(max=act_max)
+                const float u = __fadd_rn(__fmul_rn(nn_u01(rr[j]), two_s), -stoch);    // == nn_usym(rr[j], stoch)
+                code = quant_code(v, q_scale, q_max, u);
+                vmax = fmaxf(vmax, __fmul_rn(code, q_scale));
+            }
+            out[j] = __float2bfloat16_rn(code);
+        }
+        *reinterpret_cast<uint4*>(p.xp + ((size_t)pixel * p.Cp + c0)) = *reinterpret_cast<const uint4*>(out);
+    }
+    if (p.xmax_out) {
+        vmax = nn_warp_max(vmax);
+        if ((threadIdx.x & 31) == 0 && vmax > 0.f) nn_atomic_max_float(p.xmax_out, vmax);
+    }
+}
+
 // ------------------------------------------------------------------ B1: masks + per-channel sums of dv, dv*xhat
 struct BnBwdP {
     const float *g, *x, *mean, *invstd, *gamma, *beta;
@@ -582,7 +623,11 @@ extern "C" int nn_stage_fwd(const nn_stage_args* a, int device, void* stream) {
     double scale = a->q_bits > 0 ? a->q_hi / qmax : 1.0;
     if (scale < 1e-6) scale = 1e-6;
     p.q_scale = (float)scale; p.q_max = (float)qmax; p.stoch = a->stochastic; p.rng = a->rng;
-    k_bn_act_pack<<<grid_cap((int64_t)a->B * HW * (a->Cp / 8), device), 256, 0, st>>>(p);
+    const int64_t items = (int64_t)a->B * HW * (a->Cp / 8);
+    const bool lean = ST_CHUNK_FAST && p.quant && p.stoch > 0.f && !p.u_inject && !p.act &&
+                      (int64_t)a->B * a->C * HW < ((int64_t)1 << 31) && items < ((int64_t)1 << 31);
+    if (lean) k_bn_act_pack_lean<<<grid_cap(items, device), 256, 0, st>>>(p);
+    else k_bn_act_pack<<<grid_cap(items, device), 256, 0, st>>>(p);
     NN_LAUNCH_OK();
     return 0;
 }
