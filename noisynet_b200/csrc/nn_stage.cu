@@ -327,6 +327,52 @@ k_bn_bwd_apply(const BnBwdApplyP p) {
     }
 }
 
+// Hot-path variant of k_bn_bwd_apply: same thread mapping and arithmetic; pooling and the output layout are
+// compile-time, no fp32 copy, 32-bit indices, registers capped for occupancy (see k_bn_act_pack_lean).
+template <bool POOL, bool PLANES>
+__global__ void __launch_bounds__(256, 5)
+k_bn_bwd_apply_lean(const BnBwdApplyP p) {
+    const unsigned chunks = (unsigned)(p.Cp >> 3), C = (unsigned)p.C;
+    const unsigned PH = POOL ? p.OH >> 1 : p.OH, PW = POOL ? p.OW >> 1 : p.OW, PHW = PH * PW;
+    const unsigned npp = (unsigned)p.B * PHW, total = npp * chunks;
+    const float inv_count = p.inv_count;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const bool chunk_fast = ST_CHUNK_FAST && !PLANES;
+        const unsigned pp = chunk_fast ? i / chunks : i % npp;
+        const unsigned chunk = chunk_fast ? i - pp * chunks : i / npp;
+        const unsigned b = pp / PHW, r = pp - b * PHW;
+        const unsigned ph = r / PW, pw = r - ph * PW;
+        const unsigned c0 = chunk * 8;
+        const unsigned o0 = (b * C + c0) * PHW + r;                    // element index < 2^31 (host check)
+        float d[8];
+        int pos[8];
+#pragma unroll
+        for (unsigned j = 0; j < 8; ++j) {
+            const unsigned c = c0 + j;
+            d[j] = 0.f; pos[j] = -1;
+            if (c < C) {
+                const unsigned o = o0 + j * PHW;
+                float xhat;
+                const float invstd = __ldg(p.invstd + c), gamma = __ldg(p.gamma + c);
+                const float dv = stage_dv(__ldg(p.g + o), __ldg(p.x + o), __ldg(p.mean + c), invstd, gamma,
+                                          __ldg(p.beta + c), p.act_max, p.q_hi, xhat);
+                d[j] = gamma * invstd * (dv - __ldg(p.dbeta + c) * inv_count - xhat * __ldg(p.dgamma + c) * inv_count);
+                pos[j] = POOL ? (int)__ldg(p.amax + o) : 0;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < (POOL ? 4 : 1); ++q) {
+            const unsigned oh = POOL ? 2 * ph + (q >> 1) : ph, ow = POOL ? 2 * pw + (q & 1) : pw;
+            __align__(16) __nv_bfloat16 out[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) out[j] = __float2bfloat16_rn(pos[j] == q ? d[j] : 0.f);
+            const size_t off = PLANES ? ((size_t)chunk * p.plane_stride + ((size_t)b * p.vH + oh) * p.vW + ow) * 8
+                                      : (((size_t)b * p.OH + oh) * p.OW + ow) * p.Cp + c0;
+            *reinterpret_cast<uint4*>(p.gyp + off) = *reinterpret_cast<const uint4*>(out);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ input quantize + pack (noisynet.py:390-393)
 __global__ void __launch_bounds__(256)
 k_quant_pack_input(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, float* __restrict__ act, int B, int C, int HW,
@@ -660,7 +706,14 @@ extern "C" int nn_stage_bwd(const nn_stage_bwd_args* a, int device, void* stream
         const long long total = (long long)a->B * a->virt_H * a->virt_W;
         p.plane_stride = (total + 127) / 128 * 128;
     }
-    k_bn_bwd_apply<<<grid_cap((int64_t)a->B * PH * PW * (a->Cp / 8), device), 256, 0, st>>>(p);
+    const int64_t items = (int64_t)a->B * PH * PW * (a->Cp / 8);
+    const int agrid = grid_cap(items, device);
+    const bool lean = !p.gy_f32 && (int64_t)a->B * a->C * PH * PW < ((int64_t)1 << 31) && items < ((int64_t)1 << 31);
+    if (!lean) k_bn_bwd_apply<<<agrid, 256, 0, st>>>(p);
+    else if (a->pool && p.planes) k_bn_bwd_apply_lean<true, true><<<agrid, 256, 0, st>>>(p);
+    else if (a->pool) k_bn_bwd_apply_lean<true, false><<<agrid, 256, 0, st>>>(p);
+    else if (p.planes) k_bn_bwd_apply_lean<false, true><<<agrid, 256, 0, st>>>(p);
+    else k_bn_bwd_apply_lean<false, false><<<agrid, 256, 0, st>>>(p);
     NN_LAUNCH_OK();
     return 0;
 }
