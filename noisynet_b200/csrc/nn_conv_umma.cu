@@ -19,6 +19,7 @@
 // * Every mbarrier wait is bounded (clock64 watchdog): a protocol bug sets an error flag instead of
 //   hanging the GPU.
 #include <cuda_bf16.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "nn_common.cuh"
@@ -71,6 +72,25 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+// multicast variants (thread-block cluster of 2): the bulk copy lands at the same CTA-relative offset in every CTA
+// of the mask and completes bytes on the mbarrier at the same offset there; the commit arrives on every CTA's barrier
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -140,6 +160,8 @@ struct UmmaP {
     float mask_lo, mask_hi;
     int* err_flag;
     long long* dbg;                // optional per-CTA phase timestamps (clock64): [cta][8]
+    int cluster;                   // 1, or 2: pairs of m-tiles share every weight k-block (each CTA loads half, multicast)
+    int rows_tile;                 // valid rows per m-tile (<= 128): chosen so that the CTAs fill whole waves
 };
 
 // EPI selects the epilogue at compile time: 0 = generic (every option), 1 = lean noisy (main + sigma, Philox z,
@@ -168,7 +190,7 @@ k_conv_umma(const UmmaP p) {
     volatile uint32_t* abort_g = reinterpret_cast<volatile uint32_t*>(gen0 + (abort_slot - base));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * UM_BLOCK_M;
+    const int m0 = blockIdx.x * p.rows_tile;
     const int tile_n = blockIdx.y;
     long long* dbg = p.dbg ? p.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
     if (dbg && tid == 0) dbg[0] = clock64();
@@ -176,7 +198,7 @@ k_conv_umma(const UmmaP p) {
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(full_bar + 8 * s, 128 + 1);     // 128 cp.async arrivals (noinc) + 1 expect_tx arrival
-            mbar_init(empty_bar + 8 * s, 1);          // tcgen05.commit
+            mbar_init(empty_bar + 8 * s, p.cluster);  // tcgen05.commit of every CTA that reads (and refills) the stage
         }
         mbar_init(tfull_bar, 1);
         *abort_g = 0;
@@ -186,6 +208,7 @@ k_conv_umma(const UmmaP p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (p.cluster > 1) cluster_sync_all();          // the peer's barriers exist before anything is multicast to them
     const uint32_t tmem_base = *tmem_slot_g;
     if (dbg && tid == 0) dbg[1] = clock64();
 
@@ -202,7 +225,7 @@ k_conv_umma(const UmmaP p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int m = m0 + (tid >> 3) + 16 * i;
-                if (m < p.M) {
+                if (m < p.M && (tid >> 3) + 16 * i < p.rows_tile) {
                     const int b = m / ohw; const int r = m - b * ohw; const int oh = r / p.OW; const int ow = r - oh * p.OW;
                     rih[i] = oh * p.stride - p.pad; riw[i] = ow * p.stride - p.pad;
                     rbase[i] = (b * p.H + rih[i]) * p.W + riw[i];
@@ -248,7 +271,8 @@ k_conv_umma(const UmmaP p) {
 #pragma unroll
                 for (int k = 0; k < UM_BLOCK_K / 16; ++k)
                     umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-                umma_commit(empty_bar + 8 * s);           // frees the smem stage when these MMAs retire
+                if (p.cluster > 1) umma_commit_mc(empty_bar + 8 * s, 3);
+                else umma_commit(empty_bar + 8 * s);       // frees the smem stage when these MMAs retire
             }
             umma_commit(tfull_bar);                        // accumulators complete
             if (dbg) dbg[2] = clock64();
@@ -263,6 +287,11 @@ k_conv_umma(const UmmaP p) {
                 if (!mbar_wait(empty_bar + 8 * s, ((kb / S) & 1) ^ 1)) { *abort_g = 3; break; }
                 if (*abort_g) break;
                 mbar_arrive_expect_tx(full_bar + 8 * s, b_stage);
+                if (p.cluster > 1) {      // this CTA fetches its half of the k-block for both CTAs of the pair
+                    const uint32_t half = b_stage >> 1, off = cluster_ctarank() * half;
+                    bulk_g2s_mc(b_base + (uint32_t)s * b_stage + off,
+                                reinterpret_cast<const uint8_t*>(wt + (size_t)kb * p.n_mma * 64) + off, half, full_bar + 8 * s, 3);
+                } else
                 bulk_g2s(b_base + (uint32_t)s * b_stage, wt + (size_t)kb * p.n_mma * 64, b_stage, full_bar + 8 * s);
             }
         }
@@ -279,7 +308,7 @@ k_conv_umma(const UmmaP p) {
         const int q = warp & 3, half = warp >> 2;
         const int row = q * 32 + lane;
         const int m = m0 + row;
-        const bool row_ok = m < p.M;
+        const bool row_ok = m < p.M && row < p.rows_tile;
         const int ohw = p.OH * p.OW;
         int b = 0, pix = 0;
         if (row_ok) { b = m / ohw; pix = m - b * ohw; }
@@ -407,6 +436,7 @@ k_conv_umma(const UmmaP p) {
     __syncthreads();
     if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
     if (dbg && tid == 128) { dbg[5] = clock64(); unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); dbg[7] = smid; }
+    if (p.cluster > 1) cluster_sync_all();          // no CTA leaves while its peer may still signal or fill its shared memory
 }
 
 
@@ -1338,8 +1368,39 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st) {
     else if (!extras && p.main_col >= 0 && p.noise_mode == NN_NOISE_NONE && p.y) epi = 2;
     static const bool force_generic = getenv("NN_UMMA_GENERIC_EPI") != nullptr;
     if (force_generic) epi = 0;
-    dim3 grid((p.M + UM_BLOCK_M - 1) / UM_BLOCK_M, pl.n_tiles);
     UmmaP pd = p;
+    // wave shaping: with T = ceil(M/128) tiles and S resident CTA slots, ceil(T/S) rounds run anyway; shrinking the
+    // VALID rows per tile so that the CTAs fill those rounds exactly shortens every CTA (gather and epilogue scale with
+    // the valid rows; the tensor pipe has slack) instead of leaving the last round mostly empty
+    pd.rows_tile = UM_BLOCK_M;
+    // (measured round 1: conv2 forward 70 -> 78 us with 88-row tiles -- a CTA's time is dominated by the weight stream and
+    // the MMAs, which do not shrink with the valid rows; off by default, kept as a knob)
+    static const bool shape = getenv("NN_UMMA_WAVE_SHAPING") != nullptr;
+    if (shape) {
+        // resident CTAs per SM: shared memory (227 KB, 1 KB reserved per CTA), TMEM columns, and the register cap
+        // implied by the kernel's __launch_bounds__ (EPI 2: 3 blocks, else 2)
+        int per_sm = (int)((227 * 1024) / (pl.smem_bytes + 1024));
+        const int by_tmem = 512 / pl.tmem_cols, by_regs = epi == 2 ? 3 : 2;
+        if (per_sm > by_regs) per_sm = by_regs;
+        {
+            if (per_sm > by_tmem) per_sm = by_tmem;
+            if (per_sm < 1) per_sm = 1;
+            int dev = 0;
+            cudaGetDevice(&dev);
+            const long long slots = (long long)per_sm * nn_num_sms(dev) / pl.n_tiles;
+            const long long tiles = (p.M + UM_BLOCK_M - 1) / UM_BLOCK_M;
+            if (slots > 0 && tiles > slots) {
+                const long long rounds = (tiles + slots - 1) / slots;
+                long long rows = (p.M + rounds * slots - 1) / (rounds * slots);
+                rows = (rows + 7) / 8 * 8;
+                if (rows < UM_BLOCK_M && rows >= 64) pd.rows_tile = (int)rows;
+            }
+        }
+    }
+    dim3 grid((p.M + pd.rows_tile - 1) / pd.rows_tile, pl.n_tiles);
+    static const bool verbose = getenv("NN_UMMA_VERBOSE") != nullptr;
+    if (verbose) fprintf(stderr, "[umma] M=%d n_tiles=%d epi=%d smem=%zu tmem=%d stages=%d rows_tile=%d grid=%u\n", p.M, pl.n_tiles, epi,
+                         pl.smem_bytes, pl.tmem_cols, pl.stages, pd.rows_tile, grid.x);
     static const bool want_dbg = getenv("NN_UMMA_DEBUG") != nullptr;
     if (want_dbg) {
         const size_t ctas = (size_t)grid.x * grid.y;
@@ -1356,9 +1417,22 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st) {
         if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
         cudaEventRecord(g_ev0, st);
     }
-    if (epi == 1) k_conv_umma<1><<<grid, UM_THREADS, pl.smem_bytes, st>>>(pd);
-    else if (epi == 2) k_conv_umma<2><<<grid, UM_THREADS, pl.smem_bytes, st>>>(pd);
-    else k_conv_umma<0><<<grid, UM_THREADS, pl.smem_bytes, st>>>(pd);
+    // pairs of m-tiles as a 2-CTA cluster: every weight k-block is fetched once per pair (each CTA loads half and
+    // multicasts it) -- the tiled kernels are bound by operand ingest from L2, and the weights are the larger share
+    // (measured round 1: correct, but 1-3 % SLOWER on every layer -- weight ingest is not what bounds these kernels; kept as a knob)
+    static const int env_cluster = getenv("NN_UMMA_CLUSTER") ? atoi(getenv("NN_UMMA_CLUSTER")) : 1;
+    pd.cluster = (env_cluster == 2 && grid.x >= 2 && !want_dbg) ? 2 : 1;
+    if (pd.cluster == 2) grid.x = (grid.x + 1) & ~1u;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = pl.smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pd.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (epi == 1) NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<1>, pd));
+    else if (epi == 2) NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<2>, pd));
+    else NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<0>, pd));
     if (g_time_main) cudaEventRecord(g_ev1, st);
     NN_LAUNCH_OK();
     return 0;
