@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NN_ABI_VERSION 9
+#define NN_ABI_VERSION 10
 
 /* ---- common ---------------------------------------------------------------------- */
 
@@ -240,6 +240,10 @@ typedef struct nn_wprep_job {
     int32_t q_bits; double q_hi; float stochastic; const float* u_inject; nn_rng rng;
     void* packed_out;        /* nn_weight_pack_bytes(job) bytes                                       */
     int32_t layout;          /* NN_PACK_* (mode 0 only; see nn_conv_pack_layout)                       */
+    void* codes;             /* optional scratch, Cout*Cin*KHW bytes: the quantizer runs ONCE per parameter into it
+                                (one Philox call per 4 parameters) and every job naming the same scratch -- the
+                                forward and dgrad images of a layer -- packs from the codes; jobs sharing a scratch
+                                must share w_raw, q_bits, q_hi, stochastic, rng / u_inject.  q_bits <= 7.          */
 } nn_wprep_job;
 int64_t nn_weight_pack_bytes(const nn_wprep_job* job);
 int nn_prepare_weights(const nn_wprep_job* jobs, int count, int device, void* stream);

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libnoisynet_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 NOISE_NONE, NOISE_MERGED, NOISE_EXTERNAL = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
@@ -70,7 +70,7 @@ class WPrepJob(C.Structure):
     _fields_ = [("w_raw", C.c_void_p), ("Cout", C.c_int32), ("Cin", C.c_int32), ("KHW", C.c_int32),
                 ("m_rows", C.c_int32), ("mode", C.c_int32), ("noise_mode", C.c_int32), ("want_wsum", C.c_int32),
                 ("q_bits", C.c_int32), ("q_hi", C.c_double), ("stochastic", C.c_float), ("u_inject", C.c_void_p),
-                ("rng", Rng), ("packed_out", C.c_void_p), ("layout", C.c_int32)]
+                ("rng", Rng), ("packed_out", C.c_void_p), ("layout", C.c_int32), ("codes", C.c_void_p)]
 
 
 class StageArgs(C.Structure):

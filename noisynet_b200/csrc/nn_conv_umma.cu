@@ -745,9 +745,11 @@ struct PackWP {
     float q_hi, q_scale, q_max, q_stoch;
     const float* u_inject;
     nn_rng rng;
+    const int8_t* codes;           // optional: the quantizer's codes 2k - qmax, computed once per parameter (k_quant_codes)
 };
 
 __device__ __forceinline__ float pack_main_value(const PackWP& p, const NnRng& rs, int64_t idx) {
+    if (p.codes) return (float)p.codes[idx];
     if (p.q_bits > 0) {
         const float w = __ldg(p.w_raw + idx);
         float u = 0.f;
@@ -778,12 +780,28 @@ __device__ __forceinline__ void pack_w_job(const PackWP& p, int64_t start, int64
         if (shift) {
             r = (int)(i % p.n_mma); kb = (int)(i / p.n_mma); j = 0; tile = 0; kbase = kb * 8;
         } else {
-            j = (int)(i & 7);
-            int64_t t = i >> 3;
-            r = (int)(t % p.n_mma); t /= p.n_mma;
-            kb = (int)(t % p.num_kb);
-            tile = (int)(t / p.num_kb);
-            kbase = kb * 64 + j * 8;
+            // Thread -> 16-byte chunk, enumerated so that a warp READS contiguous parameters (the kernel was bound by
+            // 4-byte loads 100 B apart: one sector per lane): the parameter tensor is [n][c][tap] with tap fastest, so
+            // for KHW > 1 consecutive lanes take consecutive TAPS of one (row, 8-channel chunk) -- for each of the 8
+            // channels a warp then reads KHW contiguous floats; for a transposed 1x1 (linear dgrad) consecutive lanes
+            // take consecutive ROWS (= contiguous input features of one output unit).
+            const int cpr = p.num_kb * 8, rows_total = p.n_tiles * p.n_mma;      // chunks per row (incl. zero padding)
+            int R, qk;
+            if (p.KHW > 1) {
+                const int ch = p.Cp >> 3, real = p.KHW * ch;
+                const int q = (int)(i % cpr);
+                R = (int)(i / cpr);
+                qk = q < real ? (q % p.KHW) * ch + q / p.KHW : q;
+            } else if (p.mode == 1) {
+                R = (int)(i % rows_total);
+                qk = (int)(i / rows_total);
+            } else {
+                qk = (int)(i % cpr);
+                R = (int)(i / cpr);
+            }
+            tile = R / p.n_mma; r = R - tile * p.n_mma;
+            kb = qk >> 3; j = qk & 7;
+            kbase = qk * 8;
         }
         __align__(16) __nv_bfloat16 v[8];
         int kind = -1, rr = 0;                       // 0 main, 1 sigma, 2 wsum
@@ -792,10 +810,10 @@ __device__ __forceinline__ void pack_w_job(const PackWP& p, int64_t start, int64
         else if (p.wsum_col >= 0 && r == p.wsum_col) { kind = 2; }
         const int nrows = p.mode == 0 ? p.Cout : p.Cin;   // number of real "output" rows
         const int kdim = p.mode == 0 ? p.Cin : p.Cout;    // real channels inside a tap
+        const int tap = kbase / p.Cp, c_first = kbase - tap * p.Cp;     // Cp % 8 == 0: a chunk never straddles taps
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int k = kbase + e;
-            const int tap = k / p.Cp, c = k - tap * p.Cp;
+            const int c = c_first + e;
             float f = 0.f;
             if (tap < p.KHW && c < kdim && kind >= 0) {
                 if (kind == 2) {
@@ -835,6 +853,35 @@ k_pack_w(const PackWP p) {
 // all weight packs of a training step (forward x layers, dgrad x layers) in ONE launch: blockIdx.y = job
 constexpr int UM_MAX_PACK_JOBS = 8;
 struct PackJobs { PackWP j[UM_MAX_PACK_JOBS]; };
+
+// The weight quantizer once per parameter: 4 consecutive parameters per thread = ONE Philox call (the pack kernels
+// read every parameter from several operand images -- forward rows, dgrad rows -- and were bound by re-drawing Philox
+// per packed element: 21 M warp instructions per step).  codes[idx] = 2k - qmax, identical to pack_main_value.
+struct CodeJob { const float* w; int8_t* codes; int64_t n; float q_hi, q_scale, q_max, q_stoch; const float* u_inject; nn_rng rng; };
+struct CodeJobs { CodeJob j[UM_MAX_PACK_JOBS]; };
+
+__global__ void __launch_bounds__(256)
+k_quant_codes(const CodeJobs jobs) {
+    const CodeJob& c = jobs.j[blockIdx.y];
+    const NnRng rs = nn_rng_load(c.rng);
+    const int64_t groups = (c.n + 3) >> 2;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (c.q_stoch > 0.f && !c.u_inject) r = nn_philox(rs, (uint64_t)g);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t idx = g * 4 + e;
+            if (idx < c.n) {
+                float u = 0.f;
+                if (c.q_stoch > 0.f) u = c.u_inject ? __ldg(c.u_inject + idx) : nn_usym(rr[e], c.q_stoch);
+                float t = __fadd_rn(__fdiv_rn(__fadd_rn(__ldg(c.w + idx), c.q_hi), c.q_scale), u);
+                t = rintf(fminf(fmaxf(t, 0.f), c.q_max));
+                c.codes[idx] = (int8_t)(2.f * t - c.q_max);
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256)
 k_pack_w_batch(const PackJobs jobs) {
@@ -1732,6 +1779,32 @@ extern "C" int nn_prepare_weights(const nn_wprep_job* jobs, int count, int devic
         const int64_t total = jb.layout == NN_PACK_SHIFT ? (int64_t)pl.num_kb * pl.n_mma
                                                          : (int64_t)pl.n_tiles * pl.num_kb * pl.n_mma * 8;
         if (total > max_total) max_total = total;
+    }
+    {   // quantizer codes once per distinct (parameter, scratch) pair
+        CodeJobs cj;
+        memset(&cj, 0, sizeof(cj));
+        int nc = 0;
+        int64_t max_groups = 0;
+        for (int i = 0; i < count; ++i) {
+            const nn_wprep_job& jb = jobs[i];
+            if (!jb.codes || jb.q_bits <= 0) continue;
+            if (jb.q_bits > 7) return nn_fail("nn_prepare_weights: the code scratch serves q_bits <= 7%s", "");
+            pj.j[i].codes = (const int8_t*)jb.codes;
+            bool seen = false;
+            for (int k = 0; k < nc; ++k) seen = seen || cj.j[k].codes == (int8_t*)jb.codes;
+            if (seen) continue;
+            CodeJob& c = cj.j[nc++];
+            c.w = jb.w_raw; c.codes = (int8_t*)jb.codes; c.n = (int64_t)jb.Cout * jb.Cin * jb.KHW;
+            c.q_hi = pj.j[i].q_hi; c.q_scale = pj.j[i].q_scale; c.q_max = pj.j[i].q_max; c.q_stoch = pj.j[i].q_stoch;
+            c.u_inject = jb.u_inject; c.rng = jb.rng;
+            if ((c.n + 3) / 4 > max_groups) max_groups = (c.n + 3) / 4;
+        }
+        if (nc > 0) {
+            int gx = (int)((max_groups + 255) / 256);
+            if (gx > 4 * nn_num_sms(device)) gx = 4 * nn_num_sms(device);
+            k_quant_codes<<<dim3(gx, nc), 256, 0, (cudaStream_t)stream>>>(cj);
+            NN_LAUNCH_OK();
+        }
     }
     int gx = (int)((max_total + 255) / 256);
     if (gx > 4 * nn_num_sms(device)) gx = 4 * nn_num_sms(device);

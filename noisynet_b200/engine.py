@@ -91,6 +91,7 @@ class NoisyNetEngine:
             nbytes = int(self.lib.nn_conv_gy_planes_bytes(C.byref(self.geom[0])))
             self.gyp1 = torch.zeros(nbytes // 16, 8, dtype=torch.bfloat16, device=dev)
         self.wpack = []
+        self.wcodes = {}
         for j, (li, (co, ci, khw), mode, m_rows) in enumerate(specs):
             jb = self.jobs[j]
             jb.w_raw = W[li].data_ptr()
@@ -99,6 +100,9 @@ class NoisyNetEngine:
             jb.want_wsum = 0
             jb.layout = self.lib.nn_conv_pack_layout(C.byref(self.geom[li]), jb.noise_mode, PREC_BF16) if mode == 0 else 0
             jb.q_bits, jb.q_hi = int(a.q_w1), 1.0
+            if li not in self.wcodes:        # quantizer codes: one scratch per layer, shared by its forward and dgrad jobs
+                self.wcodes[li] = torch.zeros(W[li].numel() + 16, dtype=torch.int8, device=dev)
+            jb.codes = self.wcodes[li].data_ptr()
             buf = torch.zeros(int(self.lib.nn_weight_pack_bytes(C.byref(jb))) + 1024, dtype=torch.uint8, device=dev)
             jb.packed_out = (buf.data_ptr() + 1023) // 1024 * 1024
             self.wpack.append(buf)
