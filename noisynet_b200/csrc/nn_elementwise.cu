@@ -390,26 +390,28 @@ struct AdamWP {
     int count;
     float beta1, beta2, eps, grad_scale;
     const int64_t* step_dev;
+    const float* consts;                       // device: 1 - beta1^step, sqrt(1 - beta2^step) (written by k_step_inc)
+    int first_block[NN_ADAMW_MAX_TENSORS];     // first 1024-element slab of each tensor in the flat block list
 };
 
-__global__ void k_step_inc(int64_t* s) { *s += 1; }
+// step += 1 and the two bias-correction constants of the step, once (not per block): consts[0] = 1 - beta1^step,
+// consts[1] = sqrt(1 - beta2^step)
+__global__ void k_step_inc(int64_t* s, float beta1, float beta2, float* consts) {
+    *s += 1;
+    const double step = (double)(*s);
+    consts[0] = (float)(1.0 - pow((double)beta1, step));
+    consts[1] = (float)sqrt(1.0 - pow((double)beta2, step));
+}
 
+// blockIdx.x enumerates the 1024-element slabs of all tensors back to back (first_block[i] = first slab of tensor i)
 __global__ void __launch_bounds__(256)
 k_adamw(const AdamWP p) {
-    const nn_adamw_tensor t = p.t[blockIdx.y];
-    const int64_t base = (int64_t)blockIdx.x * blockDim.x * 4;
-    if (base >= t.n) return;
-    __shared__ float s_step_size, s_bc2_sqrt;
+    int ti = 0;
+    while (ti + 1 < p.count && (int)blockIdx.x >= p.first_block[ti + 1]) ++ti;
+    const nn_adamw_tensor t = p.t[ti];
+    const int64_t base = (int64_t)((int)blockIdx.x - p.first_block[ti]) * blockDim.x * 4;
     __shared__ float s_red[8];
-    if (threadIdx.x == 0) {
-        const double step = (double)(*p.step_dev);
-        const double bc1 = 1.0 - pow((double)p.beta1, step);
-        const double bc2 = 1.0 - pow((double)p.beta2, step);
-        s_step_size = (float)((double)t.lr / bc1);
-        s_bc2_sqrt = (float)sqrt(bc2);
-    }
-    __syncthreads();
-    const float step_size = s_step_size, bc2s = s_bc2_sqrt;
+    const float step_size = (float)((double)t.lr / (double)p.consts[0]), bc2s = p.consts[1];
     const float decay = 1.0f - t.lr * t.weight_decay;
     const float om1 = 1.0f - p.beta1, om2 = 1.0f - p.beta2;
     float amax = 0.f;
@@ -450,16 +452,21 @@ extern "C" int nn_adamw_step(const nn_adamw_tensor* tensors, int count, float be
     NN_SET_DEVICE(device);
     AdamWP p;
     p.count = count; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.grad_scale = grad_scale; p.step_dev = step_dev;
-    int64_t max_n = 0;
+    static float* consts[64] = {nullptr};
+    if (device < 0 || device >= 64) return nn_fail("nn_adamw_step: bad device%s", "");
+    if (!consts[device]) NN_CUDA_OK(cudaMalloc(&consts[device], 2 * sizeof(float)));
+    p.consts = consts[device];
+    int blocks = 0;
     for (int i = 0; i < count; ++i) {
         p.t[i] = tensors[i];
-        if (tensors[i].n > max_n) max_n = tensors[i].n;
+        p.first_block[i] = blocks;
+        blocks += (int)((tensors[i].n + 1023) / 1024);
         if (tensors[i].absmax_out) NN_CUDA_OK(cudaMemsetAsync(tensors[i].absmax_out, 0, sizeof(float), (cudaStream_t)stream));
     }
-    k_step_inc<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    k_step_inc<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, beta1, beta2, consts[device]);
     NN_LAUNCH_OK();
-    dim3 grid((unsigned)((max_n + 1023) / 1024), (unsigned)count);
-    k_adamw<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    if (blocks == 0) return 0;
+    k_adamw<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
     NN_LAUNCH_OK();
     return 0;
 }
