@@ -13,6 +13,7 @@ Parameters, BN buffers and quantizer ranges are those of a `NoisyNet` module (st
 Requires q_a > 0 and q_w > 0 (the 4-bit configuration); steady-state semantics (no i < 20 side statistics).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -113,6 +114,11 @@ class NoisyNetEngine:
             need = max(need, self.lib.nn_conv_workspace_bytes(C.byref(g), PREC_BF16),
                        self.lib.nn_conv_wgrad_workspace_bytes(C.byref(g), PREC_BF16, self.di))
         self.ws = torch.empty(int(need) + 4096, dtype=torch.uint8, device=dev)
+        # the weight gradients run on a side stream next to the dgrad -> stage-backward chain of the same layer (they
+        # only share read-only inputs): the small fc kernels and split reduces leave most SMs idle on their own
+        self.overlap_wgrad = os.environ.get("NN_ENGINE_OVERLAP_WGRAD", "1") != "0"
+        self.side = torch.cuda.Stream(device=dev) if self.overlap_wgrad else None
+        self.ws_side = torch.empty(int(need) + 4096, dtype=torch.uint8, device=dev) if self.overlap_wgrad else None
         for p in model.parameters():
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
@@ -162,13 +168,20 @@ class NoisyNetEngine:
         _lib.check(self.lib.nn_noisy_conv_fwd(C.byref(a), self.di, self._st()), "nn_noisy_conv_fwd")
 
     def _wgrad(self, idx, gyp, xp, a_cs, w_raw, gw, gy_layout=0):
+        if self.side is None:
+            return self._wgrad_on(self.ws, idx, gyp, xp, a_cs, w_raw, gw, gy_layout)
+        self.side.wait_stream(torch.cuda.current_stream(self.di))       # grad_output / activations of this layer are ready
+        with torch.cuda.stream(self.side):
+            self._wgrad_on(self.ws_side, idx, gyp, xp, a_cs, w_raw, gw, gy_layout)
+
+    def _wgrad_on(self, ws, idx, gyp, xp, a_cs, w_raw, gw, gy_layout=0):
         a = ConvWgradArgs()
         a.g = self.geom[idx]
         a.gy, a.x, a.gw = None, None, _p(gw)
         a.gy_packed, a.x_packed, a.gy_packed_layout = _p(gyp), _p(xp), gy_layout
         a.w_raw, a.w_lo, a.w_hi = _p(w_raw), -1.0, 1.0            # STE of the weight quantizer (hardware_model.py:323)
         a.precision, a.a_code_scale = PREC_BF16, a_cs
-        a.workspace, a.workspace_bytes = _p(self.ws), self.ws.numel()
+        a.workspace, a.workspace_bytes = _p(ws), ws.numel()
         _lib.check(self.lib.nn_noisy_conv_wgrad(C.byref(a), self.di, self._st()), "nn_noisy_conv_wgrad")
 
     def _dgrad(self, geom, gyp, layer, gx):
@@ -244,7 +257,15 @@ class NoisyNetEngine:
                     self.jobs[j].stochastic = stoch
                     self.jobs[j].u_inject = _p(uw)
                     self.jobs[j].rng = rng
-        _lib.check(lib.nn_prepare_weights(self.jobs, 7, di, st), "nn_prepare_weights")
+        if self.side is not None:
+            # conv1's image is needed at once; the other six (fc1 is 90 % of the bytes) are packed on the side stream
+            # while the input pack and the conv1 forward run, and joined before conv2
+            self.side.wait_stream(torch.cuda.current_stream(di))
+            with torch.cuda.stream(self.side):
+                _lib.check(lib.nn_prepare_weights(C.byref(self.jobs[1]), 6, di, self._st()), "nn_prepare_weights")
+            _lib.check(lib.nn_prepare_weights(self.jobs, 1, di, st), "nn_prepare_weights")
+        else:
+            _lib.check(lib.nn_prepare_weights(self.jobs, 7, di, st), "nn_prepare_weights")
         # ---- forward
         u = self._take("u")
         _lib.check(lib.nn_input_quant_pack(_p(x), _p(self.xp1), None, B, 3, 32 * 32, 8, int(a.q_a1), qh1, stoch, _p(u),
@@ -252,6 +273,8 @@ class NoisyNetEngine:
 
         self._fwd_gemm(0, self.xp1, s1, self.y1n, self.noise_modes[0], self._absmax(0, W[0]), self._take("z"))
         self._stage_fwd(self.y1n, C1, H1, 1, self.pool1, self.amax1, m.bn1, "bn1", a.q_a2, qh2, self.xp2, self.xmax2, self._take("u"))
+        if self.side is not None:
+            torch.cuda.current_stream(di).wait_stream(self.side)
         self._fwd_gemm(1, self.xp2, s2, self.y2n, self.noise_modes[1], self.xmax2, self._take("z"))
         self._stage_fwd(self.y2n, C2, H2, 1, self.pool2, self.amax2, m.bn2, "bn2", a.q_a3, qh3, self.xp3, None, self._take("u"))
         self._fwd_gemm(2, self.xp3, s3, self.l1n, self.noise_modes[2], self._absmax(2, W[2]), self._take("z"))
@@ -267,8 +290,12 @@ class NoisyNetEngine:
         self._dgrad(self.geom[3], self.gyp4, 3, self.gx4)
         self._stage_bwd(self.gx4, self.l1n, None, FC, 1, 0, m.bn3, "bn3", a.q_a4, qh4, self.gyp3)
         self._wgrad(2, self.gyp3, self.xp3, s3, W[2], W[2].grad)
-        if self.red is not None:
-            self.red.start_early()      # fc gradients (85 % of the payload) travel while the conv backward runs
+        if self.red is not None:        # fc gradients (85 % of the payload) travel while the conv backward runs
+            if self.side is not None:
+                with torch.cuda.stream(self.side):
+                    self.red.start_early()
+            else:
+                self.red.start_early()
         self._dgrad(self.geom_fc1_lin, self.gyp3, 2, self.gx3)
         self._stage_bwd(self.gx3, self.pool2, self.amax2, C2, H2, 1, m.bn2, "bn2", a.q_a3, qh3, self.gyp2)
         self._wgrad(1, self.gyp2, self.xp2, s2, W[1], W[1].grad)
@@ -277,6 +304,8 @@ class NoisyNetEngine:
                         planes_grid=(32, 32) if self.gy1_layout else None)
         self._wgrad(0, self.gyp1, self.xp1, s1, W[0], W[0].grad, self.gy1_layout)
         # ---- exchange + update
+        if self.side is not None:
+            torch.cuda.current_stream(di).wait_stream(self.side)
         if self.red is not None:
             self.red.all_reduce_sum_()
         if self.opt is not None:
