@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NN_ABI_VERSION 10
+#define NN_ABI_VERSION 11
 
 /* ---- common ---------------------------------------------------------------------- */
 
@@ -153,6 +153,10 @@ typedef struct nn_conv_fwd_args {
                                 noise_mode / stats choice); w_eff may then be NULL, w_code_scale must be
                                 the quantizer's s/2                                                   */
     int32_t w_packed_layout; /* NN_PACK_*: the layout `w_packed` was prepared in (nn_wprep_job.layout)      */
+    float* pooled_out;       /* optional, with argmax_out: fused MaxPool2d(2,2) (noisynet.py:419) of the (noisy)
+                                output, [B,Cout,OH/2,OW/2]; y / y_noisy are then NOT written.  Served where
+                                nn_conv_pool_fusable() says so (the shift kernel on a 32-wide input grid).          */
+    uint8_t* argmax_out;     /* window position 0..3 of the first maximum in row-major order (nn.MaxPool2d)      */
 } nn_conv_fwd_args;
 
 /* Packed-weight layouts.  NN_PACK_TILED: 128B-swizzled [n-tile][k-block] shared-memory images (every geometry).
@@ -163,6 +167,8 @@ typedef struct nn_conv_fwd_args {
 #define NN_PACK_TILED 0
 #define NN_PACK_SHIFT 1
 int nn_conv_pack_layout(const nn_conv_geom* g, int32_t noise_mode, int32_t precision);
+/* 1 if nn_noisy_conv_fwd can fuse the 2x2 max pool that follows the layer (pooled_out / argmax_out). */
+int nn_conv_pool_fusable(const nn_conv_geom* g, int32_t noise_mode, int32_t precision);
 /* Test hook: enable = 0/1 switches the shift-GEMM path off/on (< 0: query); returns the previous setting. */
 int nn_debug_shift_enable(int enable);
 

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libnoisynet_b200.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 NOISE_NONE, NOISE_MERGED, NOISE_EXTERNAL = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
@@ -39,7 +39,8 @@ class ConvFwdArgs(C.Structure):
                 ("precision", C.c_int32),
                 ("a_code_scale", C.c_float), ("w_code_scale", C.c_float),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("x_packed", C.c_void_p),
-                ("w_packed", C.c_void_p), ("w_packed_layout", C.c_int32)]
+                ("w_packed", C.c_void_p), ("w_packed_layout", C.c_int32),
+                ("pooled_out", C.c_void_p), ("argmax_out", C.c_void_p)]
 
 
 class ConvDgradArgs(C.Structure):
@@ -131,6 +132,7 @@ SIGNATURES = {
     "nn_debug_cta_timeline": (C.c_int, [C.c_void_p, C.c_int]),
     "nn_conv_pack_layout": (C.c_int, [C.POINTER(ConvGeom), C.c_int32, C.c_int32]),
     "nn_debug_shift_enable": (C.c_int, [C.c_int]),
+    "nn_conv_pool_fusable": (C.c_int, [C.POINTER(ConvGeom), C.c_int32, C.c_int32]),
     "nn_conv_wgrad_pack_layout": (C.c_int, [C.POINTER(ConvGeom), C.c_int32, C.c_int]),
     "nn_conv_gy_planes_bytes": (C.c_int64, [C.POINTER(ConvGeom)]),
     "nn_noisy_conv_fwd": (C.c_int, [C.POINTER(ConvFwdArgs), C.c_int, C.c_void_p]),

@@ -48,12 +48,14 @@ extern "C" int nn_noisy_conv_fwd(const nn_conv_fwd_args* a, int device, void* st
         return nn_fail("nn_noisy_conv_fwd: w_eff missing%s (noise-only mode needs noise_mode > 0 and y as input)", "");
     if (a->noise_mode < 0 || a->noise_mode > 2) return nn_fail("nn_noisy_conv_fwd: bad noise_mode%s", "");
     if (a->noise_mode != NN_NOISE_NONE) {
-        if ((!a->w_raw && !a->w_packed) || !a->y_noisy || !a->scale_dev)
+        if ((!a->w_raw && !a->w_packed) || (!a->y_noisy && !a->pooled_out) || !a->scale_dev)
             return nn_fail("nn_noisy_conv_fwd: noise needs w_raw, y_noisy and scale_dev%s", "");
         if (!(a->current > 0.f)) return nn_fail("nn_noisy_conv_fwd: current must be > 0%s", "");
-    } else if (!a->y) {
+    } else if (!a->y && !a->pooled_out) {
         return nn_fail("nn_noisy_conv_fwd: y missing%s", "");
     }
+    if (a->pooled_out && a->precision == NN_PREC_FP32)
+        return nn_fail("nn_noisy_conv_fwd: pooled_out is a tcgen05-path fusion%s (see nn_conv_pool_fusable)", "");
     NN_SET_DEVICE(device);
     if (a->precision == NN_PREC_FP32) return nn_simt_conv_fwd(a, device, (cudaStream_t)stream);
     if (a->precision == NN_PREC_TF32 || a->precision == NN_PREC_BF16) {

@@ -466,6 +466,8 @@ struct ShiftP {
     const __nv_bfloat16 *xp, *wp;
     float y_scale, s_scale;
     float *y, *y_noisy;
+    float* pooled;            // optional: fused MaxPool2d(2,2) of the (noisy) output [B,Cout,OH/2,OW/2]; then y / y_noisy are not written
+    uint8_t* pool_arg;        // window position 0..3 of the maximum (first maximum in row-major order, as nn.MaxPool2d)
     const float* z_inject;
     float current;
     const float* scale_dev;
@@ -536,6 +538,7 @@ k_conv_shift(const ShiftP p) {
     const uint32_t a_full = bar_base, a_empty = bar_base + 8u * SH_STAGES;
     const uint32_t acc_full = bar_base + 16u * SH_STAGES, acc_empty = acc_full + 16u, b_full = acc_empty + 16u;
     const uint32_t tmem_slot = b_full + 8u, abort_slot = tmem_slot + 4u, tab_slot = abort_slot + 4u;
+    const uint32_t pool_slot = (tab_slot + 4u * SH_MAX_PAIRS + 15u) & ~15u;      // pooling exchange: [warp pair][2][8][16] floats
     uint8_t* gen0 = smem_raw + (base - smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gen0 + (tmem_slot - base));
     volatile uint32_t* abort_g = reinterpret_cast<volatile uint32_t*>(gen0 + (abort_slot - base));
@@ -629,6 +632,7 @@ k_conv_shift(const ShiftP p) {
         if (NOISY) coef = nn_noise_coef(*p.scale_dev, p.current);
         if (MODE == 1) rs = nn_rng_load(p.rng);
         const float y_scale = p.y_scale, s_scale = p.s_scale;
+        int pool_buf = 0;
         int i = 0;
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
             if (!shift_tile_live(p, t)) continue;
@@ -648,6 +652,56 @@ k_conv_shift(const ShiftP p) {
             float* const out_main = (NOISY ? p.y_noisy : p.y) + out_row;
             float* const out_y = (NOISY && p.y) ? p.y + out_row : nullptr;
             const uint32_t t_lane = tmem_base + (uint32_t)(buf * SH_ACC_STRIDE) + ((uint32_t)(q * 32) << 16);
+            if (p.pooled) {
+                // Fused MaxPool2d(2,2) (host guarantees W == 32: a warp is one image row, a tile four rows): horizontal
+                // pairs by shuffle, vertical pairs between the two warps of a row pair (same jq, hence the same group
+                // sequence) through a double-buffered shared-memory slot and a 64-thread named barrier per group.
+                const int PW = p.OW >> 1, PHW = (p.OH >> 1) * PW;
+                const int pair = jq * 2 + (q >> 1);
+                float* xs = reinterpret_cast<float*>(gen0 + (pool_slot - base)) + pair * 256;
+                const bool top = (q & 1) == 0, left = (lane & 1) == 0;
+                const size_t pbase = (size_t)b * p.Cout * PHW + (size_t)(ih >> 1) * PW + (iw >> 1);
+                for (int g4 = (jq + i) % per_q; g4 < ngrp; g4 += per_q) {
+                    float am[4], as[4];
+                    if (NOISY) tmem_ld4x2(t_lane + (uint32_t)(p.main_col + g4 * 4), t_lane + (uint32_t)(p.sig_col + g4 * 4), am, as);
+                    else tmem_ld4(t_lane + (uint32_t)(p.main_col + g4 * 4), am);
+                    const int nb = g4 * 4;
+                    float z[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (MODE == 1) nn_normal4(rs, grp_row + (uint64_t)g4, z);
+                    float m[4];
+                    int a[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float v = am[j] * y_scale;
+                        if (NOISY) {
+                            const float zz = MODE == 2 ? ((row_ok && nb + j < p.Cout) ? __ldg(p.z_inject + out_row + (size_t)(nb + j) * ohw) : 0.f) : z[j];
+                            v = __fadd_rn(v, __fmul_rn(zz, nn_sigma(coef, as[j] * s_scale)));
+                        }
+                        const float o = __shfl_xor_sync(0xffffffffu, v, 1);
+                        m[j] = v; a[j] = 0;
+                        if (o > v) { m[j] = o; a[j] = 1; }           // meaningful on the left (even) lane of a pair
+                    }
+                    float* slot = xs + pool_buf * 128;
+                    if (!top && left) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { slot[j * 16 + (lane >> 1)] = m[j]; slot[64 + j * 16 + (lane >> 1)] = (float)a[j]; }
+                    }
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+                    if (top && left && row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (nb + j < p.Cout) {
+                                const float mb = slot[j * 16 + (lane >> 1)];
+                                if (mb > m[j]) { m[j] = mb; a[j] = 2 + (int)slot[64 + j * 16 + (lane >> 1)]; }
+                                const size_t o = pbase + (size_t)(nb + j) * PHW;
+                                p.pooled[o] = m[j];
+                                p.pool_arg[o] = (uint8_t)a[j];
+                            }
+                        }
+                    }
+                    pool_buf ^= 1;
+                }
+            } else
             // 4-channel groups (one Philox call each), dealt round-robin to the warps of this lane quarter; the deal
             // rotates with the tile so that an uneven group count (17 for 65 channels) averages out across tiles
             for (int g4 = (jq + i) % per_q; g4 < ngrp; g4 += per_q) {
@@ -1385,7 +1439,7 @@ static bool make_shift_plan(const nn_conv_geom& g, bool noisy, ShiftPlan* out) {
     sp.a_stage = pad_to(sp.a_pixels * 16, 128);
     sp.b_bytes = sp.n_chunks * sp.n_mma * 16;
     sp.n_tiles = (int)(((int64_t)g.B * g.H * g.W + UM_BLOCK_M - 1) / UM_BLOCK_M);
-    sp.smem_bytes = 128 + (size_t)sp.b_bytes + (size_t)SH_STAGES * sp.a_stage + 16 * SH_STAGES + 64 + 4 * SH_MAX_PAIRS;
+    sp.smem_bytes = 128 + (size_t)sp.b_bytes + (size_t)SH_STAGES * sp.a_stage + 16 * SH_STAGES + 64 + 4 * SH_MAX_PAIRS + 16 + 12 * 1024;
     if (sp.n_pairs > SH_MAX_PAIRS) return false;
     sp.wp_bytes = (size_t)sp.b_bytes;
     if (sp.smem_bytes > 200 * 1024) return false;
@@ -1550,6 +1604,8 @@ extern "C" int nn_debug_error_flag(int device, int reset) {
     return v;
 }
 
+extern "C" int nn_conv_pool_fusable(const nn_conv_geom* g, int32_t noise_mode, int32_t precision);
+
 static int shift_conv_fwd(const nn_conv_fwd_args* a, const ShiftPlan& sp, int device, cudaStream_t st) {
     const nn_conv_geom& g = a->g;
     int OH, OW;
@@ -1594,6 +1650,7 @@ static int shift_conv_fwd(const nn_conv_fwd_args* a, const ShiftPlan& sp, int de
     const float wsc = a->w_code_scale > 0.f ? a->w_code_scale : 1.f;
     p.y_scale = as * wsc; p.s_scale = as;
     p.y = a->y; p.y_noisy = a->y_noisy; p.z_inject = a->z_inject;
+    p.pooled = a->pooled_out; p.pool_arg = a->argmax_out;
     p.current = a->current; p.scale_dev = a->scale_dev; p.rng = a->rng;
     p.err_flag = nn_umma_err_flag(device);
     int grid = nn_num_sms(device);
@@ -1644,6 +1701,13 @@ extern "C" int nn_conv_pack_layout(const nn_conv_geom* g, int32_t noise_mode, in
     if (!g || precision != NN_PREC_BF16) return NN_PACK_TILED;
     return make_shift_plan(*g, noise_mode != NN_NOISE_NONE, nullptr) ? NN_PACK_SHIFT : NN_PACK_TILED;
 }
+extern "C" int nn_conv_pool_fusable(const nn_conv_geom* g, int32_t noise_mode, int32_t precision) {
+    if (!g || precision != NN_PREC_BF16) return 0;
+    if (!make_shift_plan(*g, noise_mode != NN_NOISE_NONE, nullptr)) return 0;
+    int OH, OW;
+    nn_out_hw(*g, OH, OW);
+    return g->W == 32 && g->H % 4 == 0 && OH % 2 == 0 && OW % 2 == 0;
+}
 extern "C" int nn_debug_shift_enable(int enable) {
     const int prev = g_shift_enable;
     if (enable >= 0) g_shift_enable = enable;
@@ -1663,6 +1727,12 @@ int nn_umma_conv_fwd(const nn_conv_fwd_args* a, int device, cudaStream_t st) {
         const bool extras = a->bias || a->z_export || a->sigma_export || a->stats;
         ShiftPlan sp;
         const bool can = has_main && !extras && make_shift_plan(g, noise, &sp);
+        if (a->pooled_out) {
+            if (!can || !a->argmax_out || !nn_conv_pool_fusable(&g, a->noise_mode, a->precision))
+                return nn_fail("nn_noisy_conv_fwd: pooled_out is not served for this call%s (see nn_conv_pool_fusable)", "");
+            if (a->w_packed && a->w_packed_layout != NN_PACK_SHIFT)
+                return nn_fail("nn_noisy_conv_fwd: pooled_out needs NN_PACK_SHIFT weights%s", "");
+        }
         const int layout = a->w_packed ? a->w_packed_layout : (can ? NN_PACK_SHIFT : NN_PACK_TILED);
         if (layout == NN_PACK_SHIFT) {
             if (!can) return nn_fail("nn_noisy_conv_fwd: w_packed_layout = NN_PACK_SHIFT is not served for this call%s", "");

@@ -87,6 +87,11 @@ class NoisyNetEngine:
         self.geom_fc1_lin = ConvGeom(B, C2 * P2 * P2, 1, 1, FC, 1, 1, 1, 0)
         # conv1 weight gradient through the in-place (shift) kernel: its grad_output lives in the planes layout on the
         # 32x32 input grid, zeroed once here -- nn_stage_bwd only ever writes the 28x28 output positions
+        # MaxPool2d fused into the conv1 epilogue (pooled_out): exact, saves the 104 MB y1n round trip, but measured
+        # SLOWER overall at batch 512 (conv1 forward 86 -> 123 us: the per-group pair barrier puts the two warps of a row
+        # pair in lock-step; pool+stats 36 -> 18 us) -- off unless NN_ENGINE_FUSE_POOL=1
+        self.fuse_pool1 = bool(self.lib.nn_conv_pool_fusable(C.byref(self.geom[0]), self.noise_modes[0], PREC_BF16)) and \
+            os.environ.get("NN_ENGINE_FUSE_POOL", "0") == "1"
         self.gy1_layout = self.lib.nn_conv_wgrad_pack_layout(C.byref(self.geom[0]), PREC_BF16, self.di)
         if self.gy1_layout:
             nbytes = int(self.lib.nn_conv_gy_planes_bytes(C.byref(self.geom[0])))
@@ -146,7 +151,7 @@ class NoisyNetEngine:
             return hit[1]
         return ops.tensor_stats(w.detach())[1:2]
 
-    def _fwd_gemm(self, idx, xp, a_cs, y_noisy, mode, scale_dev, z=None):
+    def _fwd_gemm(self, idx, xp, a_cs, y_noisy, mode, scale_dev, z=None, pooled=None, argmax=None):
         a = ConvFwdArgs()
         a.g = self.geom[idx]
         a.x = None
@@ -162,6 +167,9 @@ class NoisyNetEngine:
             a.rng = Rng(0, 0, None) if z is not None else self._rng()
         else:                                   # currentN == 0: no analog noise on this layer (noisynet.py:414)
             a.y, a.y_noisy, a.noise_mode = _p(y_noisy), None, 0
+        if pooled is not None:                  # MaxPool2d(2,2) fused into the conv epilogue: the full-size output is never written
+            a.y, a.y_noisy = None, None
+            a.pooled_out, a.argmax_out = _p(pooled), _p(argmax)
         a.precision = PREC_BF16
         a.a_code_scale, a.w_code_scale = a_cs, self.w_cs
         a.workspace, a.workspace_bytes = _p(self.ws), self.ws.numel()
@@ -271,8 +279,13 @@ class NoisyNetEngine:
         _lib.check(lib.nn_input_quant_pack(_p(x), _p(self.xp1), None, B, 3, 32 * 32, 8, int(a.q_a1), qh1, stoch, _p(u),
                                            Rng(0, 0, None) if u is not None else self._rng(), di, st), "nn_input_quant_pack")
 
-        self._fwd_gemm(0, self.xp1, s1, self.y1n, self.noise_modes[0], self._absmax(0, W[0]), self._take("z"))
-        self._stage_fwd(self.y1n, C1, H1, 1, self.pool1, self.amax1, m.bn1, "bn1", a.q_a2, qh2, self.xp2, self.xmax2, self._take("u"))
+        if self.fuse_pool1:
+            self._fwd_gemm(0, self.xp1, s1, None, self.noise_modes[0], self._absmax(0, W[0]), self._take("z"),
+                           pooled=self.pool1, argmax=self.amax1)
+            self._stage_fwd(self.pool1, C1, P1, 0, None, None, m.bn1, "bn1", a.q_a2, qh2, self.xp2, self.xmax2, self._take("u"))
+        else:
+            self._fwd_gemm(0, self.xp1, s1, self.y1n, self.noise_modes[0], self._absmax(0, W[0]), self._take("z"))
+            self._stage_fwd(self.y1n, C1, H1, 1, self.pool1, self.amax1, m.bn1, "bn1", a.q_a2, qh2, self.xp2, self.xmax2, self._take("u"))
         if self.side is not None:
             torch.cuda.current_stream(di).wait_stream(self.side)
         self._fwd_gemm(1, self.xp2, s2, self.y2n, self.noise_modes[1], self.xmax2, self._take("z"))

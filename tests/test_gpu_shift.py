@@ -204,3 +204,50 @@ def test_stage_bwd_planes_layout(dev):
     mask = torch.ones(Cp // 8, B, vH, vW, 8, dtype=torch.bool)
     mask[:, :, :H, :W] = False
     assert float(grid[mask].abs().max()) == 0.0 and float(planes[:, B * vH * vW:].abs().max() if P > B * vH * vW else 0.0) == 0.0
+
+
+@pytest.mark.parametrize("B,Cout,k", [(4, 65, 5), (3, 20, 3), (2, 7, 1)])
+def test_shift_fused_maxpool(dev, B, Cout, k):
+    """pooled_out / argmax_out of the shift kernel == MaxPool2d(2,2) (values and first-maximum window position) of the
+    output the same launch configuration writes without the fusion (same Philox stream -> bit-identical noise)."""
+    from noisynet_b200 import _lib, ops
+    from noisynet_b200._lib import NOISE_MERGED, NOISE_NONE, PREC_BF16, ConvFwdArgs, ConvGeom
+    import ctypes as C
+    lib = _lib.load()
+    H = 32
+    g = ConvGeom(B, 3, H, H, Cout, k, k, 1, 0)
+    OH = H - k + 1
+    if OH % 2:
+        pytest.skip("odd output size")
+    assert lib.nn_conv_pool_fusable(C.byref(g), NOISE_MERGED, PREC_BF16) == 1
+    gen = torch.Generator().manual_seed(B + Cout + k)
+    s_a, ka, x, cw, wq, w_raw = _mk((B, 3, H, H, Cout, k), gen)
+    xd, wqd, wrd = x.to(dev), wq.to(dev), w_raw.to(dev)
+    scale = ops.tensor_stats(wrd)[1:2]
+    for mode in (NOISE_MERGED, NOISE_NONE):
+        kw = dict(precision="bf16", a_code_scale=s_a, w_code_scale=1.0 / 15.0, noise_mode=mode)
+        if mode:
+            kw.update(current=1.0, scale_dev=scale, rng=ops._fixed_rng(3, 9), want_y=False)
+        ref = ops.noisy_conv_fwd(xd, wqd, wrd if mode else None, None, 1, 0, **kw)
+        full = ref["y_noisy"] if mode else ref["y"]
+        pv, pi = F.max_pool2d(full, 2, 2, return_indices=True)
+        # window position from torch's flat index
+        ih, iw = pi // OH, pi % OH
+        pos = ((ih % 2) * 2 + (iw % 2)).to(torch.uint8)
+        # fused launch through the C ABI
+        a = ConvFwdArgs()
+        a.g = g
+        a.x, a.w_eff, a.w_raw = xd.data_ptr(), wqd.data_ptr(), wrd.data_ptr() if mode else None
+        pooled = torch.empty(B, Cout, OH // 2, OH // 2, device=dev)
+        arg = torch.empty(B, Cout, OH // 2, OH // 2, dtype=torch.uint8, device=dev)
+        a.pooled_out, a.argmax_out = pooled.data_ptr(), arg.data_ptr()
+        a.noise_mode = mode
+        if mode:
+            a.current, a.scale_dev, a.rng = 1.0, scale.data_ptr(), ops._fixed_rng(3, 9)
+        a.precision, a.a_code_scale, a.w_code_scale = PREC_BF16, s_a, 1.0 / 15.0
+        ws = torch.empty(int(lib.nn_conv_workspace_bytes(C.byref(g), PREC_BF16)) + 4096, dtype=torch.uint8, device=dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.check(lib.nn_noisy_conv_fwd(C.byref(a), 0, torch.cuda.current_stream().cuda_stream), "nn_noisy_conv_fwd")
+        assert ops.error_flag() == 0
+        assert torch.equal(pooled, pv)
+        assert torch.equal(arg, pos)
