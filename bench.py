@@ -220,7 +220,7 @@ def run_b200(args):
     precision = pick_precision(args, dev)
     model, a, opt = build_model(args, dev, precision)
     fused_opt = args.optimizer == "fused"
-    red = dp.FlatGradAllReduce(model, world, early=[model.linear1.weight, model.linear2.weight])
+    red = dp.FlatGradAllReduce(model, world, early=[[model.linear1.weight, model.linear2.weight], [model.conv2.weight]])
     red.broadcast_parameters(model)
     B = args.batch
     gen = torch.Generator().manual_seed(1234 + rank)

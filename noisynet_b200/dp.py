@@ -36,15 +36,23 @@ class FlatGradAllReduce:
     """Owns the flat gradient buffer of ``model`` and performs the per-step mean all-reduce."""
 
     def __init__(self, model, world=None, early=None):
-        """``early``: parameters whose gradients are final early in the backward (e.g. the fully connected
-        layers of NoisyNet, 4.7 of the 5.5 MB): they are laid out first in the flat buffer so that their
-        all-reduce can be started (``start_early``) while the remaining backward still runs."""
+        """``early``: parameters whose gradients are final early in the backward -- a list of parameters (one bucket)
+        or a list of such lists (several buckets, in the order they become final; e.g. the fully connected layers of
+        NoisyNet, 4.7 of the 5.5 MB, then conv2).  They are laid out first in the flat buffer, bucket by bucket, so
+        that each bucket's all-reduce can be started (``start_early(k)``) while the remaining backward still runs."""
         params = [p for p in model.parameters() if p.requires_grad]
-        early = [p for p in (early or []) if p.requires_grad]
-        ids = {id(p) for p in early}
-        self.params = early + [p for p in params if id(p) not in ids]
-        self.n_early = sum(p.numel() for p in early)
-        self._work = None
+        buckets = early or []
+        if buckets and not isinstance(buckets[0], (list, tuple)):
+            buckets = [buckets]
+        buckets = [[p for p in b if p.requires_grad] for b in buckets]
+        flat_early = [p for b in buckets for p in b]
+        ids = {id(p) for p in flat_early}
+        self.params = flat_early + [p for p in params if id(p) not in ids]
+        self.bounds = [0]
+        for b in buckets:
+            self.bounds.append(self.bounds[-1] + sum(p.numel() for p in b))
+        self.n_early = self.bounds[-1]
+        self._works = [None] * len(buckets)
         self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
         n = sum(p.numel() for p in self.params)
         ref = self.params[0]
@@ -55,6 +63,10 @@ class FlatGradAllReduce:
             off += p.numel()
         self.nbytes = n * self.flat.element_size()
 
+    @property
+    def _work(self):            # the single-bucket interface of round 1 (tests)
+        return next((w for w in self._works if w is not None), None)
+
     def zero_(self):
         self.flat.zero_()
 
@@ -64,22 +76,30 @@ class FlatGradAllReduce:
             for t in list(model.parameters()) + list(model.buffers()):
                 dist.broadcast(t.data, src)
 
-    def start_early(self):
-        """Asynchronous SUM all-reduce of the early bucket on the process group's stream; overlaps with the
-        kernels enqueued afterwards on the compute stream (finish() joins)."""
-        if self.world > 1 and self.n_early > 0 and self._work is None:
-            self._work = dist.all_reduce(self.flat[:self.n_early], op=dist.ReduceOp.SUM, async_op=True)
+    def start_early(self, k=0):
+        """Asynchronous SUM all-reduce of early bucket ``k`` on the process group's stream (it waits for the CURRENT
+        stream at the call); overlaps with the kernels enqueued afterwards (all_reduce_sum_ joins)."""
+        if self.world > 1 and k < len(self._works) and self._works[k] is None and self.bounds[k + 1] > self.bounds[k]:
+            self._works[k] = dist.all_reduce(self.flat[self.bounds[k]:self.bounds[k + 1]], op=dist.ReduceOp.SUM, async_op=True)
 
     def all_reduce_sum_(self):
         if self.world > 1:
-            if self._work is not None:
-                rest = self.flat[self.n_early:]
-                if rest.numel():
-                    dist.all_reduce(rest, op=dist.ReduceOp.SUM)
-                self._work.wait()
-                self._work = None
-            else:
-                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            # buckets never started are folded into the final all-reduce together with the remaining parameters
+            lo = 0
+            for k, w in enumerate(self._works):
+                if w is None:
+                    break
+                lo = self.bounds[k + 1]
+            started = [w for w in self._works if w is not None]
+            if any(w is None for w in self._works[:len(started)]) or \
+               any(w is not None for w in self._works[len(started):]):
+                raise RuntimeError("early buckets must be started in order")
+            rest = self.flat[lo:]
+            if rest.numel():
+                dist.all_reduce(rest, op=dist.ReduceOp.SUM)
+            for w in started:
+                w.wait()
+            self._works = [None] * len(self._works)
         return self.flat
 
     def all_reduce_mean_(self):

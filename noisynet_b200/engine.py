@@ -312,6 +312,12 @@ class NoisyNetEngine:
         self._dgrad(self.geom_fc1_lin, self.gyp3, 2, self.gx3)
         self._stage_bwd(self.gx3, self.pool2, self.amax2, C2, H2, 1, m.bn2, "bn2", a.q_a3, qh3, self.gyp2)
         self._wgrad(1, self.gyp2, self.xp2, s2, W[1], W[1].grad)
+        if self.red is not None:        # second early bucket: conv2's weight gradient
+            if self.side is not None:
+                with torch.cuda.stream(self.side):
+                    self.red.start_early(1)
+            else:
+                self.red.start_early(1)
         self._dgrad(self.geom[1], self.gyp2, 1, self.gx2)
         self._stage_bwd(self.gx2, self.pool1, self.amax1, C1, H1, 1, m.bn1, "bn1", a.q_a2, qh2, self.gyp1,
                         planes_grid=(32, 32) if self.gy1_layout else None)

@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, two_buckets=False):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
@@ -28,8 +28,12 @@ def _worker(rank, world, port, out_dir):
     assert (r, w) == (rank, world)
     torch.manual_seed(dp.rank_seed(0, rank))                       # different init per rank on purpose
     model = torch.nn.Sequential(torch.nn.Linear(12, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
-    red = dp.FlatGradAllReduce(model, world, early=[model[2].weight])      # early bucket: last layer's weight
-    assert red.params[0] is model[2].weight and red.n_early == 21
+    if two_buckets:                                                 # buckets in the order they become final
+        red = dp.FlatGradAllReduce(model, world, early=[[model[2].weight], [model[2].bias, model[0].weight]])
+        assert red.params[:3] == [model[2].weight, model[2].bias, model[0].weight] and red.bounds == [0, 21, 21 + 3 + 84]
+    else:
+        red = dp.FlatGradAllReduce(model, world, early=[model[2].weight])      # early bucket: last layer's weight
+        assert red.params[0] is model[2].weight and red.n_early == 21
     red.broadcast_parameters(model)                                 # now identical to rank 0
     g = torch.Generator().manual_seed(123)
     X, Y = torch.randn(16, 12, generator=g), torch.randint(0, 3, (16,), generator=g)
@@ -39,6 +43,8 @@ def _worker(rank, world, port, out_dir):
     loss.backward()
     assert all(p.grad.data_ptr() >= red.flat.data_ptr() for p in model.parameters())   # grads are views
     red.start_early()                                            # async bucket, joined by all_reduce_mean_
+    if two_buckets:
+        red.start_early(1)
     red.all_reduce_mean_()
     assert red._work is None
     torch.save({"flat": red.flat.clone(), "params": [p.detach().clone() for p in model.parameters()]},
@@ -47,9 +53,13 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_flat_grad_allreduce_world2(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("two_buckets", [False, True])
+def test_flat_grad_allreduce_world2(tmp_path, two_buckets):
     world, port = 2, _free_port()
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), two_buckets), nprocs=world, join=True)
     a = torch.load(tmp_path / "rank0.pt")
     b = torch.load(tmp_path / "rank1.pt")
     assert torch.equal(a["flat"], b["flat"])
@@ -64,7 +74,8 @@ def test_flat_grad_allreduce_world2(tmp_path):
     g = torch.Generator().manual_seed(123)
     X, Y = torch.randn(16, 12, generator=g), torch.randint(0, 3, (16,), generator=g)
     torch.nn.functional.cross_entropy(model(X), Y).backward()
-    order = [model[2].weight] + [p for p in model.parameters() if p is not model[2].weight]   # early bucket first
+    first = [model[2].weight, model[2].bias, model[0].weight] if two_buckets else [model[2].weight]
+    order = first + [p for p in model.parameters() if all(p is not q for q in first)]          # early buckets first
     full = torch.cat([p.grad.flatten() for p in order])
     assert torch.allclose(a["flat"], full, atol=1e-6)
 
