@@ -15,7 +15,16 @@ namespace {
 #ifndef ST_CHUNK_FAST
 #define ST_CHUNK_FAST 1   // thread index: 16-byte channel chunk fastest (coalesced NHWC stores) vs pixel fastest
 #endif
-constexpr int ST_SPLITS = 16;   // batch slices per channel for the deterministic partial sums
+constexpr int ST_SPLITS = 16;   // MAX batch slices per channel for the deterministic partial sums (gridDim.y <= ST_SPLITS)
+
+// slices actually used: enough blocks to fill the GPU, but at least ~2048 elements per block (the fc stages have 512
+// elements per channel: 16 slices of 32 elements were pure launch overhead, 10 us for a 0.8 MB tensor)
+static inline int stage_splits(int64_t per_channel) {
+    int64_t s = per_channel / 2048;
+    if (s < 1) s = 1;
+    if (s > ST_SPLITS) s = ST_SPLITS;
+    return (int)s;
+}
 
 __device__ __forceinline__ float quant_code(float v, float s, float qmax, float u) {
     // hardware_model.py:154-166 with min_value = 0: rne(clamp(v / s + u, 0, qmax))
@@ -30,7 +39,7 @@ k_pool_stats(const float* __restrict__ y, float* __restrict__ pooled, uint8_t* _
              int B, int C, int OH, int OW) {
     const int c = blockIdx.x, sp = blockIdx.y;
     const int PH = OH >> 1, PW = OW >> 1, PHW = PH * PW;
-    const int b0 = (int)((int64_t)B * sp / ST_SPLITS), b1 = (int)((int64_t)B * (sp + 1) / ST_SPLITS);
+    const int b0 = (int)((int64_t)B * sp / (int)gridDim.y), b1 = (int)((int64_t)B * (sp + 1) / (int)gridDim.y);
     const int n = (b1 - b0) * PHW;
     double s1 = 0.0, s2 = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -54,8 +63,8 @@ k_pool_stats(const float* __restrict__ y, float* __restrict__ pooled, uint8_t* _
     if (threadIdx.x == 0) {
         double a = 0, b = 0;
         for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
-        partial[((int64_t)c * ST_SPLITS + sp) * 2 + 0] = a;
-        partial[((int64_t)c * ST_SPLITS + sp) * 2 + 1] = b;
+        partial[((int64_t)c * gridDim.y + sp) * 2 + 0] = a;
+        partial[((int64_t)c * gridDim.y + sp) * 2 + 1] = b;
     }
 }
 
@@ -63,7 +72,7 @@ k_pool_stats(const float* __restrict__ y, float* __restrict__ pooled, uint8_t* _
 __global__ void __launch_bounds__(256)
 k_chan_stats(const float* __restrict__ x, double* __restrict__ partial, int B, int C, int HW) {
     const int c = blockIdx.x, sp = blockIdx.y;
-    const int b0 = (int)((int64_t)B * sp / ST_SPLITS), b1 = (int)((int64_t)B * (sp + 1) / ST_SPLITS);
+    const int b0 = (int)((int64_t)B * sp / (int)gridDim.y), b1 = (int)((int64_t)B * (sp + 1) / (int)gridDim.y);
     const int n = (b1 - b0) * HW;
     double s1 = 0.0, s2 = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -78,20 +87,20 @@ k_chan_stats(const float* __restrict__ x, double* __restrict__ partial, int B, i
     if (threadIdx.x == 0) {
         double a = 0, b = 0;
         for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
-        partial[((int64_t)c * ST_SPLITS + sp) * 2 + 0] = a;
-        partial[((int64_t)c * ST_SPLITS + sp) * 2 + 1] = b;
+        partial[((int64_t)c * gridDim.y + sp) * 2 + 0] = a;
+        partial[((int64_t)c * gridDim.y + sp) * 2 + 1] = b;
     }
 }
 
 // finalize BN statistics: mean / invstd (biased var) + running stats update (momentum, unbiased var)
-__global__ void k_bn_finalize(const double* __restrict__ partial, int C, double count, float eps, float momentum,
+__global__ void k_bn_finalize(const double* __restrict__ partial, int splits, int C, double count, float eps, float momentum,
                               float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
                               float* __restrict__ running_var, float* __restrict__ xmax_out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && xmax_out) *xmax_out = 0.f;
     if (c >= C) return;
     double s1 = 0, s2 = 0;
-    for (int s = 0; s < ST_SPLITS; ++s) { s1 += partial[((int64_t)c * ST_SPLITS + s) * 2]; s2 += partial[((int64_t)c * ST_SPLITS + s) * 2 + 1]; }
+    for (int s = 0; s < splits; ++s) { s1 += partial[((int64_t)c * splits + s) * 2]; s2 += partial[((int64_t)c * splits + s) * 2 + 1]; }
     const double m = s1 / count;
     double var = s2 / count - m * m;
     if (var < 0) var = 0;
@@ -231,7 +240,7 @@ __device__ __forceinline__ float stage_dv(float g, float x, float mean, float in
 __global__ void __launch_bounds__(256)
 k_bn_bwd_stats(const BnBwdP p) {
     const int c = blockIdx.x, sp = blockIdx.y;
-    const int b0 = (int)((int64_t)p.B * sp / ST_SPLITS), b1 = (int)((int64_t)p.B * (sp + 1) / ST_SPLITS);
+    const int b0 = (int)((int64_t)p.B * sp / (int)gridDim.y), b1 = (int)((int64_t)p.B * (sp + 1) / (int)gridDim.y);
     const int n = (b1 - b0) * p.HW;
     const float mean = p.mean[c], invstd = p.invstd[c], gamma = p.gamma[c], beta = p.beta[c];
     double s1 = 0.0, s2 = 0.0;
@@ -249,16 +258,16 @@ k_bn_bwd_stats(const BnBwdP p) {
     if (threadIdx.x == 0) {
         double a = 0, b = 0;
         for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
-        p.partial[((int64_t)c * ST_SPLITS + sp) * 2 + 0] = a;
-        p.partial[((int64_t)c * ST_SPLITS + sp) * 2 + 1] = b;
+        p.partial[((int64_t)c * gridDim.y + sp) * 2 + 0] = a;
+        p.partial[((int64_t)c * gridDim.y + sp) * 2 + 1] = b;
     }
 }
 
-__global__ void k_bn_bwd_finalize(const double* __restrict__ partial, int C, float* __restrict__ dbeta, float* __restrict__ dgamma) {
+__global__ void k_bn_bwd_finalize(const double* __restrict__ partial, int splits, int C, float* __restrict__ dbeta, float* __restrict__ dgamma) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double s1 = 0, s2 = 0;
-    for (int s = 0; s < ST_SPLITS; ++s) { s1 += partial[((int64_t)c * ST_SPLITS + s) * 2]; s2 += partial[((int64_t)c * ST_SPLITS + s) * 2 + 1]; }
+    for (int s = 0; s < splits; ++s) { s1 += partial[((int64_t)c * splits + s) * 2]; s2 += partial[((int64_t)c * splits + s) * 2 + 1]; }
     dbeta[c] = (float)s1;        // grads are OVERWRITTEN (the step zeroes them anyway)
     dgamma[c] = (float)s2;
 }
@@ -645,19 +654,22 @@ extern "C" int nn_stage_fwd(const nn_stage_args* a, int device, void* stream) {
     const float* bn_in = a->in;
     int HW = a->H * a->W;
     double* partial = (double*)a->scratch;
+    int splits = ST_SPLITS;
     if (a->pool) {
         if (!a->pooled || !a->argmax) return nn_fail("nn_stage_fwd: pooled/argmax buffers missing%s", "");
-        dim3 grid(a->C, ST_SPLITS);
+        HW = (a->H / 2) * (a->W / 2);
+        splits = stage_splits((int64_t)a->B * HW);
+        dim3 grid(a->C, splits);
         k_pool_stats<<<grid, 256, 0, st>>>(a->in, a->pooled, a->argmax, partial, a->B, a->C, a->H, a->W);
         NN_LAUNCH_OK();
         bn_in = a->pooled;
-        HW = (a->H / 2) * (a->W / 2);
     } else {
-        dim3 grid(a->C, ST_SPLITS);
+        splits = stage_splits((int64_t)a->B * HW);
+        dim3 grid(a->C, splits);
         k_chan_stats<<<grid, 256, 0, st>>>(a->in, partial, a->B, a->C, HW);
         NN_LAUNCH_OK();
     }
-    k_bn_finalize<<<(a->C + 127) / 128, 128, 0, st>>>(partial, a->C, (double)a->B * HW, a->eps, a->momentum, a->mean,
+    k_bn_finalize<<<(a->C + 127) / 128, 128, 0, st>>>(partial, splits, a->C, (double)a->B * HW, a->eps, a->momentum, a->mean,
                                                       a->invstd, a->running_mean, a->running_var, a->xmax_out);
     NN_LAUNCH_OK();
     BnActP p;
@@ -687,10 +699,11 @@ extern "C" int nn_stage_bwd(const nn_stage_bwd_args* a, int device, void* stream
     q.g = a->g; q.x = a->x; q.mean = a->mean; q.invstd = a->invstd; q.gamma = a->gamma; q.beta = a->beta;
     q.partial = (double*)a->scratch; q.B = a->B; q.C = a->C; q.HW = PH * PW; q.act_max = a->act_max;
     q.q_hi = a->q_bits > 0 ? (float)a->q_hi : 0.f;
-    dim3 grid(a->C, ST_SPLITS);
+    const int splits = stage_splits((int64_t)a->B * PH * PW);
+    dim3 grid(a->C, splits);
     k_bn_bwd_stats<<<grid, 256, 0, st>>>(q);
     NN_LAUNCH_OK();
-    k_bn_bwd_finalize<<<(a->C + 127) / 128, 128, 0, st>>>(q.partial, a->C, a->dbeta, a->dgamma);
+    k_bn_bwd_finalize<<<(a->C + 127) / 128, 128, 0, st>>>(q.partial, splits, a->C, a->dbeta, a->dgamma);
     NN_LAUNCH_OK();
     BnBwdApplyP p;
     p.g = a->g; p.x = a->x; p.mean = a->mean; p.invstd = a->invstd; p.gamma = a->gamma; p.beta = a->beta;
