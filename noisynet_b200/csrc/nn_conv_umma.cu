@@ -92,6 +92,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
+__device__ __forceinline__ void st_global_f32(float* ptr, float v);
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -364,6 +365,21 @@ k_conv_umma(const UmmaP p) {
                     if (g4 * 4 < nvalid) {
                         float z[4];
                         if (EPI == 1) nn_normal4(rs, grp_row + (uint64_t)((nb + g4 * 4) >> 2), z);
+                        if (!vec4 && oy == nullptr && g4 * 4 + 4 <= nvalid) {
+                            // hot path of the conv layers: full group, no clean-output copy -- straight-line code with
+                            // one running pointer (the per-element predicates and 64-bit index maths below cost more
+                            // than the noise arithmetic; same restructuring as in k_conv_shift)
+                            float* o_run = o + (size_t)(g4 * 4) * ohw;
+                            asm volatile("" : "+l"(o_run));
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int e = g4 * 4 + j;
+                                const float yv = am[e] * y_scale;
+                                st_global_f32(o_run, (EPI == 1) ? __fadd_rn(yv, __fmul_rn(z[j], nn_sigma(coef, as[e] * s_scale))) : yv);
+                                o_run += ohw;
+                            }
+                            continue;
+                        }
                         if (vec4 && g4 * 4 + 4 <= nvalid) {
                             float r4[4];
 #pragma unroll
