@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NN_ABI_VERSION 11
+#define NN_ABI_VERSION 12
 
 /* ---- common ---------------------------------------------------------------------- */
 
@@ -314,6 +314,29 @@ int nn_head_fwd_bwd(const float* logits, const int64_t* labels, int B, int C, co
                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                     float* loss_out, float* out, float* g, void* g_packed, int Cp, float* dgamma, float* dbeta,
                     int device, void* stream);
+
+/* Classifier tail, fused (noisynet.py:589-594 linear2 + current noise, bn4, :1278 CrossEntropyLoss, and the way
+ * back: d loss / d logits through bn4, fc2 dgrad) for a last layer with <= 16 units: ONE thread-block cluster of 8
+ * CTAs with the two batch-wide reductions in distributed shared memory.  Same arithmetic as nn_noisy_conv_fwd
+ * (integer-code mode) + nn_head_fwd_bwd + nn_noisy_conv_dgrad; the weight gradient still goes through
+ * nn_noisy_conv_wgrad (g_packed). */
+typedef struct nn_tail_args {
+    const void* xp;           /* layer input [B][Kp] bf16 integer codes (Kp even, >= K), e.g. from nn_stage_fwd      */
+    int32_t B, K, Kp, C;
+    const int8_t* w_codes;    /* [C][K] weight quantizer codes 2k - qmax (nn_wprep_job.codes)                          */
+    const float* w_raw;       /* [C][K] raw parameter (sigma^2 rows), may be NULL when noise_mode == 0               */
+    float a_code_scale, w_code_scale;
+    int32_t noise_mode; float current; const float* scale_dev; const float* z_inject; nn_rng rng;
+    const int64_t* labels;
+    const float *gamma, *beta; float *running_mean, *running_var; float momentum, eps;
+    float* loss_out;          /* device scalar                                                                       */
+    float* logits_out;        /* optional [B][C]: the noisy fc2 output (bn4 input)                                   */
+    float* g;                 /* [B][C] d loss / d (fc2 output)                                                      */
+    void* g_packed; int32_t Cp_g;   /* optional bf16 [B][Cp_g] pack of g for the weight gradient                        */
+    float* gx;                /* [B][K] d loss / d (layer input), before the STE masks of the previous stage         */
+    float *dgamma, *dbeta;
+} nn_tail_args;
+int nn_classifier_tail(const nn_tail_args* a, int device, void* stream);
 
 #ifdef __cplusplus
 }

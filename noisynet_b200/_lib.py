@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libnoisynet_b200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 NOISE_NONE, NOISE_MERGED, NOISE_EXTERNAL = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
@@ -94,6 +94,16 @@ class StageBwdArgs(C.Structure):
                 ("gy_layout", C.c_int32), ("virt_H", C.c_int32), ("virt_W", C.c_int32)]
 
 
+class TailArgs(C.Structure):
+    _fields_ = [("xp", C.c_void_p), ("B", C.c_int32), ("K", C.c_int32), ("Kp", C.c_int32), ("C", C.c_int32),
+                ("w_codes", C.c_void_p), ("w_raw", C.c_void_p), ("a_code_scale", C.c_float), ("w_code_scale", C.c_float),
+                ("noise_mode", C.c_int32), ("current", C.c_float), ("scale_dev", C.c_void_p), ("z_inject", C.c_void_p),
+                ("rng", Rng), ("labels", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("momentum", C.c_float), ("eps", C.c_float),
+                ("loss_out", C.c_void_p), ("logits_out", C.c_void_p), ("g", C.c_void_p), ("g_packed", C.c_void_p),
+                ("Cp_g", C.c_int32), ("gx", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p)]
+
+
 # name -> (restype, argtypes); mirrors include/noisynet_b200.h one to one
 SIGNATURES = {
     "nn_last_error": (C.c_char_p, []),
@@ -133,6 +143,7 @@ SIGNATURES = {
     "nn_conv_pack_layout": (C.c_int, [C.POINTER(ConvGeom), C.c_int32, C.c_int32]),
     "nn_debug_shift_enable": (C.c_int, [C.c_int]),
     "nn_conv_pool_fusable": (C.c_int, [C.POINTER(ConvGeom), C.c_int32, C.c_int32]),
+    "nn_classifier_tail": (C.c_int, [C.POINTER(TailArgs), C.c_int, C.c_void_p]),
     "nn_conv_wgrad_pack_layout": (C.c_int, [C.POINTER(ConvGeom), C.c_int32, C.c_int]),
     "nn_conv_gy_planes_bytes": (C.c_int64, [C.POINTER(ConvGeom)]),
     "nn_noisy_conv_fwd": (C.c_int, [C.POINTER(ConvFwdArgs), C.c_int, C.c_void_p]),

@@ -6,9 +6,12 @@
 //   fc stage   : BatchNorm1d -> ReLU -> clamp -> quantize -> pack (noisynet.py:540-569) and backward.
 //   head       : BatchNorm1d(10) -> cross-entropy (mean) -> gradient (noisynet.py:594, :1278).
 // All HBM-bound elementwise/reduction work; per-channel reductions use fixed-order partials (deterministic).
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
 #include "nn_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -634,6 +637,307 @@ k_head_rows(const float* __restrict__ z, const int64_t* __restrict__ label, int 
     }
 }
 
+// ------------------------------------------------------------------ classifier tail, fused (noisynet.py:589-594, :1278)
+// fc2 forward with its current noise -> BatchNorm1d (batch statistics) -> mean cross entropy -> gradient back
+// through both -> fc2 dgrad, for a layer with <= 16 output units: three launches of a few microseconds of work each
+// sat back to back on the critical path of the step (tcgen05 forward 11 us, head 18 us, tcgen05 dgrad 9 us).
+// ONE thread-block cluster of 8 CTAs: each CTA owns B/8 samples, keeps its activation rows (bf16 codes) and the
+// whole weight matrix (codes + g(|w|)) in shared memory, and the two batch-wide reductions (BN statistics; dbeta /
+// dgamma / loss) go through distributed shared memory with a cluster barrier -- fixed summation order, identical in
+// every CTA.  Arithmetic mirrors the separate kernels: integer-code main contraction (exact), sigma^2 from
+// bf16-rounded g(|w|) with fp32 accumulation, Philox group = m * ceil(C/4) + n/4, bf16-rounded gradient as the dgrad
+// operand, dgrad scaled by the weight code scale.
+constexpr int TAIL_CTAS = 8;
+constexpr int TAIL_THREADS = 256;
+
+struct TailP {
+    const __nv_bfloat16* xp; int B, K, Kp, C, R;       // R = rows per CTA
+    const int8_t* w_codes; const float* w_raw;
+    float y_scale, s_scale, w_code_scale;
+    int noise_mode; float current; const float* scale_dev; const float* z_inject; nn_rng rng;
+    const int64_t* labels; const float *gamma, *beta; float *running_mean, *running_var; float momentum, eps;
+    float *loss_out, *logits_out, *g; __nv_bfloat16* gp; int Cp_g;
+    float* gx; float *dgamma, *dbeta;
+    int xs_stride;                                      // bf16 elements per shared activation row (odd word count)
+};
+
+__device__ __forceinline__ void tail_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t tail_pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+__device__ __forceinline__ double tail_cluster_sum(cg::cluster_group& cluster, double* slot, int idx) {
+    // slot[idx] of every CTA, summed in rank order (every CTA computes the same value); all remote loads are issued
+    // before the first add (a distributed-shared-memory read is a ~1 us round trip)
+    double v[TAIL_CTAS];
+#pragma unroll
+    for (int r = 0; r < TAIL_CTAS; ++r) v[r] = cluster.map_shared_rank(slot, r)[idx];
+    double t = 0;
+#pragma unroll
+    for (int r = 0; r < TAIL_CTAS; ++r) t += v[r];
+    return t;
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1)
+k_classifier_tail(const TailP p) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) uint8_t tsm[];
+    const int R = p.R, C = p.C, K = p.K;
+    // shared memory: operands as bf16 for mma.sync (integer codes and bf16-rounded g(|w|) are exact in bf16)
+    const int K16 = (K + 15) & ~15, KS = p.xs_stride, R16 = (R + 15) & ~15;
+    __nv_bfloat16* wq = reinterpret_cast<__nv_bfloat16*>(tsm);                      // [16][KS] weight codes (rows >= C zero)
+    __nv_bfloat16* wg = wq + 16 * KS;                                               // [16][KS] g(|w_raw|)
+    __nv_bfloat16* wqT = wg + 16 * KS;                                              // [K16][16] codes, transposed (dgrad)
+    __nv_bfloat16* xs = wqT + (size_t)K16 * 16;                                     // [R16][KS] activation codes
+    float* ysm = reinterpret_cast<float*>(xs + (size_t)R16 * KS);                   // [R16][16] logits -> dv
+    float* ssm = ysm + R16 * 16;                                                    // [R16][16] S -> xhat
+    float* gsm = ssm + R16 * 16;                                                    // [R16][16] bf16-rounded final gradient
+    __shared__ double part[2][HEAD_MAXC + 1];          // this CTA's partial sums (exchanged through DSMEM)
+    __shared__ float s_mean[HEAD_MAXC], s_invstd[HEAD_MAXC], s_g[HEAD_MAXC], s_b[HEAD_MAXC], s_db[HEAD_MAXC], s_dg[HEAD_MAXC];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = (int)cluster.block_rank() * R;
+    const int nrows = max(0, min(R, p.B - row0));
+
+    // ---- stage operands (vector loads, several in flight; everything not loaded is zero)
+    {
+        uint4* z = reinterpret_cast<uint4*>(tsm);
+        const int n16 = (int)(((size_t)(2 * 16 * KS + K16 * 16 + (size_t)R16 * KS) * 2 + (size_t)3 * R16 * 16 * 4) / 16);
+        for (int i = tid; i < n16; i += TAIL_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    {
+        const int total = C * K, groups = (total + 3) >> 2;                 // 4 consecutive parameters per thread
+        const bool vec = ((reinterpret_cast<uintptr_t>(p.w_codes) & 3) == 0) &&
+                         (p.noise_mode == NN_NOISE_NONE || (reinterpret_cast<uintptr_t>(p.w_raw) & 15) == 0);
+#pragma unroll 4
+        for (int gi = tid; gi < groups; gi += TAIL_THREADS) {
+            const int i0 = gi * 4;
+            int8_t cq[4] = {0, 0, 0, 0};
+            float wr[4] = {0.f, 0.f, 0.f, 0.f};
+            if (vec && i0 + 4 <= total) {
+                const uint32_t w4 = __ldg(reinterpret_cast<const uint32_t*>(p.w_codes) + gi);
+                cq[0] = (int8_t)(w4 & 0xff); cq[1] = (int8_t)((w4 >> 8) & 0xff); cq[2] = (int8_t)((w4 >> 16) & 0xff); cq[3] = (int8_t)(w4 >> 24);
+                if (p.noise_mode != NN_NOISE_NONE) {
+                    const float4 f = __ldg(reinterpret_cast<const float4*>(p.w_raw) + gi);
+                    wr[0] = f.x; wr[1] = f.y; wr[2] = f.z; wr[3] = f.w;
+                }
+            } else {
+                for (int e = 0; e < 4; ++e)
+                    if (i0 + e < total) { cq[e] = p.w_codes[i0 + e]; if (p.noise_mode != NN_NOISE_NONE) wr[e] = __ldg(p.w_raw + i0 + e); }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = i0 + e;
+                if (i < total) {
+                    const int n = i / K, k = i - n * K;
+                    const __nv_bfloat16 cb = __float2bfloat16_rn((float)cq[e]);
+                    wq[n * KS + k] = cb;
+                    wqT[k * 16 + n] = cb;
+                    if (p.noise_mode != NN_NOISE_NONE) {
+                        const float a = fabsf(wr[e]);
+                        wg[n * KS + k] = __float2bfloat16_rn((p.noise_mode == NN_NOISE_MERGED) ? a : __fadd_rn(__fmul_rn(a, a), a));
+                    }
+                }
+            }
+        }
+    }
+    {
+        const bool vec = (p.Kp % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.xp) & 15) == 0);
+        const int vpr = vec ? p.Kp / 8 : 0;                                // 16-byte vectors per global row
+#pragma unroll 4
+        for (int i = tid; i < nrows * vpr; i += TAIL_THREADS) {
+            const int r = i / vpr, q4 = i - r * vpr;
+            const uint4 x4 = __ldg(reinterpret_cast<const uint4*>(p.xp + (size_t)(row0 + r) * p.Kp) + q4);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(xs + (size_t)r * KS) + q4 * 4;
+            const uint32_t w[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if ((q4 * 4 + e) * 2 < K16) dst[e] = w[e];
+        }
+        if (!vec)
+            for (int i = tid; i < nrows * (p.Kp / 2); i += TAIL_THREADS) {
+                const int r = i / (p.Kp / 2), kk = (i - r * (p.Kp / 2)) * 2;
+                if (kk < K16) *reinterpret_cast<uint32_t*>(xs + (size_t)r * KS + kk) =
+                    *reinterpret_cast<const uint32_t*>(p.xp + (size_t)(row0 + r) * p.Kp + kk);
+            }
+    }
+    __syncthreads();
+
+    // ---- forward contraction on the tensor cores (mma.sync m16n8k16, bf16 x bf16 -> fp32): a warp owns 16 rows and
+    // both 8-unit column tiles; main accumulators are exact integer sums, sigma^2 accumulators fp32
+    {
+        const int gq = lane >> 2, tig = lane & 3;
+        for (int rb = warp; rb < R16 / 16; rb += TAIL_THREADS / 32) {
+            float cm[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, cs[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+            const __nv_bfloat16* xa = xs + (size_t)(rb * 16 + gq) * KS + 2 * tig;
+            for (int k0 = 0; k0 < K16; k0 += 16) {
+                uint32_t af[4];
+                af[0] = *reinterpret_cast<const uint32_t*>(xa + k0);
+                af[1] = *reinterpret_cast<const uint32_t*>(xa + 8 * KS + k0);
+                af[2] = *reinterpret_cast<const uint32_t*>(xa + k0 + 8);
+                af[3] = *reinterpret_cast<const uint32_t*>(xa + 8 * KS + k0 + 8);
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const int wo = (nt * 8 + gq) * KS + k0 + 2 * tig;
+                    tail_mma(cm[nt], af, *reinterpret_cast<const uint32_t*>(wq + wo), *reinterpret_cast<const uint32_t*>(wq + wo + 8));
+                    if (p.noise_mode != NN_NOISE_NONE)
+                        tail_mma(cs[nt], af, *reinterpret_cast<const uint32_t*>(wg + wo), *reinterpret_cast<const uint32_t*>(wg + wo + 8));
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int c0 = nt * 8 + 2 * tig, r0 = rb * 16 + gq;
+                ysm[r0 * 16 + c0] = cm[nt][0] * p.y_scale;       ysm[r0 * 16 + c0 + 1] = cm[nt][1] * p.y_scale;
+                ysm[(r0 + 8) * 16 + c0] = cm[nt][2] * p.y_scale; ysm[(r0 + 8) * 16 + c0 + 1] = cm[nt][3] * p.y_scale;
+                ssm[r0 * 16 + c0] = cs[nt][0] * p.s_scale;       ssm[r0 * 16 + c0 + 1] = cs[nt][1] * p.s_scale;
+                ssm[(r0 + 8) * 16 + c0] = cs[nt][2] * p.s_scale; ssm[(r0 + 8) * 16 + c0 + 1] = cs[nt][3] * p.s_scale;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- current noise: thread = (row, group of 4 units), the Philox mapping of every other path
+    if (p.noise_mode != NN_NOISE_NONE) {
+        const int ngrp = (C + 3) >> 2;
+        const float coef = nn_noise_coef(*p.scale_dev, p.current);
+        const NnRng rs = nn_rng_load(p.rng);
+        for (int i = tid; i < nrows * ngrp; i += TAIL_THREADS) {
+            const int r = i / ngrp, gq = i - r * ngrp, m = row0 + r;
+            float z[4];
+            if (!p.z_inject) nn_normal4(rs, (uint64_t)m * ngrp + (uint64_t)gq, z);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = gq * 4 + j;
+                if (n < C) {
+                    const float zz = p.z_inject ? __ldg(p.z_inject + (size_t)m * C + n) : z[j];
+                    ysm[r * 16 + n] = __fadd_rn(ysm[r * 16 + n], __fmul_rn(zz, nn_sigma(coef, ssm[r * 16 + n])));
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (p.logits_out)
+        for (int i = tid; i < nrows * C; i += TAIL_THREADS) p.logits_out[(size_t)(row0 + i / C) * C + i % C] = ysm[(i / C) * 16 + i % C];
+
+    // ---- BatchNorm statistics over the whole batch
+    for (int c = warp; c < C; c += TAIL_THREADS / 32) {
+        double s1 = 0, s2 = 0;
+        for (int r = lane; r < nrows; r += 32) { const double v = ysm[r * 16 + c]; s1 += v; s2 += v * v; }
+        for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+        if (lane == 0) { part[0][c] = s1; part[1][c] = s2; }
+    }
+    cluster.sync();
+    if (tid < C) {
+        const double t1 = tail_cluster_sum(cluster, &part[0][0], tid), t2 = tail_cluster_sum(cluster, &part[1][0], tid);
+        const double mean = t1 / p.B;
+        double var = t2 / p.B - mean * mean;
+        if (var < 0) var = 0;
+        s_mean[tid] = (float)mean;
+        s_invstd[tid] = (float)(1.0 / sqrt(var + (double)p.eps));
+        s_g[tid] = p.gamma[tid]; s_b[tid] = p.beta[tid];
+        if (p.running_mean && cluster.block_rank() == 0) {
+            const double unb = p.B > 1 ? var * p.B / (p.B - 1) : var;
+            p.running_mean[tid] = (float)((1.0 - p.momentum) * p.running_mean[tid] + p.momentum * mean);
+            p.running_var[tid] = (float)((1.0 - p.momentum) * p.running_var[tid] + p.momentum * unb);
+        }
+    }
+    cluster.sync();                      // everyone has read the first round of partials before they are overwritten
+    // ---- softmax / cross entropy per row; dv = (softmax - onehot) / B
+    float lrow = 0.f;
+    if (tid < nrows) {
+        const int r = tid;
+        float vv[HEAD_MAXC], xh[HEAD_MAXC];
+        float mx = -3.4e38f;
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c)
+            if (c < C) { xh[c] = (ysm[r * 16 + c] - s_mean[c]) * s_invstd[c]; vv[c] = xh[c] * s_g[c] + s_b[c]; mx = fmaxf(mx, vv[c]); }
+        float se = 0.f;
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c) if (c < C) se += expf(vv[c] - mx);
+        const int lab = (int)p.labels[row0 + r];
+        float vl = 0.f;
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c) if (c == lab) vl = vv[c];
+        lrow = logf(se) + mx - vl;
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c)
+            if (c < C) {
+                ysm[r * 16 + c] = (expf(vv[c] - mx) / se - (c == lab ? 1.f : 0.f)) / (float)p.B;     // dv
+                ssm[r * 16 + c] = xh[c];
+            }
+    }
+    __syncthreads();
+    for (int c = warp; c <= C; c += TAIL_THREADS / 32) {
+        double s1 = 0, s2 = 0;
+        if (c < C) {
+            for (int r = lane; r < nrows; r += 32) { const double dv = ysm[r * 16 + c]; s1 += dv; s2 += dv * (double)ssm[r * 16 + c]; }
+        }
+        for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+        if (lane == 0 && c < C) { part[0][c] = s1; part[1][c] = s2; }
+    }
+    {   // loss: sum of the per-row terms of this CTA (warp 0 gathers through shared memory)
+        __shared__ float lsh[TAIL_THREADS / 32];
+        float l = lrow;
+        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+        if (lane == 0) lsh[warp] = l;
+        __syncthreads();
+        if (tid == 0) { double t = 0; for (int w = 0; w < TAIL_THREADS / 32; ++w) t += lsh[w]; part[0][HEAD_MAXC] = t; }
+    }
+    cluster.sync();
+    if (tid < C) {
+        const double t1 = tail_cluster_sum(cluster, &part[0][0], tid), t2 = tail_cluster_sum(cluster, &part[1][0], tid);
+        s_db[tid] = (float)t1; s_dg[tid] = (float)t2;
+        if (cluster.block_rank() == 0) { p.dbeta[tid] = (float)t1; p.dgamma[tid] = (float)t2; }
+    }
+    if (tid == 0 && cluster.block_rank() == 0) *p.loss_out = (float)(tail_cluster_sum(cluster, &part[0][0], HEAD_MAXC) / p.B);
+    __syncthreads();
+    // ---- gradient w.r.t. the fc2 output
+    const float invB = 1.f / (float)p.B;
+    for (int i = tid; i < nrows * 16; i += TAIL_THREADS) {
+        const int r = i >> 4, c = i & 15;
+        float d = 0.f;
+        if (c < C) {
+            d = s_g[c] * s_invstd[c] * (ysm[r * 16 + c] - s_db[c] * invB - ssm[r * 16 + c] * s_dg[c] * invB);
+            p.g[(size_t)(row0 + r) * C + c] = d;
+        }
+        const __nv_bfloat16 db = __float2bfloat16_rn(d);
+        gsm[i] = __bfloat162float(db);
+        if (p.gp && c < p.Cp_g) p.gp[(size_t)(row0 + r) * p.Cp_g + c] = db;
+    }
+    __syncthreads();
+    // ---- dgrad on the tensor cores: gx[m][k] = w_code_scale * sum_n g_bf16[m][n] * code[n][k]
+    {
+        const int gq = lane >> 2, tig = lane & 3;
+        for (int rb = warp; rb < R16 / 16; rb += TAIL_THREADS / 32) {
+            const int r0 = rb * 16 + gq;
+            uint32_t af[4];
+            af[0] = tail_pack_bf16(gsm[r0 * 16 + 2 * tig], gsm[r0 * 16 + 2 * tig + 1]);
+            af[1] = tail_pack_bf16(gsm[(r0 + 8) * 16 + 2 * tig], gsm[(r0 + 8) * 16 + 2 * tig + 1]);
+            af[2] = tail_pack_bf16(gsm[r0 * 16 + 8 + 2 * tig], gsm[r0 * 16 + 8 + 2 * tig + 1]);
+            af[3] = tail_pack_bf16(gsm[(r0 + 8) * 16 + 8 + 2 * tig], gsm[(r0 + 8) * 16 + 8 + 2 * tig + 1]);
+            for (int nt = 0; nt < K16 / 8; ++nt) {
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+                const __nv_bfloat16* wb = wqT + (size_t)(nt * 8 + gq) * 16 + 2 * tig;
+                tail_mma(d, af, *reinterpret_cast<const uint32_t*>(wb), *reinterpret_cast<const uint32_t*>(wb + 8));
+                const int c0 = nt * 8 + 2 * tig;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = r0 + 8 * h;
+                    if (r < nrows) {
+                        float* o = p.gx + (size_t)(row0 + r) * K + c0;
+                        if (c0 < K) o[0] = d[2 * h] * p.w_code_scale;
+                        if (c0 + 1 < K) o[1] = d[2 * h + 1] * p.w_code_scale;
+                    }
+                }
+            }
+        }
+    }
+    cluster.sync();                      // distributed shared memory stays valid until every CTA is done reading
+}
+
 static inline int grid_cap(int64_t items, int device, int waves = 8) {
     int64_t blocks = (items + 255) / 256, cap = (int64_t)nn_num_sms(device) * waves;
     if (blocks > cap) blocks = cap;
@@ -768,6 +1072,48 @@ extern "C" int nn_head_fwd_bwd(const float* logits, const int64_t* labels, int B
     } else
     k_head<<<1, threads, 0, (cudaStream_t)stream>>>(logits, labels, B, C, gamma, beta, running_mean, running_var, momentum,
                                                     eps, loss_out, out, g, (__nv_bfloat16*)g_packed, Cp, dgamma, dbeta);
+    NN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int nn_classifier_tail(const nn_tail_args* a, int device, void* stream) {
+    if (!a || !a->xp || !a->w_codes || !a->labels || !a->gamma || !a->beta || !a->loss_out || !a->g || !a->gx || !a->dgamma || !a->dbeta)
+        return nn_fail("nn_classifier_tail: null argument%s", "");
+    if (a->C < 1 || a->C > HEAD_MAXC || a->B < 1 || a->B > TAIL_CTAS * TAIL_THREADS || a->K < 1 || a->Kp < a->K || (a->Kp & 1))
+        return nn_fail("nn_classifier_tail: served for C <= 16, B <= 2048, even Kp >= K%s", "");
+    if (a->noise_mode < 0 || a->noise_mode > 2) return nn_fail("nn_classifier_tail: bad noise_mode%s", "");
+    if (a->noise_mode != NN_NOISE_NONE && (!a->w_raw || !a->scale_dev || !(a->current > 0.f)))
+        return nn_fail("nn_classifier_tail: noise needs w_raw, scale_dev and current > 0%s", "");
+    NN_SET_DEVICE(device);
+    TailP p;
+    memset(&p, 0, sizeof(p));
+    p.xp = (const __nv_bfloat16*)a->xp; p.B = a->B; p.K = a->K; p.Kp = a->Kp; p.C = a->C;
+    p.R = (a->B + TAIL_CTAS - 1) / TAIL_CTAS;
+    p.w_codes = a->w_codes; p.w_raw = a->w_raw;
+    const float as = a->a_code_scale > 0.f ? a->a_code_scale : 1.f, ws = a->w_code_scale > 0.f ? a->w_code_scale : 1.f;
+    p.y_scale = as * ws; p.s_scale = as; p.w_code_scale = ws;
+    p.noise_mode = a->noise_mode; p.current = a->current; p.scale_dev = a->scale_dev; p.z_inject = a->z_inject; p.rng = a->rng;
+    p.labels = a->labels; p.gamma = a->gamma; p.beta = a->beta; p.running_mean = a->running_mean; p.running_var = a->running_var;
+    p.momentum = a->momentum; p.eps = a->eps; p.loss_out = a->loss_out; p.logits_out = a->logits_out; p.g = a->g;
+    p.gp = (__nv_bfloat16*)a->g_packed; p.Cp_g = a->Cp_g; p.gx = a->gx; p.dgamma = a->dgamma; p.dbeta = a->dbeta;
+    const int K16 = (a->K + 15) & ~15, R16 = (p.R + 15) & ~15;
+    p.xs_stride = K16 + 2;                                       // bf16 per shared row: K16/2 + 1 words, odd -> conflict-free fragments
+    const size_t smem = ((size_t)2 * 16 * p.xs_stride + (size_t)K16 * 16 + (size_t)R16 * p.xs_stride) * 2 +
+                        (size_t)3 * R16 * 16 * sizeof(float) + 64;
+    if (smem > 200 * 1024) return nn_fail("nn_classifier_tail: layer too large for one cluster%s", "");
+    static bool attr_set = false;
+    if (!attr_set) {
+        NN_CUDA_OK(cudaFuncSetAttribute(k_classifier_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(TAIL_CTAS); cfg.blockDim = dim3(TAIL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = TAIL_CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_classifier_tail, p));
     NN_LAUNCH_OK();
     return 0;
 }

@@ -19,7 +19,7 @@ import torch
 
 from . import _lib, ops
 from ._lib import (NOISE_EXTERNAL, NOISE_MERGED, PACK_SHIFT, PREC_BF16, ConvDgradArgs, ConvFwdArgs, ConvGeom, ConvWgradArgs,
-                   Rng, StageArgs, StageBwdArgs, WPrepJob)
+                   Rng, StageArgs, StageBwdArgs, TailArgs, WPrepJob)
 from .hardware_model import _f32
 
 
@@ -90,6 +90,10 @@ class NoisyNetEngine:
         # MaxPool2d fused into the conv1 epilogue (pooled_out): exact, saves the 104 MB y1n round trip, but measured
         # SLOWER overall at batch 512 (conv1 forward 86 -> 123 us: the per-group pair barrier puts the two warps of a row
         # pair in lock-step; pool+stats 36 -> 18 us) -- off unless NN_ENGINE_FUSE_POOL=1
+        # fc2 + bn4 + loss + their backward as ONE 8-CTA cluster launch (nn_classifier_tail): exact and tested, but 43 us
+        # against 37 us for the three separate launches it replaces (8 SMs, ten latency-bound phases) -- off unless
+        # NN_ENGINE_FUSED_TAIL=1
+        self.fused_tail = int(a.q_w1) > 0 and B <= 2048 and os.environ.get("NN_ENGINE_FUSED_TAIL", "0") == "1"
         self.fuse_pool1 = bool(self.lib.nn_conv_pool_fusable(C.byref(self.geom[0]), self.noise_modes[0], PREC_BF16)) and \
             os.environ.get("NN_ENGINE_FUSE_POOL", "0") == "1"
         self.gy1_layout = self.lib.nn_conv_wgrad_pack_layout(C.byref(self.geom[0]), PREC_BF16, self.di)
@@ -292,15 +296,34 @@ class NoisyNetEngine:
         self._stage_fwd(self.y2n, C2, H2, 1, self.pool2, self.amax2, m.bn2, "bn2", a.q_a3, qh3, self.xp3, None, self._take("u"))
         self._fwd_gemm(2, self.xp3, s3, self.l1n, self.noise_modes[2], self._absmax(2, W[2]), self._take("z"))
         self._stage_fwd(self.l1n, FC, 1, 0, None, None, m.bn3, "bn3", a.q_a4, qh4, self.xp4, self.xmax4, self._take("u"))
-        self._fwd_gemm(3, self.xp4, s4, self.l2n, self.noise_modes[3], self.xmax4, self._take("z"))
         bn4 = m.bn4
-        _lib.check(lib.nn_head_fwd_bwd(_p(self.l2n), _p(labels), B, 10, _p(bn4.weight), _p(bn4.bias), _p(bn4.running_mean),
-                                       _p(bn4.running_var), float(bn4.momentum), float(bn4.eps), _p(self.loss), None,
-                                       _p(self.g4), _p(self.gyp4), 16, _p(bn4.weight.grad), _p(bn4.bias.grad), di, st),
-                   "nn_head_fwd_bwd")
-        # ---- backward
-        self._wgrad(3, self.gyp4, self.xp4, s4, W[3], W[3].grad)
-        self._dgrad(self.geom[3], self.gyp4, 3, self.gx4)
+        if self.fused_tail:
+            # fc2 forward + noise, bn4, cross entropy, their backward and the fc2 dgrad: one 8-CTA cluster launch
+            t = TailArgs()
+            t.xp, t.B, t.K, t.Kp, t.C = _p(self.xp4), B, FC, self.xp4.shape[-1], 10
+            t.w_codes, t.w_raw = self.wcodes[3].data_ptr(), _p(W[3])
+            t.a_code_scale, t.w_code_scale = s4, self.w_cs
+            cur = float(a.layer_currents[3])
+            z = self._take("z")
+            if cur > 0:
+                t.noise_mode, t.current, t.scale_dev, t.z_inject = self.noise_modes[3], cur, _p(self.xmax4), _p(z)
+                t.rng = Rng(0, 0, None) if z is not None else self._rng()
+            t.labels, t.gamma, t.beta = _p(labels), _p(bn4.weight), _p(bn4.bias)
+            t.running_mean, t.running_var = _p(bn4.running_mean), _p(bn4.running_var)
+            t.momentum, t.eps = float(bn4.momentum), float(bn4.eps)
+            t.loss_out, t.logits_out, t.g, t.g_packed, t.Cp_g = _p(self.loss), _p(self.l2n), _p(self.g4), _p(self.gyp4), 16
+            t.gx, t.dgamma, t.dbeta = _p(self.gx4), _p(bn4.weight.grad), _p(bn4.bias.grad)
+            _lib.check(lib.nn_classifier_tail(C.byref(t), di, st), "nn_classifier_tail")
+            self._wgrad(3, self.gyp4, self.xp4, s4, W[3], W[3].grad)
+        else:
+            self._fwd_gemm(3, self.xp4, s4, self.l2n, self.noise_modes[3], self.xmax4, self._take("z"))
+            _lib.check(lib.nn_head_fwd_bwd(_p(self.l2n), _p(labels), B, 10, _p(bn4.weight), _p(bn4.bias), _p(bn4.running_mean),
+                                           _p(bn4.running_var), float(bn4.momentum), float(bn4.eps), _p(self.loss), None,
+                                           _p(self.g4), _p(self.gyp4), 16, _p(bn4.weight.grad), _p(bn4.bias.grad), di, st),
+                       "nn_head_fwd_bwd")
+            # ---- backward
+            self._wgrad(3, self.gyp4, self.xp4, s4, W[3], W[3].grad)
+            self._dgrad(self.geom[3], self.gyp4, 3, self.gx4)
         self._stage_bwd(self.gx4, self.l1n, None, FC, 1, 0, m.bn3, "bn3", a.q_a4, qh4, self.gyp3)
         self._wgrad(2, self.gyp3, self.xp3, s3, W[2], W[2].grad)
         if self.red is not None:        # fc gradients (85 % of the payload) travel while the conv backward runs

@@ -245,3 +245,67 @@ def test_engine_step_with_noise(dev):
     losses = [eng.train_step(x.to(dev), lab.to(dev)).item() for _ in range(25)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
     assert ops.error_flag() == 0
+
+
+@pytest.mark.parametrize("B,current", [(512, 1.0), (200, 1.0), (96, 0.0)])
+def test_classifier_tail_matches_separate_kernels(dev, B, current):
+    """nn_classifier_tail (one 8-CTA cluster) == nn_noisy_conv_fwd (integer-code tcgen05, same Philox stream) ->
+    nn_head_fwd_bwd -> nn_noisy_conv_dgrad on the same inputs.  The main contraction is exact in both; sigma^2 is the
+    same bf16 operands summed in a different fp32 order (1e-6 relative), everything after is fp32 on equal inputs."""
+    import ctypes as C
+    from noisynet_b200 import _lib, ops
+    from noisynet_b200._lib import NOISE_EXTERNAL, NOISE_NONE, PREC_BF16, ConvDgradArgs, ConvGeom, TailArgs
+    lib = _lib.load()
+    K, Cc, Kp = 390, 10, 392
+    gen = torch.Generator().manual_seed(B)
+    s_a, w_cs = 5.0 / 15.0, 1.0 / 15.0
+    ka = torch.randint(0, 16, (B, K), generator=gen).float() * (torch.rand(B, K, generator=gen) > 0.4).float()
+    codes = (torch.randint(0, 16, (Cc, K), generator=gen) * 2 - 15).to(torch.int8)
+    w_raw = torch.randn(Cc, K, generator=gen) * 0.2
+    lab = torch.randint(0, Cc, (B,), generator=gen)
+    gamma, beta = torch.rand(Cc, generator=gen) + 0.5, torch.randn(Cc, generator=gen) * 0.1
+    xp = torch.zeros(B, Kp, dtype=torch.bfloat16)
+    xp[:, :K] = ka.bfloat16()
+    xpd, cd, wrd, labd = xp.to(dev), codes.to(dev), w_raw.to(dev), lab.to(dev)
+    gd, bd = gamma.to(dev), beta.to(dev)
+    xd = (ka * s_a).float().to(dev).view(B, K, 1, 1)
+    wqd = (codes.float() * w_cs).to(dev).view(Cc, K, 1, 1)
+    scale = ops.tensor_stats(xd)[0:1]
+    mode = NOISE_EXTERNAL if current > 0 else NOISE_NONE
+    st = torch.cuda.current_stream().cuda_stream
+    f32 = lambda *s: torch.zeros(*s, device=dev)
+    # --- separate kernels
+    kw = dict(precision="bf16", a_code_scale=s_a, w_code_scale=w_cs, noise_mode=mode)
+    if mode:
+        kw.update(current=current, scale_dev=scale, rng=ops._fixed_rng(21, 4), want_y=False)
+    r = ops.noisy_conv_fwd(xd, wqd, wrd.view(Cc, K, 1, 1) if mode else None, None, 1, 0, **kw)
+    logits = (r["y_noisy"] if mode else r["y"]).view(B, Cc).contiguous()
+    loss0, g0, gp0, dg0, db0 = f32(1), f32(B, Cc), torch.zeros(B, 16, dtype=torch.bfloat16, device=dev), f32(Cc), f32(Cc)
+    rm0, rv0 = f32(Cc), torch.ones(Cc, device=dev)
+    _lib.check(lib.nn_head_fwd_bwd(logits.data_ptr(), labd.data_ptr(), B, Cc, gd.data_ptr(), bd.data_ptr(), rm0.data_ptr(),
+                                   rv0.data_ptr(), 0.1, 1e-5, loss0.data_ptr(), None, g0.data_ptr(), gp0.data_ptr(), 16,
+                                   dg0.data_ptr(), db0.data_ptr(), 0, st), "nn_head_fwd_bwd")
+    gx0 = ops.conv_dgrad(gp0[:, :Cc].float().view(B, Cc, 1, 1).contiguous(), wqd, (B, K, 1, 1), precision="bf16", w_code_scale=w_cs)
+    # --- fused
+    a = TailArgs()
+    a.xp, a.B, a.K, a.Kp, a.C = xpd.data_ptr(), B, K, Kp, Cc
+    a.w_codes, a.w_raw, a.a_code_scale, a.w_code_scale = cd.data_ptr(), wrd.data_ptr(), s_a, w_cs
+    a.noise_mode = mode
+    if mode:
+        a.current, a.scale_dev, a.rng = current, scale.data_ptr(), ops._fixed_rng(21, 4)
+    a.labels, a.gamma, a.beta = labd.data_ptr(), gd.data_ptr(), bd.data_ptr()
+    rm1, rv1 = f32(Cc), torch.ones(Cc, device=dev)
+    a.running_mean, a.running_var, a.momentum, a.eps = rm1.data_ptr(), rv1.data_ptr(), 0.1, 1e-5
+    loss1, lg1, g1, gp1 = f32(1), f32(B, Cc), f32(B, Cc), torch.zeros(B, 16, dtype=torch.bfloat16, device=dev)
+    gx1, dg1, db1 = f32(B, K), f32(Cc), f32(Cc)
+    a.loss_out, a.logits_out, a.g, a.g_packed, a.Cp_g = loss1.data_ptr(), lg1.data_ptr(), g1.data_ptr(), gp1.data_ptr(), 16
+    a.gx, a.dgamma, a.dbeta = gx1.data_ptr(), dg1.data_ptr(), db1.data_ptr()
+    _lib.check(lib.nn_classifier_tail(C.byref(a), 0, st), "nn_classifier_tail")
+    torch.cuda.synchronize()
+    assert torch.allclose(lg1, logits, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(loss1, loss0, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(g1, g0, rtol=1e-4, atol=2e-7)
+    assert torch.allclose(dg1, dg0, rtol=1e-4, atol=1e-6) and torch.allclose(db1, db0, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(rm1, rm0, rtol=1e-5, atol=1e-6) and torch.allclose(rv1, rv0, rtol=1e-5, atol=1e-6)
+    assert (gp1.float() - gp0.float()).abs().max().item() <= 1e-2 * g0.abs().max().item()      # one bf16 ulp where g differs by 1e-7
+    assert torch.allclose(gx1, gx0.view(B, K), rtol=1e-3, atol=2e-3 * gx0.abs().max().item())
