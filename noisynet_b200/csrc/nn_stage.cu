@@ -45,8 +45,9 @@ k_pool_stats(const float* __restrict__ y, float* __restrict__ pooled, uint8_t* _
     const int b0 = (int)((int64_t)B * sp / (int)gridDim.y), b1 = (int)((int64_t)B * (sp + 1) / (int)gridDim.y);
     const int n = (b1 - b0) * PHW;
     double s1 = 0.0, s2 = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int b = b0 + i / PHW, r = i % PHW, ph = r / PW, pw = r - ph * PW;
+    for (unsigned i = threadIdx.x; i < (unsigned)n; i += blockDim.x) {
+        const unsigned bi = i / (unsigned)PHW, r = i - bi * (unsigned)PHW, ph = r / (unsigned)PW, pw = r - ph * (unsigned)PW;
+        const int b = b0 + (int)bi;
         const float* src = y + (((int64_t)b * C + c) * OH + 2 * ph) * OW + 2 * pw;
         const float2 t0 = *reinterpret_cast<const float2*>(src);
         const float2 t1 = *reinterpret_cast<const float2*>(src + OW);
@@ -78,8 +79,9 @@ k_chan_stats(const float* __restrict__ x, double* __restrict__ partial, int B, i
     const int b0 = (int)((int64_t)B * sp / (int)gridDim.y), b1 = (int)((int64_t)B * (sp + 1) / (int)gridDim.y);
     const int n = (b1 - b0) * HW;
     double s1 = 0.0, s2 = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int b = b0 + i / HW, r = i % HW;
+    for (unsigned i = threadIdx.x; i < (unsigned)n; i += blockDim.x) {
+        const unsigned bi = i / (unsigned)HW, r = i - bi * (unsigned)HW;
+        const int b = b0 + (int)bi;
         const float m = __ldg(x + ((int64_t)b * C + c) * HW + r);
         s1 += m; s2 += (double)m * m;
     }
@@ -247,8 +249,9 @@ k_bn_bwd_stats(const BnBwdP p) {
     const int n = (b1 - b0) * p.HW;
     const float mean = p.mean[c], invstd = p.invstd[c], gamma = p.gamma[c], beta = p.beta[c];
     double s1 = 0.0, s2 = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int b = b0 + i / p.HW, r = i % p.HW;
+    for (unsigned i = threadIdx.x; i < (unsigned)n; i += blockDim.x) {
+        const unsigned bi = i / (unsigned)p.HW, r = i - bi * (unsigned)p.HW;
+        const int b = b0 + (int)bi;
         const int64_t o = ((int64_t)b * p.C + c) * p.HW + r;
         float xhat;
         const float dv = stage_dv(__ldg(p.g + o), __ldg(p.x + o), mean, invstd, gamma, beta, p.act_max, p.q_hi, xhat);
@@ -397,7 +400,10 @@ k_quant_pack_input(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, 
         const int chunk = (int)(i / npix);
         const int b = (int)(pixel / HW), r = (int)(pixel - (unsigned)b * HW);
         uint4 rnd[2];
-        if (quant && stoch > 0.f && !u_inject) { rnd[0] = nn_philox(rs, (uint64_t)i * 2); rnd[1] = nn_philox(rs, (uint64_t)i * 2 + 1); }
+        if (quant && stoch > 0.f && !u_inject) {
+            rnd[0] = nn_philox(rs, (uint64_t)i * 2);
+            if (chunk * 8 + 4 < C) rnd[1] = nn_philox(rs, (uint64_t)i * 2 + 1);       // words for channels 4..7 of the chunk
+        }
         const uint32_t* rr = reinterpret_cast<const uint32_t*>(rnd);
         __align__(16) __nv_bfloat16 out[8];
 #pragma unroll
