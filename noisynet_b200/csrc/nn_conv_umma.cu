@@ -240,13 +240,17 @@ k_conv_umma(const UmmaP p) {
                 }
             }
         }
+        // (tap, channel offset) of this thread's chunk: divisions once, then incremental (+64 channels per k-block)
+        int c0, kh, kw;
+        {
+            const int k = kb0 * UM_BLOCK_K + j * 8;
+            const int tap = k / p.Cp;
+            c0 = k - tap * p.Cp; kh = tap / p.KW; kw = tap - kh * p.KW;
+        }
+        int s = 0, ph = 1;                            // ring stage and the parity to wait for (no % / per k-block)
         for (int kb = kb0; kb < kb1; ++kb) {
-            const int it = kb - kb0, s = it % S;
-            if (!mbar_wait(empty_bar + 8 * s, ((it / S) & 1) ^ 1)) { *abort_g = 1; break; }
+            if (!mbar_wait(empty_bar + 8 * s, ph)) { *abort_g = 1; break; }
             if (*abort_g) break;
-            const int k = kb * UM_BLOCK_K + j * 8;
-            const int tap = k / p.Cp, c0 = k - tap * p.Cp;
-            const int kh = tap / p.KW, kw = tap - kh * p.KW;
             const bool tap_ok = kh < p.KH;
             const int koff = kh * p.W + kw;
             const uint32_t dst0 = a_base + (uint32_t)s * UM_A_STAGE;
@@ -259,6 +263,9 @@ k_conv_umma(const UmmaP p) {
                 cp_async_16(dst0 + (uint32_t)row * 128u + ((((uint32_t)j) ^ (uint32_t)(row & 7)) << 4), src, ok ? 16u : 0u);
             }
             cp_async_mbar_arrive_noinc(full_bar + 8 * s);
+            if (++s == S) { s = 0; ph ^= 1; }
+            c0 += UM_BLOCK_K;
+            while (c0 >= p.Cp) { c0 -= p.Cp; if (++kw == p.KW) { kw = 0; ++kh; } }
         }
         if (dbg && tid == 0) dbg[6] = clock64();
     } else if (warp == 4) {

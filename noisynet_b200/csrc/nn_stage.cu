@@ -45,10 +45,22 @@ k_pool_stats(const float* __restrict__ y, float* __restrict__ pooled, uint8_t* _
     const int b0 = (int)((int64_t)B * sp / (int)gridDim.y), b1 = (int)((int64_t)B * (sp + 1) / (int)gridDim.y);
     const int n = (b1 - b0) * PHW;
     double s1 = 0.0, s2 = 0.0;
+    // no divisions in the element loop (the kernel is issue-bound): (sample, position) advance incrementally and the
+    // window origin of a position comes from a shared table
+    __shared__ unsigned short s_org[1024];                     // 2*ph*OW + 2*pw for positions < 1024
+    const bool tab = PHW <= 1024 && 2 * OH * OW < 65536;
+    if (tab) {
+        for (int r = threadIdx.x; r < PHW; r += blockDim.x) { const int ph = r / PW; s_org[r] = (unsigned short)(2 * ph * OW + 2 * (r - ph * PW)); }
+        __syncthreads();
+    }
+    const unsigned step_b = blockDim.x / (unsigned)PHW, step_r = blockDim.x - step_b * (unsigned)PHW;
+    unsigned bi = threadIdx.x / (unsigned)PHW, r = threadIdx.x - bi * (unsigned)PHW;
     for (unsigned i = threadIdx.x; i < (unsigned)n; i += blockDim.x) {
-        const unsigned bi = i / (unsigned)PHW, r = i - bi * (unsigned)PHW, ph = r / (unsigned)PW, pw = r - ph * (unsigned)PW;
         const int b = b0 + (int)bi;
-        const float* src = y + (((int64_t)b * C + c) * OH + 2 * ph) * OW + 2 * pw;
+        unsigned org;
+        if (tab) org = s_org[r];
+        else { const unsigned ph = r / (unsigned)PW; org = 2 * ph * OW + 2 * (r - ph * (unsigned)PW); }
+        const float* src = y + ((int64_t)b * C + c) * OH * OW + org;
         const float2 t0 = *reinterpret_cast<const float2*>(src);
         const float2 t1 = *reinterpret_cast<const float2*>(src + OW);
         float m = t0.x; int a = 0;
@@ -58,6 +70,8 @@ k_pool_stats(const float* __restrict__ y, float* __restrict__ pooled, uint8_t* _
         const int64_t o = ((int64_t)b * C + c) * PHW + r;
         pooled[o] = m;
         amax[o] = (uint8_t)a;
+        bi += step_b; r += step_r;
+        if (r >= (unsigned)PHW) { r -= (unsigned)PHW; ++bi; }
         s1 += m; s2 += (double)m * m;
     }
     __shared__ double sh[2][8];
@@ -79,11 +93,14 @@ k_chan_stats(const float* __restrict__ x, double* __restrict__ partial, int B, i
     const int b0 = (int)((int64_t)B * sp / (int)gridDim.y), b1 = (int)((int64_t)B * (sp + 1) / (int)gridDim.y);
     const int n = (b1 - b0) * HW;
     double s1 = 0.0, s2 = 0.0;
+    const unsigned step_b = blockDim.x / (unsigned)HW, step_r = blockDim.x - step_b * (unsigned)HW;
+    unsigned bi = threadIdx.x / (unsigned)HW, r = threadIdx.x - bi * (unsigned)HW;
     for (unsigned i = threadIdx.x; i < (unsigned)n; i += blockDim.x) {
-        const unsigned bi = i / (unsigned)HW, r = i - bi * (unsigned)HW;
         const int b = b0 + (int)bi;
         const float m = __ldg(x + ((int64_t)b * C + c) * HW + r);
         s1 += m; s2 += (double)m * m;
+        bi += step_b; r += step_r;
+        if (r >= (unsigned)HW) { r -= (unsigned)HW; ++bi; }
     }
     __shared__ double sh[2][8];
     for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
@@ -249,13 +266,16 @@ k_bn_bwd_stats(const BnBwdP p) {
     const int n = (b1 - b0) * p.HW;
     const float mean = p.mean[c], invstd = p.invstd[c], gamma = p.gamma[c], beta = p.beta[c];
     double s1 = 0.0, s2 = 0.0;
+    const unsigned step_b = blockDim.x / (unsigned)p.HW, step_r = blockDim.x - step_b * (unsigned)p.HW;
+    unsigned bi = threadIdx.x / (unsigned)p.HW, r = threadIdx.x - bi * (unsigned)p.HW;
     for (unsigned i = threadIdx.x; i < (unsigned)n; i += blockDim.x) {
-        const unsigned bi = i / (unsigned)p.HW, r = i - bi * (unsigned)p.HW;
         const int b = b0 + (int)bi;
         const int64_t o = ((int64_t)b * p.C + c) * p.HW + r;
         float xhat;
         const float dv = stage_dv(__ldg(p.g + o), __ldg(p.x + o), mean, invstd, gamma, beta, p.act_max, p.q_hi, xhat);
         s1 += dv; s2 += (double)dv * xhat;
+        bi += step_b; r += step_r;
+        if (r >= (unsigned)p.HW) { r -= (unsigned)p.HW; ++bi; }
     }
     __shared__ double sh[2][8];
     for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
