@@ -165,6 +165,7 @@ struct UmmaP {
     int rows_tile;                 // valid rows per m-tile (<= 128): chosen so that the CTAs fill whole waves
     float* partial;                // split-K (gridDim.z > 1): raw accumulators [z][n_tile][column][m_pad] instead of the epilogue
     int m_pad;
+    int inc_taps;                  // producers track (tap, channel) incrementally instead of dividing per k-block
 };
 
 // EPI selects the epilogue at compile time: 0 = generic (every option), 1 = lean noisy (main + sigma, Philox z,
@@ -264,8 +265,14 @@ k_conv_umma(const UmmaP p) {
             }
             cp_async_mbar_arrive_noinc(full_bar + 8 * s);
             if (++s == S) { s = 0; ph ^= 1; }
-            c0 += UM_BLOCK_K;
-            while (c0 >= p.Cp) { c0 -= p.Cp; if (++kw == p.KW) { kw = 0; ++kh; } }
+            if (p.inc_taps) {
+                c0 += UM_BLOCK_K;
+                while (c0 >= p.Cp) { c0 -= p.Cp; if (++kw == p.KW) { kw = 0; ++kh; } }
+            } else {
+                const int k = (kb + 1) * UM_BLOCK_K + j * 8;
+                const int tap = k / p.Cp;
+                c0 = k - tap * p.Cp; kh = tap / p.KW; kw = tap - kh * p.KW;
+            }
         }
         if (dbg && tid == 0) dbg[6] = clock64();
     } else if (warp == 4) {
@@ -1559,6 +1566,10 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* sp
     static const bool force_generic = getenv("NN_UMMA_GENERIC_EPI") != nullptr;
     if (force_generic) epi = 0;
     UmmaP pd = p;
+    static const int env_inc = getenv("NN_UMMA_INC_TAPS") ? atoi(getenv("NN_UMMA_INC_TAPS")) : -1;
+    // measured at batch 512 (same run, A/B): incremental tap tracking takes conv2 dgrad 120 -> 110 us (3 CTAs/SM, the
+    // producers' issue slots matter) but costs the fused forward 70 -> 72.7 us (2 CTAs/SM, sigma rows): per variant
+    pd.inc_taps = env_inc >= 0 ? env_inc : (epi == 2 ? 1 : 0);
     // wave shaping: with T = ceil(M/128) tiles and S resident CTA slots, ceil(T/S) rounds run anyway; shrinking the
     // VALID rows per tile so that the CTAs fill those rounds exactly shortens every CTA (gather and epilogue scale with
     // the valid rows; the tensor pipe has slack) instead of leaving the last round mostly empty
