@@ -59,6 +59,19 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     }
     return true;
 }
+__device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity) {     // acquire at cluster scope (remote arrivals)
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return true;
+        if (clock64() - t0 > UM_TIMEOUT) return false;
+    }
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -83,6 +96,35 @@ __device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint3
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(mask) : "memory");
+}
+// CTA pair (cta_group::2): both SMs of a TPC execute ONE MMA of M = 256 -- each CTA contributes its 128 rows of A and
+// HALF of the B rows from its own shared memory, each CTA's TMEM receives its 128 rows of D
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t cta_rank) {
+    // arrive on the barrier at the same shared-memory offset in CTA `cta_rank` of the cluster
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(local_bar), "r"(cta_rank) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -175,17 +217,21 @@ struct UmmaP {
 #ifndef NN_EPI1_MINBLOCKS
 #define NN_EPI1_MINBLOCKS 2
 #endif
-template <int EPI>
+// PAIR: cta_group::2 variant (a kernel that contains cta_group::2 instructions can only be launched as 2-CTA clusters,
+// so it is a separate instantiation)
+template <int EPI, bool PAIR = false>
 __global__ void __launch_bounds__(UM_THREADS, EPI == 2 ? 3 : (EPI == 1 ? NN_EPI1_MINBLOCKS : 2))
 k_conv_umma(const UmmaP p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int S = p.stages;
-    const uint32_t b_stage = (uint32_t)p.n_mma * 128u;
+    constexpr bool pair = PAIR;                     // cta_group::2: this CTA stages only its half of the weight rows
+    const uint32_t b_stage = pair ? (uint32_t)p.n_mma * 64u : (uint32_t)p.n_mma * 128u;
     const uint32_t a_base = base;
     const uint32_t b_base = base + (uint32_t)S * UM_A_STAGE;
-    const uint32_t bar_base = b_base + (uint32_t)S * b_stage;       // 8-byte barriers: full[S], empty[S], tmem_full
+    const uint32_t bar_base = b_base + (uint32_t)S * b_stage;       // 8-byte barriers: full[S], empty[S], tmem_full, peer_full[S]
     const uint32_t full_bar = bar_base, empty_bar = bar_base + 8u * S, tfull_bar = bar_base + 16u * S;
+    const uint32_t pfull_bar = tfull_bar + 16;      // leader only: "the peer CTA's stage s is loaded"
     const uint32_t tmem_slot = tfull_bar + 8;
     const uint32_t abort_slot = tmem_slot + 4;
     // generic pointers to the two 4-byte slots
@@ -205,13 +251,18 @@ k_conv_umma(const UmmaP p) {
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(full_bar + 8 * s, 128 + 1);     // 128 cp.async arrivals (noinc) + 1 expect_tx arrival
-            mbar_init(empty_bar + 8 * s, p.cluster);  // tcgen05.commit of every CTA that reads (and refills) the stage
+            mbar_init(empty_bar + 8 * s, p.cluster == 2 ? 2 : 1);  // tcgen05.commit of every CTA that reads (and refills) the stage
+            if (pair) mbar_init(pfull_bar + 8 * s, 1);
         }
         mbar_init(tfull_bar, 1);
         *abort_g = 0;
         fence_mbar_init();
     }
-    if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (pair) {                                      // both CTAs' barriers exist before the paired allocation / any remote arrive
+        __syncthreads();
+        cluster_sync_all();
+    }
+    if (warp == 4) { if constexpr (PAIR) tmem_alloc_2cta(tmem_slot, (uint32_t)p.tmem_cols); else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -277,7 +328,39 @@ k_conv_umma(const UmmaP p) {
         if (dbg && tid == 0) dbg[6] = clock64();
     } else if (warp == 4) {
         // ---------------- MMA issuer (single thread)
-        if (lane == 0) {
+        if constexpr (PAIR) {
+          if (lane == 0) {
+            const uint32_t rank = cluster_ctarank();
+            if (rank == 0) {
+                // leader of the CTA pair: M = 256 (this CTA's 128 rows + the peer's), N = n_mma (half from each CTA)
+                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) |
+                                       ((uint32_t)(256 >> 4) << 24);
+                bool ok = true;
+                for (int kb = kb0; kb < kb1 && ok; ++kb) {
+                    const int it = kb - kb0, s = it % S;
+                    if (!mbar_wait(full_bar + 8 * s, (it / S) & 1)) { *abort_g = 2; ok = false; break; }
+                    if (!mbar_wait_cluster(pfull_bar + 8 * s, (it / S) & 1)) { *abort_g = 4; ok = false; break; }
+                    fence_proxy_async();
+                    tc_fence_after();
+                    const uint64_t ad = umma_desc_sw128(a_base + (uint32_t)s * UM_A_STAGE);
+                    const uint64_t bd = umma_desc_sw128(b_base + (uint32_t)s * b_stage);
+#pragma unroll
+                    for (int k = 0; k < UM_BLOCK_K / 16; ++k)
+                        umma_bf16_2cta(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0);
+                    umma_commit_2cta_mc(empty_bar + 8 * s, 3);    // both CTAs may refill stage s when these MMAs retire
+                }
+                umma_commit_2cta_mc(tfull_bar, 3);                // both CTAs' accumulators complete
+            } else {
+                // peer: tell the leader when this CTA's share of stage s (its A rows, its half of B) has landed
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const int it = kb - kb0, s = it % S;
+                    if (!mbar_wait(full_bar + 8 * s, (it / S) & 1)) { *abort_g = 2; break; }
+                    fence_proxy_async();            // this CTA's cp.async writes -> the pair's tensor-core reads
+                    mbar_arrive_remote(pfull_bar + 8 * s, 0);
+                }
+            }
+          }
+        } else if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) |
                                    ((uint32_t)(UM_BLOCK_M >> 4) << 24);
             bool ok = true;
@@ -291,7 +374,7 @@ k_conv_umma(const UmmaP p) {
 #pragma unroll
                 for (int k = 0; k < UM_BLOCK_K / 16; ++k)
                     umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0);
-                if (p.cluster > 1) umma_commit_mc(empty_bar + 8 * s, 3);
+                if (p.cluster == 2) umma_commit_mc(empty_bar + 8 * s, 3);
                 else umma_commit(empty_bar + 8 * s);       // frees the smem stage when these MMAs retire
             }
             umma_commit(tfull_bar);                        // accumulators complete
@@ -307,7 +390,11 @@ k_conv_umma(const UmmaP p) {
                 if (!mbar_wait(empty_bar + 8 * s, ((it / S) & 1) ^ 1)) { *abort_g = 3; break; }
                 if (*abort_g) break;
                 mbar_arrive_expect_tx(full_bar + 8 * s, b_stage);
-                if (p.cluster > 1) {      // this CTA fetches its half of the k-block for both CTAs of the pair
+                if (pair) {               // this CTA's half of the weight rows only (the MMA reads the other half from the peer)
+                    bulk_g2s(b_base + (uint32_t)s * b_stage,
+                             reinterpret_cast<const uint8_t*>(wt + (size_t)kb * p.n_mma * 64) + cluster_ctarank() * b_stage, b_stage,
+                             full_bar + 8 * s);
+                } else if (p.cluster > 1) {      // this CTA fetches its half of the k-block for both CTAs of the pair
                     const uint32_t half = b_stage >> 1, off = cluster_ctarank() * half;
                     bulk_g2s_mc(b_base + (uint32_t)s * b_stage + off,
                                 reinterpret_cast<const uint8_t*>(wt + (size_t)kb * p.n_mma * 64) + off, half, full_bar + 8 * s, 3);
@@ -483,7 +570,8 @@ k_conv_umma(const UmmaP p) {
     if (dbg && tid == 0) dbg[4] = clock64();
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+    if (pair) cluster_sync_all();                    // both CTAs are done with the paired accumulators
+    if (warp == 4) { tc_fence_after(); if constexpr (PAIR) tmem_dealloc_2cta(tmem_base, (uint32_t)p.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
     if (dbg && tid == 128) { dbg[5] = clock64(); unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); dbg[7] = smid; }
     if (p.cluster > 1) cluster_sync_all();          // no CTA leaves while its peer may still signal or fill its shared memory
 }
@@ -1623,7 +1711,21 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* sp
     // (measured round 1: correct, but 1-3 % SLOWER on every layer -- weight ingest is not what bounds these kernels; kept as a knob)
     static const int env_cluster = getenv("NN_UMMA_CLUSTER") ? atoi(getenv("NN_UMMA_CLUSTER")) : 1;
     pd.cluster = (env_cluster == 2 && grid.x >= 2 && !want_dbg) ? 2 : 1;
-    if (pd.cluster == 2) grid.x = (grid.x + 1) & ~1u;
+    // NN_UMMA_CLUSTER=3: CTA pairs (cta_group::2) -- one M = 256 MMA per pair, each SM stages and RECEIVES only half of
+    // the weight rows of a k-block (delivered bytes per SM: A 16 KB + B/2), which also makes room for deeper pipelines
+    size_t smem_bytes = pl.smem_bytes;
+    if (env_cluster == 3 && grid.x >= 2 && !want_dbg && (epi == 1 || epi == 2) && p.OH * p.OW != 1) {
+        pd.cluster = 3;
+        const int stage_bytes = UM_A_STAGE + pl.n_mma * 64;
+        const int budget_kb = (pl.tmem_cols <= 128 && p.noise_mode == NN_NOISE_NONE) ? 72 : 100;
+        int stages = (budget_kb * 1024 - 2048) / stage_bytes;
+        if (stages > 4) stages = 4;
+        if (stages < 2) stages = 2;
+        if (stages > pl.num_kb) stages = pl.num_kb;
+        pd.stages = stages;
+        smem_bytes = 1024 + (size_t)stages * stage_bytes + 16 * stages + 64;
+    }
+    if (pd.cluster >= 2) grid.x = (grid.x + 1) & ~1u;
     // split-K for skinny linear layers (few m-tiles x n-tiles, long K: fc1 forward at batch 512 is 52 CTAs walking 47
     // k-blocks each -- a latency chain on a third of the SMs): the k-blocks are dealt to gridDim.z CTAs that dump raw
     // accumulators, and k_splitk_epilogue sums them and applies the noise epilogue
@@ -1641,14 +1743,25 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* sp
         pd.partial = (float*)splitk_ws;
         pd.m_pad = (int)grid.x * UM_BLOCK_M;
     }
+    if (verbose) fprintf(stderr, "[umma]   launch grid=(%u,%u,%u) cluster=%d stages=%d smem=%zu\n", grid.x, grid.y, grid.z, pd.cluster,
+                         pd.stages, smem_bytes);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid; cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = pl.smem_bytes; cfg.stream = st;
+    cfg.gridDim = grid; cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = pd.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = pd.cluster >= 2 ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (epi == 1) NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<1>, pd));
+    if (pd.cluster == 3) {
+        static bool pair_attr = false;
+        if (!pair_attr) {
+            NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            pair_attr = true;
+        }
+        if (epi == 1) NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<1, true>, pd));
+        else NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<2, true>, pd));
+    } else if (epi == 1) NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<1>, pd));
     else if (epi == 2) NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<2>, pd));
     else NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<0>, pd));
     if (g_time_main) cudaEventRecord(g_ev1, st);
