@@ -51,9 +51,27 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok;
 }
+__device__ int g_mbar_spin = 0;          // experiment knob: 1 = poll with test_wait (never suspends the thread)
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
+    if (g_mbar_spin) {
+        while (!mbar_test_wait(bar, parity)) {
+            if (clock64() - t0 > UM_TIMEOUT) return false;
+        }
+        return true;
+    }
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > UM_TIMEOUT) return false;
     }
@@ -135,6 +153,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     return r;
 }
 __device__ __forceinline__ void st_global_f32(float* ptr, float v);
+__device__ __forceinline__ void mbar_arrive(uint32_t bar);
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -208,6 +227,8 @@ struct UmmaP {
     float* partial;                // split-K (gridDim.z > 1): raw accumulators [z][n_tile][column][m_pad] instead of the epilogue
     int m_pad;
     int inc_taps;                  // producers track (tap, channel) incrementally instead of dividing per k-block
+    int halo_bytes;                // HALO: shared-memory bytes reserved for the tile's input footprint
+    int b_stages;                  // HALO: depth of the separate weight ring (the A ring has `stages`)
 };
 
 // EPI selects the epilogue at compile time: 0 = generic (every option), 1 = lean noisy (main + sigma, Philox z,
@@ -219,7 +240,9 @@ struct UmmaP {
 #endif
 // PAIR: cta_group::2 variant (a kernel that contains cta_group::2 instructions can only be launched as 2-CTA clusters,
 // so it is a separate instantiation)
-template <int EPI, bool PAIR = false>
+// HALO: the tile's input footprint (a contiguous range of NHWC pixels) is loaded ONCE into shared memory by bulk copies
+// and the im2col stages are built shared-to-shared: the A operand no longer makes an L2 round trip per k-block
+template <int EPI, bool PAIR = false, bool HALO = false>
 __global__ void __launch_bounds__(UM_THREADS, EPI == 2 ? 3 : (EPI == 1 ? NN_EPI1_MINBLOCKS : 2))
 k_conv_umma(const UmmaP p) {
     extern __shared__ uint8_t smem_raw[];
@@ -227,11 +250,15 @@ k_conv_umma(const UmmaP p) {
     const int S = p.stages;
     constexpr bool pair = PAIR;                     // cta_group::2: this CTA stages only its half of the weight rows
     const uint32_t b_stage = pair ? (uint32_t)p.n_mma * 64u : (uint32_t)p.n_mma * 128u;
+    const int SB = HALO ? p.b_stages : S;           // HALO: the weight k-blocks have their own, deeper ring
     const uint32_t a_base = base;
     const uint32_t b_base = base + (uint32_t)S * UM_A_STAGE;
-    const uint32_t bar_base = b_base + (uint32_t)S * b_stage;       // 8-byte barriers: full[S], empty[S], tmem_full, peer_full[S]
+    const uint32_t bar_base = b_base + (uint32_t)SB * b_stage;      // 8-byte barriers: full[S], empty[S], tmem_full, peer_full[S]
     const uint32_t full_bar = bar_base, empty_bar = bar_base + 8u * S, tfull_bar = bar_base + 16u * S;
     const uint32_t pfull_bar = tfull_bar + 16;      // leader only: "the peer CTA's stage s is loaded"
+    const uint32_t halo_bar = pfull_bar + 8u * S;   // HALO: the input footprint has landed
+    const uint32_t bfull_bar = halo_bar + 8u, bempty_bar = bfull_bar + 8u * SB;     // HALO: weight ring
+    const uint32_t halo_base = (bempty_bar + 8u * SB + 127u) & ~127u;
     const uint32_t tmem_slot = tfull_bar + 8;
     const uint32_t abort_slot = tmem_slot + 4;
     // generic pointers to the two 4-byte slots
@@ -250,11 +277,15 @@ k_conv_umma(const UmmaP p) {
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_bar + 8 * s, 128 + 1);     // 128 cp.async arrivals (noinc) + 1 expect_tx arrival
+            mbar_init(full_bar + 8 * s, HALO ? 128 : 128 + 1);     // 128 producer arrivals (+ 1 expect_tx arrival of the weights)
             mbar_init(empty_bar + 8 * s, p.cluster == 2 ? 2 : 1);  // tcgen05.commit of every CTA that reads (and refills) the stage
             if (pair) mbar_init(pfull_bar + 8 * s, 1);
         }
         mbar_init(tfull_bar, 1);
+        if (HALO) {
+            mbar_init(halo_bar, 1);
+            for (int sb = 0; sb < SB; ++sb) { mbar_init(bfull_bar + 8 * sb, 1); mbar_init(bempty_bar + 8 * sb, 1); }
+        }
         *abort_g = 0;
         fence_mbar_init();
     }
@@ -269,6 +300,20 @@ k_conv_umma(const UmmaP p) {
     if (p.cluster > 1) cluster_sync_all();          // the peer's barriers exist before anything is multicast to them
     const uint32_t tmem_base = *tmem_slot_g;
     if (dbg && tid == 0) dbg[1] = clock64();
+
+    // HALO: the input pixels this tile can touch form one contiguous NHWC range [pmin, pend) (stride 1)
+    int pmin = 0, pend = 0;
+    if (HALO) {
+        const int ohw = p.OH * p.OW;
+        const int m_last = min(m0 + p.rows_tile - 1, p.M - 1);
+        const int b0 = m0 / ohw, oh0 = (m0 - b0 * ohw) / p.OW;
+        const int b1 = m_last / ohw, oh1 = (m_last - b1 * ohw) / p.OW;
+        const int ih_lo = max(oh0 - p.pad, 0), ih_hi = min(oh1 - p.pad + p.KH - 1, p.H - 1);
+        pmin = (b0 * p.H + ih_lo) * p.W;
+        pend = (b1 * p.H + ih_hi) * p.W + p.W;
+        if (m0 >= p.M || pend <= pmin) { pmin = 0; pend = 0; }
+        if ((pend - pmin) * p.Cp * 2 > p.halo_bytes) { if (tid == 0) *abort_g = 7; pend = pmin; }
+    }
 
     // ================================================================ main loop roles
     if (warp < 4) {
@@ -300,6 +345,7 @@ k_conv_umma(const UmmaP p) {
             c0 = k - tap * p.Cp; kh = tap / p.KW; kw = tap - kh * p.KW;
         }
         int s = 0, ph = 1;                            // ring stage and the parity to wait for (no % / per k-block)
+        if (HALO) { if (!mbar_wait(halo_bar, 0)) *abort_g = 6; }
         for (int kb = kb0; kb < kb1; ++kb) {
             if (!mbar_wait(empty_bar + 8 * s, ph)) { *abort_g = 1; break; }
             if (*abort_g) break;
@@ -311,10 +357,21 @@ k_conv_umma(const UmmaP p) {
                 const int row = (tid >> 3) + 16 * i;
                 const int ih = rih[i] + kh, iw = riw[i] + kw;
                 const bool ok = tap_ok && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
-                const __nv_bfloat16* src = ok ? p.xp + (size_t)(rbase[i] + koff) * p.Cp + c0 : p.xp;
-                cp_async_16(dst0 + (uint32_t)row * 128u + ((((uint32_t)j) ^ (uint32_t)(row & 7)) << 4), src, ok ? 16u : 0u);
+                const uint32_t dst = dst0 + (uint32_t)row * 128u + ((((uint32_t)j) ^ (uint32_t)(row & 7)) << 4);
+                if (HALO) {
+                    uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                    if (ok) {
+                        const uint32_t src = halo_base + (uint32_t)(((rbase[i] + koff - pmin) * p.Cp + c0) * 2);
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(src) : "memory");
+                    }
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+                } else {
+                    const __nv_bfloat16* src = ok ? p.xp + (size_t)(rbase[i] + koff) * p.Cp + c0 : p.xp;
+                    cp_async_16(dst, src, ok ? 16u : 0u);
+                }
             }
-            cp_async_mbar_arrive_noinc(full_bar + 8 * s);
+            if (HALO) { fence_proxy_async(); mbar_arrive(full_bar + 8 * s); }     // generic stores -> tensor-core reads
+            else cp_async_mbar_arrive_noinc(full_bar + 8 * s);
             if (++s == S) { s = 0; ph ^= 1; }
             if (p.inc_taps) {
                 c0 += UM_BLOCK_K;
@@ -365,17 +422,19 @@ k_conv_umma(const UmmaP p) {
                                    ((uint32_t)(UM_BLOCK_M >> 4) << 24);
             bool ok = true;
             for (int kb = kb0; kb < kb1 && ok; ++kb) {
-                const int it = kb - kb0, s = it % S;
+                const int it = kb - kb0, s = it % S, sb = it % SB;
                 if (!mbar_wait(full_bar + 8 * s, (it / S) & 1)) { *abort_g = 2; ok = false; break; }
+                if (HALO && !mbar_wait(bfull_bar + 8 * sb, (it / SB) & 1)) { *abort_g = 8; ok = false; break; }
                 fence_proxy_async();            // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
                 tc_fence_after();
                 const uint64_t ad = umma_desc_sw128(a_base + (uint32_t)s * UM_A_STAGE);
-                const uint64_t bd = umma_desc_sw128(b_base + (uint32_t)s * b_stage);
+                const uint64_t bd = umma_desc_sw128(b_base + (uint32_t)(HALO ? sb : s) * b_stage);
 #pragma unroll
                 for (int k = 0; k < UM_BLOCK_K / 16; ++k)
                     umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0);
                 if (p.cluster == 2) umma_commit_mc(empty_bar + 8 * s, 3);
                 else umma_commit(empty_bar + 8 * s);       // frees the smem stage when these MMAs retire
+                if (HALO) umma_commit(bempty_bar + 8 * sb);
             }
             umma_commit(tfull_bar);                        // accumulators complete
             if (dbg) dbg[2] = clock64();
@@ -385,8 +444,21 @@ k_conv_umma(const UmmaP p) {
         // ---------------- B loader: one bulk copy (TMA engine) per k-block
         if (lane == 0) {
             const __nv_bfloat16* wt = p.wp + (size_t)tile_n * p.num_kb * p.n_mma * 64;
+            if (HALO) {
+                const uint32_t bytes = (uint32_t)((pend - pmin) * p.Cp * 2);
+                mbar_arrive_expect_tx(halo_bar, bytes);
+                if (bytes) bulk_g2s(halo_base, p.xp + (size_t)pmin * p.Cp, bytes, halo_bar);
+            }
             for (int kb = kb0; kb < kb1; ++kb) {
                 const int it = kb - kb0, s = it % S;
+                if (HALO) {                  // own ring, as deep as shared memory allows: the weights run far ahead
+                    const int sb = it % SB;
+                    if (!mbar_wait(bempty_bar + 8 * sb, ((it / SB) & 1) ^ 1)) { *abort_g = 3; break; }
+                    if (*abort_g) break;
+                    mbar_arrive_expect_tx(bfull_bar + 8 * sb, b_stage);
+                    bulk_g2s(b_base + (uint32_t)sb * b_stage, wt + (size_t)kb * p.n_mma * 64, b_stage, bfull_bar + 8 * sb);
+                    continue;
+                }
                 if (!mbar_wait(empty_bar + 8 * s, ((it / S) & 1) ^ 1)) { *abort_g = 3; break; }
                 if (*abort_g) break;
                 mbar_arrive_expect_tx(full_bar + 8 * s, b_stage);
@@ -1654,6 +1726,12 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* sp
     static const bool force_generic = getenv("NN_UMMA_GENERIC_EPI") != nullptr;
     if (force_generic) epi = 0;
     UmmaP pd = p;
+    static bool spin_set = false;
+    if (!spin_set) {
+        const int spin = getenv("NN_UMMA_SPIN") ? atoi(getenv("NN_UMMA_SPIN")) : 0;
+        if (spin) cudaMemcpyToSymbol(g_mbar_spin, &spin, sizeof(int));
+        spin_set = true;
+    }
     static const int env_inc = getenv("NN_UMMA_INC_TAPS") ? atoi(getenv("NN_UMMA_INC_TAPS")) : -1;
     // measured at batch 512 (same run, A/B): incremental tap tracking takes conv2 dgrad 120 -> 110 us (3 CTAs/SM, the
     // producers' issue slots matter) but costs the fused forward 70 -> 72.7 us (2 CTAs/SM, sigma rows): per variant
@@ -1726,6 +1804,30 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* sp
         smem_bytes = 1024 + (size_t)stages * stage_bytes + 16 * stages + 64;
     }
     if (pd.cluster >= 2) grid.x = (grid.x + 1) & ~1u;
+    // NN_UMMA_HALO=1 (lean plain variant: dgrad) / 2 (both lean variants): input footprint resident in shared memory
+    static const int env_halo = getenv("NN_UMMA_HALO") ? atoi(getenv("NN_UMMA_HALO")) : 0;
+    bool halo = false;
+    if (pd.cluster == 1 && p.stride == 1 && !want_dbg && ((env_halo >= 1 && epi == 2) || (env_halo >= 2 && epi == 1)) &&
+        p.OH * p.OW != 1 && pd.rows_tile == UM_BLOCK_M) {
+        const int dR = (UM_BLOCK_M - 1) / p.OW + 2, crossings = dR / p.OH + 1;
+        const int rows = dR + crossings * (p.H > p.OH ? p.H - p.OH : 0) + p.KH;
+        const int halo_bytes = (rows * p.W * p.Cp * 2 + 127) & ~127;
+        static const int env_hs = getenv("NN_UMMA_HALO_STAGES") ? atoi(getenv("NN_UMMA_HALO_STAGES")) : 2;
+        static const int env_hkb = getenv("NN_UMMA_HALO_KB") ? atoi(getenv("NN_UMMA_HALO_KB")) : 110;    // smem budget per CTA
+        int stages = env_hs;
+        if (stages > pl.num_kb) stages = pl.num_kb;
+        const long long fixed = 1024 + (long long)stages * UM_A_STAGE + 24 * stages + 512 + halo_bytes;
+        int bst = (int)(((long long)env_hkb * 1024 - fixed) / (pl.n_mma * 128 + 16));
+        if (bst > 12) bst = 12;
+        if (bst > pl.num_kb) bst = pl.num_kb;
+        if (bst >= 2 && stages >= 1) {
+            halo = true;
+            pd.halo_bytes = halo_bytes;
+            pd.stages = stages;
+            pd.b_stages = bst;
+            smem_bytes = (size_t)fixed + (size_t)bst * (pl.n_mma * 128 + 16);
+        }
+    }
     // split-K for skinny linear layers (few m-tiles x n-tiles, long K: fc1 forward at batch 512 is 52 CTAs walking 47
     // k-blocks each -- a latency chain on a third of the SMs): the k-blocks are dealt to gridDim.z CTAs that dump raw
     // accumulators, and k_splitk_epilogue sums them and applies the noise epilogue
@@ -1743,8 +1845,8 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* sp
         pd.partial = (float*)splitk_ws;
         pd.m_pad = (int)grid.x * UM_BLOCK_M;
     }
-    if (verbose) fprintf(stderr, "[umma]   launch grid=(%u,%u,%u) cluster=%d stages=%d smem=%zu\n", grid.x, grid.y, grid.z, pd.cluster,
-                         pd.stages, smem_bytes);
+    if (verbose) fprintf(stderr, "[umma]   launch grid=(%u,%u,%u) cluster=%d stages=%d b_stages=%d halo=%d smem=%zu\n", grid.x, grid.y, grid.z,
+                         pd.cluster, pd.stages, pd.b_stages, pd.halo_bytes, smem_bytes);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid; cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
@@ -1752,7 +1854,16 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* sp
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = pd.cluster >= 2 ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (pd.cluster == 3) {
+    if (halo) {
+        static bool halo_attr = false;
+        if (!halo_attr) {
+            NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            halo_attr = true;
+        }
+        if (epi == 1) NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<1, false, true>, pd));
+        else NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<2, false, true>, pd));
+    } else if (pd.cluster == 3) {
         static bool pair_attr = false;
         if (!pair_attr) {
             NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
