@@ -229,6 +229,7 @@ struct UmmaP {
     int inc_taps;                  // producers track (tap, channel) incrementally instead of dividing per k-block
     int halo_bytes;                // HALO: shared-memory bytes reserved for the tile's input footprint
     int b_stages;                  // HALO: depth of the separate weight ring (the A ring has `stages`)
+    long long* kdbg;               // optional per-k-block stamps [cta][num_kb][4]: producer woke / arrived, MMA woke / committed
 };
 
 // EPI selects the epilogue at compile time: 0 = generic (every option), 1 = lean noisy (main + sigma, Philox z,
@@ -349,6 +350,8 @@ k_conv_umma(const UmmaP p) {
         for (int kb = kb0; kb < kb1; ++kb) {
             if (!mbar_wait(empty_bar + 8 * s, ph)) { *abort_g = 1; break; }
             if (*abort_g) break;
+            long long* const kd = (p.kdbg && tid == 0) ? p.kdbg + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * p.num_kb + kb) * 4 : nullptr;
+            if (kd) kd[0] = clock64();
             const bool tap_ok = kh < p.KH;
             const int koff = kh * p.W + kw;
             const uint32_t dst0 = a_base + (uint32_t)s * UM_A_STAGE;
@@ -372,6 +375,7 @@ k_conv_umma(const UmmaP p) {
             }
             if (HALO) { fence_proxy_async(); mbar_arrive(full_bar + 8 * s); }     // generic stores -> tensor-core reads
             else cp_async_mbar_arrive_noinc(full_bar + 8 * s);
+            if (kd) kd[1] = clock64();
             if (++s == S) { s = 0; ph ^= 1; }
             if (p.inc_taps) {
                 c0 += UM_BLOCK_K;
@@ -425,6 +429,8 @@ k_conv_umma(const UmmaP p) {
                 const int it = kb - kb0, s = it % S, sb = it % SB;
                 if (!mbar_wait(full_bar + 8 * s, (it / S) & 1)) { *abort_g = 2; ok = false; break; }
                 if (HALO && !mbar_wait(bfull_bar + 8 * sb, (it / SB) & 1)) { *abort_g = 8; ok = false; break; }
+                long long* const kd = p.kdbg ? p.kdbg + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * p.num_kb + kb) * 4 : nullptr;
+                if (kd) kd[2] = clock64();
                 fence_proxy_async();            // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
                 tc_fence_after();
                 const uint64_t ad = umma_desc_sw128(a_base + (uint32_t)s * UM_A_STAGE);
@@ -435,6 +441,7 @@ k_conv_umma(const UmmaP p) {
                 if (p.cluster == 2) umma_commit_mc(empty_bar + 8 * s, 3);
                 else umma_commit(empty_bar + 8 * s);       // frees the smem stage when these MMAs retire
                 if (HALO) umma_commit(bempty_bar + 8 * sb);
+                if (kd) kd[3] = clock64();
             }
             umma_commit(tfull_bar);                        // accumulators complete
             if (dbg) dbg[2] = clock64();
@@ -1844,6 +1851,18 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* sp
         grid.z = splits;
         pd.partial = (float*)splitk_ws;
         pd.m_pad = (int)grid.x * UM_BLOCK_M;
+    }
+    static const bool want_kdbg = getenv("NN_UMMA_KDEBUG") != nullptr;
+    if (want_kdbg) {
+        const size_t rows = ((size_t)grid.x * grid.y * pl.num_kb * 4 + 7) / 8;      // rows of 8 longs, as nn_debug_cta_timeline copies
+        if (rows > g_dbg_ctas) {
+            if (g_dbg_buf) cudaFree(g_dbg_buf);
+            cudaMalloc(&g_dbg_buf, rows * 8 * sizeof(long long));
+            g_dbg_ctas = rows;
+        }
+        cudaMemsetAsync(g_dbg_buf, 0, rows * 8 * sizeof(long long), st);
+        pd.kdbg = g_dbg_buf;
+        g_dbg_last = rows;
     }
     if (verbose) fprintf(stderr, "[umma]   launch grid=(%u,%u,%u) cluster=%d stages=%d b_stages=%d halo=%d smem=%zu\n", grid.x, grid.y, grid.z,
                          pd.cluster, pd.stages, pd.b_stages, pd.halo_bytes, smem_bytes);
