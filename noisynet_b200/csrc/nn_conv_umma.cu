@@ -51,27 +51,10 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok;
 }
-__device__ int g_mbar_spin = 0;          // experiment knob: 1 = poll with test_wait (never suspends the thread)
-__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok;
-}
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    // (polling with mbarrier.test_wait instead of try_wait was measured: no difference)
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
-    if (g_mbar_spin) {
-        while (!mbar_test_wait(bar, parity)) {
-            if (clock64() - t0 > UM_TIMEOUT) return false;
-        }
-        return true;
-    }
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > UM_TIMEOUT) return false;
     }
@@ -346,11 +329,16 @@ k_conv_umma(const UmmaP p) {
             c0 = k - tap * p.Cp; kh = tap / p.KW; kw = tap - kh * p.KW;
         }
         int s = 0, ph = 1;                            // ring stage and the parity to wait for (no % / per k-block)
+#ifdef NN_KDEBUG      // per-k-block clock stamps (tools/kblock_timeline.py): build with NN_EXTRA_NVCC=-DNN_KDEBUG
+        long long* const kd0 = (p.kdbg && tid == 0) ? p.kdbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * p.num_kb * 4 : nullptr;
+#else
+        long long* const kd0 = nullptr;
+#endif
         if (HALO) { if (!mbar_wait(halo_bar, 0)) *abort_g = 6; }
         for (int kb = kb0; kb < kb1; ++kb) {
             if (!mbar_wait(empty_bar + 8 * s, ph)) { *abort_g = 1; break; }
             if (*abort_g) break;
-            long long* const kd = (p.kdbg && tid == 0) ? p.kdbg + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * p.num_kb + kb) * 4 : nullptr;
+            long long* const kd = kd0 ? kd0 + kb * 4 : nullptr;
             if (kd) kd[0] = clock64();
             const bool tap_ok = kh < p.KH;
             const int koff = kh * p.W + kw;
@@ -425,11 +413,16 @@ k_conv_umma(const UmmaP p) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) |
                                    ((uint32_t)(UM_BLOCK_M >> 4) << 24);
             bool ok = true;
+#ifdef NN_KDEBUG
+            long long* const kd0 = p.kdbg ? p.kdbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * p.num_kb * 4 : nullptr;
+#else
+            long long* const kd0 = nullptr;
+#endif
             for (int kb = kb0; kb < kb1 && ok; ++kb) {
-                const int it = kb - kb0, s = it % S, sb = it % SB;
+                const int it = kb - kb0, s = it % S, sb = HALO ? it % SB : s;
                 if (!mbar_wait(full_bar + 8 * s, (it / S) & 1)) { *abort_g = 2; ok = false; break; }
                 if (HALO && !mbar_wait(bfull_bar + 8 * sb, (it / SB) & 1)) { *abort_g = 8; ok = false; break; }
-                long long* const kd = p.kdbg ? p.kdbg + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * p.num_kb + kb) * 4 : nullptr;
+                long long* const kd = kd0 ? kd0 + kb * 4 : nullptr;
                 if (kd) kd[2] = clock64();
                 fence_proxy_async();            // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
                 tc_fence_after();
@@ -1733,12 +1726,6 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* sp
     static const bool force_generic = getenv("NN_UMMA_GENERIC_EPI") != nullptr;
     if (force_generic) epi = 0;
     UmmaP pd = p;
-    static bool spin_set = false;
-    if (!spin_set) {
-        const int spin = getenv("NN_UMMA_SPIN") ? atoi(getenv("NN_UMMA_SPIN")) : 0;
-        if (spin) cudaMemcpyToSymbol(g_mbar_spin, &spin, sizeof(int));
-        spin_set = true;
-    }
     static const int env_inc = getenv("NN_UMMA_INC_TAPS") ? atoi(getenv("NN_UMMA_INC_TAPS")) : -1;
     // measured at batch 512 (same run, A/B): incremental tap tracking takes conv2 dgrad 120 -> 110 us (3 CTAs/SM, the
     // producers' issue slots matter) but costs the fused forward 70 -> 72.7 us (2 CTAs/SM, sigma rows): per variant

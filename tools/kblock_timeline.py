@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Per-k-block hand-off timeline of the tiled tcgen05 kernel (NN_UMMA_KDEBUG=1): for every k-block of every CTA, when
-producer thread 0 woke from the empty barrier / arrived on the full barrier, and when the MMA thread woke / committed."""
+producer thread 0 woke from the empty barrier / arrived on the full barrier, and when the MMA thread woke / committed.
+The stamps are compiled in only with -DNN_KDEBUG:  NN_EXTRA_NVCC=-DNN_KDEBUG python __graft_entry__.py --force"""
 import ctypes as C
 import os
 import sys
