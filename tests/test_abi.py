@@ -34,13 +34,51 @@ def test_abi_version(lib):
     assert int(m.group(1)) == _lib.ABI_VERSION
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """Every struct of include/noisynet_b200.h, compiled by gcc, against its ctypes mirror: total size, the offset of
+    every field and the field ORDER (names are allowed to differ only by the trailing underscore of `in_`)."""
     import ctypes as C
+    import subprocess
     assert C.sizeof(_lib.ConvGeom) == 36
     assert C.sizeof(_lib.Rng) == 24
-    # pointers are 8-byte aligned after the 36-byte geometry
-    assert _lib.ConvFwdArgs.x.offset == 40
-    assert _lib.ConvFwdArgs.rng.offset % 8 == 0
+    pairs = {"nn_rng": _lib.Rng, "nn_conv_geom": _lib.ConvGeom, "nn_conv_fwd_args": _lib.ConvFwdArgs,
+             "nn_conv_dgrad_args": _lib.ConvDgradArgs, "nn_conv_wgrad_args": _lib.ConvWgradArgs,
+             "nn_adamw_tensor": _lib.AdamWTensor, "nn_wprep_job": _lib.WPrepJob, "nn_stage_args": _lib.StageArgs,
+             "nn_stage_bwd_args": _lib.StageBwdArgs, "nn_tail_args": _lib.TailArgs}
+    hdr = open(os.path.join(ROOT, "include", "noisynet_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"typedef struct (nn_[a-z0-9_]+)\s*\{", body))
+    assert declared == set(pairs), declared ^ set(pairs)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "noisynet_b200.h"', 'int main(void) {']
+    for cname, ct in pairs.items():
+        lines.append('printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        m = re.search(r"typedef struct %s\s*\{(.*?)\}\s*%s;" % (cname, cname), body, flags=re.S)
+        fields = []
+        for decl in m.group(1).split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            # "const float *gamma, *beta" / "int32_t B, C, H, W, pool" / "nn_rng rng" / "void* xp"
+            names = [re.sub(r"[^A-Za-z0-9_]", "", part.split()[-1]) for part in decl.split(",")]
+            fields += names
+        for f in fields:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, f, cname, f))
+        ct_names = [n.rstrip("_") for n, _ in ct._fields_]
+        assert ct_names == fields, (cname, ct_names, fields)
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = subprocess.check_output([str(exe)], text=True)
+    for line in out.splitlines():
+        cname, field, val = line.split()
+        ct = pairs[cname]
+        if field == "size":
+            assert C.sizeof(ct) == int(val), (cname, C.sizeof(ct), val)
+        else:
+            cf = field if hasattr(ct, field) else field + "_"
+            assert getattr(ct, cf).offset == int(val), (cname, field, getattr(ct, cf).offset, val)
 
 
 def test_cpu_tensors_are_rejected_loudly(lib):
