@@ -30,7 +30,8 @@ def parse():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=30)
     p.add_argument("--warmup", type=int, default=5)
-    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_gpu"])
+    p.add_argument("--no-library-baseline", action="store_true")
     p.add_argument("--batch", type=int, default=512, help="per-GPU batch")
     p.add_argument("--variant", default="q4", choices=["q4", "fp"], help="q4: --q_a 4 --q_w 4; fp: README flags")
     p.add_argument("--flow", default="engine", choices=["engine", "fused", "dropin"],
@@ -141,6 +142,53 @@ def oracle_arm(batch, variant, steps, warmup, seconds=None):
         if (seconds is not None and el >= seconds) or (seconds is None and n >= steps):
             break
     return {"img_s": n * batch / el, "steps": n, "seconds": el, "cores": torch.get_num_threads(), "batch": batch}
+
+
+def torch_gpu_arm(batch, variant, steps, warmup, dev):
+    """The bar SURVEY.md section 2.2 / BASELINE.md section 3 name: the reference's step in PyTorch-eager on the SAME B200
+    (cuDNN / cuBLAS contractions, ATen elementwise + Philox kernels, torch.optim.AdamW) -- the oracle port of the reference
+    step moved to the GPU unchanged, inputs resident on the device, timed with CUDA events.  Not the product path."""
+    from oracle import noisynet_oracle as O
+    q = 4 if variant == "q4" else 0
+    a = O.default_args(q_a=q, q_w=q, quant_max2=5.0, quant_max4=5.0)
+    torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True          # noisynet.py:319
+    m = O.OracleNet(a).init_like_reference().to(dev)
+    opt = O.make_optimizer(m, a)
+    m.train()
+    xs, ls = [], []
+    for k in range(8):
+        x, lab = O.synthetic_cifar(batch, seed=k)
+        xs.append(x.to(dev)); ls.append(lab.to(dev))
+    l0 = None
+    for s in range(max(warmup, 3)):
+        l0, _ = O.train_step(m, opt, xs[s % 8], ls[s % 8], i=100)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(steps):
+        l0, _ = O.train_step(m, opt, xs[s % 8], ls[s % 8], i=100)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    return {"img_s": steps * batch / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "batch": batch,
+            "final_loss": float(l0)}
+
+
+def run_torch_gpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    r = torch_gpu_arm(args.batch, args.variant, args.steps, args.warmup, dev)
+    line = {
+        "impl": "torch_gpu", "metric": "NoisyNet CIFAR-10 4-bit training images/sec", "value": r["img_s"], "unit": "img/s",
+        "n_gpus": 1, "steps": r["steps"], "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1), "final_loss": r["final_loss"],
+        "note": "PyTorch-eager (cuDNN/cuBLAS/ATen) run of the reference step (oracle port) on one B200: the library bar",
+    }
+    print(json.dumps(line), flush=True)
 
 
 def run_reference(args):
@@ -426,6 +474,15 @@ def run_b200(args):
         r = oracle_arm(128, args.variant, 0, 2, seconds=args.cpu_baseline_seconds)
         cpu = {"value": r["img_s"], "unit": "img/s", "cores": r["cores"], "kind": "port",
                "sample": "%d steps of batch 128 in %.1f s (oracle port of the reference training step, torch CPU fp32)" % (r["steps"], r["seconds"])}
+    lib_base = None
+    if world == 1 and not args.no_library_baseline:
+        try:
+            r = torch_gpu_arm(B, args.variant, 20, 5, dev)
+            lib_base = {"value": r["img_s"], "unit": "img/s", "ms_per_step": r["ms_per_step"], "kind": "pytorch-eager",
+                        "sample": "20 steps of batch %d on the same GPU: the reference step (oracle port) in PyTorch eager -- "
+                                  "cuDNN / cuBLAS / ATen Philox, fp32" % B}
+        except Exception as e:  # noqa: BLE001
+            lib_base = {"unavailable": str(e)[:200]}
     h2d = B * 3 * 32 * 32 * 4 + B * 8
     line = {
         "metric": "NoisyNet CIFAR-10 4-bit training images/sec", "value": value, "unit": "img/s", "n_gpus": world,
@@ -434,7 +491,7 @@ def run_b200(args):
         "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e_val, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-        "cuda_graph": graph is not None, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "cuda_graph": graph is not None, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "library_baseline": lib_base,
         "final_loss": final_loss,
     }
     print(json.dumps(line), flush=True)
@@ -444,6 +501,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_gpu":
+        run_torch_gpu(args)
     else:
         run_b200(args)
     try:

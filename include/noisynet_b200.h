@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NN_ABI_VERSION 12
+#define NN_ABI_VERSION 13
 
 /* ---- common ---------------------------------------------------------------------- */
 
@@ -166,7 +166,15 @@ typedef struct nn_conv_fwd_args {
  * NN_PACK_TILED). */
 #define NN_PACK_TILED 0
 #define NN_PACK_SHIFT 1
+/* NN_PACK_TMA: [n-tile][tap][stage][CTA rank] image of the persistent CTA-pair kernel whose activations arrive by
+ * im2col-mode tensor-map copies (cp.async.bulk.tensor, cuTensorMapEncodeIm2col): conv layers (output larger than 1x1,
+ * more than 8 input channels, square kernels) on the lean path (no bias / statistics / exports / injected draws). */
+#define NN_PACK_TMA 2
 int nn_conv_pack_layout(const nn_conv_geom* g, int32_t noise_mode, int32_t precision);
+/* Layout the dgrad of a geometry prefers for its (transposed, tap-flipped) weight image: NN_PACK_TMA or NN_PACK_TILED. */
+int nn_conv_dgrad_pack_layout(const nn_conv_geom* g, int32_t precision);
+/* Test hook: enable = 0/1 switches the TMA-im2col path off/on (< 0: query); returns the previous setting. */
+int nn_debug_tma_enable(int enable);
 /* 1 if nn_noisy_conv_fwd can fuse the 2x2 max pool that follows the layer (pooled_out / argmax_out). */
 int nn_conv_pool_fusable(const nn_conv_geom* g, int32_t noise_mode, int32_t precision);
 /* Test hook: enable = 0/1 switches the shift-GEMM path off/on (< 0: query); returns the previous setting. */
@@ -201,6 +209,7 @@ typedef struct nn_conv_dgrad_args {
     void* workspace; int64_t workspace_bytes;
     const void* gy_packed;   /* optional: grad_output already NHWC bf16 [B,OH,OW,ceil8(Cout)] (nn_stage_bwd) */
     const void* w_packed;    /* optional: weights already packed by nn_prepare_weights (mode 1)        */
+    int32_t w_packed_layout; /* NN_PACK_*: the layout `w_packed` was prepared in (nn_conv_dgrad_pack_layout)  */
 } nn_conv_dgrad_args;
 int nn_noisy_conv_dgrad(const nn_conv_dgrad_args* a, int device, void* stream);
 
@@ -245,7 +254,7 @@ typedef struct nn_wprep_job {
     int32_t want_wsum;       /* mode 0, external DAC: add the colsum row (power statistic)            */
     int32_t q_bits; double q_hi; float stochastic; const float* u_inject; nn_rng rng;
     void* packed_out;        /* nn_weight_pack_bytes(job) bytes                                       */
-    int32_t layout;          /* NN_PACK_* (mode 0 only; see nn_conv_pack_layout)                       */
+    int32_t layout;          /* NN_PACK_* (mode 0: nn_conv_pack_layout, mode 1: nn_conv_dgrad_pack_layout) */
     void* codes;             /* optional scratch, Cout*Cin*KHW bytes: the quantizer runs ONCE per parameter into it
                                 (one Philox call per 4 parameters) and every job naming the same scratch -- the
                                 forward and dgrad images of a layer -- packs from the codes; jobs sharing a scratch

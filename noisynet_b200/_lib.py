@@ -7,12 +7,12 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnoisynet_b200.so")
-ABI_VERSION = 12
+LIB_PATH = os.environ.get("NN_LIB_PATH") or os.path.join(_HERE, "lib", "libnoisynet_b200.so")   # NN_LIB_PATH: instrumented debug builds
+ABI_VERSION = 13
 
 NOISE_NONE, NOISE_MERGED, NOISE_EXTERNAL = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
-PACK_TILED, PACK_SHIFT = 0, 1
+PACK_TILED, PACK_SHIFT, PACK_TMA = 0, 1, 2
 
 c_f32p = C.c_void_p      # device pointers travel as void* (int addresses from tensor.data_ptr())
 
@@ -49,7 +49,7 @@ class ConvDgradArgs(C.Structure):
                 ("x_pre", C.c_void_p), ("x_lo", C.c_double), ("x_hi", C.c_double),
                 ("precision", C.c_int32), ("w_code_scale", C.c_float),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("gy_packed", C.c_void_p),
-                ("w_packed", C.c_void_p)]
+                ("w_packed", C.c_void_p), ("w_packed_layout", C.c_int32)]
 
 
 class ConvWgradArgs(C.Structure):
@@ -142,6 +142,8 @@ SIGNATURES = {
     "nn_debug_cta_timeline": (C.c_int, [C.c_void_p, C.c_int]),
     "nn_conv_pack_layout": (C.c_int, [C.POINTER(ConvGeom), C.c_int32, C.c_int32]),
     "nn_debug_shift_enable": (C.c_int, [C.c_int]),
+    "nn_debug_tma_enable": (C.c_int, [C.c_int]),
+    "nn_conv_dgrad_pack_layout": (C.c_int, [C.POINTER(ConvGeom), C.c_int32]),
     "nn_conv_pool_fusable": (C.c_int, [C.POINTER(ConvGeom), C.c_int32, C.c_int32]),
     "nn_classifier_tail": (C.c_int, [C.POINTER(TailArgs), C.c_int, C.c_void_p]),
     "nn_conv_wgrad_pack_layout": (C.c_int, [C.POINTER(ConvGeom), C.c_int32, C.c_int]),

@@ -26,7 +26,34 @@ static inline int nn_fail(const char* fmt, const char* a = "", long long b = 0) 
         }                                                                             \
     } while (0)
 
-#define NN_SET_DEVICE(dev) NN_CUDA_OK(cudaSetDevice(dev))
+// Entry points take `device` per call: switch to it for the duration of the call and restore the caller's current
+// device on return (a library must not leave torch's "current device" changed behind the caller's back).
+struct NnDeviceGuard {
+    int prev;
+    cudaError_t err;
+    explicit NnDeviceGuard(int dev) : prev(-1) {
+        int cur = -1;
+        err = cudaGetDevice(&cur);
+        if (err == cudaSuccess && cur != dev) {
+            err = cudaSetDevice(dev);
+            if (err == cudaSuccess) prev = cur;
+        }
+    }
+    ~NnDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define NN_SET_DEVICE(dev) NnDeviceGuard _nn_dev_guard(dev); NN_CUDA_OK(_nn_dev_guard.err)
+
+// Function attributes (opt-in dynamic shared memory) are PER DEVICE: run `body` once per device of this process.
+#define NN_ONCE_PER_DEVICE(body)                                   \
+    do {                                                           \
+        static bool _nn_done[64] = {false};                        \
+        int _nn_d = 0;                                             \
+        cudaGetDevice(&_nn_d);                                     \
+        if (_nn_d < 0 || _nn_d >= 64 || !_nn_done[_nn_d]) {        \
+            body;                                                  \
+            if (_nn_d >= 0 && _nn_d < 64) _nn_done[_nn_d] = true;  \
+        }                                                          \
+    } while (0)
 extern unsigned long long g_nn_launches;
 #define NN_LAUNCH_OK() do { ++g_nn_launches; NN_CUDA_OK(cudaGetLastError()); } while (0)
 #define NN_LAUNCHED(n) (g_nn_launches += (n))

@@ -1,0 +1,452 @@
+// Persistent implicit-GEMM conv on CTA pairs with TMA-staged operands (sm_100a): the tiled noisy-conv forward and
+// the dgrad of the layers whose im2col rows cannot be read in place (conv2 of NoisyNet, the ResNet 3x3 layers).
+//
+//   D[m, n] = sum_{tap, c} X[pixel(m) + tap, c] * Wp[n, tap, c]      m = output pixel, n = accumulator column
+//
+// * A operand: ONE cp.async.bulk.tensor (im2col-mode tensor map, cuTensorMapEncodeIm2col) per (tap, channel chunk)
+//   lands 128 output pixels x 64 channels as a SWIZZLE_128B K-major tile; the channel remainder of a tap is a second,
+//   narrower box (16 / 32 channels -> SWIZZLE_32B / 64B tile, its own descriptor kind) instead of padding every tap to
+//   a multiple of 64 channels (65 channels -> K = 80 per tap, not 128).  Padding taps and tile rows past the tensor are
+//   zero-filled by the TMA unit: no thread computes an address.
+// * B operand: pre-swizzled weight image [n-tile][tap][group][cta rank], one cp.async.bulk per stage and CTA.
+// * CTA pair (cluster of 2, tcgen05 cta_group::2): one M = 256 MMA per K = 16 step covers both CTAs' 128 pixels; each CTA
+//   stages only HALF of the weight rows, which halves the L2 -> SM weight stream that bounded the one-CTA kernel.
+// * Persistent: a cluster walks (pixel-tile pair, n-tile) items; accumulators are double-buffered in TMEM (2 x 256
+//   columns), so the epilogue warps (tcgen05.ld -> scale, Philox / Box-Muller current noise -> NCHW stores) of item i
+//   overlap the MMAs of item i + 1.
+// * Warp roles: warps 0..P-1 producers (one elected thread each; a thread owns whole stages round-robin: a tensor-map
+//   copy costs its issuing thread ~800 cycles, tools/microbench/tma_probe.cu), warp P MMA issuer (leader CTA) /
+//   stage relay (peer CTA), warp P+1 TMEM allocator, 8 epilogue warps.
+#include "nn_conv_tma.h"
+
+#include <cuda.h>
+
+#include "nn_tcgen05.cuh"
+
+namespace {
+
+constexpr int TC_MAX_EPI_WARPS = 16;    // epilogue warps per CTA: 8 or 16 (4 or 8 column slices per TMEM lane quarter)
+constexpr int TC_ACC_STRIDE = 256;       // TMEM columns between the two accumulator buffers
+constexpr int TC_MAX_STAGES = 8;
+
+struct TmaConvP {
+    CUtensorMap map64, map_tail;         // im2col maps: 64-channel SWIZZLE_128B box, tail box
+    int M, OH, OW, Cout, stride, pad, KW, taps;
+    int n_c64, tail_w, nc, gpt, n_groups;
+    int n_t, n_mma, n_half, n_tiles, main_col, sig_col;
+    int items, stages, a_stage, b_stage, n_prod, n_epi, tap_bytes;
+    const uint8_t* wp;
+    float y_scale, s_scale;
+    float *y, *y_noisy;
+    int noise_mode;
+    float current;
+    const float* scale_dev;
+    nn_rng rng;
+    int* err_flag;
+    long long* prof;                     // NN_KDEBUG builds: [cta][16] cycle counters of the roles (nn_debug_tma_profile)
+};
+
+#ifdef NN_KDEBUG
+#define TC_T(var) const long long var = clock64()
+#define TC_ACC(slot, t0) prof_acc[slot] += clock64() - (t0)
+#else
+#define TC_T(var)
+#define TC_ACC(slot, t0)
+#endif
+
+// EPI 1: noisy (main + sigma accumulators, Philox z), EPI 2: plain
+template <int EPI>
+__global__ void __launch_bounds__((4 + 2 + TC_MAX_EPI_WARPS) * 32, 1)
+k_conv_tma(const __grid_constant__ TmaConvP p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int S = p.stages;
+    const uint32_t stage_bytes = (uint32_t)(p.a_stage + p.b_stage);
+    const uint32_t bar_base = base + (uint32_t)S * stage_bytes;
+    const uint32_t full_bar = bar_base, empty_bar = bar_base + 8u * TC_MAX_STAGES, pfull_bar = bar_base + 16u * TC_MAX_STAGES;
+    const uint32_t accf_bar = bar_base + 24u * TC_MAX_STAGES, acce_bar = accf_bar + 16u, tmem_slot = acce_bar + 16u;
+    uint8_t* gen0 = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gen0 + (tmem_slot - base));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cl = (int)(blockIdx.x >> 1), ncl = (int)(gridDim.x >> 1);
+    const int P = p.n_prod;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar + 8 * s, 1);          // the owning producer's arrive.expect_tx (A boxes + weight block)
+            mbar_init(empty_bar + 8 * s, 1);         // the leader's tcgen05.commit (multicast to both CTAs)
+            mbar_init(pfull_bar + 8 * s, 1);         // leader only: "the peer's share of stage s has landed"
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(accf_bar + 8 * b, 1);                     // leader's commit: accumulator buffer b complete (both CTAs)
+            mbar_init(acce_bar + 8 * b, 2 * (uint32_t)p.n_epi);      // leader only: both CTAs' epilogue warps have drained buffer b
+        }
+        fence_mbar_init();
+        tma_prefetch_desc(&p.map64);
+        tma_prefetch_desc(&p.map_tail);
+    }
+    __syncthreads();
+    cluster_sync_all();                 // both CTAs' barriers exist before the paired allocation / any remote arrive
+    if (warp == P + 1) tmem_alloc_2cta(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_g;
+    const int ohw = p.OH * p.OW;
+
+    if (warp < P) {
+        // ---------------------------------------------------------------- producers
+        if (lane == 0) {
+#ifdef NN_KDEBUG
+            long long prof_acc[4] = {0, 0, 0, 0};
+            const long long t_begin = clock64();
+#endif
+            int gg = 0;                                          // global group counter (same sequence in every role)
+            for (int it = cl; it < p.items; it += ncl) {
+                const int pi = it / p.n_tiles, nt = it - pi * p.n_tiles;
+                const int m0 = (2 * pi + (int)rank) * 128;
+                const int b0 = m0 / ohw, r0 = m0 - b0 * ohw, oh0 = r0 / p.OW, ow0 = r0 - oh0 * p.OW;
+                const int iw0 = ow0 * p.stride - p.pad, ih0 = oh0 * p.stride - p.pad;
+                const uint8_t* wt = p.wp + (size_t)nt * p.taps * p.tap_bytes;
+                int kh = 0, kw = 0, gi = 0;
+                for (int g = 0; g < p.n_groups; ++g, ++gg) {
+                    if (gg % P == warp) {
+                        const int s = gg % S;
+                        TC_T(t0);
+                        if (!mbar_wait(empty_bar + 8 * s, (((uint32_t)(gg / S)) & 1u) ^ 1u)) nn_pipeline_abort(p.err_flag, 401);
+                        TC_ACC(0, t0);
+                        TC_T(t1);
+                        const int ca = 2 * gi, cb = 2 * gi + 1;
+                        const int wa = ca < p.n_c64 ? 64 : p.tail_w;
+                        const int wb = cb < p.nc ? (cb < p.n_c64 ? 64 : p.tail_w) : 0;
+                        const uint32_t b_bytes = (uint32_t)(p.n_half * 2 * (wa + wb));
+                        const uint32_t a_dst = base + (uint32_t)s * stage_bytes, b_dst = a_dst + (uint32_t)p.a_stage;
+                        const uint32_t bar = full_bar + 8 * s;
+                        mbar_arrive_expect_tx(bar, (uint32_t)(256 * (wa + wb)) + b_bytes);
+                        tma_im2col_4d(a_dst, ca < p.n_c64 ? &p.map64 : &p.map_tail, bar, 64 * ca, iw0, ih0, b0, (uint16_t)kw, (uint16_t)kh);
+                        if (wb) tma_im2col_4d(a_dst + 256u * (uint32_t)wa, cb < p.n_c64 ? &p.map64 : &p.map_tail, bar, 64 * cb, iw0, ih0, b0,
+                                              (uint16_t)kw, (uint16_t)kh);
+                        const int tap = kh * p.KW + kw;
+                        bulk_g2s(b_dst, wt + (size_t)tap * p.tap_bytes + (size_t)gi * (size_t)(p.n_half * 512) + (size_t)rank * b_bytes,
+                                 b_bytes, bar);
+                        TC_ACC(1, t1);
+                    }
+                    if (++gi == p.gpt) { gi = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
+                }
+            }
+#ifdef NN_KDEBUG
+            if (p.prof && warp == 0) {      // producer 0: [0] waiting for a free stage, [1] issuing copies, [2] total
+                long long* o = p.prof + (size_t)blockIdx.x * 16;
+                o[0] = prof_acc[0]; o[1] = prof_acc[1]; o[2] = clock64() - t_begin;
+            }
+#endif
+        }
+        __syncwarp();
+    } else if (warp == P) {
+        // ---------------------------------------------------------------- MMA issuer (leader) / stage relay (peer)
+        if (lane == 0) {
+            if (rank == 0) {
+                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+                int gg = 0, li = 0;
+#ifdef NN_KDEBUG
+                long long prof_acc[4] = {0, 0, 0, 0};
+                const long long t_begin = clock64();
+#endif
+                for (int it = cl; it < p.items; it += ncl, ++li) {
+                    const int buf = li & 1;
+                    TC_T(ta);
+                    if (!mbar_wait_cluster(acce_bar + 8 * buf, (((uint32_t)(li >> 1)) & 1u) ^ 1u)) nn_pipeline_abort(p.err_flag, 402);
+                    TC_ACC(0, ta);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)(buf * TC_ACC_STRIDE);
+                    int gi = 0;
+                    for (int g = 0; g < p.n_groups; ++g, ++gg) {
+                        const int s = gg % S;
+                        const uint32_t ph = ((uint32_t)(gg / S)) & 1u;
+                        TC_T(tf);
+                        if (!mbar_wait(full_bar + 8 * s, ph)) nn_pipeline_abort(p.err_flag, 403);
+                        TC_ACC(1, tf);
+                        TC_T(tp);
+                        if (!mbar_wait_cluster(pfull_bar + 8 * s, ph)) nn_pipeline_abort(p.err_flag, 404);
+                        TC_ACC(2, tp);
+                        TC_T(ti);
+                        tc_fence_after();
+                        const int ca = 2 * gi, cb = 2 * gi + 1;
+                        const int wa = ca < p.n_c64 ? 64 : p.tail_w;
+                        const int wb = cb < p.nc ? (cb < p.n_c64 ? 64 : p.tail_w) : 0;
+                        const uint32_t a_s = base + (uint32_t)s * stage_bytes, b_s = a_s + (uint32_t)p.a_stage;
+                        {
+                            const uint64_t ad = umma_desc_kmajor(a_s, 2u * wa), bd = umma_desc_kmajor(b_s, 2u * wa);
+                            for (int k = 0; k < (wa >> 4); ++k) umma_bf16_2cta(d, ad + 2 * k, bd + 2 * k, idesc, (g | k) != 0);
+                        }
+                        if (wb) {
+                            const uint64_t ad = umma_desc_kmajor(a_s + 256u * (uint32_t)wa, 2u * wb);
+                            const uint64_t bd = umma_desc_kmajor(b_s + (uint32_t)(p.n_half * 2 * wa), 2u * wb);
+                            for (int k = 0; k < (wb >> 4); ++k) umma_bf16_2cta(d, ad + 2 * k, bd + 2 * k, idesc, 1u);
+                        }
+                        umma_commit_2cta_mc(empty_bar + 8 * s, 3);       // both CTAs may refill stage s when these MMAs retire
+                        TC_ACC(3, ti);
+                        if (++gi == p.gpt) gi = 0;
+                    }
+                    umma_commit_2cta_mc(accf_bar + 8 * buf, 3);          // both CTAs' accumulators of this item complete
+                }
+#ifdef NN_KDEBUG
+                if (p.prof) {     // MMA thread: waiting for [4] a drained accumulator, [5] own stage, [6] peer stage; [7] issuing; [8] total
+                    long long* o = p.prof + (size_t)blockIdx.x * 16;
+                    o[4] = prof_acc[0]; o[5] = prof_acc[1]; o[6] = prof_acc[2]; o[7] = prof_acc[3]; o[8] = clock64() - t_begin;
+                }
+#endif
+            } else {
+                int gg = 0;
+                for (int it = cl; it < p.items; it += ncl) {
+                    for (int g = 0; g < p.n_groups; ++g, ++gg) {
+                        const int s = gg % S;
+                        if (!mbar_wait(full_bar + 8 * s, ((uint32_t)(gg / S)) & 1u)) nn_pipeline_abort(p.err_flag, 405);
+                        mbar_arrive_remote(pfull_bar + 8 * s, 0);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= P + 2) {
+        // ---------------------------------------------------------------- epilogue warps
+        const int ew = warp - (P + 2);
+        const int q = warp & 3, slice = ew >> 2, nslices = p.n_epi >> 2;   // TMEM lane quarter = warp % 4; column slices round-robin
+        const bool noise = EPI == 1;
+        float coef = 0.f;
+        NnRng rs = {0, 0, 0, 0};
+        if (noise) { coef = nn_noise_coef(*p.scale_dev, p.current); rs = nn_rng_load(p.rng); }
+        const int ngrp = (p.Cout + 3) >> 2;
+        const int nchunks = (p.n_t + 15) >> 4;
+        const float y_scale = p.y_scale, s_scale = p.s_scale;
+        int li = 0;
+#ifdef NN_KDEBUG
+        long long prof_acc[4] = {0, 0, 0, 0};
+        const long long t_begin = clock64();
+#endif
+        for (int it = cl; it < p.items; it += ncl, ++li) {
+            const int pi = it / p.n_tiles, nt = it - pi * p.n_tiles;
+            const int buf = li & 1;
+            TC_T(tw);
+            if (!mbar_wait(accf_bar + 8 * buf, ((uint32_t)(li >> 1)) & 1u)) nn_pipeline_abort(p.err_flag, 406);
+            TC_ACC(0, tw);
+            tc_fence_after();
+            const int row = q * 32 + lane;
+            const int m = (2 * pi + (int)rank) * 128 + row;
+            const bool row_ok = m < p.M;
+            int b = 0, pix = 0;
+            if (row_ok) { b = m / ohw; pix = m - b * ohw; }
+            const size_t out_row = (size_t)b * p.Cout * ohw + pix;
+            const uint32_t t_lane = tmem_base + (uint32_t)(buf * TC_ACC_STRIDE) + ((uint32_t)(q * 32) << 16);
+            const int n_base = nt * p.n_t;
+            const uint64_t grp_row = (uint64_t)m * ngrp;
+            float* const out_main = (EPI == 1 ? p.y_noisy : p.y) + out_row;
+            for (int ci = slice; ci < nchunks; ci += nslices) {
+                const int cc = ci * 16;
+                float am[16], as[16];
+                tmem_ld16(t_lane + (uint32_t)(p.main_col + cc), am);
+                if (EPI == 1) tmem_ld16(t_lane + (uint32_t)(p.sig_col + cc), as);
+                if (!row_ok) continue;
+                const int nb = n_base + cc;
+                const int nvalid = min(16, min(p.n_t - cc, p.Cout - nb));
+                float* o = out_main + (size_t)nb * ohw;
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    if (g4 * 4 < nvalid) {
+                        float z[4];
+                        if (EPI == 1) nn_normal4(rs, grp_row + (uint64_t)((nb + g4 * 4) >> 2), z);
+                        if (g4 * 4 + 4 <= nvalid) {
+                            float* o_run = o + (size_t)(g4 * 4) * ohw;
+                            asm volatile("" : "+l"(o_run));
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int e = g4 * 4 + j;
+                                const float yv = am[e] * y_scale;
+                                st_global_f32(o_run, (EPI == 1) ? __fadd_rn(yv, __fmul_rn(z[j], nn_sigma(coef, as[e] * s_scale))) : yv);
+                                o_run += ohw;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int e = g4 * 4 + j;
+                                if (e < nvalid) {
+                                    const float yv = am[e] * y_scale;
+                                    o[(size_t)e * ohw] = (EPI == 1) ? __fadd_rn(yv, __fmul_rn(z[j], nn_sigma(coef, as[e] * s_scale))) : yv;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {                                  // this warp has drained buffer `buf`: tell the leader's MMA thread
+                if (rank == 0) mbar_arrive(acce_bar + 8 * buf);
+                else mbar_arrive_remote(acce_bar + 8 * buf, 0);
+            }
+        }
+#ifdef NN_KDEBUG
+        if (p.prof && ew == 0 && lane == 0) {   // first epilogue warp: [10] waiting for accumulators, [11] total, [12] items
+            long long* o = p.prof + (size_t)blockIdx.x * 16;
+            o[10] = prof_acc[0]; o[11] = clock64() - t_begin; o[12] = li;
+        }
+#endif
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                 // both CTAs are done with the paired accumulators / no remote arrive is in flight
+    if (warp == P + 1) { tc_fence_after(); tmem_dealloc_2cta(tmem_base, 512); }
+}
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                   const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeIm2colFn get_encode_im2col() {
+    static EncodeIm2colFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeIm2colFn)f;
+    }
+    return fn;
+}
+
+int encode_map(CUtensorMap* map, const TmaConvCall& c, int box_c) {
+    EncodeIm2colFn enc = get_encode_im2col();
+    if (!enc) return nn_fail("nn_conv_tma: cuTensorMapEncodeIm2col is not available%s", "");
+    const cuuint64_t Cp = (cuuint64_t)c.pl.Cp;
+    cuuint64_t dims[4] = {Cp, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.B};
+    cuuint64_t strides[3] = {Cp * 2, (cuuint64_t)c.W * Cp * 2, (cuuint64_t)c.H * c.W * Cp * 2};
+    int lower[2] = {-c.pad, -c.pad};
+    int upper[2] = {c.pad - (c.KW - 1), c.pad - (c.KH - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
+    const CUtensorMapSwizzle sw = box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(c.xp), dims, strides, lower, upper, (cuuint32_t)box_c, 128,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return nn_fail("nn_conv_tma: cuTensorMapEncodeIm2col failed%s (CUresult %lld)", "", (long long)r);
+    // (as CUTLASS does for drivers <= 13.1: small tensors must not carry bit 21 of descriptor word 1)
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    if (drv <= 13010 && (size_t)c.B * c.H * c.W * Cp * 2 < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+    return 0;
+}
+
+int g_tma_enable = 1;
+long long* g_prof_buf = nullptr;
+int g_prof_ctas = 0;
+
+}  // namespace
+
+// NN_KDEBUG builds: per-CTA role cycle counters [cta][16] of the last k_conv_tma launch (tools/tma_profile.py)
+extern "C" int nn_debug_tma_profile(long long* host_out, int max_ctas) {
+    if (!g_prof_buf) return 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    const int n = g_prof_ctas < max_ctas ? g_prof_ctas : max_ctas;
+    if (cudaMemcpy(host_out, g_prof_buf, (size_t)n * 16 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return n;
+}
+
+extern "C" int nn_debug_tma_enable(int enable) {
+    const int prev = g_tma_enable;
+    if (enable >= 0) g_tma_enable = enable;
+    return prev;
+}
+
+static inline int tc_pad_to(int v, int a) { return (v + a - 1) / a * a; }
+
+bool nn_tma_make_plan(int Cin_k, int KH, int KW, int stride, int pad, int n_out, bool has_sigma, int OH, int OW, TmaPlan* out) {
+    if (!g_tma_enable) return false;
+    if (KH != KW || stride < 1 || stride > 8 || pad < 0 || pad > 127 || (KH - 1) > 127 + pad || KH > 200) return false;
+    if (OH * OW <= 1) return false;                 // linear layers: the split-K path of the tiled kernel
+    TmaPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.Cp = tc_pad_to(Cin_k, 8);
+    if (pl.Cp <= 8) return false;                   // narrow inputs: the shift kernels
+    pl.taps = KH * KW;
+    pl.n_c64 = pl.Cp / 64;
+    const int rem = pl.Cp - 64 * pl.n_c64;
+    pl.tail_w = rem == 0 ? 0 : (rem <= 16 ? 16 : (rem <= 32 ? 32 : 64));
+    pl.nc = pl.n_c64 + (pl.tail_w ? 1 : 0);
+    pl.wt = 64 * pl.n_c64 + pl.tail_w;
+    pl.gpt = (pl.nc + 1) / 2;
+    pl.n_groups = pl.taps * pl.gpt;
+    const int max_nt = has_sigma ? 120 : 256;
+    pl.n_tiles = (n_out + max_nt - 1) / max_nt;
+    pl.n_t = tc_pad_to((n_out + pl.n_tiles - 1) / pl.n_tiles, 8);
+    pl.n_tiles = (n_out + pl.n_t - 1) / pl.n_t;
+    pl.main_col = 0;
+    pl.sig_col = has_sigma ? pl.n_t : -1;
+    pl.n_mma = tc_pad_to(has_sigma ? 2 * pl.n_t : pl.n_t, 16);
+    if (pl.n_mma < 32) pl.n_mma = 32;
+    if (pl.n_mma > 256) return false;
+    pl.n_half = pl.n_mma / 2;
+    // the epilogue reads 16-column groups: every read must stay inside the 256-column buffer
+    if ((has_sigma ? pl.sig_col : pl.main_col) + tc_pad_to(pl.n_t, 16) > TC_ACC_STRIDE) return false;
+    int gw = 0;                                     // widest group of a tap (channels)
+    for (int gi = 0; gi < pl.gpt; ++gi) {
+        const int ca = 2 * gi, cb = 2 * gi + 1;
+        const int wa = ca < pl.n_c64 ? 64 : pl.tail_w, wb = cb < pl.nc ? (cb < pl.n_c64 ? 64 : pl.tail_w) : 0;
+        if (wa + wb > gw) gw = wa + wb;
+    }
+    pl.a_stage = tc_pad_to(256 * gw, 1024);
+    pl.b_stage = tc_pad_to(pl.n_half * 2 * gw, 1024);
+    const int budget = 222 * 1024 - 2048;
+    pl.stages = budget / (pl.a_stage + pl.b_stage);
+    if (pl.stages > TC_MAX_STAGES) pl.stages = TC_MAX_STAGES;
+    if (pl.stages < 2) return false;
+    pl.n_prod = pl.stages < 4 ? pl.stages : 4;      // a producer may run at most one ring revolution ahead: n_prod <= stages
+    pl.n_epi = (has_sigma && pl.n_t > 64) ? 16 : 8;     // the noise epilogue (Philox + Box-Muller per output) needs the issue slots
+    pl.threads = (pl.n_prod + 2 + pl.n_epi) * 32;
+    pl.tap_bytes = 2 * pl.n_half * 2 * pl.wt;
+    pl.smem_bytes = 1024 + (size_t)pl.stages * (pl.a_stage + pl.b_stage) + 24 * TC_MAX_STAGES + 64;
+    pl.wp_bytes = (size_t)pl.n_tiles * pl.taps * pl.tap_bytes;
+    if (out) *out = pl;
+    return true;
+}
+
+int nn_tma_conv_launch(const TmaConvCall& c, int device, cudaStream_t st) {
+    const TmaPlan& pl = c.pl;
+    TmaConvP p;
+    memset(&p, 0, sizeof(p));
+    if (pl.n_c64 > 0) { if (int e = encode_map(&p.map64, c, 64)) return e; }
+    if (pl.tail_w > 0) { if (int e = encode_map(&p.map_tail, c, pl.tail_w)) return e; }
+    if (pl.n_c64 == 0) p.map64 = p.map_tail;
+    if (pl.tail_w == 0) p.map_tail = p.map64;
+    p.M = c.B * c.OH * c.OW; p.OH = c.OH; p.OW = c.OW; p.Cout = c.Cout; p.stride = c.stride; p.pad = c.pad; p.KW = c.KW; p.taps = pl.taps;
+    p.n_c64 = pl.n_c64; p.tail_w = pl.tail_w; p.nc = pl.nc; p.gpt = pl.gpt; p.n_groups = pl.n_groups;
+    p.n_t = pl.n_t; p.n_mma = pl.n_mma; p.n_half = pl.n_half; p.n_tiles = pl.n_tiles; p.main_col = pl.main_col; p.sig_col = pl.sig_col;
+    const int m_tiles = (p.M + 127) / 128, m_pairs = (m_tiles + 1) / 2;
+    p.items = m_pairs * pl.n_tiles;
+    p.stages = pl.stages; p.a_stage = pl.a_stage; p.b_stage = pl.b_stage; p.n_prod = pl.n_prod; p.n_epi = pl.n_epi; p.tap_bytes = pl.tap_bytes;
+    p.wp = (const uint8_t*)c.wp;
+    p.y_scale = c.y_scale; p.s_scale = c.s_scale; p.y = c.y; p.y_noisy = c.y_noisy; p.noise_mode = c.noise_mode;
+    p.current = c.current; p.scale_dev = c.scale_dev; p.rng = c.rng; p.err_flag = c.err_flag;
+    int clusters = nn_num_sms(device) / 2;
+    if (clusters > p.items) clusters = p.items;
+    if (clusters < 1) clusters = 1;
+#ifdef NN_KDEBUG
+    if (!g_prof_buf) cudaMalloc(&g_prof_buf, 512 * 16 * sizeof(long long));
+    cudaMemsetAsync(g_prof_buf, 0, 512 * 16 * sizeof(long long), st);
+    p.prof = g_prof_buf;
+    g_prof_ctas = 2 * clusters;
+#endif
+    NN_ONCE_PER_DEVICE({
+        NN_CUDA_OK(cudaFuncSetAttribute(k_conv_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NN_CUDA_OK(cudaFuncSetAttribute(k_conv_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    });
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(pl.threads); cfg.dynamicSmemBytes = pl.smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (c.noise_mode != NN_NOISE_NONE) NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_tma<1>, p));
+    else NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_tma<2>, p));
+    NN_LAUNCH_OK();
+    return 0;
+}

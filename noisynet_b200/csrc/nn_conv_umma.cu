@@ -23,6 +23,8 @@
 #include <stdlib.h>
 
 #include "nn_common.cuh"
+#include "nn_tcgen05.cuh"
+#include "nn_conv_tma.h"
 
 namespace {
 
@@ -31,157 +33,6 @@ constexpr int UM_BLOCK_K = 64;                       // bf16 per k-block = 128 b
 constexpr int UM_THREADS = 256;
 constexpr int UM_A_STAGE = UM_BLOCK_M * 128;         // 16 KB
 constexpr int UM_MAX_NT = 120;                       // output channels per n-tile when sigma rows are present
-constexpr long long UM_TIMEOUT = 4000000000LL;       // ~2 s of SM clocks
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok;
-}
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-    // (polling with mbarrier.test_wait instead of try_wait was measured: no difference)
-    if (mbar_try_wait(bar, parity)) return true;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > UM_TIMEOUT) return false;
-    }
-    return true;
-}
-__device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity) {     // acquire at cluster scope (remote arrivals)
-    const long long t0 = clock64();
-    for (;;) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) return true;
-        if (clock64() - t0 > UM_TIMEOUT) return false;
-    }
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-// multicast variants (thread-block cluster of 2): the bulk copy lands at the same CTA-relative offset in every CTA
-// of the mask and completes bytes on the mbarrier at the same offset there; the commit arrives on every CTA's barrier
-__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
-                 : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(mask) : "memory");
-}
-// CTA pair (cta_group::2): both SMs of a TPC execute ONE MMA of M = 256 -- each CTA contributes its 128 rows of A and
-// HALF of the B rows from its own shared memory, each CTA's TMEM receives its 128 rows of D
-__device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_2cta_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t cta_rank) {
-    // arrive on the barrier at the same shared-memory offset in CTA `cta_rank` of the cluster
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
-        ::"r"(local_bar), "r"(cta_rank) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void st_global_f32(float* ptr, float v);
-__device__ __forceinline__ void mbar_arrive(uint32_t bar);
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1): 8-row groups of
-// 1024 bytes (SBO), swizzle atom = 8 rows x 128 B.  Advancing 16 bf16 along K = +32 bytes = +2 units.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 
 // ------------------------------------------------------------------ kernel parameters
 struct UmmaP {
@@ -482,7 +333,7 @@ k_conv_umma(const UmmaP p) {
     tc_fence_after();
     if (dbg && tid == 0) dbg[3] = clock64();
     if (!acc_ok || *abort_g) {
-        if (tid == 0 && p.err_flag) atomicExch(p.err_flag, 100 + (int)*abort_g);
+        if (tid == 0) nn_pipeline_abort(p.err_flag, 100 + (int)*abort_g);
     } else if (p.partial) {
         // split-K: raw fp32 accumulators, column-major per n-tile (lanes = consecutive rows: coalesced); the noise
         // epilogue runs in k_splitk_epilogue once all shares are summed.  A share without k-blocks contributes zeros.
@@ -726,41 +577,6 @@ struct ShiftP {
     long long* dbg;          // optional [cta][32 tiles][4] clock64 stamps: MMA ready / issued, accumulator seen / epilogue done
 };
 
-__device__ __forceinline__ void st_global_f32(float* ptr, float v) {
-    asm volatile("st.global.f32 [%0], %1;" ::"l"(ptr), "f"(v) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float v[4]) {
-    uint32_t r[4];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld4x2(uint32_t ta, uint32_t tb, float a[4], float b[4]) {
-    uint32_t r[8];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%8];\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4,%5,%6,%7}, [%9];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-        : "r"(ta), "r"(tb) : "memory");
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[4 + i]); }
-}
-// K-major SWIZZLE_NONE descriptor: core matrix = 8 rows x 16 B contiguous; lbo = distance between the two
-// K chunks of one MMA, sbo = distance between 8-row groups (both in 16-byte units).
-__device__ __forceinline__ uint64_t umma_desc_none(uint32_t smem_addr, uint32_t lbo_units, uint32_t sbo_units) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)(lbo_units & 0x3FFF) << 16;
-    d |= (uint64_t)(sbo_units & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-
 // a tile is skipped when none of its 128 positions can be a real output (whole rows oh >= OH of one image).
 // 32-bit arithmetic: the host rejects inputs with 2^31 pixels or more.
 __device__ __forceinline__ bool shift_tile_live(const ShiftP& p, int t) {
@@ -1001,7 +817,7 @@ k_conv_shift(const ShiftP p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (*abort_g && tid == 0 && p.err_flag) atomicExch(p.err_flag, 200 + (int)*abort_g);
+    if (*abort_g && tid == 0) nn_pipeline_abort(p.err_flag, 200 + (int)*abort_g);
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
@@ -1050,6 +866,9 @@ struct PackWP {
     const float* u_inject;
     nn_rng rng;
     const int8_t* codes;           // optional: the quantizer's codes 2k - qmax, computed once per parameter (k_quant_codes)
+    // layout 2 (NN_PACK_TMA, nn_conv_tma.cu): [n-tile][tap][group][cta rank][chunk a rows | chunk b rows], chunks of 64
+    // channels (128-byte swizzled rows) plus a tail chunk of t_tail channels (32 / 64 / 128-byte rows)
+    int t_nc64, t_tail, t_nc, t_wt, t_nhalf, t_tapbytes;
 };
 
 __device__ __forceinline__ float pack_main_value(const PackWP& p, const NnRng& rs, int64_t idx) {
@@ -1076,12 +895,35 @@ __device__ __forceinline__ float pack_main_value(const PackWP& p, const NnRng& r
 
 __device__ __forceinline__ void pack_w_job(const PackWP& p, int64_t start, int64_t stride) {
     const NnRng rs = nn_rng_load(p.rng);
-    const bool shift = p.layout == 1;
+    const bool shift = p.layout == 1, tma = p.layout == 2;
     const int64_t total = shift ? (int64_t)p.num_kb * p.n_mma
+                          : tma ? (int64_t)p.n_tiles * p.n_mma * p.KHW * (p.t_wt >> 3)
                                 : (int64_t)p.n_tiles * p.num_kb * p.n_mma * 8;     // one thread per 16-byte chunk
     for (int64_t i = start; i < total; i += stride) {
         int j, r, kb, tile, kbase;
-        if (shift) {
+        int tap_t = 0, c_first_t = 0;
+        int64_t off_t = 0;
+        if (tma) {
+            // consecutive lanes take consecutive TAPS of one (row, 8-channel chunk): contiguous parameter reads
+            const int cpt = p.t_wt >> 3;
+            tap_t = (int)(i % p.KHW);
+            const int qc = (int)((i / p.KHW) % cpt);
+            const int R = (int)(i / ((int64_t)p.KHW * cpt));
+            tile = R / p.n_mma; r = R - tile * p.n_mma;
+            c_first_t = qc * 8;
+            int ci = c_first_t >> 6;
+            if (ci > p.t_nc64) ci = p.t_nc64;
+            const int w = ci < p.t_nc64 ? 64 : p.t_tail;
+            j = (c_first_t - 64 * ci) >> 3;
+            const int gi = ci >> 1, slot = ci & 1;
+            const int wa = (2 * gi < p.t_nc64) ? 64 : p.t_tail;
+            const int wb = (2 * gi + 1 < p.t_nc) ? ((2 * gi + 1 < p.t_nc64) ? 64 : p.t_tail) : 0;
+            const int rank = r / p.t_nhalf, rr = r - rank * p.t_nhalf;
+            const int swz = w == 64 ? (rr & 7) : (w == 32 ? ((rr >> 1) & 3) : ((rr >> 2) & 1));
+            off_t = ((int64_t)tile * p.KHW + tap_t) * p.t_tapbytes + (int64_t)gi * (p.t_nhalf * 512) +
+                    (int64_t)rank * (p.t_nhalf * 2 * (wa + wb)) + (slot ? p.t_nhalf * 2 * wa : 0) + (int64_t)rr * (2 * w) + ((j ^ swz) << 4);
+            kb = 0; kbase = 0;
+        } else if (shift) {
             r = (int)(i % p.n_mma); kb = (int)(i / p.n_mma); j = 0; tile = 0; kbase = kb * 8;
         } else {
             // Thread -> 16-byte chunk, enumerated so that a warp READS contiguous parameters (the kernel was bound by
@@ -1114,7 +956,8 @@ __device__ __forceinline__ void pack_w_job(const PackWP& p, int64_t start, int64
         else if (p.wsum_col >= 0 && r == p.wsum_col) { kind = 2; }
         const int nrows = p.mode == 0 ? p.Cout : p.Cin;   // number of real "output" rows
         const int kdim = p.mode == 0 ? p.Cin : p.Cout;    // real channels inside a tap
-        const int tap = kbase / p.Cp, c_first = kbase - tap * p.Cp;     // Cp % 8 == 0: a chunk never straddles taps
+        const int tap = tma ? tap_t : kbase / p.Cp;                     // Cp % 8 == 0: a chunk never straddles taps
+        const int c_first = tma ? c_first_t : kbase - tap * p.Cp;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int c = c_first + e;
@@ -1144,7 +987,7 @@ __device__ __forceinline__ void pack_w_job(const PackWP& p, int64_t start, int64
             v[e] = __float2bfloat16_rn(f);
         }
         const int64_t blk = ((int64_t)tile * p.num_kb + kb) * p.n_mma * 64;          // elements
-        const int64_t off = shift ? i * 8 : blk + (int64_t)r * 64 + (((j ^ (r & 7))) << 3);   // 128B swizzle
+        const int64_t off = tma ? (off_t >> 1) : (shift ? i * 8 : blk + (int64_t)r * 64 + (((j ^ (r & 7))) << 3));   // 128B swizzle
         *reinterpret_cast<uint4*>(p.wp + off) = *reinterpret_cast<const uint4*>(v);
     }
 }
@@ -1331,7 +1174,7 @@ k_wgrad_umma(const WgUP p) {
     bool acc_ok = mbar_wait(tfull_bar, 0);
     tc_fence_after();
     if (!acc_ok || *abort_g) {
-        if (tid == 0 && p.err_flag) atomicExch(p.err_flag, 200 + (int)*abort_g);
+        if (tid == 0) nn_pipeline_abort(p.err_flag, 200 + (int)*abort_g);
     } else {
         const int q = warp & 3, half = warp >> 2;
         const int n = tile_n * 128 + q * 32 + lane;
@@ -1529,7 +1372,7 @@ k_wgrad_shift(const WgShiftP p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (*abort_g && tid == 0 && p.err_flag) atomicExch(p.err_flag, 300 + (int)*abort_g);
+    if (*abort_g && tid == 0) nn_pipeline_abort(p.err_flag, 300 + (int)*abort_g);
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
 
@@ -1712,13 +1555,11 @@ static int nn_num_sms_cached() {
 }
 
 static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* splitk_ws = nullptr, size_t splitk_ws_bytes = 0) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    NN_ONCE_PER_DEVICE({
         NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    });
     const bool extras = p.bias || p.mask_x || p.z_inject || p.z_export || p.sigma_export || p.stats;
     int epi = 0;
     if (!extras && p.main_col >= 0 && p.noise_mode != NN_NOISE_NONE && p.y_noisy) epi = 1;
@@ -1861,21 +1702,17 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* sp
     attr[0].val.clusterDim.x = pd.cluster >= 2 ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     if (halo) {
-        static bool halo_attr = false;
-        if (!halo_attr) {
+        NN_ONCE_PER_DEVICE({
             NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            halo_attr = true;
-        }
+        });
         if (epi == 1) NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<1, false, true>, pd));
         else NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<2, false, true>, pd));
     } else if (pd.cluster == 3) {
-        static bool pair_attr = false;
-        if (!pair_attr) {
+        NN_ONCE_PER_DEVICE({
             NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            pair_attr = true;
-        }
+        });
         if (epi == 1) NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<1, true>, pd));
         else NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<2, true>, pd));
     } else if (epi == 1) NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<1>, pd));
@@ -1916,6 +1753,17 @@ int64_t nn_umma_fwd_workspace(const nn_conv_geom* g, int precision) {
                        (g->B * g->H * g->W + 127) / 128);
     size_t a = align_up(f.xp_bytes, 1024) + align_up(f.wp_bytes, 1024);
     size_t b = align_up(d.xp_bytes, 1024) + align_up(d.wp_bytes, 1024);
+    {   // the TMA-im2col path pads every tap to whole channel chunks: its weight image can be the larger one
+        TmaPlan tp;
+        if (nn_tma_make_plan(g->Cin, g->KH, g->KW, g->stride, g->pad, g->Cout, true, OH, OW, &tp)) {
+            const size_t t = align_up((size_t)g->B * g->H * g->W * tp.Cp * 2, 1024) + align_up(tp.wp_bytes, 1024);
+            if (t > a) a = t;
+        }
+        if (g->stride == 1 && nn_tma_make_plan(g->Cout, g->KH, g->KW, 1, g->KH - 1 - g->pad, g->Cin, false, g->H, g->W, &tp)) {
+            const size_t t = align_up((size_t)g->B * OH * OW * tp.Cp * 2, 1024) + align_up(tp.wp_bytes, 1024);
+            if (t > b) b = t;
+        }
+    }
     if (OH * OW == 1)          // split-K partial sums of a skinny linear forward (up to 4 shares)
         a += (size_t)4 * f.n_tiles * f.n_mma * ((g->B + UM_BLOCK_M - 1) / UM_BLOCK_M * UM_BLOCK_M) * sizeof(float) + 1024;
     return (int64_t)((a > b ? a : b) + 2048);
@@ -2035,11 +1883,9 @@ static int shift_conv_fwd(const nn_conv_fwd_args* a, const ShiftPlan& sp, int de
     const int mode = !noise ? 0 : (a->z_inject ? 2 : 1);
 #define NN_SHIFT_LAUNCH(MODE, EW)                                                                                      \
     do {                                                                                                               \
-        static bool attr = false;                                                                                      \
-        if (!attr) {                                                                                                   \
+        NN_ONCE_PER_DEVICE({ \
             NN_CUDA_OK(cudaFuncSetAttribute(k_conv_shift<MODE, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-            attr = true;                                                                                               \
-        }                                                                                                              \
+        });                                                                                                              \
         k_conv_shift<MODE, EW><<<grid, (2 + EW) * 32, sp.smem_bytes, st>>>(p);                                          \
     } while (0)
 #define NN_SHIFT_MODES(EW)                                                                                             \
@@ -2059,7 +1905,15 @@ static int shift_conv_fwd(const nn_conv_fwd_args* a, const ShiftPlan& sp, int de
 
 extern "C" int nn_conv_pack_layout(const nn_conv_geom* g, int32_t noise_mode, int32_t precision) {
     if (!g || precision != NN_PREC_BF16) return NN_PACK_TILED;
-    return make_shift_plan(*g, noise_mode != NN_NOISE_NONE, nullptr) ? NN_PACK_SHIFT : NN_PACK_TILED;
+    if (make_shift_plan(*g, noise_mode != NN_NOISE_NONE, nullptr)) return NN_PACK_SHIFT;
+    int OH, OW;
+    nn_out_hw(*g, OH, OW);
+    return nn_tma_make_plan(g->Cin, g->KH, g->KW, g->stride, g->pad, g->Cout, noise_mode != NN_NOISE_NONE, OH, OW, nullptr) ? NN_PACK_TMA
+                                                                                                                          : NN_PACK_TILED;
+}
+extern "C" int nn_conv_dgrad_pack_layout(const nn_conv_geom* g, int32_t precision) {
+    if (!g || precision != NN_PREC_BF16 || g->stride != 1) return NN_PACK_TILED;
+    return nn_tma_make_plan(g->Cout, g->KH, g->KW, 1, g->KH - 1 - g->pad, g->Cin, false, g->H, g->W, nullptr) ? NN_PACK_TMA : NN_PACK_TILED;
 }
 extern "C" int nn_conv_pool_fusable(const nn_conv_geom* g, int32_t noise_mode, int32_t precision) {
     if (!g || precision != NN_PREC_BF16) return 0;
@@ -2072,6 +1926,79 @@ extern "C" int nn_debug_shift_enable(int enable) {
     const int prev = g_shift_enable;
     if (enable >= 0) g_shift_enable = enable;
     return prev;
+}
+
+// ---- TMA-im2col pair kernel (nn_conv_tma.cu): packer parameters of the NN_PACK_TMA weight image
+static void fill_pack_tma(PackWP& pw, const TmaPlan& tp) {
+    pw.Cp = tp.Cp; pw.n_t = tp.n_t; pw.n_mma = tp.n_mma; pw.num_kb = 0; pw.n_tiles = tp.n_tiles;
+    pw.main_col = tp.main_col; pw.sig_col = tp.sig_col; pw.wsum_col = -1; pw.layout = NN_PACK_TMA;
+    pw.t_nc64 = tp.n_c64; pw.t_tail = tp.tail_w; pw.t_nc = tp.nc; pw.t_wt = tp.wt; pw.t_nhalf = tp.n_half; pw.t_tapbytes = tp.tap_bytes;
+}
+static int64_t pack_tma_chunks(const TmaPlan& tp) { return (int64_t)tp.n_tiles * tp.n_mma * tp.taps * (tp.wt >> 3); }
+
+// lean calls only (what the training step issues): no bias / statistics / export / injected draws / clean-output copy
+static bool tma_fwd_plan(const nn_conv_fwd_args* a, TmaPlan* tp) {
+    const nn_conv_geom& g = a->g;
+    int OH, OW;
+    nn_out_hw(g, OH, OW);
+    const bool noise = a->noise_mode != NN_NOISE_NONE;
+    const bool has_main = a->w_eff != nullptr || a->w_packed != nullptr;
+    const bool lean = has_main && !a->bias && !a->z_inject && !a->z_export && !a->sigma_export && !a->stats && !a->pooled_out &&
+                      !(noise && a->y);
+    return lean && nn_tma_make_plan(g.Cin, g.KH, g.KW, g.stride, g.pad, g.Cout, noise, OH, OW, tp);
+}
+
+static int tma_conv_fwd(const nn_conv_fwd_args* a, const TmaPlan& tp, int device, cudaStream_t st) {
+    const nn_conv_geom& g = a->g;
+    int OH, OW;
+    nn_out_hw(g, OH, OW);
+    const size_t xp_bytes = (size_t)g.B * g.H * g.W * tp.Cp * 2;
+    const size_t need = (a->x_packed ? 0 : align_up(xp_bytes, 1024)) + (a->w_packed ? 0 : align_up(tp.wp_bytes, 1024)) + 1024;
+    if ((!a->x_packed || !a->w_packed) && (!a->workspace || (size_t)a->workspace_bytes < need))
+        return nn_fail("nn_noisy_conv_fwd: workspace too small%s (need %lld bytes)", "", (long long)need);
+    uint8_t* ws = (uint8_t*)align_up((size_t)a->workspace, 1024);
+    const void* xp = a->x_packed;
+    const void* wp = a->w_packed;
+    if (!xp) {
+        const int64_t total = (int64_t)g.B * g.H * g.W * (tp.Cp / 8);
+        int grid = (int)((total + 255) / 256);
+        if (grid > 16 * nn_num_sms(device)) grid = 16 * nn_num_sms(device);
+        k_pack_act<<<grid, 256, 0, st>>>(a->x, (__nv_bfloat16*)ws, g.B, g.Cin, g.H * g.W, tp.Cp, a->a_code_scale);
+        NN_LAUNCH_OK();
+        xp = ws;
+        ws += align_up(xp_bytes, 1024);
+    }
+    if (!wp) {
+        PackWP pw;
+        memset(&pw, 0, sizeof(pw));
+        pw.w_eff = a->w_eff; pw.w_raw = a->w_raw; pw.wp = (__nv_bfloat16*)ws;
+        pw.Cout = g.Cout; pw.Cin = g.Cin; pw.KHW = g.KH * g.KW; pw.noise_mode = a->noise_mode; pw.mode = 0;
+        pw.w_code_scale = a->w_code_scale;
+        fill_pack_tma(pw, tp);
+        const int64_t total = pack_tma_chunks(tp);
+        int grid = (int)((total + 255) / 256);
+        if (grid > 8 * nn_num_sms(device)) grid = 8 * nn_num_sms(device);
+        k_pack_w<<<grid, 256, 0, st>>>(pw);
+        NN_LAUNCH_OK();
+        wp = ws;
+    }
+    TmaConvCall c;
+    memset(&c, 0, sizeof(c));
+    c.pl = tp;
+    c.B = g.B; c.H = g.H; c.W = g.W; c.OH = OH; c.OW = OW; c.KH = g.KH; c.KW = g.KW; c.stride = g.stride; c.pad = g.pad; c.Cout = g.Cout;
+    c.xp = xp; c.wp = wp;
+    const float as = a->a_code_scale > 0.f ? a->a_code_scale : 1.f;
+    const float wsc = a->w_code_scale > 0.f ? a->w_code_scale : 1.f;
+    c.y_scale = as * wsc; c.s_scale = as;
+    c.y = a->y; c.y_noisy = a->y_noisy; c.noise_mode = a->noise_mode; c.current = a->current; c.scale_dev = a->scale_dev; c.rng = a->rng;
+    c.err_flag = nn_umma_err_flag(device);
+    if (g_time_main) {
+        if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+        cudaEventRecord(g_ev0, st);
+    }
+    const int rc = nn_tma_conv_launch(c, device, st);
+    if (g_time_main) cudaEventRecord(g_ev1, st);
+    return rc;
 }
 
 int nn_umma_conv_fwd(const nn_conv_fwd_args* a, int device, cudaStream_t st) {
@@ -2097,6 +2024,15 @@ int nn_umma_conv_fwd(const nn_conv_fwd_args* a, int device, cudaStream_t st) {
         if (layout == NN_PACK_SHIFT) {
             if (!can) return nn_fail("nn_noisy_conv_fwd: w_packed_layout = NN_PACK_SHIFT is not served for this call%s", "");
             return shift_conv_fwd(a, sp, device, st);
+        }
+    }
+    {   // conv layers on the lean path: persistent CTA-pair kernel with TMA-im2col operands
+        TmaPlan tp;
+        const bool can = tma_fwd_plan(a, &tp);
+        const int layout = a->w_packed ? a->w_packed_layout : (can ? NN_PACK_TMA : NN_PACK_TILED);
+        if (layout == NN_PACK_TMA) {
+            if (!can) return nn_fail("nn_noisy_conv_fwd: w_packed_layout = NN_PACK_TMA is not served for this call%s", "");
+            return tma_conv_fwd(a, tp, device, st);
         }
     }
     Plan pl = make_plan(g.Cin, g.KH * g.KW, g.Cout, has_main, noise, has_wsum, (int64_t)g.B * g.H * g.W,
@@ -2169,8 +2105,18 @@ static void shift_plan_for_job(const nn_wprep_job& jb, ShiftPlan* sp) {
     sp->b_bytes = sp->n_chunks * sp->n_mma * 16; sp->wp_bytes = (size_t)sp->b_bytes;
 }
 
+// NN_PACK_TMA jobs: the plan depends on the channel counts, the tap count and the sigma rows only
+static bool tma_plan_for_job(const nn_wprep_job& jb, TmaPlan* tp) {
+    int k = 1;
+    while (k * k < jb.KHW) ++k;
+    if (k * k != jb.KHW) return false;
+    if (jb.mode == 0) return nn_tma_make_plan(jb.Cin, k, k, 1, 0, jb.Cout, jb.noise_mode != NN_NOISE_NONE, 2, 2, tp);
+    return nn_tma_make_plan(jb.Cout, k, k, 1, 0, jb.Cin, false, 2, 2, tp);
+}
+
 extern "C" int64_t nn_weight_pack_bytes(const nn_wprep_job* jb) {
     if (!jb) return 0;
+    if (jb->layout == NN_PACK_TMA) { TmaPlan tp; return tma_plan_for_job(*jb, &tp) ? (int64_t)align_up(tp.wp_bytes, 1024) : 0; }
     if (jb->layout == NN_PACK_SHIFT) { ShiftPlan sp; shift_plan_for_job(*jb, &sp); return (int64_t)align_up(sp.wp_bytes, 1024); }
     return (int64_t)align_up(plan_for_job(*jb).wp_bytes, 1024);
 }
@@ -2187,7 +2133,11 @@ extern "C" int nn_prepare_weights(const nn_wprep_job* jobs, int count, int devic
         if (!jb.w_raw || !jb.packed_out) return nn_fail("nn_prepare_weights: null pointer%s", "");
         if (jb.q_bits > 0 && !(jb.q_hi > 0)) return nn_fail("nn_prepare_weights: symmetric range needs q_hi > 0%s", "");
         Plan pl = plan_for_job(jb);
-        if (jb.layout == NN_PACK_SHIFT) {
+        TmaPlan tp;
+        if (jb.layout == NN_PACK_TMA) {
+            if (jb.want_wsum || !tma_plan_for_job(jb, &tp))
+                return nn_fail("nn_prepare_weights: NN_PACK_TMA is not served for this job%s (see nn_conv_pack_layout)", "");
+        } else if (jb.layout == NN_PACK_SHIFT) {
             if (jb.mode != 0 || jb.Cin > 8 || jb.want_wsum)
                 return nn_fail("nn_prepare_weights: NN_PACK_SHIFT needs a forward job with Cin <= 8 and no colsum row%s", "");
             ShiftPlan sp;
@@ -2209,8 +2159,9 @@ extern "C" int nn_prepare_weights(const nn_wprep_job* jobs, int count, int devic
             pw.q_hi = (float)jb.q_hi; pw.q_scale = (float)sc; pw.q_max = (float)qmax; pw.q_stoch = jb.stochastic;
             pw.u_inject = jb.u_inject; pw.rng = jb.rng;
         }
-        const int64_t total = jb.layout == NN_PACK_SHIFT ? (int64_t)pl.num_kb * pl.n_mma
-                                                         : (int64_t)pl.n_tiles * pl.num_kb * pl.n_mma * 8;
+        int64_t total = jb.layout == NN_PACK_SHIFT ? (int64_t)pl.num_kb * pl.n_mma
+                                                   : (int64_t)pl.n_tiles * pl.num_kb * pl.n_mma * 8;
+        if (jb.layout == NN_PACK_TMA) { fill_pack_tma(pw, tp); total = pack_tma_chunks(tp); }
         if (total > max_total) max_total = total;
     }
     {   // quantizer codes once per distinct (parameter, scratch) pair
@@ -2255,6 +2206,52 @@ int nn_umma_conv_dgrad(const nn_conv_dgrad_args* a, int device, cudaStream_t st)
     nn_out_hw(g, OH, OW);
     // dgrad(stride 1) == forward conv of gy [B,Cout,OH,OW] with the transposed, tap-flipped weights and
     // padding K-1-pad, producing [B,Cin,H,W]
+    {   // conv layers without an STE mask: persistent CTA-pair kernel with TMA-im2col operands over grad_output
+        TmaPlan tp;
+        const bool can = !a->x_pre && g.stride == 1 &&
+                         nn_tma_make_plan(g.Cout, g.KH, g.KW, 1, g.KH - 1 - g.pad, g.Cin, false, g.H, g.W, &tp);
+        const int layout = a->w_packed ? a->w_packed_layout : (can ? NN_PACK_TMA : NN_PACK_TILED);
+        if (layout == NN_PACK_TMA) {
+            if (!can) return nn_fail("nn_noisy_conv_dgrad: w_packed_layout = NN_PACK_TMA is not served for this call%s", "");
+            const size_t xp_bytes = (size_t)g.B * OH * OW * tp.Cp * 2;
+            const size_t need = (a->gy_packed ? 0 : align_up(xp_bytes, 1024)) + (a->w_packed ? 0 : align_up(tp.wp_bytes, 1024)) + 1024;
+            if ((!a->gy_packed || !a->w_packed) && (!a->workspace || (size_t)a->workspace_bytes < need))
+                return nn_fail("nn_noisy_conv_dgrad: workspace too small%s (need %lld bytes)", "", (long long)need);
+            uint8_t* ws = (uint8_t*)align_up((size_t)a->workspace, 1024);
+            const void* xp = a->gy_packed;
+            const void* wp = a->w_packed;
+            if (!xp) {
+                const int64_t total = (int64_t)g.B * OH * OW * (tp.Cp / 8);
+                int grid = (int)((total + 255) / 256);
+                if (grid > 16 * nn_num_sms(device)) grid = 16 * nn_num_sms(device);
+                k_pack_act<<<grid, 256, 0, st>>>(a->gy, (__nv_bfloat16*)ws, g.B, g.Cout, OH * OW, tp.Cp, 0.f);
+                NN_LAUNCH_OK();
+                xp = ws;
+                ws += align_up(xp_bytes, 1024);
+            }
+            if (!wp) {
+                PackWP pw;
+                memset(&pw, 0, sizeof(pw));
+                pw.w_eff = a->w_eff; pw.w_raw = nullptr; pw.wp = (__nv_bfloat16*)ws;
+                pw.Cout = g.Cout; pw.Cin = g.Cin; pw.KHW = g.KH * g.KW; pw.noise_mode = 0; pw.mode = 1; pw.w_code_scale = a->w_code_scale;
+                fill_pack_tma(pw, tp);
+                const int64_t total = pack_tma_chunks(tp);
+                int grid = (int)((total + 255) / 256);
+                if (grid > 8 * nn_num_sms(device)) grid = 8 * nn_num_sms(device);
+                k_pack_w<<<grid, 256, 0, st>>>(pw);
+                NN_LAUNCH_OK();
+                wp = ws;
+            }
+            TmaConvCall c;
+            memset(&c, 0, sizeof(c));
+            c.pl = tp;
+            c.B = g.B; c.H = OH; c.W = OW; c.OH = g.H; c.OW = g.W; c.KH = g.KH; c.KW = g.KW; c.stride = 1; c.pad = g.KH - 1 - g.pad;
+            c.Cout = g.Cin; c.xp = xp; c.wp = wp;
+            c.y_scale = a->w_code_scale > 0.f ? a->w_code_scale : 1.f; c.s_scale = 1.f;
+            c.y = a->gx; c.noise_mode = NN_NOISE_NONE; c.err_flag = nn_umma_err_flag(device);
+            return nn_tma_conv_launch(c, device, st);
+        }
+    }
     Plan pl = make_plan(g.Cout, g.KH * g.KW, g.Cin, true, false, false, (int64_t)g.B * OH * OW,
                         (g.B * g.H * g.W + 127) / 128);
     const size_t need = align_up(pl.xp_bytes, 1024) + align_up(pl.wp_bytes, 1024) + 1024;
@@ -2447,11 +2444,9 @@ static int shift_conv_wgrad(const nn_conv_wgrad_args* a, const WgShiftPlan& w, i
     static const int env_order = getenv("NN_WS_ORDER") ? atoi(getenv("NN_WS_ORDER")) : 1;   // 1: kernel row outermost (8 MMAs per accumulator in a row: 56 -> 40 ns per MMA)
     p.order = env_order;
     p.xp = xp; p.gyv = gyv; p.partial = partial; p.err_flag = nn_umma_err_flag(device);
-    static bool attr_set = false;
-    if (!attr_set) {
+    NN_ONCE_PER_DEVICE({
         NN_CUDA_OK(cudaFuncSetAttribute(k_wgrad_shift, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    });
     static const bool want_dbg = getenv("NN_UMMA_DEBUG") != nullptr;
     if (want_dbg) {
         const size_t rows = (size_t)w.grid * 16;
@@ -2526,11 +2521,9 @@ int nn_umma_conv_wgrad(const nn_conv_wgrad_args* a, int device, cudaStream_t st)
     p.Ktot = w.Ktot; p.NT = w.NT; p.ktot_pad = w.ktot_pad; p.num_kb = w.num_kb; p.kb_per_split = w.kb_per_split;
     p.stages = w.stages; p.tmem_cols = w.tmem_cols; p.xp = xp; p.gyp = gyp; p.partial = partial;
     p.err_flag = nn_umma_err_flag(device);
-    static bool attr_set = false;
-    if (!attr_set) {
+    NN_ONCE_PER_DEVICE({
         NN_CUDA_OK(cudaFuncSetAttribute(k_wgrad_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    });
     dim3 grid(w.n_tiles_k, w.m_tiles_n, w.splits);
     k_wgrad_umma<<<grid, UM_THREADS, w.smem_bytes, st>>>(p);
     NN_LAUNCH_OK();

@@ -1086,11 +1086,9 @@ extern "C" int nn_head_fwd_bwd(const float* logits, const int64_t* labels, int B
     if (threads < 32) threads = 32;
     const size_t hsm = ((size_t)2 * C * B + B) * sizeof(float);
     if (B <= 1024 && hsm <= 160 * 1024) {        // one thread per row, warp-per-channel reductions
-        static bool attr_set = false;
-        if (!attr_set) {
+        NN_ONCE_PER_DEVICE({
             NN_CUDA_OK(cudaFuncSetAttribute(k_head_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            attr_set = true;
-        }
+        });
         if (threads < 32 * (C + 1) && 32 * (C + 1) <= 1024) threads = 32 * (C + 1);      // a warp per channel + the loss
         k_head_rows<<<1, threads, hsm, (cudaStream_t)stream>>>(logits, labels, B, C, gamma, beta, running_mean, running_var,
                                                               momentum, eps, loss_out, out, g, (__nv_bfloat16*)g_packed, Cp,
@@ -1127,11 +1125,9 @@ extern "C" int nn_classifier_tail(const nn_tail_args* a, int device, void* strea
     const size_t smem = ((size_t)2 * 16 * p.xs_stride + (size_t)K16 * 16 + (size_t)R16 * p.xs_stride) * 2 +
                         (size_t)3 * R16 * 16 * sizeof(float) + 64;
     if (smem > 200 * 1024) return nn_fail("nn_classifier_tail: layer too large for one cluster%s", "");
-    static bool attr_set = false;
-    if (!attr_set) {
+    NN_ONCE_PER_DEVICE({
         NN_CUDA_OK(cudaFuncSetAttribute(k_classifier_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    });
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(TAIL_CTAS); cfg.blockDim = dim3(TAIL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;

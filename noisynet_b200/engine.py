@@ -108,7 +108,10 @@ class NoisyNetEngine:
             jb.Cout, jb.Cin, jb.KHW, jb.mode, jb.m_rows = co, ci, khw, mode, m_rows
             jb.noise_mode = self.noise_modes[li] if mode == 0 else 0
             jb.want_wsum = 0
-            jb.layout = self.lib.nn_conv_pack_layout(C.byref(self.geom[li]), jb.noise_mode, PREC_BF16) if mode == 0 else 0
+            if mode == 0:
+                jb.layout = self.lib.nn_conv_pack_layout(C.byref(self.geom[li]), jb.noise_mode, PREC_BF16)
+            else:       # dgrad image: the conv layer asks the library, the fc layers run as linear GEMMs (tiled layout)
+                jb.layout = self.lib.nn_conv_dgrad_pack_layout(C.byref(self.geom[li]), PREC_BF16) if li == 1 else 0
             jb.q_bits, jb.q_hi = int(a.q_w1), 1.0
             if li not in self.wcodes:        # quantizer codes: one scratch per layer, shared by its forward and dgrad jobs
                 self.wcodes[li] = torch.zeros(W[li].numel() + 16, dtype=torch.int8, device=dev)
@@ -118,6 +121,7 @@ class NoisyNetEngine:
             self.wpack.append(buf)
         self.wp_fwd = [self.jobs[i].packed_out for i in range(4)]
         self.wp_dgrad = {3: self.jobs[4].packed_out, 2: self.jobs[5].packed_out, 1: self.jobs[6].packed_out}
+        self.wp_dgrad_layout = {3: self.jobs[4].layout, 2: self.jobs[5].layout, 1: self.jobs[6].layout}
         need = 0
         for g in self.geom + [self.geom_fc1_lin]:
             need = max(need, self.lib.nn_conv_workspace_bytes(C.byref(g), PREC_BF16),
@@ -200,6 +204,7 @@ class NoisyNetEngine:
         a = ConvDgradArgs()
         a.g = geom
         a.gy, a.gy_packed, a.w_eff, a.w_packed, a.gx = None, _p(gyp), None, self.wp_dgrad[layer], _p(gx)
+        a.w_packed_layout = self.wp_dgrad_layout[layer]
         a.precision, a.w_code_scale = PREC_BF16, self.w_cs
         a.workspace, a.workspace_bytes = _p(self.ws), self.ws.numel()
         _lib.check(self.lib.nn_noisy_conv_dgrad(C.byref(a), self.di, self._st()), "nn_noisy_conv_dgrad")

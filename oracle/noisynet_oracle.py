@@ -140,7 +140,7 @@ def noisy_linear_fwd(x, w_eff, bias=None):
 # a7  add_noise_calculate_power, accurate model   hardware_model.py:43-88, 122-127
 # --------------------------------------------------------------------------
 
-def noise_sigma(x, w_raw, current, layer_type="conv", merged_dac=True, stride=1, padding=0):
+def noise_sigma(x, w_raw, current, layer_type="conv", merged_dac=True, stride=1, padding=0, want_plain=True):
     """Returns (sigma, S_plain, x_max, w_max).
 
     merged DAC  (:47-59):  S = conv(x,|W|),        sigma = sqrt(0.1 * (max|W| / I) * S)
@@ -156,7 +156,8 @@ def noise_sigma(x, w_raw, current, layer_type="conv", merged_dac=True, stride=1,
         contract = lambda k: F.conv2d(x, k, None, stride, padding)
     else:
         contract = lambda k: F.linear(x, k, None)
-    s_plain = contract(absw)
+    # the external-DAC branch needs conv(x,|W|) only for the i < 20 power statistic (:67-68, :74-75)
+    s_plain = contract(absw) if (merged_dac or want_plain) else None
     if merged_dac:
         sig = torch.sqrt(0.1 * (w_max / current) * s_plain)
     else:
@@ -171,7 +172,7 @@ def add_noise_calculate_power(x, w_raw, y, current, layer_type="conv", merged_da
     as appended at hardware_model.py:86-88 when i < 20."""
     with torch.no_grad():
         sig, s_plain, x_max, w_max = noise_sigma(x, w_raw, current, layer_type, merged_dac,
-                                                 stride, padding)
+                                                 stride, padding, want_plain=want_stats)
         if z is None:
             z = torch.randn_like(sig)
         noise = z * sig                       # torch.normal(0, sig) == normal_(0,1) * sig

@@ -247,6 +247,81 @@ def test_engine_step_with_noise(dev):
     assert ops.error_flag() == 0
 
 
+def test_engine_benchmark_config_vs_oracle(dev):
+    """The configuration bench.py measures -- NoisyNetEngine.train_step at batch 512, full widths (65 / 120 / 390),
+    q_a = q_w = 4, I = 1 nA on every layer -- against the CPU oracle's training step (oracle/noisynet_oracle.py, pinned to
+    the unmodified reference by tests/golden) with the SAME injected draws (stochastic-rounding uniforms of the four
+    activation and four weight quantizers, the four Gaussian noise tensors).
+
+    What can differ: the engine's sigma uses bf16-rounded g(|w|) (<= 3e-3 relative), its BatchNorm statistics are summed
+    in a different order (1e-6), the Box-Muller-free injected z is identical.  A perturbation of 1e-3 sigma moves a
+    pre-quantizer activation by ~1e-4 of a 4-bit step (5/15), so a small FRACTION of codes lands on the other side of a
+    rounding boundary; every flipped code is a full-step difference that the next layer sees.  Stated tolerances:
+      * loss: |d| <= 2e-3;
+      * 4-bit codes entering conv1 identical, entering conv2 / fc1 / fc2: <= 0.5 % differ, none by more than one level;
+      * BatchNorm running statistics: rtol 2e-3;
+      * gradients of every parameter against the ORACLE's: relative L2 error <= 3e-2 (bf16 grad_output operands +
+        the flipped codes), cosine >= 0.999.
+    """
+    from noisynet_b200 import ops
+    from noisynet_b200.engine import NoisyNetEngine
+    from noisynet_b200.net import NoisyNet, default_args, make_fused_optimizer, with_quant
+    from test_gpu_net import _make_rnd
+    B, q, current = 512, 4, 1.0
+    oa = O.default_args(q_a=q, q_w=q, quant_max2=5.0, quant_max4=5.0, current=current)
+    torch.manual_seed(3)
+    om = O.OracleNet(oa).init_like_reference()
+    na = with_quant(default_args(layer_currents=[current] * 4), q, q)
+    nm = NoisyNet(na, fused=True, precision="bf16").to(dev)
+    nm.load_state_dict(om.state_dict(), strict=False)
+    nm.quantize2.running_max = torch.tensor(5.0, device=dev)
+    nm.quantize4.running_max = torch.tensor(5.0, device=dev)
+    om.train(), nm.train()
+    oopt = O.make_optimizer(om, oa)
+    eng = NoisyNetEngine(nm, B, opt=make_fused_optimizer(nm, na))
+    x, lab = O.synthetic_cifar(B, seed=20)
+    rnd = _make_rnd(oa, B, q, 300)
+    rec = {}
+    orig_q = om._q
+
+    def rec_q(t, bits, lo, hi, r, name):
+        y = orig_q(t, bits, lo, hi, r, name)
+        if name.startswith("ua"):
+            s = O.quant_scale(bits, lo, hi)
+            rec[name] = torch.round((y.detach() - lo) / s)
+        return y
+    om._q = rec_q
+    oloss, _ = O.train_step(om, oopt, x, lab, i=100, rnd=rnd)
+    eng.inject = dict(u=[rnd[k].to(dev) for k in ("ua1", "ua2", "ua3", "ua4")],
+                      uw=[rnd[k].to(dev) for k in ("uw0", "uw1", "uw2", "uw3")],
+                      z=[rnd[k].to(dev) for k in ("z0", "z1", "z2", "z3")])
+    loss = eng.train_step(x.to(dev), lab.to(dev))
+    assert ops.error_flag() == 0 and not eng.inject["u"] and not eng.inject["z"] and not eng.inject["uw"]
+    report = {"loss": (loss.item(), oloss.item())}
+    assert abs(loss.item() - oloss.item()) <= 2e-3, report
+    # 4-bit activation codes, layer by layer
+    codes = {"ua1": eng.xp1[..., :3].permute(0, 3, 1, 2), "ua2": eng.xp2[..., :65].permute(0, 3, 1, 2),
+             "ua3": eng.xp3[..., :120].permute(0, 3, 1, 2).reshape(B, -1), "ua4": eng.xp4[:, :390]}
+    for k, c in codes.items():
+        d = (c.float().cpu() - rec[k].reshape(c.shape)).abs()
+        frac, worst = (d > 0).float().mean().item(), d.max().item()
+        report[k] = (frac, worst)
+        assert frac <= (0.0 if k == "ua1" else 5e-3) and worst <= 1.0, report
+    for k in ("bn1", "bn2", "bn3", "bn4"):
+        assert torch.allclose(getattr(nm, k).running_mean.cpu(), getattr(om, k).running_mean, rtol=2e-3, atol=1e-4), k
+        assert torch.allclose(getattr(nm, k).running_var.cpu(), getattr(om, k).running_var, rtol=2e-3, atol=1e-5), k
+    og = dict(om.named_parameters())
+    for k, p in nm.named_parameters():
+        a, b = p.grad.cpu().flatten().double(), og[k].grad.flatten().double()
+        rel = ((a - b).norm() / (b.norm() + 1e-30)).item()
+        cos = (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+        report["g:" + k] = (rel, cos)
+    print("engine vs oracle at the benchmark configuration:", report)
+    for k, v in report.items():
+        if k.startswith("g:"):
+            assert v[0] <= 3e-2 and v[1] >= 0.999, (k, v, report)
+
+
 @pytest.mark.parametrize("B,current", [(512, 1.0), (200, 1.0), (96, 0.0)])
 def test_classifier_tail_matches_separate_kernels(dev, B, current):
     """nn_classifier_tail (one 8-CTA cluster) == nn_noisy_conv_fwd (integer-code tcgen05, same Philox stream) ->
