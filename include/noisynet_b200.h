@@ -58,6 +58,23 @@ int nn_quantize_fwd(const float* x, float* y, int64_t n, int bits, double min_va
 int nn_quantize_bwd(const float* x, const float* gy, float* gx, int64_t n, double min_value,
                     double max_value, int device, void* stream);
 
+/* ---- a3 on the device: QuantMeasure range selection (hardware_model.py:232-259) without host syncs -----------
+ * mode 0 (activations, :240-259): out4[0] = kthvalue(x, k_rank), k_rank = the caller's int(n * pctl / 100) (hardware_model.py:249)
+ *        or int(n * pctl) (quant.py:109)  (what the script appends to running_list),
+ *        out4[1] = max(x); the quantisation range of THIS call is out4[2..3] = {min_value, max(x)}  (:253).
+ * mode 1 (signed weights, :232-239): out4[0] = running_min = -kthvalue(|x[x<0]|, int(count * pctl_percent / 100)),
+ *        out4[1] = running_max = kthvalue(x[x>0], ...); range out4[2..3] = {running_min, running_max}.
+ * Exact (radix select on the floats' ordered integer image), deterministic, graph-capturable; `scratch` is
+ * nn_range_scratch_bytes() of device memory.  out4 + 2 is the `range_dev` of the two entry points below. */
+int64_t nn_range_scratch_bytes(void);
+int nn_range_select(const float* x, int64_t n, int64_t k_rank, double pctl_percent, int mode, double min_value, float* out4,
+                    void* scratch, int device, void* stream);
+/* nn_quantize_fwd / nn_quantize_bwd with the range {min, max} read from device memory (scale = max((max-min)/(2^b-1), 1e-6)
+ * evaluated in doubles on the device, as the host does at :148-151). */
+int nn_quantize_fwd_dev(const float* x, float* y, int64_t n, int bits, const float* range_dev, float stochastic,
+                        const float* u_inject, nn_rng rng, int device, void* stream);
+int nn_quantize_bwd_dev(const float* x, const float* gy, float* gx, int64_t n, const float* range_dev, int device, void* stream);
+
 /* ---- a4: AddNoise  (hardware_model.py:291-307) ------------------------------------- */
 /* out = w + w * U(-noise, noise). */
 int nn_weight_noise_fwd(const float* w, float* out, int64_t n, float noise,
@@ -288,6 +305,8 @@ typedef struct nn_stage_args {
     float* xmax_out;          /* optional out: max of the activation (device scalar)                  */
     void* scratch;            /* nn_stage_scratch_bytes(C) bytes, ZEROED once by the caller (kernels keep it
                                  consistent); shared by the forward and backward of all stages          */
+    int32_t eval_mode;        /* 1: model.eval() -- BatchNorm normalises with running_mean / running_var and updates
+                                 nothing (noisynet.py:1560-1567); the caller passes stochastic = 0 (hardware_model.py:283-286) */
 } nn_stage_args;
 int64_t nn_stage_scratch_bytes(int C);
 int nn_stage_fwd(const nn_stage_args* a, int device, void* stream);
@@ -323,6 +342,10 @@ int nn_head_fwd_bwd(const float* logits, const int64_t* labels, int B, int C, co
                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                     float* loss_out, float* out, float* g, void* g_packed, int Cp, float* dgamma, float* dbeta,
                     int device, void* stream);
+
+/* Head in eval mode: out = BatchNorm1d(x) with the running statistics (noisynet.py:594 under model.eval()). */
+int nn_head_eval(const float* x, int B, int C, const float* gamma, const float* beta, const float* running_mean,
+                 const float* running_var, float eps, float* out, int device, void* stream);
 
 /* Classifier tail, fused (noisynet.py:589-594 linear2 + current noise, bn4, :1278 CrossEntropyLoss, and the way
  * back: d loss / d logits through bn4, fc2 dgrad) for a last layer with <= 16 units: ONE thread-block cluster of 8

@@ -81,7 +81,7 @@ class StageArgs(C.Structure):
                 ("momentum", C.c_float), ("eps", C.c_float), ("mean", C.c_void_p), ("invstd", C.c_void_p),
                 ("act_max", C.c_float), ("q_bits", C.c_int32), ("q_hi", C.c_double), ("stochastic", C.c_float),
                 ("u_inject", C.c_void_p), ("rng", Rng), ("xp", C.c_void_p), ("Cp", C.c_int32),
-                ("act", C.c_void_p), ("xmax_out", C.c_void_p), ("scratch", C.c_void_p)]
+                ("act", C.c_void_p), ("xmax_out", C.c_void_p), ("scratch", C.c_void_p), ("eval_mode", C.c_int32)]
 
 
 class StageBwdArgs(C.Structure):
@@ -115,6 +115,12 @@ SIGNATURES = {
                                   C.c_float, C.c_void_p, Rng, C.c_int, C.c_void_p]),
     "nn_quantize_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double,
                                   C.c_int, C.c_void_p]),
+    "nn_range_scratch_bytes": (C.c_int64, []),
+    "nn_range_select": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_void_p]),
+    "nn_quantize_fwd_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_float, C.c_void_p, Rng,
+                                      C.c_int, C.c_void_p]),
+    "nn_quantize_bwd_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
     "nn_weight_noise_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, Rng,
                                       C.c_int, C.c_void_p]),
     "nn_adamw_step": (C.c_int, [C.POINTER(AdamWTensor), C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
@@ -129,6 +135,8 @@ SIGNATURES = {
     "nn_head_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "nn_head_eval": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
+                               C.c_int, C.c_void_p]),
     "nn_tensor_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
     "nn_clamp_absmax": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "nn_noise_epilogue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,

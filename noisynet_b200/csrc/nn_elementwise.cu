@@ -51,7 +51,14 @@ __device__ __forceinline__ float quant_one(float x, float neg_min, float scale, 
 
 __global__ void __launch_bounds__(256)
 k_quantize_fwd(const float* __restrict__ x, float* __restrict__ y, int64_t n, float neg_min, float min_v,
-               float scale, float qmax, float stoch, const float* __restrict__ u_inject, nn_rng rng) {
+               float scale, float qmax, float stoch, const float* __restrict__ u_inject, nn_rng rng,
+               const float* __restrict__ range_dev) {
+    if (range_dev) {        // range selected on the device (nn_range_select): the host arithmetic of :148-151 in doubles
+        const double mn = (double)range_dev[0], mx = (double)range_dev[1];
+        double sc = (mx - mn) / (double)qmax;
+        if (sc < 1e-6) sc = 1e-6;
+        scale = (float)sc; neg_min = (float)(-mn); min_v = (float)mn;
+    }
     const NnRng s = nn_rng_load(rng);
     const int64_t ngroups = (n + 3) >> 2;
     const bool vec = ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)u_inject) & 15) == 0);
@@ -102,7 +109,20 @@ extern "C" int nn_quantize_fwd(const float* x, float* y, int64_t n, int bits, do
     int threads = 256;
     int grid = nn_grid_for((n + 3) / 4, threads, device);
     k_quantize_fwd<<<grid, threads, 0, (cudaStream_t)stream>>>(
-        x, y, n, (float)(-min_value), (float)min_value, (float)scale, (float)qmax, stochastic, u_inject, rng);
+        x, y, n, (float)(-min_value), (float)min_value, (float)scale, (float)qmax, stochastic, u_inject, rng, nullptr);
+    NN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int nn_quantize_fwd_dev(const float* x, float* y, int64_t n, int bits, const float* range_dev, float stochastic,
+                                   const float* u_inject, nn_rng rng, int device, void* stream) {
+    if (n <= 0) return 0;
+    if (bits < 1 || bits > 16) return nn_fail("nn_quantize_fwd_dev: bits out of range%s (%lld)", "", bits);
+    if (!range_dev) return nn_fail("nn_quantize_fwd_dev: range_dev missing%s", "");
+    NN_SET_DEVICE(device);
+    const double qmax = (double)((1u << bits) - 1u);
+    k_quantize_fwd<<<nn_grid_for((n + 3) / 4, 256, device), 256, 0, (cudaStream_t)stream>>>(
+        x, y, n, 0.f, 0.f, 1.f, (float)qmax, stochastic, u_inject, rng, range_dev);
     NN_LAUNCH_OK();
     return 0;
 }
@@ -110,7 +130,8 @@ extern "C" int nn_quantize_fwd(const float* x, float* y, int64_t n, int bits, do
 // ------------------------------------------------------------------ a2 quantize bwd (STE)
 __global__ void __launch_bounds__(256)
 k_quantize_bwd(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
-               int64_t n, float lo, float hi) {
+               int64_t n, float lo, float hi, const float* __restrict__ range_dev) {
+    if (range_dev) { lo = range_dev[0]; hi = range_dev[1]; }
     const bool vec = ((((uintptr_t)x | (uintptr_t)gy | (uintptr_t)gx) & 15) == 0);
     const int64_t ngroups = (n + 3) >> 2;
     for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < ngroups;
@@ -139,8 +160,138 @@ extern "C" int nn_quantize_bwd(const float* x, const float* gy, float* gx, int64
     NN_SET_DEVICE(device);
     int threads = 256;
     int grid = nn_grid_for((n + 3) / 4, threads, device);
-    k_quantize_bwd<<<grid, threads, 0, (cudaStream_t)stream>>>(x, gy, gx, n, (float)min_value, (float)max_value);
+    k_quantize_bwd<<<grid, threads, 0, (cudaStream_t)stream>>>(x, gy, gx, n, (float)min_value, (float)max_value, nullptr);
     NN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int nn_quantize_bwd_dev(const float* x, const float* gy, float* gx, int64_t n, const float* range_dev, int device,
+                                   void* stream) {
+    if (n <= 0) return 0;
+    if (!range_dev) return nn_fail("nn_quantize_bwd_dev: range_dev missing%s", "");
+    NN_SET_DEVICE(device);
+    k_quantize_bwd<<<nn_grid_for((n + 3) / 4, 256, device), 256, 0, (cudaStream_t)stream>>>(x, gy, gx, n, 0.f, 0.f, range_dev);
+    NN_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ a3 on the device: range selection of QuantMeasure
+// hardware_model.py:232-259 picks the quantisation range with torch.kthvalue (a sort) and input.max().item() (a host
+// sync per layer per batch while calibrating).  Here: an exact radix select over the order-preserving integer image of
+// the floats -- 4 passes of 256-bin histograms restricted to the prefix found so far -- and an atomic max, all on the
+// stream; the results stay in device memory and feed nn_quantize_fwd_dev / nn_quantize_bwd_dev directly.
+//   domain 0: every element       (activations, :249)           rank k given by the host: int(n * pctl / 100)
+//   domain 1: elements > 0        (signed weights, :233-235)    rank int(count * pctl / 100) computed on the device
+//   domain 2: |elements < 0|
+struct RangeSel {                    // device scratch of one selection
+    unsigned long long hist[256];
+    unsigned long long k;            // remaining rank (1-based) inside the current prefix
+    unsigned int prefix;             // key bits decided so far (high bits)
+    unsigned int pass;
+    float max_all;                   // max over ALL elements (domain 0 only)
+    float result;
+};
+
+__device__ __forceinline__ unsigned int nn_float_key(float f) {
+    const unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float nn_key_float(unsigned int k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+__global__ void k_range_init(RangeSel* sel, int nsel, long long k0) {
+    for (int j = 0; j < nsel; ++j) {
+        RangeSel& r = sel[j];
+        if (threadIdx.x < 256) r.hist[threadIdx.x] = 0ull;
+        if (threadIdx.x == 0) { r.k = (unsigned long long)k0; r.prefix = 0u; r.pass = 0u; r.max_all = __int_as_float(0xff800000); r.result = 0.f; }
+    }
+}
+
+// histogram of byte (3 - pass) of the keys that match the decided prefix; pass 0 also takes max(x)
+__global__ void __launch_bounds__(256)
+k_range_hist(const float* __restrict__ x, int64_t n, RangeSel* sel, int first_domain, int nsel) {
+    __shared__ unsigned int sh[2][256];
+    for (int j = 0; j < nsel; ++j) sh[j][threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned int pass = sel[0].pass;
+    const int shift = 24 - 8 * (int)pass;
+    unsigned int pre[2], mask = pass == 0 ? 0u : (0xFFFFFFFFu << (32 - 8 * pass));
+    for (int j = 0; j < nsel; ++j) pre[j] = sel[j].prefix;
+    float mx = __int_as_float(0xff800000);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = __ldg(x + i);
+        mx = fmaxf(mx, v);
+        for (int j = 0; j < nsel; ++j) {
+            const int d = first_domain + j;
+            float t = v;
+            bool in = true;
+            if (d == 1) in = v > 0.f;
+            else if (d == 2) { in = v < 0.f; t = -v; }
+            if (!in) continue;
+            const unsigned int key = nn_float_key(t);
+            if ((key & mask) == pre[j]) atomicAdd(&sh[j][(key >> shift) & 255u], 1u);
+        }
+    }
+    __syncthreads();
+    for (int j = 0; j < nsel; ++j)
+        if (sh[j][threadIdx.x]) atomicAdd(&sel[j].hist[threadIdx.x], (unsigned long long)sh[j][threadIdx.x]);
+    if (pass == 0 && first_domain == 0) {
+        mx = nn_warp_max(mx);
+        if ((threadIdx.x & 31) == 0) nn_atomic_max_float(&sel[0].max_all, mx);
+    }
+}
+
+// one warp: find the bin that holds rank k, descend into it
+__global__ void k_range_pick(RangeSel* sel, int nsel, double pctl, int rank_from_count, float* out4, int mode, double min_value) {
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < nsel; ++j) {
+            RangeSel& r = sel[j];
+            if (r.pass == 0 && rank_from_count) {
+                unsigned long long cnt = 0;
+                for (int b = 0; b < 256; ++b) cnt += r.hist[b];
+                r.k = (unsigned long long)((double)cnt * pctl / 100.);          // int(numel * pctl / 100.)   (:233-234)
+            }
+            unsigned long long k = r.k, cum = 0;
+            int bin = 255;
+            for (int b = 0; b < 256; ++b) {
+                if (cum + r.hist[b] >= k && k >= 1) { bin = b; break; }
+                cum += r.hist[b];
+            }
+            r.k = k - cum;
+            r.prefix |= (unsigned int)bin << (24 - 8 * r.pass);
+            r.pass += 1;
+            for (int b = 0; b < 256; ++b) r.hist[b] = 0ull;
+            if (r.pass == 4) r.result = nn_key_float(r.prefix);
+        }
+        if (sel[0].pass == 4) {
+            if (mode == 0) { out4[0] = sel[0].result; out4[1] = sel[0].max_all; out4[2] = (float)min_value; out4[3] = sel[0].max_all; }
+            else { out4[0] = -sel[1].result; out4[1] = sel[0].result; out4[2] = -sel[1].result; out4[3] = sel[0].result; }
+        }
+    }
+}
+
+extern "C" int64_t nn_range_scratch_bytes(void) { return (int64_t)(2 * sizeof(RangeSel) + 64); }
+
+extern "C" int nn_range_select(const float* x, int64_t n, int64_t k_rank, double pctl_percent, int mode, double min_value, float* out4,
+                               void* scratch, int device, void* stream) {
+    if (!x || !out4 || !scratch || n <= 0) return nn_fail("nn_range_select: bad arguments%s", "");
+    if (mode != 0 && mode != 1) return nn_fail("nn_range_select: mode must be 0 (activations) or 1 (signed weights)%s", "");
+    NN_SET_DEVICE(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    RangeSel* sel = (RangeSel*)(((uintptr_t)scratch + 15) & ~(uintptr_t)15);
+    const int nsel = mode == 0 ? 1 : 2, first_domain = mode == 0 ? 0 : 1;
+    const long long k0 = mode == 0 ? (long long)k_rank : 0;      // the caller's int(input.numel() * self.pctl / 100.)  (:249, quant.py:109)
+    if (mode == 0 && (k0 < 1 || k0 > n)) return nn_fail("nn_range_select: percentile rank out of range%s (%lld)", "", k0);
+    k_range_init<<<1, 256, 0, st>>>(sel, nsel, k0);
+    NN_LAUNCH_OK();
+    const int grid = nn_grid_for(n, 256, device, 4);
+    for (int pass = 0; pass < 4; ++pass) {
+        k_range_hist<<<grid, 256, 0, st>>>(x, n, sel, first_domain, nsel);
+        NN_LAUNCH_OK();
+        k_range_pick<<<1, 32, 0, st>>>(sel, nsel, pctl_percent, mode == 1 ? 1 : 0, out4, mode, min_value);
+        NN_LAUNCH_OK();
+    }
     return 0;
 }
 

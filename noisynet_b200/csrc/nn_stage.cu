@@ -117,10 +117,15 @@ k_chan_stats(const float* __restrict__ x, double* __restrict__ partial, int B, i
 // finalize BN statistics: mean / invstd (biased var) + running stats update (momentum, unbiased var)
 __global__ void k_bn_finalize(const double* __restrict__ partial, int splits, int C, double count, float eps, float momentum,
                               float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
-                              float* __restrict__ running_var, float* __restrict__ xmax_out) {
+                              float* __restrict__ running_var, float* __restrict__ xmax_out, int eval_mode) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && xmax_out) *xmax_out = 0.f;
     if (c >= C) return;
+    if (eval_mode) {          // model.eval(): normalise with the running statistics, update nothing (noisynet.py:1560-1567)
+        mean[c] = running_mean[c];
+        invstd[c] = (float)(1.0 / sqrt((double)running_var[c] + (double)eps));
+        return;
+    }
     double s1 = 0, s2 = 0;
     for (int s = 0; s < splits; ++s) { s1 += partial[((int64_t)c * splits + s) * 2]; s2 += partial[((int64_t)c * splits + s) * 2 + 1]; }
     const double m = s1 / count;
@@ -979,6 +984,7 @@ extern "C" int nn_stage_fwd(const nn_stage_args* a, int device, void* stream) {
         return nn_fail("nn_stage_fwd: null argument%s", "");
     if (a->pool && ((a->H | a->W) & 1)) return nn_fail("nn_stage_fwd: pooling needs even H, W%s", "");
     if (a->Cp % 8 || a->Cp < a->C) return nn_fail("nn_stage_fwd: bad Cp%s", "");
+    if (a->eval_mode && (!a->running_mean || !a->running_var)) return nn_fail("nn_stage_fwd: eval_mode needs the running statistics%s", "");
     NN_SET_DEVICE(device);
     cudaStream_t st = (cudaStream_t)stream;
     const float* bn_in = a->in;
@@ -1000,7 +1006,7 @@ extern "C" int nn_stage_fwd(const nn_stage_args* a, int device, void* stream) {
         NN_LAUNCH_OK();
     }
     k_bn_finalize<<<(a->C + 127) / 128, 128, 0, st>>>(partial, splits, a->C, (double)a->B * HW, a->eps, a->momentum, a->mean,
-                                                      a->invstd, a->running_mean, a->running_var, a->xmax_out);
+                                                      a->invstd, a->running_mean, a->running_var, a->xmax_out, a->eval_mode);
     NN_LAUNCH_OK();
     BnActP p;
     p.x = bn_in; p.mean = a->mean; p.invstd = a->invstd; p.gamma = a->gamma; p.beta = a->beta; p.u_inject = a->u_inject;
@@ -1096,6 +1102,25 @@ extern "C" int nn_head_fwd_bwd(const float* logits, const int64_t* labels, int B
     } else
     k_head<<<1, threads, 0, (cudaStream_t)stream>>>(logits, labels, B, C, gamma, beta, running_mean, running_var, momentum,
                                                     eps, loss_out, out, g, (__nv_bfloat16*)g_packed, Cp, dgamma, dbeta);
+    NN_LAUNCH_OK();
+    return 0;
+}
+
+// BatchNorm1d in eval mode on the last layer's output (noisynet.py:594 under model.eval()): the logits
+__global__ void k_head_eval(const float* __restrict__ x, int B, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                            const float* __restrict__ rm, const float* __restrict__ rv, float eps, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * C) return;
+    const int c = i % C;
+    const float inv = (float)(1.0 / sqrt((double)rv[c] + (double)eps));
+    out[i] = (x[i] - rm[c]) * inv * gamma[c] + beta[c];
+}
+
+extern "C" int nn_head_eval(const float* x, int B, int C, const float* gamma, const float* beta, const float* running_mean,
+                            const float* running_var, float eps, float* out, int device, void* stream) {
+    if (!x || !gamma || !beta || !running_mean || !running_var || !out || B < 1 || C < 1) return nn_fail("nn_head_eval: bad argument%s", "");
+    NN_SET_DEVICE(device);
+    k_head_eval<<<(B * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, B, C, gamma, beta, running_mean, running_var, eps, out);
     NN_LAUNCH_OK();
     return 0;
 }

@@ -10,7 +10,9 @@ of this library's kernels, with static buffers (CUDA-graph capturable, no autogr
 Activations travel between layers as NHWC bf16 integer codes (exact 4-bit operands for the tensor cores);
 fp32 NCHW tensors exist only where the maths needs them (noisy conv outputs, pooled BN inputs, gradients).
 Parameters, BN buffers and quantizer ranges are those of a `NoisyNet` module (state_dict compatible).
-Requires q_a > 0 and q_w > 0 (the 4-bit configuration); steady-state semantics (no i < 20 side statistics).
+Requires q_a > 0 and q_w > 0 on every layer (per-layer bit widths and act_max1..3 are honoured); steady-state
+semantics (the i < 20 side statistics, bias, dropout and the alternative noise models are the module path's).
+``eval_forward`` is the model.eval() forward (running BN statistics, no stochastic rounding, noise still injected).
 """
 import ctypes as C
 import os
@@ -34,10 +36,21 @@ class _Layer:
 class NoisyNetEngine:
     def __init__(self, model, batch, opt=None, reducer=None):
         a = model.args
-        if not (a.q_a1 > 0 and a.q_a2 > 0 and a.q_a3 > 0 and a.q_a4 > 0 and a.q_w1 > 0):
-            raise ValueError("NoisyNetEngine implements the quantized configuration (q_a > 0, q_w > 0)")
+        self.q_w = [int(a.q_w1), int(a.q_w2), int(a.q_w3), int(a.q_w4)]          # per-layer weight bits (noisynet.py:898-900)
+        if not (a.q_a1 > 0 and a.q_a2 > 0 and a.q_a3 > 0 and a.q_a4 > 0 and min(self.q_w) > 0):
+            raise ValueError("NoisyNetEngine implements the quantized configuration (q_a > 0, q_w > 0 on every layer)")
+        if max(self.q_w) > 7:
+            raise ValueError("NoisyNetEngine: weight codes are int8 (q_w <= 7)")
         if a.use_bias or a.dropout > 0 or a.dropout_conv > 0:
-            raise NotImplementedError("NoisyNetEngine: bias / dropout are not on the benchmark path")
+            raise NotImplementedError("NoisyNetEngine: bias / dropout are served by the module path (net.NoisyNet), not the engine")
+        if any(getattr(a, k, 0) for k in ("distort_act", "uniform_ind", "uniform_dep", "normal_ind", "normal_dep")):
+            raise NotImplementedError("NoisyNetEngine: alternative noise models are served by the module path")
+        for mod in (model.conv1, model.conv2, model.linear1, model.linear2):
+            qm = mod.quantize_weights
+            # the engine quantizes weights on the fixed range [-1, 1] (hardware_model.py:323): a percentile-calibrated
+            # weight range (--calculate_running flips every QuantMeasure, noisynet.py:1209) is the module path's business
+            if qm.calculate_running or qm.min_value != -1.0 or qm.max_value != 1.0 or float(qm.running_min.reshape(-1)[0]) < 0:
+                raise NotImplementedError("NoisyNetEngine: weight quantizers must be on the fixed range [-1, 1]")
         self.m, self.a, self.B = model, a, int(batch)
         self.opt, self.red = opt, reducer
         self.dev = model.conv1.weight.device
@@ -93,7 +106,7 @@ class NoisyNetEngine:
         # fc2 + bn4 + loss + their backward as ONE 8-CTA cluster launch (nn_classifier_tail): exact and tested, but 43 us
         # against 37 us for the three separate launches it replaces (8 SMs, ten latency-bound phases) -- off unless
         # NN_ENGINE_FUSED_TAIL=1
-        self.fused_tail = int(a.q_w1) > 0 and B <= 2048 and os.environ.get("NN_ENGINE_FUSED_TAIL", "0") == "1"
+        self.fused_tail = B <= 2048 and os.environ.get("NN_ENGINE_FUSED_TAIL", "0") == "1"
         self.fuse_pool1 = bool(self.lib.nn_conv_pool_fusable(C.byref(self.geom[0]), self.noise_modes[0], PREC_BF16)) and \
             os.environ.get("NN_ENGINE_FUSE_POOL", "0") == "1"
         self.gy1_layout = self.lib.nn_conv_wgrad_pack_layout(C.byref(self.geom[0]), PREC_BF16, self.di)
@@ -112,7 +125,7 @@ class NoisyNetEngine:
                 jb.layout = self.lib.nn_conv_pack_layout(C.byref(self.geom[li]), jb.noise_mode, PREC_BF16)
             else:       # dgrad image: the conv layer asks the library, the fc layers run as linear GEMMs (tiled layout)
                 jb.layout = self.lib.nn_conv_dgrad_pack_layout(C.byref(self.geom[li]), PREC_BF16) if li == 1 else 0
-            jb.q_bits, jb.q_hi = int(a.q_w1), 1.0
+            jb.q_bits, jb.q_hi = self.q_w[li], 1.0
             if li not in self.wcodes:        # quantizer codes: one scratch per layer, shared by its forward and dgrad jobs
                 self.wcodes[li] = torch.zeros(W[li].numel() + 16, dtype=torch.int8, device=dev)
             jb.codes = self.wcodes[li].data_ptr()
@@ -136,6 +149,67 @@ class NoisyNetEngine:
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
         self.inject = None          # parity hook: dict(u=[...], z=[...]) consumed in the reference's draw order
+        self.steps_done = 0         # training steps since the last sync_bn_counters()
+        self.logits = f32(B, 10)    # eval_forward output
+
+    def sync_bn_counters(self):
+        """BatchNorm.num_batches_tracked of the four BN modules (state_dict key of the reference model): the kernels keep
+        the running statistics, this host-side counter keeps the step count -- call before saving a checkpoint."""
+        if self.steps_done:
+            for bn in (self.m.bn1, self.m.bn2, self.m.bn3, self.m.bn4):
+                if bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked += self.steps_done
+            self.steps_done = 0
+
+    # ------------------------------------------------------------------ evaluation forward (noisynet.py:1560-1567)
+    @torch.no_grad()
+    def eval_forward(self, x, currents=None):
+        """model.eval() forward of the step's kernels: BatchNorm with running statistics, stochastic rounding off
+        (hardware_model.py:283-286), analog noise STILL injected wherever currentN > 0 -- the accurate noise model has no
+        training test (hardware_model.py:43); the script switches test noise by mutating args.layer_currents
+        (noisynet.py:1551-1553), here: ``currents`` (default: the model's).  Returns the logits [B, 10]."""
+        m, a, B, lib, di = self.m, self.a, self.B, self.lib, self.di
+        C1, C2, FC, H1, P1, H2, P2 = self.dims
+        st = self._st()
+        W = self._weights()
+        cur_saved = list(a.layer_currents)
+        if currents is not None:
+            a.layer_currents = list(currents)
+        modes_saved = list(self.noise_modes)
+        try:
+            base = [NOISE_MERGED if a.merged_dac else NOISE_EXTERNAL, NOISE_EXTERNAL,
+                    NOISE_MERGED if a.merged_dac else NOISE_EXTERNAL, NOISE_EXTERNAL]
+            self.noise_modes = [mo if a.layer_currents[i] > 0 else 0 for i, mo in enumerate(base)]
+            if self.noise_modes != modes_saved:
+                raise NotImplementedError("eval_forward: the set of noisy layers must match the training configuration "
+                                          "(the weight images carry the sigma rows); change the current values only")
+            qh1, qh2, qh3, qh4 = (self._qhi(q) for q in (m.quantize1, m.quantize2, m.quantize3, m.quantize4))
+            s1, s2, s3, s4 = (_f32(max(h / (2.0 ** b - 1.0), 1e-6))
+                              for h, b in ((qh1, a.q_a1), (qh2, a.q_a2), (qh3, a.q_a3), (qh4, a.q_a4)))
+            am1, am2, am3 = (float(getattr(a, k, a.act_max)) for k in ("act_max1", "act_max2", "act_max3"))
+            self.w_cs = [_f32(max(2.0 / (2.0 ** b - 1.0), 1e-6)) / 2.0 for b in self.q_w]
+            for j in range(4):                                  # forward images only, round-to-nearest weights
+                self.jobs[j].stochastic, self.jobs[j].u_inject, self.jobs[j].rng = 0.0, None, Rng(0, 0, None)
+            _lib.check(lib.nn_prepare_weights(self.jobs, 4, di, st), "nn_prepare_weights")
+            _lib.check(lib.nn_input_quant_pack(_p(x), _p(self.xp1), None, B, 3, 32 * 32, 8, int(a.q_a1), qh1, 0.0, None,
+                                               Rng(0, 0, None), di, st), "nn_input_quant_pack")
+            self._fwd_gemm(0, self.xp1, s1, self.y1n, self.noise_modes[0], self._absmax(0, W[0]))
+            self._stage_fwd(self.y1n, C1, H1, 1, self.pool1, self.amax1, m.bn1, "bn1", a.q_a2, qh2, self.xp2, self.xmax2,
+                            act_max=am1, eval_mode=True)
+            self._fwd_gemm(1, self.xp2, s2, self.y2n, self.noise_modes[1], self.xmax2)
+            self._stage_fwd(self.y2n, C2, H2, 1, self.pool2, self.amax2, m.bn2, "bn2", a.q_a3, qh3, self.xp3, None,
+                            act_max=am2, eval_mode=True)
+            self._fwd_gemm(2, self.xp3, s3, self.l1n, self.noise_modes[2], self._absmax(2, W[2]))
+            self._stage_fwd(self.l1n, FC, 1, 0, None, None, m.bn3, "bn3", a.q_a4, qh4, self.xp4, self.xmax4,
+                            act_max=am3, eval_mode=True)
+            self._fwd_gemm(3, self.xp4, s4, self.l2n, self.noise_modes[3], self.xmax4)
+            bn4 = m.bn4
+            _lib.check(lib.nn_head_eval(_p(self.l2n), B, 10, _p(bn4.weight), _p(bn4.bias), _p(bn4.running_mean),
+                                        _p(bn4.running_var), float(bn4.eps), _p(self.logits), di, st), "nn_head_eval")
+        finally:
+            a.layer_currents = cur_saved
+            self.noise_modes = modes_saved
+        return self.logits
 
     # ------------------------------------------------------------------ helpers
     def _weights(self):
@@ -179,7 +253,7 @@ class NoisyNetEngine:
             a.y, a.y_noisy = None, None
             a.pooled_out, a.argmax_out = _p(pooled), _p(argmax)
         a.precision = PREC_BF16
-        a.a_code_scale, a.w_code_scale = a_cs, self.w_cs
+        a.a_code_scale, a.w_code_scale = a_cs, self.w_cs[idx]
         a.workspace, a.workspace_bytes = _p(self.ws), self.ws.numel()
         _lib.check(self.lib.nn_noisy_conv_fwd(C.byref(a), self.di, self._st()), "nn_noisy_conv_fwd")
 
@@ -205,12 +279,13 @@ class NoisyNetEngine:
         a.g = geom
         a.gy, a.gy_packed, a.w_eff, a.w_packed, a.gx = None, _p(gyp), None, self.wp_dgrad[layer], _p(gx)
         a.w_packed_layout = self.wp_dgrad_layout[layer]
-        a.precision, a.w_code_scale = PREC_BF16, self.w_cs
+        a.precision, a.w_code_scale = PREC_BF16, self.w_cs[layer]
         a.workspace, a.workspace_bytes = _p(self.ws), self.ws.numel()
         _lib.check(self.lib.nn_noisy_conv_dgrad(C.byref(a), self.di, self._st()), "nn_noisy_conv_dgrad")
 
-    def _stage_fwd(self, x_in, C_, H, pool, pooled, amax, bn, key, q_bits, q_hi, xp, xmax, u=None):
+    def _stage_fwd(self, x_in, C_, H, pool, pooled, amax, bn, key, q_bits, q_hi, xp, xmax, u=None, act_max=None, eval_mode=False):
         a = StageArgs()
+        a.eval_mode = 1 if eval_mode else 0
         a.in_ = _p(x_in)
         a.B, a.C, a.H, a.W, a.pool = self.B, C_, H, H, pool
         a.pooled, a.argmax = _p(pooled), _p(amax)
@@ -218,9 +293,9 @@ class NoisyNetEngine:
         a.running_mean, a.running_var = _p(bn.running_mean), _p(bn.running_var)
         a.momentum, a.eps = float(bn.momentum), float(bn.eps)
         a.mean, a.invstd = _p(self.stat[key][0]), _p(self.stat[key][1])
-        a.act_max = float(self.a.act_max)
+        a.act_max = float(self.a.act_max if act_max is None else act_max)
         a.q_bits, a.q_hi = int(q_bits), float(q_hi)
-        a.stochastic = float(self.a.stochastic) if self.m.training else 0.0
+        a.stochastic = float(self.a.stochastic) if (self.m.training and not eval_mode) else 0.0
         a.u_inject = _p(u)
         a.rng = Rng(0, 0, None) if u is not None else self._rng()
         a.xp, a.Cp = _p(xp), xp.shape[-1]
@@ -228,13 +303,13 @@ class NoisyNetEngine:
         a.scratch = _p(self.scratch)
         _lib.check(self.lib.nn_stage_fwd(C.byref(a), self.di, self._st()), "nn_stage_fwd")
 
-    def _stage_bwd(self, g, x, amax, C_, H, pool, bn, key, q_bits, q_hi, gyp, planes_grid=None):
+    def _stage_bwd(self, g, x, amax, C_, H, pool, bn, key, q_bits, q_hi, gyp, planes_grid=None, act_max=None):
         a = StageBwdArgs()
         a.g, a.x, a.argmax = _p(g), _p(x), _p(amax)
         a.B, a.C, a.H, a.W, a.pool = self.B, C_, H, H, pool
         a.mean, a.invstd = _p(self.stat[key][0]), _p(self.stat[key][1])
         a.gamma, a.beta = _p(bn.weight), _p(bn.bias)
-        a.act_max, a.q_bits, a.q_hi = float(self.a.act_max), int(q_bits), float(q_hi)
+        a.act_max, a.q_bits, a.q_hi = float(self.a.act_max if act_max is None else act_max), int(q_bits), float(q_hi)
         a.dgamma, a.dbeta = _p(bn.weight.grad), _p(bn.bias.grad)
         a.gyp, a.Cp, a.gy_f32 = _p(gyp), (C_ + 7) // 8 * 8, None
         if planes_grid is not None:
@@ -259,10 +334,12 @@ class NoisyNetEngine:
         st = self._st()
         W = self._weights()
         stoch = float(a.stochastic) if m.training else 0.0
+        am1, am2, am3 = (float(getattr(a, k, a.act_max)) for k in ("act_max1", "act_max2", "act_max3"))   # noisynet.py:887-889
+        self.steps_done += 1
         qh1, qh2, qh3, qh4 = (self._qhi(q) for q in (m.quantize1, m.quantize2, m.quantize3, m.quantize4))
         s1, s2, s3, s4 = (_f32(max(h / (2.0 ** b - 1.0), 1e-6))
                           for h, b in ((qh1, a.q_a1), (qh2, a.q_a2), (qh3, a.q_a3), (qh4, a.q_a4)))
-        self.w_cs = _f32(max(2.0 / (2.0 ** a.q_w1 - 1.0), 1e-6)) / 2.0
+        self.w_cs = [_f32(max(2.0 / (2.0 ** b - 1.0), 1e-6)) / 2.0 for b in self.q_w]
         # ---- weights: quantize (stochastic rounding) + pack for forward and dgrad, all layers, ONE launch
         self._uw_keep = []
         for li in range(4):
@@ -291,23 +368,23 @@ class NoisyNetEngine:
         if self.fuse_pool1:
             self._fwd_gemm(0, self.xp1, s1, None, self.noise_modes[0], self._absmax(0, W[0]), self._take("z"),
                            pooled=self.pool1, argmax=self.amax1)
-            self._stage_fwd(self.pool1, C1, P1, 0, None, None, m.bn1, "bn1", a.q_a2, qh2, self.xp2, self.xmax2, self._take("u"))
+            self._stage_fwd(self.pool1, C1, P1, 0, None, None, m.bn1, "bn1", a.q_a2, qh2, self.xp2, self.xmax2, self._take("u"), act_max=am1)
         else:
             self._fwd_gemm(0, self.xp1, s1, self.y1n, self.noise_modes[0], self._absmax(0, W[0]), self._take("z"))
-            self._stage_fwd(self.y1n, C1, H1, 1, self.pool1, self.amax1, m.bn1, "bn1", a.q_a2, qh2, self.xp2, self.xmax2, self._take("u"))
+            self._stage_fwd(self.y1n, C1, H1, 1, self.pool1, self.amax1, m.bn1, "bn1", a.q_a2, qh2, self.xp2, self.xmax2, self._take("u"), act_max=am1)
         if self.side is not None:
             torch.cuda.current_stream(di).wait_stream(self.side)
         self._fwd_gemm(1, self.xp2, s2, self.y2n, self.noise_modes[1], self.xmax2, self._take("z"))
-        self._stage_fwd(self.y2n, C2, H2, 1, self.pool2, self.amax2, m.bn2, "bn2", a.q_a3, qh3, self.xp3, None, self._take("u"))
+        self._stage_fwd(self.y2n, C2, H2, 1, self.pool2, self.amax2, m.bn2, "bn2", a.q_a3, qh3, self.xp3, None, self._take("u"), act_max=am2)
         self._fwd_gemm(2, self.xp3, s3, self.l1n, self.noise_modes[2], self._absmax(2, W[2]), self._take("z"))
-        self._stage_fwd(self.l1n, FC, 1, 0, None, None, m.bn3, "bn3", a.q_a4, qh4, self.xp4, self.xmax4, self._take("u"))
+        self._stage_fwd(self.l1n, FC, 1, 0, None, None, m.bn3, "bn3", a.q_a4, qh4, self.xp4, self.xmax4, self._take("u"), act_max=am3)
         bn4 = m.bn4
         if self.fused_tail:
             # fc2 forward + noise, bn4, cross entropy, their backward and the fc2 dgrad: one 8-CTA cluster launch
             t = TailArgs()
             t.xp, t.B, t.K, t.Kp, t.C = _p(self.xp4), B, FC, self.xp4.shape[-1], 10
             t.w_codes, t.w_raw = self.wcodes[3].data_ptr(), _p(W[3])
-            t.a_code_scale, t.w_code_scale = s4, self.w_cs
+            t.a_code_scale, t.w_code_scale = s4, self.w_cs[3]
             cur = float(a.layer_currents[3])
             z = self._take("z")
             if cur > 0:
@@ -329,7 +406,7 @@ class NoisyNetEngine:
             # ---- backward
             self._wgrad(3, self.gyp4, self.xp4, s4, W[3], W[3].grad)
             self._dgrad(self.geom[3], self.gyp4, 3, self.gx4)
-        self._stage_bwd(self.gx4, self.l1n, None, FC, 1, 0, m.bn3, "bn3", a.q_a4, qh4, self.gyp3)
+        self._stage_bwd(self.gx4, self.l1n, None, FC, 1, 0, m.bn3, "bn3", a.q_a4, qh4, self.gyp3, act_max=am3)
         self._wgrad(2, self.gyp3, self.xp3, s3, W[2], W[2].grad)
         if self.red is not None:        # fc gradients (85 % of the payload) travel while the conv backward runs
             if self.side is not None:
@@ -338,7 +415,7 @@ class NoisyNetEngine:
             else:
                 self.red.start_early()
         self._dgrad(self.geom_fc1_lin, self.gyp3, 2, self.gx3)
-        self._stage_bwd(self.gx3, self.pool2, self.amax2, C2, H2, 1, m.bn2, "bn2", a.q_a3, qh3, self.gyp2)
+        self._stage_bwd(self.gx3, self.pool2, self.amax2, C2, H2, 1, m.bn2, "bn2", a.q_a3, qh3, self.gyp2, act_max=am2)
         self._wgrad(1, self.gyp2, self.xp2, s2, W[1], W[1].grad)
         if self.red is not None:        # second early bucket: conv2's weight gradient
             if self.side is not None:
@@ -348,7 +425,7 @@ class NoisyNetEngine:
                 self.red.start_early(1)
         self._dgrad(self.geom[1], self.gyp2, 1, self.gx2)
         self._stage_bwd(self.gx2, self.pool1, self.amax1, C1, H1, 1, m.bn1, "bn1", a.q_a2, qh2, self.gyp1,
-                        planes_grid=(32, 32) if self.gy1_layout else None)
+                        planes_grid=(32, 32) if self.gy1_layout else None, act_max=am1)
         self._wgrad(0, self.gyp1, self.xp1, s1, W[0], W[0].grad, self.gy1_layout)
         # ---- exchange + update
         if self.side is not None:

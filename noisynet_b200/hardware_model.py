@@ -129,25 +129,31 @@ class QuantMeasure(nn.Module):
         return hit[1]
 
     def _range(self, input):
+        """Returns (min_value, max_value, stoch, range_dev).  range_dev (float32[2] device tensor) is set where the
+        reference reads the range back from the device per call (``input.max().item()``, ``running_max.item()`` right
+        after computing it): there the range is selected ON the device (ops.range_select: exact radix-select kthvalue +
+        atomic max) and handed to the quantizer kernels as a device pointer -- no host sync."""
+        range_dev = None
         with torch.no_grad():
             min_value = self.min_value
+            max_value = self.max_value
             if self.calculate_running:
                 if self.min_value < 0:                                         # hm:232-239 signed weights
-                    pos = input[input > 0].flatten()
-                    neg = torch.abs(input[input < 0]).flatten()
-                    pctl_pos, _ = torch.kthvalue(pos, int(pos.numel() * self.pctl / 100.))
-                    pctl_neg, _ = torch.kthvalue(neg, int(neg.numel() * self.pctl / 100.))
-                    self.running_min = -pctl_neg
-                    self.running_max = pctl_pos
+                    out4 = ops.range_select(input.detach(), self.pctl, mode=1)
+                    self.running_min = out4[0].reshape([])
+                    self.running_max = out4[1].reshape([])
                     self.calculate_running = False
-                    min_value = self.running_min.item()
-                    max_value = self.running_max.item()
+                    range_dev = out4[2:4]
                 else:                                                          # hm:240-259
                     if 224 in list(input.shape):
                         pctl = torch.tensor(0.92) if self.num_bits == 4 else torch.tensor(1.0)
+                        mx = ops.tensor_stats(input.detach())[0:1]
+                        range_dev = torch.cat([torch.full_like(mx, float(min_value)), mx])
                     else:
-                        pctl, _ = torch.kthvalue(input.flatten(), int(input.numel() * self.pctl / 100.))
-                    max_value = input.max().item()
+                        out4 = ops.range_select(input.detach(), mode=0, min_value=min_value,
+                                                k_rank=int(input.numel() * self.pctl / 100.))
+                        pctl = out4[0].reshape([])
+                        range_dev = out4[2:4]
                     self.running_list.append(pctl)
             else:                                                              # hm:260-274
                 if self.min_value < 0 and self._host('running_min') < 0:
@@ -159,12 +165,15 @@ class QuantMeasure(nn.Module):
                     max_value = self._host('running_max')
                 else:
                     print('\n\nSetting max_value to input.max\nrunning_max is ', self._host('running_max'))
-                    max_value = input.max().item()
+                    mx = ops.tensor_stats(input.detach())[0:1]
+                    range_dev = torch.cat([torch.full_like(mx, float(min_value)), mx])
             stoch = self.stochastic if self.training else 0                    # hm:283-286
-        return min_value, max_value, stoch
+        return min_value, max_value, stoch, range_dev
 
     def forward(self, input):
-        min_value, max_value, stoch = self._range(input)
+        min_value, max_value, stoch, range_dev = self._range(input)
+        if range_dev is not None:
+            return UniformQuantize.apply(input, self.num_bits, None, None, stoch, self.inplace, False, None, range_dev)
         out = UniformQuantize.apply(input, self.num_bits, min_value, max_value, stoch, self.inplace, False)
         # tag for the integer-code tensor-core path (consumed by NoisyConv2d / NoisyLinear)
         out._nn_quant = (int(self.num_bits), float(min_value), float(max_value))
@@ -197,7 +206,9 @@ def _prepare_weight(mod, linear):
     quant_on = (0 < mod.num_bits_weight < 8) if linear else (mod.num_bits_weight > 0)
     if quant_on:
         qm = mod.quantize_weights
-        lo, hi, stoch = qm._range(mod.weight)
+        lo, hi, stoch, range_dev = qm._range(mod.weight)
+        if range_dev is not None:        # percentile calibration of the weight range just ran (once per module, hm:232-239):
+            lo, hi = range_dev.tolist()  # the STE bounds of the fused wgrad are host scalars -> one sync, this call only
         with torch.no_grad():
             wq = ops.quantize_fwd(mod.weight.detach(), qm.num_bits, lo, hi, stoch)
         wq._nn_quant = (int(qm.num_bits), float(lo), float(hi))

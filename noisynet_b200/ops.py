@@ -170,6 +170,50 @@ def quantize_bwd(x, gy, min_value, max_value):
     return gx
 
 
+_range_scratch = {}
+
+
+def range_select(x, pctl_percent=0.0, mode=0, min_value=0.0, k_rank=0):
+    """QuantMeasure's range selection on the device (hardware_model.py:232-259): returns a float32[4] DEVICE tensor
+    [percentile, max(x), range_min, range_max] (mode 0) / [running_min, running_max, running_min, running_max]
+    (mode 1, signed weights) -- exact kthvalue by radix select, no host sync.  mode 0 takes the rank ``k_rank`` the caller
+    computed from numel (hardware_model.py:249 / quant.py:109); mode 1 derives its ranks from the on-device counts."""
+    x = _req(x, "input")
+    dev = _dev(x)
+    lib = _lib.load()
+    sc = _range_scratch.get(dev)
+    if sc is None:
+        sc = _range_scratch[dev] = torch.empty(int(lib.nn_range_scratch_bytes()), dtype=torch.uint8, device=x.device)
+    out4 = torch.empty(4, dtype=torch.float32, device=x.device)
+    _lib.check(lib.nn_range_select(_p(x), x.numel(), int(k_rank), float(pctl_percent), int(mode), float(min_value), _p(out4), _p(sc),
+                                   dev, _stream(dev)), "nn_range_select")
+    return out4
+
+
+def quantize_fwd_dev(x, num_bits, range_dev, stochastic=0.0, u=None, out=None, rng=None):
+    """quantize_fwd with the range {min, max} in device memory (float32[2], e.g. range_select(...)[2:4])."""
+    x = _req(x, "input")
+    dev = _dev(x)
+    y = torch.empty_like(x) if out is None else out
+    if u is None and stochastic > 0 and rng is None:
+        u = _pop_inject("u", x.shape)
+    if u is not None:
+        u = _req(u, "u")
+    r = rng if rng is not None else (next_rng(dev) if (stochastic > 0 and u is None) else Rng(0, 0, None))
+    _lib.check(_lib.load().nn_quantize_fwd_dev(_p(x), _p(y), x.numel(), int(num_bits), _p(_req(range_dev, "range_dev")),
+                                               float(stochastic), _p(u), r, dev, _stream(dev)), "nn_quantize_fwd_dev")
+    return y
+
+
+def quantize_bwd_dev(x, gy, range_dev):
+    x, gy = _req(x, "input"), _req(gy, "grad_output")
+    dev = _dev(x)
+    gx = torch.empty_like(gy)
+    _lib.check(_lib.load().nn_quantize_bwd_dev(_p(x), _p(gy), _p(gx), x.numel(), _p(_req(range_dev, "range_dev")), dev, _stream(dev)),
+               "nn_quantize_bwd_dev")
+    return gx
+
+
 def weight_noise(w, noise, u=None, rng=None):
     w = _req(w, "weight")
     dev = _dev(w)
@@ -379,25 +423,36 @@ class UniformQuantize(InplaceFunction):
 
     @staticmethod
     def forward(ctx, input, num_bits=8, min_value=None, max_value=None, stochastic=0.5, inplace=False,
-                debug=False, u=None):
-        ctx.min_value = float(min_value)
-        ctx.max_value = float(max_value)
+                debug=False, u=None, range_dev=None):
+        """``range_dev`` (float32[2] device tensor {min, max}, from ops.range_select) replaces min_value / max_value: the
+        range never visits the host (the reference's ``input.max().item()`` / ``running_max.item()`` syncs)."""
+        ctx.range_dev = range_dev
+        if range_dev is None:
+            ctx.min_value = float(min_value)
+            ctx.max_value = float(max_value)
         ctx.bits = int(num_bits)
+        if inplace and not input.is_contiguous():
+            raise ValueError("noisynet_b200: UniformQuantize(inplace=True) needs a contiguous input (the kernel writes "
+                             "numel contiguous floats)")
         x = _req(input, "input")
+        fwd = (lambda out=None: quantize_fwd_dev(x, num_bits, range_dev, stochastic, u, out=out)) if range_dev is not None else \
+            (lambda out=None: quantize_fwd(x, num_bits, min_value, max_value, stochastic, u, out=out))
         if inplace:
             # the backward needs the pre-quantisation values -> keep a copy, write in place
             ctx.save_for_backward(x.clone())
             ctx.mark_dirty(input)
-            quantize_fwd(x, num_bits, min_value, max_value, stochastic, u, out=input)
+            fwd(out=input)
             return input
         ctx.save_for_backward(x)
-        return quantize_fwd(x, num_bits, min_value, max_value, stochastic, u)
+        return fwd()
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
         (x,) = ctx.saved_tensors
-        return quantize_bwd(x, grad_output, ctx.min_value, ctx.max_value), None, None, None, None, None, None, None
+        if ctx.range_dev is not None:
+            return quantize_bwd_dev(x, grad_output, ctx.range_dev), None, None, None, None, None, None, None, None
+        return quantize_bwd(x, grad_output, ctx.min_value, ctx.max_value), None, None, None, None, None, None, None, None
 
 
 class AddNoise(InplaceFunction):

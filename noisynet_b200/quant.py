@@ -42,13 +42,19 @@ class QuantMeasure(nn.Module):
         return hit[1]
 
     def forward(self, input):
+        from . import ops
+        range_dev = None
+        max_value = self.max_value
         with torch.no_grad():
             if self.calculate_running and self.training:                      # quant.py:102-115
                 if 224 in list(input.shape):
                     pctl = torch.tensor(0.92) if self.num_bits == 4 else torch.tensor(1.0)
-                else:
-                    pctl, _ = torch.kthvalue(input.view(-1), int(input.numel() * self.pctl))
-                max_value = input.max().item()
+                    mx = ops.tensor_stats(input.detach())[0:1]
+                    range_dev = torch.cat([torch.full_like(mx, float(self.min_value)), mx])
+                else:       # kthvalue + input.max().item() on the device: exact radix select, no host sync
+                    out4 = ops.range_select(input.detach(), mode=0, min_value=float(self.min_value),
+                                            k_rank=int(input.numel() * self.pctl))
+                    pctl, range_dev = out4[0].reshape([]), out4[2:4]
                 self.running_list.append(pctl)
             else:                                                             # quant.py:117-124
                 if self.max_value > 0:
@@ -56,8 +62,11 @@ class QuantMeasure(nn.Module):
                 elif self._host_running_max() > 0:
                     max_value = self._host_running_max()
                 else:
-                    max_value = input.max()
+                    mx = ops.tensor_stats(input.detach())[0:1]
+                    range_dev = torch.cat([torch.full_like(mx, float(self.min_value)), mx])
             stoch = self.stochastic if self.training else 0                   # quant.py:132-135
+        if range_dev is not None:
+            return UniformQuantize.apply(input, self.num_bits, None, None, stoch, self.inplace, self.debug_quant, None, range_dev)
         out = UniformQuantize.apply(input, self.num_bits, float(self.min_value), float(max_value), stoch,
                                       self.inplace, self.debug_quant)
         out._nn_quant = (int(self.num_bits), float(self.min_value), float(max_value))

@@ -247,6 +247,36 @@ def test_engine_step_with_noise(dev):
     assert ops.error_flag() == 0
 
 
+def test_engine_eval_forward_vs_oracle(dev):
+    """model.eval() forward (noisynet.py:1560-1567) on the engine's kernels: BatchNorm with running statistics, no
+    stochastic rounding.  I = 0: exact integer tensor-core arithmetic -> logits equal the oracle's to 2e-4 after a
+    training step has moved the running statistics.  I = 1 nA: the accurate noise model is injected in eval too
+    (hardware_model.py:43) -> logits differ from the noise-free ones, reproducibly for a fixed seed."""
+    from noisynet_b200 import ops
+    om, nm, eng, oloss, loss, x, lab = _engine_pair(dev, dict(fm1=9, fm2=12, fc=24), 8, 0.0)
+    om.eval(), nm.eval()
+    with torch.no_grad():
+        ref = om(x, i=100)
+    out = eng.eval_forward(x.to(dev)).cpu()
+    assert ops.error_flag() == 0
+    # both models took one (slightly different: bf16 gradients) optimizer step: compare on the ORACLE's state
+    nm.load_state_dict(om.state_dict(), strict=False)
+    nm.w_absmax.clear()
+    out = eng.eval_forward(x.to(dev)).cpu()
+    assert torch.allclose(out, ref, rtol=2e-4, atol=2e-4), (out - ref).abs().max()
+    eng.sync_bn_counters()
+    assert int(nm.bn1.num_batches_tracked) == int(om.bn1.num_batches_tracked) == 1
+    om1, nm1, eng1, _, _, x1, _ = _engine_pair(dev, dict(fm1=9, fm2=12, fc=24), 8, 1.0)
+    nm1.eval()
+    torch.manual_seed(5)
+    a = eng1.eval_forward(x1.to(dev)).clone()
+    b = eng1.eval_forward(x1.to(dev), currents=[1e9] * 4).clone()         # practically noise-free
+    torch.manual_seed(5)
+    c = eng1.eval_forward(x1.to(dev)).clone()
+    assert torch.isfinite(a).all() and (a - b).abs().max().item() > 1e-3
+    assert torch.equal(a, c)
+
+
 def test_engine_benchmark_config_vs_oracle(dev):
     """The configuration bench.py measures -- NoisyNetEngine.train_step at batch 512, full widths (65 / 120 / 390),
     q_a = q_w = 4, I = 1 nA on every layer -- against the CPU oracle's training step (oracle/noisynet_oracle.py, pinned to

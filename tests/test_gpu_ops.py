@@ -112,6 +112,60 @@ def test_quant_measure_ranges(dev, golden):
     assert torch.equal(qq.running_list[0].cpu(), T(g["qq_pctl"]))
 
 
+@pytest.mark.parametrize("n,pctl", [(1000, 99.0), (65 * 14 * 14 * 64, 99.98), (3000 * 512 + 7, 90.0), (37, 50.0)])
+def test_range_select_matches_kthvalue(dev, n, pctl):
+    """the device radix select is torch.kthvalue bit for bit (hardware_model.py:249, :233-235), and the max."""
+    from noisynet_b200 import ops
+    gen = torch.Generator().manual_seed(n)
+    x = (torch.randn(n, generator=gen).abs() * 2).to(dev)
+    x[::7] = 0.0                                            # ties and zeros, as after ReLU
+    k = int(n * pctl / 100.)
+    out = ops.range_select(x, mode=0, min_value=0.0, k_rank=k).cpu()
+    ref, _ = torch.kthvalue(x.flatten().cpu(), k)
+    assert out[0].item() == ref.item() and out[1].item() == x.max().item()
+    assert out[2].item() == 0.0 and out[3].item() == x.max().item()
+    w = torch.randn(n, generator=gen).to(dev) * 0.3
+    o1 = ops.range_select(w, pctl, mode=1).cpu()
+    wc = w.cpu()
+    pos, neg = wc[wc > 0], wc[wc < 0].abs()
+    rp, _ = torch.kthvalue(pos, int(pos.numel() * pctl / 100.))
+    rn, _ = torch.kthvalue(neg, int(neg.numel() * pctl / 100.))
+    assert o1[1].item() == rp.item() and o1[0].item() == -rn.item()
+    assert o1[2].item() == -rn.item() and o1[3].item() == rp.item()
+
+
+def test_quant_measure_calibration_has_no_host_sync(dev, golden):
+    """While calibrating (noisynet.py:1251-1259) the reference syncs twice per QuantMeasure call (kthvalue result kept on
+    the device, input.max().item()); the drop-in selects the range on the device and hands it to the quantizer kernels
+    as a pointer: forward AND backward run under torch's sync-debug mode 'error'.  Output = the reference's (golden)."""
+    from noisynet_b200 import hardware_model as hm, ops, quant as q
+    g = golden("quant")
+    x = T(g["qm_run_x"]).to(dev).requires_grad_(True)
+    u = T(g["qm_run_u"]).to(dev)
+    qm = hm.QuantMeasure(4, stochastic=0.5, pctl=99.0, calculate_running=True).to(dev).train()
+    qq = q.QuantMeasure(4, pctl=0.99, calculate_running=True).to(dev).train()
+    gy = torch.ones_like(x)
+    qfix = hm.QuantMeasure(4, stochastic=0.0).to(dev).eval()          # running_max == 0, max_value == 0 -> live input.max()
+    qfix(x.detach())                                                  # (reads the running_max buffer once; cached until it changes)
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        with ops.inject_random([u], []):
+            y = qm(x)
+        y.backward(gy)
+        y2 = qq(x.detach())
+        y3 = qfix(x.detach())
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    assert torch.equal(y.detach().cpu(), T(g["qm_run_y"]))
+    assert torch.equal(qm.running_list[0].cpu(), T(g["qm_run_pctl"]))
+    xc = x.detach().cpu()
+    assert torch.equal(x.grad.cpu(), ((xc >= 0) & (xc <= xc.max())).float())
+    assert torch.equal(qq.running_list[0].cpu(), T(g["qq_pctl"]))
+    assert torch.equal(y3.cpu(), O.uniform_quantize_fwd(xc, 4, 0.0, xc.max().item(), 0.0))
+    assert y2.shape == x.shape
+
+
 # ------------------------------------------------------------------------------ a4 / a9 / stats
 def test_weight_noise(dev, golden):
     from noisynet_b200 import ops
