@@ -32,6 +32,7 @@ def parse():
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_gpu"])
     p.add_argument("--no-library-baseline", action="store_true")
+    p.add_argument("--no-second-variant", action="store_true")
     p.add_argument("--batch", type=int, default=512, help="per-GPU batch")
     p.add_argument("--variant", default="q4", choices=["q4", "fp"], help="q4: --q_a 4 --q_w 4; fp: README flags")
     p.add_argument("--flow", default="engine", choices=["engine", "fused", "dropin"],
@@ -232,12 +233,68 @@ def build_model(args, dev, precision):
     return m, a, make_optimizer(m, a, capturable=bool(args.graph))
 
 
+def time_second_variant(args, dev, precision, variant):
+    """Device-resident engine step of the OTHER operand variant (same timing method as `value`)."""
+    import copy
+    from noisynet_b200 import _lib, ops
+    from noisynet_b200.engine import NoisyNetEngine
+    a2 = copy.copy(args)
+    a2.variant = variant
+    model, a, opt = build_model(a2, dev, precision)
+    B = args.batch
+    gen = torch.Generator().manual_seed(4321)
+    xs = [(torch.randint(0, 16, (B, 3, 32, 32), generator=gen).float() / 15).to(dev) for _ in range(args.pool)]
+    ys = [torch.randint(0, 10, (B,), generator=gen).to(dev) for _ in range(args.pool)]
+    sx, sy = torch.empty_like(xs[0]), torch.empty_like(ys[0])
+    engine = NoisyNetEngine(model, B, opt=opt)
+    loss_out = torch.zeros((), device=dev)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for s in range(3):
+            loss_out.copy_(engine.train_step(xs[s], ys[s])[0])
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    lib = _lib.load()
+    l0 = lib.nn_launch_count()
+    engine.train_step(xs[0], ys[0])
+    torch.cuda.synchronize()
+    launches = int(lib.nn_launch_count() - l0)
+    step_ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+    graph = torch.cuda.CUDAGraph()
+    with ops.graph_rng(step_ctr, seed=99):
+        with torch.cuda.graph(graph):
+            loss_out.copy_(engine.train_step(sx, sy)[0])
+            ops.rng_advance(step_ctr, 1)
+    torch.cuda.synchronize()
+
+    def run(i):
+        sx.copy_(xs[i % args.pool], non_blocking=True)
+        sy.copy_(ys[i % args.pool], non_blocking=True)
+        graph.replay()
+    for i in range(max(args.warmup, 3)):
+        run(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        run(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    assert ops.error_flag() == 0
+    return {"variant": variant, "value": B * args.steps / (ms * 1e-3), "unit": "img/s", "ms_per_step": ms / args.steps,
+            "gpu_launches_per_step": launches, "final_loss": loss_out.item(),
+            "dtype": "bf16 operands (exact 4-bit codes)" if variant == "q4" else "bf16-rounded operands (README flags q_a=q_w=0), fp32 accumulate",
+            "config": workload_config(a2, 1)["workload"]}
+
+
 def pick_precision(args, dev):
     """auto: the tcgen05 path (bf16 integer codes for q4, tf32 otherwise) if it passes a self-check, else fp32."""
     if args.precision != "auto":
         return args.precision
     from noisynet_b200 import ops
-    want = "bf16" if args.variant == "q4" else "tf32"
+    want = "bf16"          # q4: exact integer codes in bf16; fp (README flags): bf16-rounded operands, fp32 accumulate
     try:
         x = torch.rand(8, 65, 14, 14, device=dev)
         w = torch.randn(120, 65, 5, 5, device=dev) * 0.05
@@ -268,7 +325,7 @@ def run_b200(args):
     precision = pick_precision(args, dev)
     model, a, opt = build_model(args, dev, precision)
     fused_opt = args.optimizer == "fused"
-    red = dp.FlatGradAllReduce(model, world, early=[[model.linear1.weight, model.linear2.weight], [model.conv2.weight]])
+    red = dp.make_grad_reducer(model, world, early=[[model.linear1.weight, model.linear2.weight], [model.conv2.weight]])
     red.broadcast_parameters(model)
     B = args.batch
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -281,8 +338,8 @@ def run_b200(args):
 
     engine = None
     if args.flow == "engine":
-        if not (fused_opt and args.variant == "q4" and precision == "bf16"):
-            raise SystemExit("--flow engine needs --variant q4, the tcgen05 path and --optimizer fused")
+        if not (fused_opt and precision == "bf16"):
+            raise SystemExit("--flow engine needs the tcgen05 path (bf16) and --optimizer fused")
         from noisynet_b200.engine import NoisyNetEngine
         engine = NoisyNetEngine(model, B, opt=opt, reducer=red if world > 1 else None)
 
@@ -474,6 +531,14 @@ def run_b200(args):
         r = oracle_arm(128, args.variant, 0, 2, seconds=args.cpu_baseline_seconds)
         cpu = {"value": r["img_s"], "unit": "img/s", "cores": r["cores"], "kind": "port",
                "sample": "%d steps of batch 128 in %.1f s (oracle port of the reference training step, torch CPU fp32)" % (r["steps"], r["seconds"])}
+    other = None
+    if world == 1 and engine is not None and not args.no_second_variant:
+        # SURVEY 8d "report both": the other operand variant (q4 <-> README flags q_a = q_w = 0) through the same engine,
+        # device-resident, CUDA graph, same K steps
+        try:
+            other = time_second_variant(args, dev, precision, "fp" if args.variant == "q4" else "q4")
+        except Exception as e:  # noqa: BLE001
+            other = {"unavailable": str(e)[:300]}
     lib_base = None
     if world == 1 and not args.no_library_baseline:
         try:
@@ -491,7 +556,7 @@ def run_b200(args):
         "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e_val, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-        "cuda_graph": graph is not None, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "library_baseline": lib_base,
+        "cuda_graph": graph is not None, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "library_baseline": lib_base, "second_variant": other,
         "final_loss": final_loss,
     }
     print(json.dumps(line), flush=True)

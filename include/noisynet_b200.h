@@ -336,6 +336,15 @@ int nn_stage_bwd(const nn_stage_bwd_args* a, int device, void* stream);
 int nn_input_quant_pack(const float* x, void* xp, float* act, int B, int C, int HW, int Cp, int q_bits,
                         double q_hi, float stochastic, const float* u_inject, nn_rng rng, int device, void* stream);
 
+/* Data path (section 8f.4): batch assembly of noisynet.py:1232-1269 on the device -- gather B images BY INDEX (idx [B]
+ * int64 on the device, NULL = the first B) from the resident, zero-padded dataset [N,C,Hp,Wp] fp32 (utils.py:165-167), crop
+ * H x W at (off_y, off_x), optional horizontal flip, then quantize1 + NHWC bf16 code pack as nn_input_quant_pack.
+ * aug_dev (optional, device int32[3] = {off_y, off_x, flip}) overrides the three host values: a captured CUDA graph then
+ * replays with each step's own crop / flip / indices. */
+int nn_input_gather_quant_pack(const float* data, const int64_t* idx, int B, int C, int Hp, int Wp, int H, int W, int off_y,
+                               int off_x, int flip, const int32_t* aug_dev, void* xp, float* act, int Cp, int q_bits, double q_hi,
+                               float stochastic, const float* u_inject, nn_rng rng, int device, void* stream);
+
 /* Head (noisynet.py:594, :1278): BatchNorm1d(C <= 16, batch statistics) -> mean cross-entropy, and the
  * gradient back through both: g [B,C] fp32 (+ optional bf16 [B,Cp] pack), dgamma / dbeta (overwritten). */
 int nn_head_fwd_bwd(const float* logits, const int64_t* labels, int B, int C, const float* gamma,
@@ -369,6 +378,20 @@ typedef struct nn_tail_args {
     float *dgamma, *dbeta;
 } nn_tail_args;
 int nn_classifier_tail(const nn_tail_args* a, int device, void* stream);
+
+/* ---- section 8e: the step's one exchange -- SUM all-reduce of the gradients (main.py:786-802) over symmetric memory ----
+ * Every rank maps a buffer of identical size [nn_allreduce_ctl_bytes() control words, zeroed once | gradient data]
+ * (peer_ptrs[world]: this process's mappings of all ranks' buffers, its own included; mc_ptr: the NVSwitch multicast
+ * mapping of the same buffers, or NULL).  nn_allreduce_start enqueues the in-place two-shot exchange of `count` floats at
+ * byte offset data_off (rank r reduces slice r with multimem.ld_reduce -- in-switch reduction -- and writes the sum into
+ * every rank's buffer with multimem.st; plain peer loads / stores without multicast); nn_allreduce_wait, enqueued on the
+ * stream that consumes the sums, completes it.  `bucket` (< 8) names independent exchanges that may be in flight together
+ * (e.g. the fully connected layers' gradients while the conv backward still runs).  CUDA-graph capturable; every rank
+ * must issue the same sequence of calls per bucket.  count * 4 must be a multiple of 16 * world. */
+int64_t nn_allreduce_ctl_bytes(void);
+int nn_allreduce_start(const void* const* peer_ptrs, const void* mc_ptr, int rank, int world, int bucket, int64_t data_off,
+                       int64_t count, int ctas, int device, void* stream);
+int nn_allreduce_wait(const void* local_ptr, int world, int bucket, int device, void* stream);
 
 #ifdef __cplusplus
 }

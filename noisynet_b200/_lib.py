@@ -132,9 +132,16 @@ SIGNATURES = {
     "nn_stage_bwd": (C.c_int, [C.POINTER(StageBwdArgs), C.c_int, C.c_void_p]),
     "nn_input_quant_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_double, C.c_float, C.c_void_p, Rng, C.c_int, C.c_void_p]),
+    "nn_input_gather_quant_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double,
+                                             C.c_float, C.c_void_p, Rng, C.c_int, C.c_void_p]),
     "nn_head_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "nn_allreduce_ctl_bytes": (C.c_int64, []),
+    "nn_allreduce_start": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int,
+                                     C.c_int, C.c_void_p]),
+    "nn_allreduce_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nn_head_eval": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                C.c_int, C.c_void_p]),
     "nn_tensor_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),

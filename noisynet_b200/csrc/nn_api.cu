@@ -58,7 +58,10 @@ extern "C" int nn_noisy_conv_fwd(const nn_conv_fwd_args* a, int device, void* st
         return nn_fail("nn_noisy_conv_fwd: pooled_out is a tcgen05-path fusion%s (see nn_conv_pool_fusable)", "");
     NN_SET_DEVICE(device);
     if (a->precision == NN_PREC_FP32) return nn_simt_conv_fwd(a, device, (cudaStream_t)stream);
-    if (a->precision == NN_PREC_TF32 || a->precision == NN_PREC_BF16) {
+    if (a->precision == NN_PREC_TF32)
+        return nn_fail("nn_noisy_conv_fwd: NN_PREC_TF32 is not implemented%s; unquantized operands run as NN_PREC_BF16 (bf16-rounded, "
+                       "fp32 accumulate, 1.5e-2 tolerance) or NN_PREC_FP32", "");
+    if (a->precision == NN_PREC_BF16) {
         if (!nn_umma_supports(&a->g, 0))
             return nn_fail("nn_noisy_conv_fwd: geometry not supported by the tcgen05 path%s; use NN_PREC_FP32", "");
         return nn_umma_conv_fwd(a, device, (cudaStream_t)stream);
@@ -74,6 +77,7 @@ extern "C" int nn_noisy_conv_dgrad(const nn_conv_dgrad_args* a, int device, void
         return nn_fail("nn_noisy_conv_dgrad: null tensor%s", "");
     NN_SET_DEVICE(device);
     if (a->precision == NN_PREC_FP32) return nn_simt_conv_dgrad(a, device, (cudaStream_t)stream);
+    if (a->precision != NN_PREC_BF16) return nn_fail("nn_noisy_conv_dgrad: precision not implemented%s (NN_PREC_FP32 / NN_PREC_BF16)", "");
     if (!nn_umma_supports(&a->g, 1))
         return nn_fail("nn_noisy_conv_dgrad: geometry not supported by the tcgen05 path%s; use NN_PREC_FP32", "");
     return nn_umma_conv_dgrad(a, device, (cudaStream_t)stream);
@@ -92,6 +96,7 @@ extern "C" int nn_noisy_conv_wgrad(const nn_conv_wgrad_args* a, int device, void
         return nn_fail("nn_noisy_conv_wgrad: null tensor%s", "");
     NN_SET_DEVICE(device);
     if (a->precision == NN_PREC_FP32) return nn_simt_conv_wgrad(a, device, (cudaStream_t)stream);
+    if (a->precision != NN_PREC_BF16) return nn_fail("nn_noisy_conv_wgrad: precision not implemented%s (NN_PREC_FP32 / NN_PREC_BF16)", "");
     if (!nn_umma_supports(&a->g, 2))
         return nn_fail("nn_noisy_conv_wgrad: geometry not supported by the tcgen05 path%s; use NN_PREC_FP32", "");
     return nn_umma_conv_wgrad(a, device, (cudaStream_t)stream);

@@ -1067,6 +1067,76 @@ extern "C" int nn_stage_bwd(const nn_stage_bwd_args* a, int device, void* stream
     return 0;
 }
 
+// ------------------------------------------------------------------ data path (section 8f.4): batch assembly on the device
+// noisynet.py:1232-1269 permutes the whole resident dataset every epoch (a 600 MB gather), slices a batch, crops it at a
+// random offset of the zero-padded images and flips it; here the batch is gathered BY INDEX from the padded dataset with
+// the crop offset / flip folded into the read, and handed to quantize1 + the NHWC pack in the same pass.
+struct GatherP {
+    const float* data; const int64_t* idx; const int32_t* aug_dev; int B, C, Hp, Wp, H, W, off_y, off_x, flip, Cp, quant;
+    __nv_bfloat16* xp; float* act; float q_scale, q_max, stoch; const float* u_inject; nn_rng rng;
+};
+__global__ void __launch_bounds__(256)
+k_gather_quant_pack(const GatherP p) {
+    const NnRng rs = nn_rng_load(p.rng);
+    const int chunks = p.Cp >> 3, HW = p.H * p.W;
+    const unsigned npix = (unsigned)p.B * HW, total = npix * chunks;
+    int off_y = p.off_y, off_x = p.off_x, flip = p.flip;
+    if (p.aug_dev) {        // crop offset / flip of this step in device memory: a captured CUDA graph replays with new values
+        off_y = min(max(p.aug_dev[0], 0), p.Hp - p.H); off_x = min(max(p.aug_dev[1], 0), p.Wp - p.W); flip = p.aug_dev[2] != 0;
+    }
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned pixel = i % npix;
+        const int chunk = (int)(i / npix);
+        const int b = (int)(pixel / HW), r = (int)(pixel - (unsigned)b * HW);
+        const int y = r / p.W, x = r - y * p.W;
+        const int sx = off_x + (flip ? p.W - 1 - x : x), sy = off_y + y;
+        const int64_t img = p.idx ? p.idx[b] : (int64_t)b;
+        uint4 rnd[2];
+        if (p.quant && p.stoch > 0.f && !p.u_inject) {
+            rnd[0] = nn_philox(rs, (uint64_t)i * 2);
+            if (chunk * 8 + 4 < p.C) rnd[1] = nn_philox(rs, (uint64_t)i * 2 + 1);
+        }
+        const uint32_t* rr = reinterpret_cast<const uint32_t*>(rnd);
+        __align__(16) __nv_bfloat16 out[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = chunk * 8 + j;
+            float code = 0.f;
+            if (c < p.C) {
+                const float v = __ldg(p.data + ((img * p.C + c) * p.Hp + sy) * p.Wp + sx);
+                const int64_t o = ((int64_t)b * p.C + c) * HW + r;
+                if (p.quant) {
+                    code = quant_code(v, p.q_scale, p.q_max, p.stoch > 0.f ? (p.u_inject ? __ldg(p.u_inject + o) : nn_usym(rr[j], p.stoch)) : 0.f);
+                    if (p.act) p.act[o] = __fmul_rn(code, p.q_scale);
+                } else {
+                    code = v;
+                    if (p.act) p.act[o] = v;
+                }
+            }
+            out[j] = __float2bfloat16_rn(code);
+        }
+        *reinterpret_cast<uint4*>(p.xp + ((size_t)pixel * p.Cp + chunk * 8)) = *reinterpret_cast<const uint4*>(out);
+    }
+}
+
+extern "C" int nn_input_gather_quant_pack(const float* data, const int64_t* idx, int B, int C, int Hp, int Wp, int H, int W, int off_y,
+                                          int off_x, int flip, const int32_t* aug_dev, void* xp, float* act, int Cp, int q_bits,
+                                          double q_hi, float stochastic, const float* u_inject, nn_rng rng, int device, void* stream) {
+    if (!data || !xp || Cp % 8 || Cp < C || off_y < 0 || off_x < 0 || off_y + H > Hp || off_x + W > Wp)
+        return nn_fail("nn_input_gather_quant_pack: bad argument%s", "");
+    NN_SET_DEVICE(device);
+    double qmax = q_bits > 0 ? (double)((1u << q_bits) - 1u) : 0.0;
+    double scale = q_bits > 0 ? q_hi / qmax : 1.0;
+    if (scale < 1e-6) scale = 1e-6;
+    GatherP p;
+    p.data = data; p.idx = idx; p.aug_dev = aug_dev; p.B = B; p.C = C; p.Hp = Hp; p.Wp = Wp; p.H = H; p.W = W; p.off_y = off_y; p.off_x = off_x; p.flip = flip;
+    p.Cp = Cp; p.quant = q_bits > 0; p.xp = (__nv_bfloat16*)xp; p.act = act; p.q_scale = (float)scale; p.q_max = (float)qmax;
+    p.stoch = stochastic; p.u_inject = u_inject; p.rng = rng;
+    k_gather_quant_pack<<<grid_cap((int64_t)B * H * W * (Cp / 8), device), 256, 0, (cudaStream_t)stream>>>(p);
+    NN_LAUNCH_OK();
+    return 0;
+}
+
 extern "C" int nn_input_quant_pack(const float* x, void* xp, float* act, int B, int C, int HW, int Cp, int q_bits,
                                    double q_hi, float stochastic, const float* u_inject, nn_rng rng, int device,
                                    void* stream) {

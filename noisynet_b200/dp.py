@@ -109,6 +109,108 @@ class FlatGradAllReduce:
         return self.flat
 
 
+class SymmGradAllReduce(FlatGradAllReduce):
+    """FlatGradAllReduce whose flat gradient buffer lives in SYMMETRIC memory (every rank maps every rank's buffer and
+    the NVSwitch multicast alias of all of them, torch.distributed._symmetric_memory) and whose exchange is this
+    library's own kernel instead of an NCCL call: nn_allreduce_start / nn_allreduce_wait (csrc/nn_collective.cu) --
+    rank r reduces slice r of a bucket with multimem.ld_reduce (in-switch reduction) and multicasts the sums back with
+    multimem.st, in place; epoch flags in the same buffer order the ranks.  Same interface as the NCCL class:
+    ``start_early(k)`` launches bucket k's exchange on the current stream (the engine calls it on its side stream, under
+    the conv backward), ``all_reduce_sum_()`` launches the remaining range and waits for every bucket on the current
+    stream.  Capturable in the step's CUDA graph; no host synchronisation."""
+
+    def __init__(self, model, world=None, early=None, ctas=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self._C, self._lib_mod = C, _lib
+        params = [p for p in model.parameters() if p.requires_grad]
+        buckets = early or []
+        if buckets and not isinstance(buckets[0], (list, tuple)):
+            buckets = [buckets]
+        buckets = [[p for p in b if p.requires_grad] for b in buckets]
+        ids = {id(p) for b in buckets for p in b}
+        buckets = buckets + [[p for p in params if id(p) not in ids]]           # the last range: everything else
+        self.world = world if world is not None else dist.get_world_size()
+        self.rank = dist.get_rank()
+        ref = params[0]
+        dev = ref.device
+        self.dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        lib = _lib.load()
+        self.ctl = int(lib.nn_allreduce_ctl_bytes())
+        q = 4 * self.world                                                       # floats: ranges are multiples of 16 B * world
+        self.ranges, off = [], 0
+        for b in buckets:
+            n = sum(p.numel() for p in b)
+            n_pad = (n + q - 1) // q * q
+            self.ranges.append((off, n_pad))
+            off += n_pad
+        total = off
+        self.buf = symm.empty(self.ctl + total * 4, dtype=torch.uint8, device=dev)
+        self.buf.zero_()
+        torch.cuda.synchronize(dev)
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        dist.barrier()                                                           # every rank's control words are zero
+        self.flat = self.buf[self.ctl:].view(torch.float32)
+        self.params = [p for b in buckets for p in b]
+        for (o, _), b in zip(self.ranges, buckets):
+            for p in b:
+                p.grad = self.flat[o:o + p.numel()].view_as(p)
+                o += p.numel()
+        self.nbytes = total * 4
+        self.n_buckets = len(self.ranges)
+        self._started = [False] * self.n_buckets
+        ptrs = list(self.hdl.buffer_ptrs)
+        self._peer = (C.c_void_p * self.world)(*ptrs)
+        self._mc = 0 if os.environ.get("NN_DP_MULTICAST", "1") == "0" else int(self.hdl.multicast_ptr or 0)
+        self._local = ptrs[self.rank]
+        assert self._local == self.buf.data_ptr()
+        self.ctas = int(ctas) if ctas else int(os.environ.get("NN_DP_CTAS", "16"))
+        self.n_early = sum(n for _, n in self.ranges[:-1])
+        self.bounds = [0]
+        for _, n in self.ranges[:-1]:
+            self.bounds.append(self.bounds[-1] + n)
+        self._works = [None] * (self.n_buckets - 1)
+
+    def _st(self):
+        return torch.cuda.current_stream(self.dev_index).cuda_stream
+
+    def _start(self, k):
+        o, n = self.ranges[k]
+        if n and not self._started[k]:
+            lib = self._lib_mod.load()
+            self._lib_mod.check(lib.nn_allreduce_start(self._peer, self._mc or None, self.rank, self.world, k, self.ctl + o * 4, n,
+                                                       self.ctas, self.dev_index, self._st()), "nn_allreduce_start")
+            self._started[k] = True
+
+    def start_early(self, k=0):
+        if self.world > 1 and k < self.n_buckets - 1:
+            self._start(k)
+
+    def all_reduce_sum_(self):
+        if self.world > 1:
+            lib = self._lib_mod.load()
+            for k in range(self.n_buckets):
+                self._start(k)                   # whatever has not been started yet, the tail range included
+            for k in range(self.n_buckets):
+                if self._started[k]:
+                    self._lib_mod.check(lib.nn_allreduce_wait(self._local, self.world, k, self.dev_index, self._st()), "nn_allreduce_wait")
+                    self._started[k] = False
+        return self.flat
+
+
+def make_grad_reducer(model, world, early=None):
+    """SymmGradAllReduce (this library's NVSwitch kernel) on NCCL process groups with CUDA tensors; the NCCL / gloo
+    all-reduce class otherwise (CPU tests) or when NN_DP_SYMM=0."""
+    if world > 1 and dist.is_initialized() and dist.get_backend() == "nccl" and os.environ.get("NN_DP_SYMM", "1") != "0":
+        try:
+            return SymmGradAllReduce(model, world, early=early)
+        except Exception as e:      # noqa: BLE001  (no symmetric memory on this system: peer access / driver)
+            import sys
+            sys.stderr.write("[dp] symmetric-memory all-reduce unavailable (%s); using NCCL\n" % (e,))
+    return FlatGradAllReduce(model, world, early=early)
+
+
 def rank_seed(seed, rank):
     """Independent shuffles / crops / Philox noise per rank (train_efficientnet.py:240: seed + rank)."""
     return int(seed) + int(rank)

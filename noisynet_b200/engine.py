@@ -37,15 +37,20 @@ class NoisyNetEngine:
     def __init__(self, model, batch, opt=None, reducer=None):
         a = model.args
         self.q_w = [int(a.q_w1), int(a.q_w2), int(a.q_w3), int(a.q_w4)]          # per-layer weight bits (noisynet.py:898-900)
-        if not (a.q_a1 > 0 and a.q_a2 > 0 and a.q_a3 > 0 and a.q_a4 > 0 and min(self.q_w) > 0):
-            raise ValueError("NoisyNetEngine implements the quantized configuration (q_a > 0, q_w > 0 on every layer)")
+        self.q_a = [int(a.q_a1), int(a.q_a2), int(a.q_a3), int(a.q_a4)]
+        # q = 0 on a layer (the README flags, noisynet.py:282-283): its operands travel as bf16-ROUNDED values instead of
+        # exact integer codes (bf16 training tolerance 1.5e-2, fp32 accumulation), same kernels, scale factors 1
+        if any(getattr(a, k, 0) > 0 for k in ("n_w1", "n_w2", "n_w3", "n_w4")) and min(self.q_w) == 0:
+            raise NotImplementedError("NoisyNetEngine: multiplicative weight noise (--n_w) is served by the module path")
         if max(self.q_w) > 7:
             raise ValueError("NoisyNetEngine: weight codes are int8 (q_w <= 7)")
         if a.use_bias or a.dropout > 0 or a.dropout_conv > 0:
             raise NotImplementedError("NoisyNetEngine: bias / dropout are served by the module path (net.NoisyNet), not the engine")
         if any(getattr(a, k, 0) for k in ("distort_act", "uniform_ind", "uniform_dep", "normal_ind", "normal_dep")):
             raise NotImplementedError("NoisyNetEngine: alternative noise models are served by the module path")
-        for mod in (model.conv1, model.conv2, model.linear1, model.linear2):
+        for li, mod in enumerate((model.conv1, model.conv2, model.linear1, model.linear2)):
+            if self.q_w[li] == 0:
+                continue
             qm = mod.quantize_weights
             # the engine quantizes weights on the fixed range [-1, 1] (hardware_model.py:323): a percentile-calibrated
             # weight range (--calculate_running flips every QuantMeasure, noisynet.py:1209) is the module path's business
@@ -106,7 +111,7 @@ class NoisyNetEngine:
         # fc2 + bn4 + loss + their backward as ONE 8-CTA cluster launch (nn_classifier_tail): exact and tested, but 43 us
         # against 37 us for the three separate launches it replaces (8 SMs, ten latency-bound phases) -- off unless
         # NN_ENGINE_FUSED_TAIL=1
-        self.fused_tail = B <= 2048 and os.environ.get("NN_ENGINE_FUSED_TAIL", "0") == "1"
+        self.fused_tail = B <= 2048 and self.q_w[3] > 0 and self.q_a[3] > 0 and os.environ.get("NN_ENGINE_FUSED_TAIL", "0") == "1"
         self.fuse_pool1 = bool(self.lib.nn_conv_pool_fusable(C.byref(self.geom[0]), self.noise_modes[0], PREC_BF16)) and \
             os.environ.get("NN_ENGINE_FUSE_POOL", "0") == "1"
         self.gy1_layout = self.lib.nn_conv_wgrad_pack_layout(C.byref(self.geom[0]), PREC_BF16, self.di)
@@ -128,7 +133,7 @@ class NoisyNetEngine:
             jb.q_bits, jb.q_hi = self.q_w[li], 1.0
             if li not in self.wcodes:        # quantizer codes: one scratch per layer, shared by its forward and dgrad jobs
                 self.wcodes[li] = torch.zeros(W[li].numel() + 16, dtype=torch.int8, device=dev)
-            jb.codes = self.wcodes[li].data_ptr()
+            jb.codes = self.wcodes[li].data_ptr() if self.q_w[li] > 0 else None
             buf = torch.zeros(int(self.lib.nn_weight_pack_bytes(C.byref(jb))) + 1024, dtype=torch.uint8, device=dev)
             jb.packed_out = (buf.data_ptr() + 1023) // 1024 * 1024
             self.wpack.append(buf)
@@ -184,10 +189,10 @@ class NoisyNetEngine:
                 raise NotImplementedError("eval_forward: the set of noisy layers must match the training configuration "
                                           "(the weight images carry the sigma rows); change the current values only")
             qh1, qh2, qh3, qh4 = (self._qhi(q) for q in (m.quantize1, m.quantize2, m.quantize3, m.quantize4))
-            s1, s2, s3, s4 = (_f32(max(h / (2.0 ** b - 1.0), 1e-6))
+            s1, s2, s3, s4 = (_f32(max(h / (2.0 ** b - 1.0), 1e-6)) if b > 0 else 0.0
                               for h, b in ((qh1, a.q_a1), (qh2, a.q_a2), (qh3, a.q_a3), (qh4, a.q_a4)))
             am1, am2, am3 = (float(getattr(a, k, a.act_max)) for k in ("act_max1", "act_max2", "act_max3"))
-            self.w_cs = [_f32(max(2.0 / (2.0 ** b - 1.0), 1e-6)) / 2.0 for b in self.q_w]
+            self.w_cs = [(_f32(max(2.0 / (2.0 ** b - 1.0), 1e-6)) / 2.0 if b > 0 else 0.0) for b in self.q_w]
             for j in range(4):                                  # forward images only, round-to-nearest weights
                 self.jobs[j].stochastic, self.jobs[j].u_inject, self.jobs[j].rng = 0.0, None, Rng(0, 0, None)
             _lib.check(lib.nn_prepare_weights(self.jobs, 4, di, st), "nn_prepare_weights")
@@ -269,7 +274,8 @@ class NoisyNetEngine:
         a.g = self.geom[idx]
         a.gy, a.x, a.gw = None, None, _p(gw)
         a.gy_packed, a.x_packed, a.gy_packed_layout = _p(gyp), _p(xp), gy_layout
-        a.w_raw, a.w_lo, a.w_hi = _p(w_raw), -1.0, 1.0            # STE of the weight quantizer (hardware_model.py:323)
+        if self.q_w[idx] > 0:
+            a.w_raw, a.w_lo, a.w_hi = _p(w_raw), -1.0, 1.0        # STE of the weight quantizer (hardware_model.py:323)
         a.precision, a.a_code_scale = PREC_BF16, a_cs
         a.workspace, a.workspace_bytes = _p(ws), ws.numel()
         _lib.check(self.lib.nn_noisy_conv_wgrad(C.byref(a), self.di, self._st()), "nn_noisy_conv_wgrad")
@@ -319,6 +325,8 @@ class NoisyNetEngine:
 
     def _qhi(self, qm):
         """Fixed quantisation range of a QuantMeasure (hardware_model.py:265-271, host values cached)."""
+        if qm.num_bits <= 0:
+            return 0.0
         if qm.max_value > 0:
             return float(qm.max_value)
         v = qm._host('running_max')
@@ -328,7 +336,11 @@ class NoisyNetEngine:
 
     # ------------------------------------------------------------------ one training step
     @torch.no_grad()
-    def train_step(self, x, labels):
+    def train_step(self, x, labels, gather=None):
+        """One training step.  ``x`` [B,3,32,32] fp32 + ``labels`` [B] int64 on the device; or, with
+        ``gather=(idx, aug)``, ``x`` is the whole resident zero-padded dataset [N,3,Hp,Wp] (utils.py:165-167), ``idx`` [B]
+        int64 the batch's sample indices and ``aug`` a device int32[3] {off_y, off_x, flip} (noisynet.py:1261-1269):
+        the batch is assembled inside the input-quantizer kernel; ``labels`` are then the batch's labels."""
         m, a, B, lib, di = self.m, self.a, self.B, self.lib, self.di
         C1, C2, FC, H1, P1, H2, P2 = self.dims
         st = self._st()
@@ -337,9 +349,9 @@ class NoisyNetEngine:
         am1, am2, am3 = (float(getattr(a, k, a.act_max)) for k in ("act_max1", "act_max2", "act_max3"))   # noisynet.py:887-889
         self.steps_done += 1
         qh1, qh2, qh3, qh4 = (self._qhi(q) for q in (m.quantize1, m.quantize2, m.quantize3, m.quantize4))
-        s1, s2, s3, s4 = (_f32(max(h / (2.0 ** b - 1.0), 1e-6))
+        s1, s2, s3, s4 = (_f32(max(h / (2.0 ** b - 1.0), 1e-6)) if b > 0 else 0.0
                           for h, b in ((qh1, a.q_a1), (qh2, a.q_a2), (qh3, a.q_a3), (qh4, a.q_a4)))
-        self.w_cs = [_f32(max(2.0 / (2.0 ** b - 1.0), 1e-6)) / 2.0 for b in self.q_w]
+        self.w_cs = [(_f32(max(2.0 / (2.0 ** b - 1.0), 1e-6)) / 2.0 if b > 0 else 0.0) for b in self.q_w]
         # ---- weights: quantize (stochastic rounding) + pack for forward and dgrad, all layers, ONE launch
         self._uw_keep = []
         for li in range(4):
@@ -362,8 +374,15 @@ class NoisyNetEngine:
             _lib.check(lib.nn_prepare_weights(self.jobs, 7, di, st), "nn_prepare_weights")
         # ---- forward
         u = self._take("u")
-        _lib.check(lib.nn_input_quant_pack(_p(x), _p(self.xp1), None, B, 3, 32 * 32, 8, int(a.q_a1), qh1, stoch, _p(u),
-                                           Rng(0, 0, None) if u is not None else self._rng(), di, st), "nn_input_quant_pack")
+        if gather is not None:
+            idx, aug = gather
+            _lib.check(lib.nn_input_gather_quant_pack(_p(x), _p(idx), B, 3, x.shape[2], x.shape[3], 32, 32, 0, 0, 0, _p(aug),
+                                                      _p(self.xp1), None, 8, int(a.q_a1), qh1, stoch, _p(u),
+                                                      Rng(0, 0, None) if u is not None else self._rng(), di, st),
+                       "nn_input_gather_quant_pack")
+        else:
+            _lib.check(lib.nn_input_quant_pack(_p(x), _p(self.xp1), None, B, 3, 32 * 32, 8, int(a.q_a1), qh1, stoch, _p(u),
+                                               Rng(0, 0, None) if u is not None else self._rng(), di, st), "nn_input_quant_pack")
 
         if self.fuse_pool1:
             self._fwd_gemm(0, self.xp1, s1, None, self.noise_modes[0], self._absmax(0, W[0]), self._take("z"),

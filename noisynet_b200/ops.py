@@ -14,14 +14,23 @@ from . import _lib
 from ._lib import (NOISE_EXTERNAL, NOISE_MERGED, NOISE_NONE, PREC_BF16, PREC_FP32, PREC_TF32,
                    ConvDgradArgs, ConvFwdArgs, ConvGeom, ConvWgradArgs, Rng)
 
-# Default arithmetic of the contraction kernels.  PREC_FP32 = CUDA-core fp32 (reference
-# arithmetic); PREC_TF32 / PREC_BF16 = tcgen05.  Overridable per call or globally.
+# Default arithmetic of the contraction kernels.  PREC_FP32 = CUDA-core fp32 (reference arithmetic);
+# PREC_BF16 = tcgen05 (exact for integer codes, bf16-rounded operands otherwise).  Overridable per call or globally.
+# "tf32" is declared in the C ABI but not implemented: asking for it raises instead of silently running something else.
 _default_precision = PREC_FP32
+_PREC_NAMES = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+
+
+def _prec_by_name(p):
+    if p == "tf32" or p == PREC_TF32:
+        raise ValueError("noisynet_b200: precision 'tf32' is not implemented; use 'bf16' (tcgen05, bf16-rounded operands, "
+                         "fp32 accumulate, 1.5e-2 tolerance) or 'fp32' (CUDA cores)")
+    return _PREC_NAMES[p]
 
 
 def set_default_precision(p):
     global _default_precision
-    _default_precision = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16}.get(p, p)
+    _default_precision = _prec_by_name(p) if isinstance(p, str) else int(p)
 
 
 def get_default_precision():
@@ -32,7 +41,9 @@ def _prec(p):
     if p is None:
         return _default_precision
     if isinstance(p, str):
-        return {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16}[p]
+        return _prec_by_name(p)
+    if int(p) == PREC_TF32:
+        _prec_by_name("tf32")
     return int(p)
 
 
