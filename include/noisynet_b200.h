@@ -185,7 +185,7 @@ typedef struct nn_conv_fwd_args {
 #define NN_PACK_SHIFT 1
 /* NN_PACK_TMA: [n-tile][tap][stage][CTA rank] image of the persistent CTA-pair kernel whose activations arrive by
  * im2col-mode tensor-map copies (cp.async.bulk.tensor, cuTensorMapEncodeIm2col): conv layers (output larger than 1x1,
- * more than 8 input channels, square kernels) on the lean path (no bias / statistics / exports / injected draws). */
+ * more than 8 input channels, square kernels) on the lean path (no bias / statistics / exports / clean-output copy). */
 #define NN_PACK_TMA 2
 int nn_conv_pack_layout(const nn_conv_geom* g, int32_t noise_mode, int32_t precision);
 /* Layout the dgrad of a geometry prefers for its (transposed, tap-flipped) weight image: NN_PACK_TMA or NN_PACK_TILED. */

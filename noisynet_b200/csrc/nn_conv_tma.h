@@ -29,7 +29,9 @@ struct TmaConvCall {
     int noise_mode;
     float current;
     const float* scale_dev;
+    const float* z_inject;       // optional N(0,1) draws replacing the Philox stream (parity tests)
     nn_rng rng;
     int* err_flag;
+    void *ev0, *ev1;             // optional cudaEvent_t pair recorded immediately around the kernel launch (nn_debug_main_kernel_ms)
 };
 int nn_tma_conv_launch(const TmaConvCall& c, int device, cudaStream_t st);

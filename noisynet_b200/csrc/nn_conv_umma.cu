@@ -56,13 +56,10 @@ struct UmmaP {
     float mask_lo, mask_hi;
     int* err_flag;
     long long* dbg;                // optional per-CTA phase timestamps (clock64): [cta][8]
-    int cluster;                   // 1, or 2: pairs of m-tiles share every weight k-block (each CTA loads half, multicast)
-    int rows_tile;                 // valid rows per m-tile (<= 128): chosen so that the CTAs fill whole waves
+    int rows_tile;                 // valid rows per m-tile (128)
     float* partial;                // split-K (gridDim.z > 1): raw accumulators [z][n_tile][column][m_pad] instead of the epilogue
     int m_pad;
     int inc_taps;                  // producers track (tap, channel) incrementally instead of dividing per k-block
-    int halo_bytes;                // HALO: shared-memory bytes reserved for the tile's input footprint
-    int b_stages;                  // HALO: depth of the separate weight ring (the A ring has `stages`)
     long long* kdbg;               // optional per-k-block stamps [cta][num_kb][4]: producer woke / arrived, MMA woke / committed
 };
 
@@ -73,27 +70,17 @@ struct UmmaP {
 #ifndef NN_EPI1_MINBLOCKS
 #define NN_EPI1_MINBLOCKS 2
 #endif
-// PAIR: cta_group::2 variant (a kernel that contains cta_group::2 instructions can only be launched as 2-CTA clusters,
-// so it is a separate instantiation)
-// HALO: the tile's input footprint (a contiguous range of NHWC pixels) is loaded ONCE into shared memory by bulk copies
-// and the im2col stages are built shared-to-shared: the A operand no longer makes an L2 round trip per k-block
-template <int EPI, bool PAIR = false, bool HALO = false>
+template <int EPI>
 __global__ void __launch_bounds__(UM_THREADS, EPI == 2 ? 3 : (EPI == 1 ? NN_EPI1_MINBLOCKS : 2))
 k_conv_umma(const UmmaP p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int S = p.stages;
-    constexpr bool pair = PAIR;                     // cta_group::2: this CTA stages only its half of the weight rows
-    const uint32_t b_stage = pair ? (uint32_t)p.n_mma * 64u : (uint32_t)p.n_mma * 128u;
-    const int SB = HALO ? p.b_stages : S;           // HALO: the weight k-blocks have their own, deeper ring
+    const uint32_t b_stage = (uint32_t)p.n_mma * 128u;
     const uint32_t a_base = base;
     const uint32_t b_base = base + (uint32_t)S * UM_A_STAGE;
-    const uint32_t bar_base = b_base + (uint32_t)SB * b_stage;      // 8-byte barriers: full[S], empty[S], tmem_full, peer_full[S]
+    const uint32_t bar_base = b_base + (uint32_t)S * b_stage;      // 8-byte barriers: full[S], empty[S], tmem_full
     const uint32_t full_bar = bar_base, empty_bar = bar_base + 8u * S, tfull_bar = bar_base + 16u * S;
-    const uint32_t pfull_bar = tfull_bar + 16;      // leader only: "the peer CTA's stage s is loaded"
-    const uint32_t halo_bar = pfull_bar + 8u * S;   // HALO: the input footprint has landed
-    const uint32_t bfull_bar = halo_bar + 8u, bempty_bar = bfull_bar + 8u * SB;     // HALO: weight ring
-    const uint32_t halo_base = (bempty_bar + 8u * SB + 127u) & ~127u;
     const uint32_t tmem_slot = tfull_bar + 8;
     const uint32_t abort_slot = tmem_slot + 4;
     // generic pointers to the two 4-byte slots
@@ -101,7 +88,8 @@ k_conv_umma(const UmmaP p) {
     volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gen0 + (tmem_slot - base));
     volatile uint32_t* abort_g = reinterpret_cast<volatile uint32_t*>(gen0 + (abort_slot - base));
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler (see elect_one_sync)
     const int m0 = blockIdx.x * p.rows_tile;
     const int tile_n = blockIdx.y;
     // split-K: this CTA's share of the k-blocks (gridDim.z == 1: all of them)
@@ -112,43 +100,19 @@ k_conv_umma(const UmmaP p) {
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_bar + 8 * s, HALO ? 128 : 128 + 1);     // 128 producer arrivals (+ 1 expect_tx arrival of the weights)
-            mbar_init(empty_bar + 8 * s, p.cluster == 2 ? 2 : 1);  // tcgen05.commit of every CTA that reads (and refills) the stage
-            if (pair) mbar_init(pfull_bar + 8 * s, 1);
+            mbar_init(full_bar + 8 * s, 128 + 1);                  // 128 producer arrivals + 1 expect_tx arrival of the weights
+            mbar_init(empty_bar + 8 * s, 1);                       // tcgen05.commit: the stage may be refilled
         }
         mbar_init(tfull_bar, 1);
-        if (HALO) {
-            mbar_init(halo_bar, 1);
-            for (int sb = 0; sb < SB; ++sb) { mbar_init(bfull_bar + 8 * sb, 1); mbar_init(bempty_bar + 8 * sb, 1); }
-        }
         *abort_g = 0;
         fence_mbar_init();
     }
-    if (pair) {                                      // both CTAs' barriers exist before the paired allocation / any remote arrive
-        __syncthreads();
-        cluster_sync_all();
-    }
-    if (warp == 4) { if constexpr (PAIR) tmem_alloc_2cta(tmem_slot, (uint32_t)p.tmem_cols); else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols); }
+    if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (p.cluster > 1) cluster_sync_all();          // the peer's barriers exist before anything is multicast to them
-    const uint32_t tmem_base = *tmem_slot_g;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_g, 0);
     if (dbg && tid == 0) dbg[1] = clock64();
-
-    // HALO: the input pixels this tile can touch form one contiguous NHWC range [pmin, pend) (stride 1)
-    int pmin = 0, pend = 0;
-    if (HALO) {
-        const int ohw = p.OH * p.OW;
-        const int m_last = min(m0 + p.rows_tile - 1, p.M - 1);
-        const int b0 = m0 / ohw, oh0 = (m0 - b0 * ohw) / p.OW;
-        const int b1 = m_last / ohw, oh1 = (m_last - b1 * ohw) / p.OW;
-        const int ih_lo = max(oh0 - p.pad, 0), ih_hi = min(oh1 - p.pad + p.KH - 1, p.H - 1);
-        pmin = (b0 * p.H + ih_lo) * p.W;
-        pend = (b1 * p.H + ih_hi) * p.W + p.W;
-        if (m0 >= p.M || pend <= pmin) { pmin = 0; pend = 0; }
-        if ((pend - pmin) * p.Cp * 2 > p.halo_bytes) { if (tid == 0) *abort_g = 7; pend = pmin; }
-    }
 
     // ================================================================ main loop roles
     if (warp < 4) {
@@ -185,7 +149,6 @@ k_conv_umma(const UmmaP p) {
 #else
         long long* const kd0 = nullptr;
 #endif
-        if (HALO) { if (!mbar_wait(halo_bar, 0)) *abort_g = 6; }
         for (int kb = kb0; kb < kb1; ++kb) {
             if (!mbar_wait(empty_bar + 8 * s, ph)) { *abort_g = 1; break; }
             if (*abort_g) break;
@@ -200,20 +163,10 @@ k_conv_umma(const UmmaP p) {
                 const int ih = rih[i] + kh, iw = riw[i] + kw;
                 const bool ok = tap_ok && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
                 const uint32_t dst = dst0 + (uint32_t)row * 128u + ((((uint32_t)j) ^ (uint32_t)(row & 7)) << 4);
-                if (HALO) {
-                    uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-                    if (ok) {
-                        const uint32_t src = halo_base + (uint32_t)(((rbase[i] + koff - pmin) * p.Cp + c0) * 2);
-                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(src) : "memory");
-                    }
-                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
-                } else {
-                    const __nv_bfloat16* src = ok ? p.xp + (size_t)(rbase[i] + koff) * p.Cp + c0 : p.xp;
-                    cp_async_16(dst, src, ok ? 16u : 0u);
-                }
+                const __nv_bfloat16* src = ok ? p.xp + (size_t)(rbase[i] + koff) * p.Cp + c0 : p.xp;
+                cp_async_16(dst, src, ok ? 16u : 0u);
             }
-            if (HALO) { fence_proxy_async(); mbar_arrive(full_bar + 8 * s); }     // generic stores -> tensor-core reads
-            else cp_async_mbar_arrive_noinc(full_bar + 8 * s);
+            cp_async_mbar_arrive_noinc(full_bar + 8 * s);
             if (kd) kd[1] = clock64();
             if (++s == S) { s = 0; ph ^= 1; }
             if (p.inc_taps) {
@@ -227,105 +180,55 @@ k_conv_umma(const UmmaP p) {
         }
         if (dbg && tid == 0) dbg[6] = clock64();
     } else if (warp == 4) {
-        // ---------------- MMA issuer (single thread)
-        if constexpr (PAIR) {
-          if (lane == 0) {
-            const uint32_t rank = cluster_ctarank();
-            if (rank == 0) {
-                // leader of the CTA pair: M = 256 (this CTA's 128 rows + the peer's), N = n_mma (half from each CTA)
-                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) |
-                                       ((uint32_t)(256 >> 4) << 24);
-                bool ok = true;
-                for (int kb = kb0; kb < kb1 && ok; ++kb) {
-                    const int it = kb - kb0, s = it % S;
-                    if (!mbar_wait(full_bar + 8 * s, (it / S) & 1)) { *abort_g = 2; ok = false; break; }
-                    if (!mbar_wait_cluster(pfull_bar + 8 * s, (it / S) & 1)) { *abort_g = 4; ok = false; break; }
-                    fence_proxy_async();
-                    tc_fence_after();
-                    const uint64_t ad = umma_desc_sw128(a_base + (uint32_t)s * UM_A_STAGE);
-                    const uint64_t bd = umma_desc_sw128(b_base + (uint32_t)s * b_stage);
-#pragma unroll
-                    for (int k = 0; k < UM_BLOCK_K / 16; ++k)
-                        umma_bf16_2cta(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0);
-                    umma_commit_2cta_mc(empty_bar + 8 * s, 3);    // both CTAs may refill stage s when these MMAs retire
-                }
-                umma_commit_2cta_mc(tfull_bar, 3);                // both CTAs' accumulators complete
-            } else {
-                // peer: tell the leader when this CTA's share of stage s (its A rows, its half of B) has landed
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    const int it = kb - kb0, s = it % S;
-                    if (!mbar_wait(full_bar + 8 * s, (it / S) & 1)) { *abort_g = 2; break; }
-                    fence_proxy_async();            // this CTA's cp.async writes -> the pair's tensor-core reads
-                    mbar_arrive_remote(pfull_bar + 8 * s, 0);
-                }
-            }
-          }
-        } else if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) |
-                                   ((uint32_t)(UM_BLOCK_M >> 4) << 24);
-            bool ok = true;
+        // ---------------- MMA issuer: the whole warp walks the k-blocks (warp-uniform control flow), one elected lane issues
+        // -- under `if (lane == 0)` the compiler moves every descriptor through R2UR in an ELECT loop per MMA (nn_tcgen05.cuh)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) |
+                               ((uint32_t)(UM_BLOCK_M >> 4) << 24);
+        const uint64_t d0 = umma_desc_sw128(0u);
+        int s = 0, fail = 0;
+        uint32_t ph = 0u;
 #ifdef NN_KDEBUG
-            long long* const kd0 = p.kdbg ? p.kdbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * p.num_kb * 4 : nullptr;
+        long long* const kd0 = p.kdbg ? p.kdbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * p.num_kb * 4 : nullptr;
 #else
-            long long* const kd0 = nullptr;
+        long long* const kd0 = nullptr;
 #endif
-            for (int kb = kb0; kb < kb1 && ok; ++kb) {
-                const int it = kb - kb0, s = it % S, sb = HALO ? it % SB : s;
-                if (!mbar_wait(full_bar + 8 * s, (it / S) & 1)) { *abort_g = 2; ok = false; break; }
-                if (HALO && !mbar_wait(bfull_bar + 8 * sb, (it / SB) & 1)) { *abort_g = 8; ok = false; break; }
-                long long* const kd = kd0 ? kd0 + kb * 4 : nullptr;
-                if (kd) kd[2] = clock64();
-                fence_proxy_async();            // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
-                tc_fence_after();
-                const uint64_t ad = umma_desc_sw128(a_base + (uint32_t)s * UM_A_STAGE);
-                const uint64_t bd = umma_desc_sw128(b_base + (uint32_t)(HALO ? sb : s) * b_stage);
+        for (int kb = kb0; kb < kb1; ++kb) {
+            if (!mbar_wait(full_bar + 8 * s, ph)) { fail = 2; break; }
+            long long* const kd = (kd0 && lane == 0) ? kd0 + kb * 4 : nullptr;
+            if (kd) kd[2] = clock64();
+            fence_proxy_async();            // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+            // (no tcgen05.fence here: the operands come from cp.async / bulk copies, not from tcgen05 ops of other threads)
+            const uint32_t a_s = (a_base + (uint32_t)s * UM_A_STAGE) >> 4, b_s = (b_base + (uint32_t)s * b_stage) >> 4;
+            if (elect_one_sync()) {
+                const uint64_t ad = d0 | (uint64_t)(a_s & 0x3FFFu), bd = d0 | (uint64_t)(b_s & 0x3FFFu);
+                umma_bf16(tmem_base, ad, bd, idesc, kb != kb0);
 #pragma unroll
-                for (int k = 0; k < UM_BLOCK_K / 16; ++k)
-                    umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0);
-                if (p.cluster == 2) umma_commit_mc(empty_bar + 8 * s, 3);
-                else umma_commit(empty_bar + 8 * s);       // frees the smem stage when these MMAs retire
-                if (HALO) umma_commit(bempty_bar + 8 * sb);
-                if (kd) kd[3] = clock64();
+                for (int k = 1; k < UM_BLOCK_K / 16; ++k) umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, 1u);
+                umma_commit(empty_bar + 8 * s);       // frees the smem stage when these MMAs retire
             }
-            umma_commit(tfull_bar);                        // accumulators complete
-            if (dbg) dbg[2] = clock64();
+            __syncwarp();
+            if (kd) kd[3] = clock64();
+            if (++s == S) { s = 0; ph ^= 1u; }
         }
+        if (fail) *abort_g = (uint32_t)fail;
+        if (elect_one_sync()) umma_commit(tfull_bar);                        // accumulators complete
         __syncwarp();
+        if (dbg && lane == 0) dbg[2] = clock64();
     } else if (warp == 5) {
         // ---------------- B loader: one bulk copy (TMA engine) per k-block
-        if (lane == 0) {
-            const __nv_bfloat16* wt = p.wp + (size_t)tile_n * p.num_kb * p.n_mma * 64;
-            if (HALO) {
-                const uint32_t bytes = (uint32_t)((pend - pmin) * p.Cp * 2);
-                mbar_arrive_expect_tx(halo_bar, bytes);
-                if (bytes) bulk_g2s(halo_base, p.xp + (size_t)pmin * p.Cp, bytes, halo_bar);
-            }
-            for (int kb = kb0; kb < kb1; ++kb) {
-                const int it = kb - kb0, s = it % S;
-                if (HALO) {                  // own ring, as deep as shared memory allows: the weights run far ahead
-                    const int sb = it % SB;
-                    if (!mbar_wait(bempty_bar + 8 * sb, ((it / SB) & 1) ^ 1)) { *abort_g = 3; break; }
-                    if (*abort_g) break;
-                    mbar_arrive_expect_tx(bfull_bar + 8 * sb, b_stage);
-                    bulk_g2s(b_base + (uint32_t)sb * b_stage, wt + (size_t)kb * p.n_mma * 64, b_stage, bfull_bar + 8 * sb);
-                    continue;
-                }
-                if (!mbar_wait(empty_bar + 8 * s, ((it / S) & 1) ^ 1)) { *abort_g = 3; break; }
-                if (*abort_g) break;
+        const __nv_bfloat16* wt = p.wp + (size_t)tile_n * p.num_kb * p.n_mma * 64;
+        int s = 0;
+        uint32_t ph = 1u;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            if (!mbar_wait(empty_bar + 8 * s, ph)) { *abort_g = 3; break; }
+            if (*abort_g) break;
+            if (elect_one_sync()) {
                 mbar_arrive_expect_tx(full_bar + 8 * s, b_stage);
-                if (pair) {               // this CTA's half of the weight rows only (the MMA reads the other half from the peer)
-                    bulk_g2s(b_base + (uint32_t)s * b_stage,
-                             reinterpret_cast<const uint8_t*>(wt + (size_t)kb * p.n_mma * 64) + cluster_ctarank() * b_stage, b_stage,
-                             full_bar + 8 * s);
-                } else if (p.cluster > 1) {      // this CTA fetches its half of the k-block for both CTAs of the pair
-                    const uint32_t half = b_stage >> 1, off = cluster_ctarank() * half;
-                    bulk_g2s_mc(b_base + (uint32_t)s * b_stage + off,
-                                reinterpret_cast<const uint8_t*>(wt + (size_t)kb * p.n_mma * 64) + off, half, full_bar + 8 * s, 3);
-                } else
                 bulk_g2s(b_base + (uint32_t)s * b_stage, wt + (size_t)kb * p.n_mma * 64, b_stage, full_bar + 8 * s);
             }
+            __syncwarp();
+            if (++s == S) { s = 0; ph ^= 1u; }
         }
-        __syncwarp();
     }
 
     // ================================================================ epilogue (all 8 warps)
@@ -493,10 +396,8 @@ k_conv_umma(const UmmaP p) {
     if (dbg && tid == 0) dbg[4] = clock64();
     tc_fence_before();
     __syncthreads();
-    if (pair) cluster_sync_all();                    // both CTAs are done with the paired accumulators
-    if (warp == 4) { tc_fence_after(); if constexpr (PAIR) tmem_dealloc_2cta(tmem_base, (uint32_t)p.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+    if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
     if (dbg && tid == 128) { dbg[5] = clock64(); unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); dbg[7] = smid; }
-    if (p.cluster > 1) cluster_sync_all();          // no CTA leaves while its peer may still signal or fill its shared memory
 }
 
 
@@ -610,7 +511,8 @@ k_conv_shift(const ShiftP p) {
     volatile uint32_t* abort_g = reinterpret_cast<volatile uint32_t*>(gen0 + (abort_slot - base));
     uint32_t* tap_tab = reinterpret_cast<uint32_t*>(gen0 + (tab_slot - base));   // per tap pair: shift | lbo << 16
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler (see elect_one_sync)
     if (tid < p.n_pairs) {       // descriptor increments of every tap pair (no divisions in the issue loop)
         const int khw = p.KH * p.KW, t0 = 2 * tid, t1 = 2 * tid + 1;
         const int sh0 = (t0 / p.KW) * p.W + (t0 % p.KW);
@@ -635,59 +537,67 @@ k_conv_shift(const ShiftP p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot_g;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_g, 0);
     const int hw = p.H * p.W;
 
+    // loader and MMA issuer: the whole warp walks the tiles (warp-uniform control flow), one elected lane issues the
+    // single-thread instructions (nn_tcgen05.cuh: elect_one_sync)
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_arrive_expect_tx(b_full, (uint32_t)p.b_bytes);
             bulk_g2s(b_base, p.wp, (uint32_t)p.b_bytes, b_full);
-            int i = 0;
-            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-                if (!shift_tile_live(p, t)) continue;
-                const int s = i % SH_STAGES;
-                if (!mbar_wait(a_empty + 8 * s, ((i / SH_STAGES) & 1) ^ 1)) { *abort_g = 1; break; }
-                if (*abort_g) break;
-                const long long v0 = (long long)t * UM_BLOCK_M;
-                long long px = p.total_pixels - v0;
-                if (px > p.a_pixels) px = p.a_pixels;
-                const uint32_t bytes = (uint32_t)px * 16u;
-                mbar_arrive_expect_tx(a_full + 8 * s, bytes);
-                bulk_g2s(a_base + (uint32_t)s * p.a_stage, p.xp + v0 * 8, bytes, a_full + 8 * s);
-                ++i;
-            }
         }
         __syncwarp();
+        int s = 0;
+        uint32_t ph = 1u;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+            if (!shift_tile_live(p, t)) continue;
+            if (!mbar_wait(a_empty + 8 * s, ph)) { *abort_g = 1; break; }
+            if (*abort_g) break;
+            const long long v0 = (long long)t * UM_BLOCK_M;
+            long long px = p.total_pixels - v0;
+            if (px > p.a_pixels) px = p.a_pixels;
+            const uint32_t bytes = (uint32_t)px * 16u;
+            if (elect_one_sync()) {
+                mbar_arrive_expect_tx(a_full + 8 * s, bytes);
+                bulk_g2s(a_base + (uint32_t)s * p.a_stage, p.xp + v0 * 8, bytes, a_full + 8 * s);
+            }
+            __syncwarp();
+            if (++s == SH_STAGES) { s = 0; ph ^= 1u; }
+        }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) |
-                                   ((uint32_t)(UM_BLOCK_M >> 4) << 24);
-            bool ok = mbar_wait(b_full, 0);
-            if (!ok) *abort_g = 2;
-            int i = 0;
-            for (int t = blockIdx.x; t < p.n_tiles && ok; t += gridDim.x) {
-                if (!shift_tile_live(p, t)) continue;
-                const int s = i % SH_STAGES, buf = i & 1;
-                if (!mbar_wait(acc_empty + 8 * buf, ((i >> 1) & 1) ^ 1)) { *abort_g = 3; break; }
-                if (!mbar_wait(a_full + 8 * s, (i / SH_STAGES) & 1)) { *abort_g = 4; break; }
-                if (*abort_g) break;
-                tc_fence_after();
-                if (p.dbg && i < 32) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 0] = clock64();
-                const uint32_t a_s = a_base + (uint32_t)s * p.a_stage;
-                const uint32_t d = tmem_base + (uint32_t)(buf * SH_ACC_STRIDE);
-                const uint64_t bd0 = umma_desc_none(b_base, (uint32_t)p.n_mma, 8u);
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) |
+                               ((uint32_t)(UM_BLOCK_M >> 4) << 24);
+        bool ok = mbar_wait(b_full, 0);
+        if (!ok) *abort_g = 2;
+        int i = 0, s = 0;
+        uint32_t ph = 0u;
+        const uint64_t bd0 = umma_desc_none(b_base, (uint32_t)p.n_mma, 8u);
+        const uint64_t ad_t = umma_desc_none(0u, 0u, 8u);           // A template: start address and LBO vary per tap pair
+        for (int t = blockIdx.x; t < p.n_tiles && ok; t += gridDim.x) {
+            if (!shift_tile_live(p, t)) continue;
+            const int buf = i & 1;
+            if (!mbar_wait(acc_empty + 8 * buf, ((i >> 1) & 1) ^ 1)) { *abort_g = 3; break; }
+            if (!mbar_wait(a_full + 8 * s, ph)) { *abort_g = 4; break; }
+            if (*abort_g) break;
+            tc_fence_after();               // the epilogue warps' tcgen05.ld of this buffer are ordered before the new MMAs
+            if (p.dbg && i < 32 && lane == 0) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 0] = clock64();
+            const uint32_t a_s = a_base + (uint32_t)s * p.a_stage;
+            const uint32_t d = tmem_base + (uint32_t)(buf * SH_ACC_STRIDE);
+            if (elect_one_sync()) {
                 for (int j = 0; j < p.n_pairs; ++j) {
                     const uint32_t e = tap_tab[j];
-                    const uint64_t ad = umma_desc_none(a_s + (e & 0xFFFFu) * 16u, e >> 16, 8u);
+                    const uint64_t ad = ad_t | (uint64_t)(((a_s >> 4) + (e & 0xFFFFu)) & 0x3FFFu) | ((uint64_t)((e >> 16) & 0x3FFFu) << 16);
                     umma_bf16(d, ad, bd0 + (uint64_t)(2 * j * p.n_mma), idesc, j != 0);
                 }
                 umma_commit(a_empty + 8 * s);
                 umma_commit(acc_full + 8 * buf);
-                if (p.dbg && i < 32) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 1] = clock64();
-                ++i;
             }
+            __syncwarp();
+            if (p.dbg && i < 32 && lane == 0) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 1] = clock64();
+            ++i;
+            if (++s == SH_STAGES) { s = 0; ph ^= 1u; }
         }
-        __syncwarp();
     } else {
         const int q = warp & 3, jq = (warp - 2) >> 2;
         constexpr int per_q = SH_EPI_WARPS / 4;
@@ -1068,7 +978,8 @@ k_wgrad_umma(const WgUP p) {
     volatile uint32_t* abort_g = reinterpret_cast<volatile uint32_t*>(gen0 + (abort_slot - base));
     int4* tab = reinterpret_cast<int4*>(gen0 + (tab_base - base));  // per 16-byte column chunk: {kh, kw, c0, valid}
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler (see elect_one_sync)
     const int tile_k = blockIdx.x, tile_n = blockIdx.y, split = blockIdx.z;
     const int kb0 = split * p.kb_per_split;
     const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
@@ -1091,7 +1002,7 @@ k_wgrad_umma(const WgUP p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot_g;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_g, 0);
 
     if (warp < 4) {
         // Lane mapping (as in the forward producer): consecutive lanes fetch consecutive 16-byte chunks of one
@@ -1149,25 +1060,29 @@ k_wgrad_umma(const WgUP p) {
             cp_async_mbar_arrive_noinc(full_bar + 8 * s);
         }
     } else if (warp == 4) {
-        if (lane == 0) {
-            // MN-major A and B (bits 15, 16), bf16 x bf16 -> f32, M = 128, N = NT
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                                   ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(UM_BLOCK_M >> 4) << 24);
-            const uint64_t lbo = (uint64_t)((64u * 128u) >> 4) << 16;        // MN-atom stride = 8192 B
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % S;
-                if (!mbar_wait(full_bar + 8 * s, (i / S) & 1)) { *abort_g = 2; break; }
-                fence_proxy_async();
-                tc_fence_after();
-                const uint64_t ad = umma_desc_sw128(a_base + (uint32_t)s * UM_A_STAGE) | lbo;
-                const uint64_t bd = umma_desc_sw128(b_base + (uint32_t)s * b_stage) | lbo;
+        // MN-major A and B (bits 15, 16), bf16 x bf16 -> f32, M = 128, N = NT; whole warp walks, elected lane issues
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(UM_BLOCK_M >> 4) << 24);
+        const uint64_t d0 = umma_desc_sw128(0u) | ((uint64_t)((64u * 128u) >> 4) << 16);        // LBO = MN-atom stride = 8192 B
+        int s = 0;
+        uint32_t ph = 0u;
+        for (int i = 0; i < nkb; ++i) {
+            if (!mbar_wait(full_bar + 8 * s, ph)) { *abort_g = 2; break; }
+            fence_proxy_async();
+            // (no tcgen05.fence per k-block, see k_conv_umma)
+            const uint32_t a_s = (a_base + (uint32_t)s * UM_A_STAGE) >> 4, b_s = (b_base + (uint32_t)s * b_stage) >> 4;
+            if (elect_one_sync()) {
+                const uint64_t ad = d0 | (uint64_t)(a_s & 0x3FFFu), bd = d0 | (uint64_t)(b_s & 0x3FFFu);
+                umma_bf16(tmem_base, ad, bd, idesc, i != 0);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)                                  // 16 reduction rows = 2048 B = 128 units
-                    umma_bf16(tmem_base, ad + 128 * k, bd + 128 * k, idesc, (i | k) != 0);
+                for (int k = 1; k < 4; ++k)                                  // 16 reduction rows = 2048 B = 128 units
+                    umma_bf16(tmem_base, ad + 128 * k, bd + 128 * k, idesc, 1u);
                 umma_commit(empty_bar + 8 * s);
             }
-            umma_commit(tfull_bar);
+            __syncwarp();
+            if (++s == S) { s = 0; ph ^= 1u; }
         }
+        if (elect_one_sync()) umma_commit(tfull_bar);
         __syncwarp();
     }
 
@@ -1258,7 +1173,8 @@ k_wgrad_shift(const WgShiftP p) {
     volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gen0 + (tmem_slot - base));
     volatile uint32_t* abort_g = reinterpret_cast<volatile uint32_t*>(gen0 + (abort_slot - base));
     volatile uint32_t* work_g = reinterpret_cast<volatile uint32_t*>(gen0 + (work_slot - base));
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler (see elect_one_sync)
     if (tid == 0) {
         for (int s = 0; s < WS_STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
         mbar_init(acc_bar, 1);
@@ -1277,45 +1193,45 @@ k_wgrad_shift(const WgShiftP p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot_g;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_g, 0);
 
     if (warp == 0) {
-        if (lane == 0) {
-            int i = 0;
-            for (int t = blockIdx.x; t < p.n_chunks; t += gridDim.x) {
-                if (!wgshift_chunk_live(p, t)) continue;
-                const int s = i % WS_STAGES;
-                if (!mbar_wait(empty_bar + 8 * s, ((i / WS_STAGES) & 1) ^ 1)) { *abort_g = 1; break; }
-                if (*abort_g) break;
-                const long long v0 = (long long)t * WS_KP;
-                const long long pa = WS_KP;              // planes are padded to a multiple of WS_KP pixels
-                long long pb = p.total_pixels - v0;
-                if (pb > p.b_pixels) pb = p.b_pixels;
+        int s = 0;
+        uint32_t ph = 1u;
+        for (int t = blockIdx.x; t < p.n_chunks; t += gridDim.x) {
+            if (!wgshift_chunk_live(p, t)) continue;
+            if (!mbar_wait(empty_bar + 8 * s, ph)) { *abort_g = 1; break; }
+            if (*abort_g) break;
+            const long long v0 = (long long)t * WS_KP;
+            const long long pa = WS_KP;              // planes are padded to a multiple of WS_KP pixels
+            long long pb = p.total_pixels - v0;
+            if (pb > p.b_pixels) pb = p.b_pixels;
+            if (elect_one_sync()) {
                 mbar_arrive_expect_tx(full_bar + 8 * s, (uint32_t)(pa * 16 * p.n_planes + pb * 16));
                 bulk_g2s(b_base + (uint32_t)s * p.b_stage, p.xp + v0 * 8, (uint32_t)pb * 16u, full_bar + 8 * s);
                 for (int c = 0; c < p.n_planes; ++c)
                     bulk_g2s(a_base + (uint32_t)s * p.a_stage + (uint32_t)c * (WS_KP * 16u),
                              p.gyv + ((long long)c * p.plane_stride + v0) * 8, (uint32_t)pa * 16u, full_bar + 8 * s);
-                ++i;
             }
+            __syncwarp();
+            if (++s == WS_STAGES) { s = 0; ph ^= 1u; }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            // MN-major A and B (bits 15, 16), bf16 x bf16 -> fp32, M = 128, N = n_row
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                                   ((uint32_t)(p.n_row >> 3) << 17) | ((uint32_t)(UM_BLOCK_M >> 4) << 24);
-            int i = 0;
-            for (int t = blockIdx.x; t < p.n_chunks; t += gridDim.x) {
-                if (!wgshift_chunk_live(p, t)) continue;
-                const int s = i % WS_STAGES;
-                if (p.dbg && i < 32) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 0] = clock64();
-                if (!mbar_wait(full_bar + 8 * s, (i / WS_STAGES) & 1)) { *abort_g = 2; break; }
-                if (*abort_g) break;
-                tc_fence_after();
-                if (p.dbg && i < 32) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 1] = clock64();
-                const uint64_t ad0 = umma_desc_none_mn(a_base + (uint32_t)s * p.a_stage, 8u, (uint32_t)WS_KP);
-                const uint64_t bd0 = umma_desc_none_mn(b_base + (uint32_t)s * p.b_stage, 8u, 1u);
+        // MN-major A and B (bits 15, 16), bf16 x bf16 -> fp32, M = 128, N = n_row; whole warp walks, elected lane issues
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(p.n_row >> 3) << 17) | ((uint32_t)(UM_BLOCK_M >> 4) << 24);
+        int i = 0, s = 0;
+        uint32_t ph = 0u;
+        for (int t = blockIdx.x; t < p.n_chunks; t += gridDim.x) {
+            if (!wgshift_chunk_live(p, t)) continue;
+            if (p.dbg && i < 32 && lane == 0) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 0] = clock64();
+            if (!mbar_wait(full_bar + 8 * s, ph)) { *abort_g = 2; break; }
+            if (*abort_g) break;
+            // (no tcgen05.fence per chunk, see k_conv_umma)
+            if (p.dbg && i < 32 && lane == 0) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 1] = clock64();
+            const uint64_t ad0 = umma_desc_none_mn(a_base + (uint32_t)s * p.a_stage, 8u, (uint32_t)WS_KP);
+            const uint64_t bd0 = umma_desc_none_mn(b_base + (uint32_t)s * p.b_stage, 8u, 1u);
+            if (elect_one_sync()) {
                 if (p.order) {
 #pragma unroll 1
                     for (int kh = 0; kh < p.KH; ++kh)
@@ -1331,12 +1247,14 @@ k_wgrad_shift(const WgShiftP p) {
                     }
                 }
                 umma_commit(empty_bar + 8 * s);
-                if (p.dbg && i < 32) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 2] = clock64();
-                ++i;
             }
-            *work_g = (uint32_t)i;
-            umma_commit(acc_bar);
+            __syncwarp();
+            if (p.dbg && i < 32 && lane == 0) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 2] = clock64();
+            ++i;
+            if (++s == WS_STAGES) { s = 0; ph ^= 1u; }
         }
+        if (lane == 0) *work_g = (uint32_t)i;
+        if (elect_one_sync()) umma_commit(acc_bar);
         __syncwarp();
     }
     if (warp >= 2) {
@@ -1466,7 +1384,7 @@ static Plan make_plan(int Cin_k, int KHW, int n_out, bool has_main, bool has_sig
     pl.Cp = pad_to(Cin_k, 8);
     pl.K_total = KHW * pl.Cp;
     pl.num_kb = (pl.K_total + UM_BLOCK_K - 1) / UM_BLOCK_K;
-    static const int env_max_nt = getenv("NN_UMMA_MAX_NT") ? atoi(getenv("NN_UMMA_MAX_NT")) : UM_MAX_NT;   // tuning knob
+    const int env_max_nt = UM_MAX_NT;
     const int max_nt = has_sigma ? (has_main ? env_max_nt : 248) : 256;
     pl.n_tiles = (n_out + max_nt - 1) / max_nt;
     // skinny problems (few 128-row m-tiles, e.g. the fully connected layers at batch 512) are latency-bound:
@@ -1491,8 +1409,7 @@ static Plan make_plan(int Cin_k, int KHW, int n_out, bool has_main, bool has_sig
     pl.tmem_cols = 32;
     while (pl.tmem_cols < need) pl.tmem_cols <<= 1;
     const int stage_bytes = UM_A_STAGE + pl.n_mma * 128;
-    static const int budget_kb = getenv("NN_UMMA_SMEM_KB") ? atoi(getenv("NN_UMMA_SMEM_KB")) : 100;   // tuning knob
-    static const int max_stages = getenv("NN_UMMA_MAX_STAGES") ? atoi(getenv("NN_UMMA_MAX_STAGES")) : 4;
+    const int budget_kb = 100, max_stages = 4;          // 2 CTAs / SM; deeper rings per CTA measured slower than more CTAs
     // kernels whose accumulators fit 128 TMEM columns (dgrad, narrow layers) run 3 CTAs/SM: more resident CTAs hide
     // the load / barrier round-trip latency better than deeper per-CTA pipelines (measured: conv2 dgrad 144 -> 121 us)
     const int budget = (pl.tmem_cols <= 128 && !has_sigma && budget_kb > 72) ? 72 : budget_kb;
@@ -1513,7 +1430,7 @@ struct ShiftPlan {
     int n_t, n_mma, main_col, sig_col, n_chunks, n_pairs, a_pixels, a_stage, b_bytes, n_tiles;
     size_t smem_bytes, wp_bytes;
 };
-int g_shift_enable = getenv("NN_SHIFT_OFF") ? 0 : 1;
+int g_shift_enable = 1;        // test hook: nn_debug_shift_enable
 
 static bool make_shift_plan(const nn_conv_geom& g, bool noisy, ShiftPlan* out) {
     if (!g_shift_enable) return false;
@@ -1564,46 +1481,14 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* sp
     int epi = 0;
     if (!extras && p.main_col >= 0 && p.noise_mode != NN_NOISE_NONE && p.y_noisy) epi = 1;
     else if (!extras && p.main_col >= 0 && p.noise_mode == NN_NOISE_NONE && p.y) epi = 2;
-    static const bool force_generic = getenv("NN_UMMA_GENERIC_EPI") != nullptr;
-    if (force_generic) epi = 0;
     UmmaP pd = p;
-    static const int env_inc = getenv("NN_UMMA_INC_TAPS") ? atoi(getenv("NN_UMMA_INC_TAPS")) : -1;
     // measured at batch 512 (same run, A/B): incremental tap tracking takes conv2 dgrad 120 -> 110 us (3 CTAs/SM, the
     // producers' issue slots matter) but costs the fused forward 70 -> 72.7 us (2 CTAs/SM, sigma rows): per variant
-    pd.inc_taps = env_inc >= 0 ? env_inc : (epi == 2 ? 1 : 0);
-    // wave shaping: with T = ceil(M/128) tiles and S resident CTA slots, ceil(T/S) rounds run anyway; shrinking the
-    // VALID rows per tile so that the CTAs fill those rounds exactly shortens every CTA (gather and epilogue scale with
-    // the valid rows; the tensor pipe has slack) instead of leaving the last round mostly empty
+    pd.inc_taps = epi == 2 ? 1 : 0;
     pd.rows_tile = UM_BLOCK_M;
-    // (measured round 1: conv2 forward 70 -> 78 us with 88-row tiles -- a CTA's time is dominated by the weight stream and
-    // the MMAs, which do not shrink with the valid rows; off by default, kept as a knob)
-    static const bool shape = getenv("NN_UMMA_WAVE_SHAPING") != nullptr;
-    if (shape) {
-        // resident CTAs per SM: shared memory (227 KB, 1 KB reserved per CTA), TMEM columns, and the register cap
-        // implied by the kernel's __launch_bounds__ (EPI 2: 3 blocks, else 2)
-        int per_sm = (int)((227 * 1024) / (pl.smem_bytes + 1024));
-        const int by_tmem = 512 / pl.tmem_cols, by_regs = epi == 2 ? 3 : 2;
-        if (per_sm > by_regs) per_sm = by_regs;
-        {
-            if (per_sm > by_tmem) per_sm = by_tmem;
-            if (per_sm < 1) per_sm = 1;
-            int dev = 0;
-            cudaGetDevice(&dev);
-            const long long slots = (long long)per_sm * nn_num_sms(dev) / pl.n_tiles;
-            const long long tiles = (p.M + UM_BLOCK_M - 1) / UM_BLOCK_M;
-            if (slots > 0 && tiles > slots) {
-                const long long rounds = (tiles + slots - 1) / slots;
-                long long rows = (p.M + rounds * slots - 1) / (rounds * slots);
-                rows = (rows + 7) / 8 * 8;
-                if (rows < UM_BLOCK_M && rows >= 64) pd.rows_tile = (int)rows;
-            }
-        }
-    }
     dim3 grid((p.M + pd.rows_tile - 1) / pd.rows_tile, pl.n_tiles);
-    static const bool verbose = getenv("NN_UMMA_VERBOSE") != nullptr;
-    if (verbose) fprintf(stderr, "[umma] M=%d n_tiles=%d epi=%d smem=%zu tmem=%d stages=%d rows_tile=%d grid=%u\n", p.M, pl.n_tiles, epi,
-                         pl.smem_bytes, pl.tmem_cols, pl.stages, pd.rows_tile, grid.x);
-    static const bool want_dbg = getenv("NN_UMMA_DEBUG") != nullptr;
+#ifdef NN_KDEBUG
+    static const bool want_dbg = getenv("NN_UMMA_DEBUG") != nullptr;      // per-CTA phase stamps (tools/cta_timeline.py)
     if (want_dbg) {
         const size_t ctas = (size_t)grid.x * grid.y;
         if (ctas > g_dbg_ctas) {
@@ -1615,62 +1500,15 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* sp
         pd.dbg = g_dbg_buf;
         g_dbg_last = ctas;
     }
-    if (g_time_main) {
-        if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
-        cudaEventRecord(g_ev0, st);
-    }
-    // pairs of m-tiles as a 2-CTA cluster: every weight k-block is fetched once per pair (each CTA loads half and
-    // multicasts it) -- the tiled kernels are bound by operand ingest from L2, and the weights are the larger share
-    // (measured round 1: correct, but 1-3 % SLOWER on every layer -- weight ingest is not what bounds these kernels; kept as a knob)
-    static const int env_cluster = getenv("NN_UMMA_CLUSTER") ? atoi(getenv("NN_UMMA_CLUSTER")) : 1;
-    pd.cluster = (env_cluster == 2 && grid.x >= 2 && !want_dbg) ? 2 : 1;
-    // NN_UMMA_CLUSTER=3: CTA pairs (cta_group::2) -- one M = 256 MMA per pair, each SM stages and RECEIVES only half of
-    // the weight rows of a k-block (delivered bytes per SM: A 16 KB + B/2), which also makes room for deeper pipelines
-    size_t smem_bytes = pl.smem_bytes;
-    if (env_cluster == 3 && grid.x >= 2 && !want_dbg && (epi == 1 || epi == 2) && p.OH * p.OW != 1) {
-        pd.cluster = 3;
-        const int stage_bytes = UM_A_STAGE + pl.n_mma * 64;
-        const int budget_kb = (pl.tmem_cols <= 128 && p.noise_mode == NN_NOISE_NONE) ? 72 : 100;
-        int stages = (budget_kb * 1024 - 2048) / stage_bytes;
-        if (stages > 4) stages = 4;
-        if (stages < 2) stages = 2;
-        if (stages > pl.num_kb) stages = pl.num_kb;
-        pd.stages = stages;
-        smem_bytes = 1024 + (size_t)stages * stage_bytes + 16 * stages + 64;
-    }
-    if (pd.cluster >= 2) grid.x = (grid.x + 1) & ~1u;
-    // NN_UMMA_HALO=1 (lean plain variant: dgrad) / 2 (both lean variants): input footprint resident in shared memory
-    static const int env_halo = getenv("NN_UMMA_HALO") ? atoi(getenv("NN_UMMA_HALO")) : 0;
-    bool halo = false;
-    if (pd.cluster == 1 && p.stride == 1 && !want_dbg && ((env_halo >= 1 && epi == 2) || (env_halo >= 2 && epi == 1)) &&
-        p.OH * p.OW != 1 && pd.rows_tile == UM_BLOCK_M) {
-        const int dR = (UM_BLOCK_M - 1) / p.OW + 2, crossings = dR / p.OH + 1;
-        const int rows = dR + crossings * (p.H > p.OH ? p.H - p.OH : 0) + p.KH;
-        const int halo_bytes = (rows * p.W * p.Cp * 2 + 127) & ~127;
-        static const int env_hs = getenv("NN_UMMA_HALO_STAGES") ? atoi(getenv("NN_UMMA_HALO_STAGES")) : 2;
-        static const int env_hkb = getenv("NN_UMMA_HALO_KB") ? atoi(getenv("NN_UMMA_HALO_KB")) : 110;    // smem budget per CTA
-        int stages = env_hs;
-        if (stages > pl.num_kb) stages = pl.num_kb;
-        const long long fixed = 1024 + (long long)stages * UM_A_STAGE + 24 * stages + 512 + halo_bytes;
-        int bst = (int)(((long long)env_hkb * 1024 - fixed) / (pl.n_mma * 128 + 16));
-        if (bst > 12) bst = 12;
-        if (bst > pl.num_kb) bst = pl.num_kb;
-        if (bst >= 2 && stages >= 1) {
-            halo = true;
-            pd.halo_bytes = halo_bytes;
-            pd.stages = stages;
-            pd.b_stages = bst;
-            smem_bytes = (size_t)fixed + (size_t)bst * (pl.n_mma * 128 + 16);
-        }
-    }
+#else
+    const bool want_dbg = false;
+#endif
     // split-K for skinny linear layers (few m-tiles x n-tiles, long K: fc1 forward at batch 512 is 52 CTAs walking 47
     // k-blocks each -- a latency chain on a third of the SMs): the k-blocks are dealt to gridDim.z CTAs that dump raw
-    // accumulators, and k_splitk_epilogue sums them and applies the noise epilogue
+    // accumulators, and k_splitk_epilogue sums them and applies the noise epilogue (measured: 1: 0.805, 3: 0.788, 4: 0.785 ms/step)
     int splits = 1;
-    static const int env_splits = getenv("NN_UMMA_SPLITK") ? atoi(getenv("NN_UMMA_SPLITK")) : 4;   // measured: 1: 0.805, 3: 0.788, 4: 0.785 ms/step
-    if ((epi == 1 || epi == 2) && p.OH * p.OW == 1 && pd.cluster == 1 && !want_dbg && env_splits > 1 &&
-        (int)(grid.x * grid.y) * 2 <= nn_num_sms_cached() && pl.num_kb >= 8 && pd.rows_tile == UM_BLOCK_M && splitk_ws) {
-        splits = env_splits;
+    if ((epi == 1 || epi == 2) && p.OH * p.OW == 1 && !want_dbg && (int)(grid.x * grid.y) * 2 <= nn_num_sms_cached() && pl.num_kb >= 8 && splitk_ws) {
+        splits = 4;
         while (splits > 1 && pl.num_kb / splits < 4) --splits;
         const size_t need = (size_t)splits * pl.n_tiles * pl.n_mma * grid.x * UM_BLOCK_M * sizeof(float);
         if (need > splitk_ws_bytes) splits = 1;
@@ -1680,6 +1518,7 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* sp
         pd.partial = (float*)splitk_ws;
         pd.m_pad = (int)grid.x * UM_BLOCK_M;
     }
+#ifdef NN_KDEBUG
     static const bool want_kdbg = getenv("NN_UMMA_KDEBUG") != nullptr;
     if (want_kdbg) {
         const size_t rows = ((size_t)grid.x * grid.y * pl.num_kb * 4 + 7) / 8;      // rows of 8 longs, as nn_debug_cta_timeline copies
@@ -1692,32 +1531,14 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* sp
         pd.kdbg = g_dbg_buf;
         g_dbg_last = rows;
     }
-    if (verbose) fprintf(stderr, "[umma]   launch grid=(%u,%u,%u) cluster=%d stages=%d b_stages=%d halo=%d smem=%zu\n", grid.x, grid.y, grid.z,
-                         pd.cluster, pd.stages, pd.b_stages, pd.halo_bytes, smem_bytes);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid; cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = pd.cluster >= 2 ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    if (halo) {
-        NN_ONCE_PER_DEVICE({
-            NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        });
-        if (epi == 1) NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<1, false, true>, pd));
-        else NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<2, false, true>, pd));
-    } else if (pd.cluster == 3) {
-        NN_ONCE_PER_DEVICE({
-            NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            NN_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        });
-        if (epi == 1) NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<1, true>, pd));
-        else NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<2, true>, pd));
-    } else if (epi == 1) NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<1>, pd));
-    else if (epi == 2) NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<2>, pd));
-    else NN_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma<0>, pd));
+#endif
+    if (g_time_main) {
+        if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+        cudaEventRecord(g_ev0, st);
+    }
+    if (epi == 1) k_conv_umma<1><<<grid, UM_THREADS, pl.smem_bytes, st>>>(pd);
+    else if (epi == 2) k_conv_umma<2><<<grid, UM_THREADS, pl.smem_bytes, st>>>(pd);
+    else k_conv_umma<0><<<grid, UM_THREADS, pl.smem_bytes, st>>>(pd);
     if (g_time_main) cudaEventRecord(g_ev1, st);
     NN_LAUNCH_OK();
     if (splits > 1) {
@@ -1863,7 +1684,11 @@ static int shift_conv_fwd(const nn_conv_fwd_args* a, const ShiftPlan& sp, int de
     p.err_flag = nn_umma_err_flag(device);
     int grid = nn_num_sms(device);
     if (grid > sp.n_tiles) grid = sp.n_tiles;
+#ifdef NN_KDEBUG
     static const bool want_dbg = getenv("NN_UMMA_DEBUG") != nullptr;
+#else
+    const bool want_dbg = false;
+#endif
     if (want_dbg) {
         const size_t rows = (size_t)grid * 16;           // 32 tiles x 4 stamps = 16 rows of 8
         if (rows > g_dbg_ctas) {
@@ -1879,8 +1704,7 @@ static int shift_conv_fwd(const nn_conv_fwd_args* a, const ShiftPlan& sp, int de
         if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
         cudaEventRecord(g_ev0, st);
     }
-    static const int env_ew = getenv("NN_SH_EPI_WARPS") ? atoi(getenv("NN_SH_EPI_WARPS")) : 16;   // tuning knob
-    const int mode = !noise ? 0 : (a->z_inject ? 2 : 1);
+    const int mode = !noise ? 0 : (a->z_inject ? 2 : 1);      // 16 epilogue warps (12 / 20 / 24 measured slower)
 #define NN_SHIFT_LAUNCH(MODE, EW)                                                                                      \
     do {                                                                                                               \
         NN_ONCE_PER_DEVICE({ \
@@ -1888,15 +1712,7 @@ static int shift_conv_fwd(const nn_conv_fwd_args* a, const ShiftPlan& sp, int de
         });                                                                                                              \
         k_conv_shift<MODE, EW><<<grid, (2 + EW) * 32, sp.smem_bytes, st>>>(p);                                          \
     } while (0)
-#define NN_SHIFT_MODES(EW)                                                                                             \
-    do {                                                                                                               \
-        if (mode == 0) NN_SHIFT_LAUNCH(0, EW); else if (mode == 1) NN_SHIFT_LAUNCH(1, EW); else NN_SHIFT_LAUNCH(2, EW);  \
-    } while (0)
-    if (env_ew == 12) NN_SHIFT_MODES(12);
-    else if (env_ew == 20) NN_SHIFT_MODES(20);
-    else if (env_ew == 24) NN_SHIFT_MODES(24);
-    else NN_SHIFT_MODES(16);
-#undef NN_SHIFT_MODES
+    if (mode == 0) NN_SHIFT_LAUNCH(0, 16); else if (mode == 1) NN_SHIFT_LAUNCH(1, 16); else NN_SHIFT_LAUNCH(2, 16);
 #undef NN_SHIFT_LAUNCH
     if (g_time_main) cudaEventRecord(g_ev1, st);
     NN_LAUNCH_OK();
@@ -1936,15 +1752,14 @@ static void fill_pack_tma(PackWP& pw, const TmaPlan& tp) {
 }
 static int64_t pack_tma_chunks(const TmaPlan& tp) { return (int64_t)tp.n_tiles * tp.n_mma * tp.taps * (tp.wt >> 3); }
 
-// lean calls only (what the training step issues): no bias / statistics / export / injected draws / clean-output copy
+// lean calls only (what the training step issues): no bias / statistics / exports / clean-output copy
 static bool tma_fwd_plan(const nn_conv_fwd_args* a, TmaPlan* tp) {
     const nn_conv_geom& g = a->g;
     int OH, OW;
     nn_out_hw(g, OH, OW);
     const bool noise = a->noise_mode != NN_NOISE_NONE;
     const bool has_main = a->w_eff != nullptr || a->w_packed != nullptr;
-    const bool lean = has_main && !a->bias && !a->z_inject && !a->z_export && !a->sigma_export && !a->stats && !a->pooled_out &&
-                      !(noise && a->y);
+    const bool lean = has_main && !a->bias && !a->z_export && !a->sigma_export && !a->stats && !a->pooled_out && !(noise && a->y);
     return lean && nn_tma_make_plan(g.Cin, g.KH, g.KW, g.stride, g.pad, g.Cout, noise, OH, OW, tp);
 }
 
@@ -1991,14 +1806,13 @@ static int tma_conv_fwd(const nn_conv_fwd_args* a, const TmaPlan& tp, int device
     const float wsc = a->w_code_scale > 0.f ? a->w_code_scale : 1.f;
     c.y_scale = as * wsc; c.s_scale = as;
     c.y = a->y; c.y_noisy = a->y_noisy; c.noise_mode = a->noise_mode; c.current = a->current; c.scale_dev = a->scale_dev; c.rng = a->rng;
+    c.z_inject = a->noise_mode != NN_NOISE_NONE ? a->z_inject : nullptr;
     c.err_flag = nn_umma_err_flag(device);
     if (g_time_main) {
         if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
-        cudaEventRecord(g_ev0, st);
+        c.ev0 = g_ev0; c.ev1 = g_ev1;
     }
-    const int rc = nn_tma_conv_launch(c, device, st);
-    if (g_time_main) cudaEventRecord(g_ev1, st);
-    return rc;
+    return nn_tma_conv_launch(c, device, st);
 }
 
 int nn_umma_conv_fwd(const nn_conv_fwd_args* a, int device, cudaStream_t st) {
@@ -2365,7 +2179,7 @@ bool make_wg_shift_plan(const nn_conv_geom& g, int device, WgShiftPlan* out) {
     const int fixed = 128 + 16 * WS_KP * 16 + 16 * WS_MAX_STAGES + 64;
     // two CTAs per SM when the accumulators leave room in TMEM: one CTA's MMA stream has issue gaps (barrier waits,
     // commits, accumulator switches) that a second stream fills -- measured at batch 512: CTA span 70 -> 35 us
-    static const int env_ctas = getenv("NN_WS_CTAS") ? atoi(getenv("NN_WS_CTAS")) : 2;      // tuning knob: CTAs per SM
+    const int env_ctas = 2;
     const int ctas = (env_ctas == 2 && w.tmem_cols <= 256) ? 2 : 1;
     w.stages = ((ctas == 2 ? 100 : 190) * 1024 - fixed) / (w.a_stage + w.b_stage);
     if (w.stages > WS_MAX_STAGES) w.stages = WS_MAX_STAGES;
@@ -2441,13 +2255,17 @@ static int shift_conv_wgrad(const nn_conv_wgrad_args* a, const WgShiftPlan& w, i
     p.n_planes = w.n_planes; p.n_row = w.n_row; p.n_chunks = w.n_chunks; p.b_pixels = w.b_pixels;
     p.a_stage = w.a_stage; p.b_stage = w.b_stage; p.stages = w.stages; p.tmem_cols = w.tmem_cols;
     p.total_pixels = (long long)g.B * g.H * g.W; p.plane_stride = w.plane_stride;
-    static const int env_order = getenv("NN_WS_ORDER") ? atoi(getenv("NN_WS_ORDER")) : 1;   // 1: kernel row outermost (8 MMAs per accumulator in a row: 56 -> 40 ns per MMA)
+    const int env_order = 1;      // kernel row outermost (8 MMAs per accumulator in a row)
     p.order = env_order;
     p.xp = xp; p.gyv = gyv; p.partial = partial; p.err_flag = nn_umma_err_flag(device);
     NN_ONCE_PER_DEVICE({
         NN_CUDA_OK(cudaFuncSetAttribute(k_wgrad_shift, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     });
+#ifdef NN_KDEBUG
     static const bool want_dbg = getenv("NN_UMMA_DEBUG") != nullptr;
+#else
+    const bool want_dbg = false;
+#endif
     if (want_dbg) {
         const size_t rows = (size_t)w.grid * 16;
         if (rows > g_dbg_ctas) {

@@ -48,6 +48,17 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     }
     return true;
 }
+// waiting roles that are not on the critical path (producers waiting for a free stage, epilogue warps waiting for an
+// accumulator): sleep between polls instead of competing with the MMA thread for issue slots and the barrier unit
+__device__ __forceinline__ bool mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(64);
+        if (clock64() - t0 > UM_TIMEOUT) return false;
+    }
+    return true;
+}
 __device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity) {     // acquire at cluster scope (remote arrivals)
     const long long t0 = clock64();
     for (;;) {
@@ -224,6 +235,28 @@ __device__ __forceinline__ void tma_im2col_4d(uint32_t dst, const void* map, uin
                                               uint16_t off_w, uint16_t off_h) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
+// CTA-pair variants (cta_group::2): issued by BOTH CTAs of a pair for their own shared memory, but the transaction bytes
+// are counted on the barrier of the pair's LEADER (the even CTA: bit 24 of the shared::cluster address cleared), so the
+// leader's MMA thread waits on ONE barrier for both CTAs' operands.
+constexpr uint32_t NN_PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_im2col_4d_2cta(uint32_t dst, const void* map, uint32_t bar, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h) {
+    asm volatile("cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+                 ::"r"(dst), "l"(map), "r"(bar & NN_PEER_BIT_MASK), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
+__device__ __forceinline__ void tma_tile_2d_2cta(uint32_t dst, const void* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar & NN_PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
+}
+// One lane of a CONVERGED warp.  The single-thread instructions of this file (tcgen05.mma / commit, TMA copies) take
+// their operands from uniform registers; issued under `if (lane == 0)` inside divergent code the compiler cannot prove the
+// operands warp-uniform and moves every one of them through R2UR in an ELECT loop on each use (5 per MMA, ~250 cycles per
+// MMA measured).  Role loops therefore run on the whole warp with warp-uniform control flow and elect the issuing lane.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tma_prefetch_desc(const void* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");

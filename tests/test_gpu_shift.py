@@ -98,7 +98,10 @@ def test_shift_layout_rejected_when_not_served(dev):
     lib = _lib.load()
     for g in (ConvGeom(4, 65, 14, 14, 120, 5, 5, 1, 0), ConvGeom(4, 3, 32, 32, 65, 5, 5, 1, 2),
               ConvGeom(4, 3, 32, 32, 65, 5, 5, 2, 0), ConvGeom(4, 3, 32, 32, 200, 5, 5, 1, 0)):
-        assert lib.nn_conv_pack_layout(C.byref(g), NOISE_MERGED, PREC_BF16) == PACK_TILED
+        assert lib.nn_conv_pack_layout(C.byref(g), NOISE_MERGED, PREC_BF16) != PACK_SHIFT
+    # wider inputs go to the TMA-im2col kernel, narrow ones that the shift kernel cannot serve to the tiled one
+    assert lib.nn_conv_pack_layout(C.byref(ConvGeom(4, 65, 14, 14, 120, 5, 5, 1, 0)), NOISE_MERGED, PREC_BF16) == _lib.PACK_TMA
+    assert lib.nn_conv_pack_layout(C.byref(ConvGeom(4, 3, 32, 32, 65, 5, 5, 2, 0)), NOISE_MERGED, PREC_BF16) == PACK_TILED
     g = ConvGeom(4, 3, 32, 32, 200, 5, 5, 1, 0)
     assert lib.nn_conv_pack_layout(C.byref(g), 0, PREC_BF16) == PACK_SHIFT      # 200 plain columns fit, 400 do not
 

@@ -90,6 +90,9 @@ def test_tma_forward_code_mode(dev, shape):
         # same operands (bf16 g(|w|), integer codes), different K order of the fp32 accumulation of sigma^2 only
         assert (r["y_noisy"] - r_old["y_noisy"]).abs().max().item() <= 1e-4 * noise_max + 1e-5
         assert (r["y_noisy"] - r32["y_noisy"]).abs().max().item() <= 3e-3 * noise_max + 1e-5
+        # injected draws (the parity hook the engine tests use): same kernel family, z read from memory
+        rz = ops.noisy_conv_fwd(xd, wqd, wrd, None, s, p, precision="bf16", z=r32["z"], **kw)
+        assert (rz["y_noisy"] - r32["y_noisy"]).abs().max().item() <= 3e-3 * noise_max + 1e-5
         assert ops.error_flag() == 0
 
 

@@ -108,7 +108,10 @@ def test_plain_operands_and_dgrad(dev, shape):
     gxm = ops.conv_dgrad(gy.to(dev), w.to(dev), x.shape, s, p, x_pre=x.to(dev), x_lo=-0.5, x_hi=0.5,
                          precision="bf16").cpu()
     keep = ((x >= -0.5) & (x <= 0.5)).float()
-    assert torch.equal(gxm, gx * keep)
+    # (the unmasked call may run on the TMA-im2col kernel, the masked one on the gathered-im2col kernel: same bf16 operands,
+    #  different order of the fp32 accumulation)
+    assert torch.allclose(gxm, gx * keep, rtol=1e-4, atol=1e-5 * ref.abs().max().item())
+    assert torch.equal(gxm == 0, (gx * keep) == 0) or (gxm[keep == 0] == 0).all()
 
 
 def test_full_size_conv2_properties(dev):

@@ -33,6 +33,26 @@ def dump(lib, title):
     print("  epilogue warp 0   : wait acc-full %s  total %s  items/CTA %.2f" % (f(lead[:, 10]), f(lead[:, 11]), float(np.mean(lead[:, 12]))))
 
 
+def trace(lib, title, n=75):
+    buf = (C.c_longlong * (1024 * 4))()
+    lib.nn_debug_tma_trace.restype = C.c_int
+    lib.nn_debug_tma_trace.argtypes = [C.c_void_p, C.c_int]
+    k = lib.nn_debug_tma_trace(buf, 1024)
+    a = np.frombuffer(buf, dtype=np.int64).reshape(1024, 4)[:n]
+    t0 = a[0, 0]
+    print("== %s: MMA thread of cluster 0, per group (cycles): wait for the stage | issue MMAs + commit | start-to-start" % title)
+    prev = None
+    line = []
+    for g in range(n):
+        w, i = a[g, 1] - a[g, 0], a[g, 2] - a[g, 1]
+        line.append("%4d|%4d|%5d" % (w, i, (a[g, 0] - prev) if prev is not None else 0))
+        prev = a[g, 0]
+        if len(line) == 5:
+            print("   " + "   ".join(line)); line = []
+    if line:
+        print("   " + "   ".join(line))
+
+
 def main():
     B = int(os.environ.get("B", "512"))
     dev = torch.device("cuda:0")
@@ -42,17 +62,39 @@ def main():
     w_raw = torch.randn(120, 65, 5, 5, device=dev) * 0.1
     wq = ops.quantize_fwd(w_raw, 4, -1.0, 1.0, 0.0)
     scale = ops.tensor_stats(x)[0:1]
+    fwd = lambda: ops.noisy_conv_fwd(x, wq, w_raw, None, 1, 0, noise_mode=NOISE_EXTERNAL, current=1.0, scale_dev=scale, precision="bf16",
+                                     a_code_scale=s_a, w_code_scale=1.0 / 15.0, want_y=False)
     for _ in range(3):
-        r = ops.noisy_conv_fwd(x, wq, w_raw, None, 1, 0, noise_mode=NOISE_EXTERNAL, current=1.0, scale_dev=scale, precision="bf16",
-                               a_code_scale=s_a, w_code_scale=1.0 / 15.0, want_y=False)
+        r = fwd()
     dump(lib, "conv2 forward (noisy)")
+    trace(lib, "conv2 forward (noisy)")
     gy = torch.randn_like(r["y_noisy"])
+    dgrad = lambda: ops.conv_dgrad(gy, wq, x.shape, precision="bf16", w_code_scale=1.0 / 15.0)
     for _ in range(3):
-        ops.conv_dgrad(gy, wq, x.shape, precision="bf16", w_code_scale=1.0 / 15.0)
+        dgrad()
     dump(lib, "conv2 dgrad")
-    for _ in range(3):
-        ops.noisy_conv_fwd(x, wq, None, None, 1, 0, precision="bf16", a_code_scale=s_a, w_code_scale=1.0 / 15.0)
-    dump(lib, "conv2 forward (plain)")
+    # experiments (kdebug build): which role bounds the kernel?  mode bits: 1 no epilogue work, 2 stale operands (no copies
+    # after the first ring revolution), 4 no per-group clock reads
+    lib.nn_debug_tma_mode.restype = C.c_int
+    lib.nn_debug_tma_mode.argtypes = [C.c_int]
+    names = {4: "all roles", 5: "no epilogue work", 6: "no operand copies", 7: "MMA issue only", 13: "free-running MMA thread", 29: "MMA thread alone"}
+    lib.nn_debug_main_kernel_ms(1)
+    for title, call in (("conv2 forward (noisy)", fwd), ("conv2 dgrad", None)):
+        for mode in (4, 7, 13, 29):
+            lib.nn_debug_tma_mode(mode)
+            ts = []
+            for _ in range(5):
+                if call is not None:
+                    call()
+                    ts.append(lib.nn_debug_main_kernel_ms(-1))
+                else:
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); dgrad(); e1.record(); torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+            print("  %-24s %-20s %.1f us%s" % (title, names[mode], 1e3 * min(ts), "" if call is not None else "  (incl. the two pack kernels, ~20 us)"))
+    lib.nn_debug_main_kernel_ms(0)
+    lib.nn_debug_tma_mode(0)
     assert ops.error_flag() == 0
 
 
