@@ -573,7 +573,13 @@ def main():
     try:
         import torch.distributed as dist
         if dist.is_initialized():
-            dist.destroy_process_group()
+            # symmetric-memory handles (dp.SymmGradAllReduce) can block the process-group teardown: every rank has printed
+            # and synchronised by now, so leave through _exit after a last barrier
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
     except Exception:
         pass
 

@@ -97,10 +97,20 @@ k_allreduce_twoshot(const ArP p) {
     // ---- reduce my slice, broadcast the sums
     const long long per = p.n_vec / p.world, v0 = (long long)p.rank * per;
     if (p.mc_base) {
-        char* mc = reinterpret_cast<char*>(p.mc_base) + p.data_off;
-        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
-            const float4 s = mc_ld_reduce(mc + (v0 + i) * 16);
-            mc_st(mc + (v0 + i) * 16, s);
+        // four independent switch round trips in flight per thread: the loop is bound by the ld_reduce latency (~2-3 us), not
+        // by bandwidth (measured at 2 ranks: one vector per iteration 103 us for 5.5 MB, NCCL 43 us)
+        char* mc = reinterpret_cast<char*>(p.mc_base) + p.data_off + v0 * 16;
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < per; i += 4 * stride) {
+            const float4 s0 = mc_ld_reduce(mc + i * 16), s1 = mc_ld_reduce(mc + (i + stride) * 16);
+            const float4 s2 = mc_ld_reduce(mc + (i + 2 * stride) * 16), s3 = mc_ld_reduce(mc + (i + 3 * stride) * 16);
+            mc_st(mc + i * 16, s0); mc_st(mc + (i + stride) * 16, s1);
+            mc_st(mc + (i + 2 * stride) * 16, s2); mc_st(mc + (i + 3 * stride) * 16, s3);
+        }
+        for (; i < per; i += stride) {
+            const float4 s0 = mc_ld_reduce(mc + i * 16);
+            mc_st(mc + i * 16, s0);
         }
     } else {
         for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
@@ -155,9 +165,9 @@ extern "C" int nn_allreduce_start(const void* const* peer_ptrs, const void* mc_p
     for (int r = 0; r < world; ++r) p.peer_base[r] = (unsigned long long)(uintptr_t)peer_ptrs[r];
     p.mc_base = (unsigned long long)(uintptr_t)mc_ptr;
     p.rank = rank; p.world = world; p.bucket = bucket; p.data_off = data_off; p.n_vec = count / 4;
-    if (ctas < 1) ctas = 16;
+    if (ctas < 1) ctas = 32;
     const long long per = p.n_vec / world;
-    if ((long long)ctas * 512 > per) ctas = (int)((per + 511) / 512);
+    if ((long long)ctas * 512 * 2 > per) ctas = (int)((per + 1023) / 1024);      // at least two vectors per thread
     if (ctas < 1) ctas = 1;
     k_allreduce_twoshot<<<ctas, 512, 0, (cudaStream_t)stream>>>(p);
     NN_LAUNCH_OK();

@@ -146,10 +146,15 @@ class SymmGradAllReduce(FlatGradAllReduce):
             self.ranges.append((off, n_pad))
             off += n_pad
         total = off
+        group_name = dist.group.WORLD.group_name
+        try:
+            symm.enable_symm_mem_for_group(group_name)
+        except Exception:       # noqa: BLE001  (newer torch enables it implicitly)
+            pass
         self.buf = symm.empty(self.ctl + total * 4, dtype=torch.uint8, device=dev)
         self.buf.zero_()
         torch.cuda.synchronize(dev)
-        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.hdl = symm.rendezvous(self.buf, group_name)
         dist.barrier()                                                           # every rank's control words are zero
         self.flat = self.buf[self.ctl:].view(torch.float32)
         self.params = [p for b in buckets for p in b]
@@ -165,7 +170,8 @@ class SymmGradAllReduce(FlatGradAllReduce):
         self._mc = 0 if os.environ.get("NN_DP_MULTICAST", "1") == "0" else int(self.hdl.multicast_ptr or 0)
         self._local = ptrs[self.rank]
         assert self._local == self.buf.data_ptr()
-        self.ctas = int(ctas) if ctas else int(os.environ.get("NN_DP_CTAS", "16"))
+        self.ctas = int(ctas) if ctas else 32
+        self.comm = None                 # the exchange's own stream (created on first use, joins CUDA-graph captures)
         self.n_early = sum(n for _, n in self.ranges[:-1])
         self.bounds = [0]
         for _, n in self.ranges[:-1]:
@@ -176,11 +182,16 @@ class SymmGradAllReduce(FlatGradAllReduce):
         return torch.cuda.current_stream(self.dev_index).cuda_stream
 
     def _start(self, k):
+        """Bucket k's exchange on the reducer's OWN stream, ordered after everything enqueued so far on the current stream:
+        the kernel waits in-stream for the slowest rank, which must not hold up whatever the caller enqueues next."""
         o, n = self.ranges[k]
         if n and not self._started[k]:
             lib = self._lib_mod.load()
+            if self.comm is None:
+                self.comm = torch.cuda.Stream(device=self.dev_index)
+            self.comm.wait_stream(torch.cuda.current_stream(self.dev_index))
             self._lib_mod.check(lib.nn_allreduce_start(self._peer, self._mc or None, self.rank, self.world, k, self.ctl + o * 4, n,
-                                                       self.ctas, self.dev_index, self._st()), "nn_allreduce_start")
+                                                       self.ctas, self.dev_index, self.comm.cuda_stream), "nn_allreduce_start")
             self._started[k] = True
 
     def start_early(self, k=0):
@@ -192,6 +203,7 @@ class SymmGradAllReduce(FlatGradAllReduce):
             lib = self._lib_mod.load()
             for k in range(self.n_buckets):
                 self._start(k)                   # whatever has not been started yet, the tail range included
+            torch.cuda.current_stream(self.dev_index).wait_stream(self.comm)
             for k in range(self.n_buckets):
                 if self._started[k]:
                     self._lib_mod.check(lib.nn_allreduce_wait(self._local, self.world, k, self.dev_index, self._st()), "nn_allreduce_wait")

@@ -25,12 +25,19 @@ class Toy(torch.nn.Module):
         self.e = torch.nn.Parameter(torch.zeros(65))
 
 
+def log(rank, msg):
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "symm_rank%d.log" % rank), "a") as f:
+        f.write(msg + "\n")
+
+
 def main():
     rank, world, local = dp.init_from_env()
+    log(rank, "process group up")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     m = Toy().to(dev)
     red = dp.SymmGradAllReduce(m, world, early=[[m.a, m.d], [m.b]])
+    log(rank, "reducer built: multicast=%s ranges=%s" % (hex(red._mc), red.ranges))
     ref = torch.empty_like(red.flat)
     ok = True
     for it in range(3):
@@ -45,7 +52,9 @@ def main():
             red.start_early(1)
         torch.cuda.current_stream().wait_stream(side)
         red.all_reduce_sum_()
+        log(rank, "iter %d launched" % it)
         torch.cuda.synchronize()
+        log(rank, "iter %d done" % it)
         err = ((red.flat - ref).abs().max() / ref.abs().max()).item()
         gathered = [torch.empty_like(red.flat) for _ in range(world)]
         dist.all_gather(gathered, red.flat)
@@ -80,9 +89,10 @@ def main():
     torch.cuda.synchronize()
     ok = ok and bool((red.flat == float(world)).all())
     if rank == 0:
-        print("RESULT", "ok" if ok else "FAILED")
-    dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+        print("RESULT", "ok" if ok else "FAILED", flush=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0 if ok else 1)        # (tearing the symmetric-memory handles down with the process group can block at exit)
 
 
 if __name__ == "__main__":
