@@ -35,3 +35,20 @@ struct TmaConvCall {
     void *ev0, *ev1;             // optional cudaEvent_t pair recorded immediately around the kernel launch (nn_debug_main_kernel_ms)
 };
 int nn_tma_conv_launch(const TmaConvCall& c, int device, cudaStream_t st);
+
+// ---- weight gradient with TMA-staged operands (k_wgrad_tma): the (tap, 64-channel chunk) columns of the gradient
+struct TmaWgradPlan {
+    int Cp, Coutp, taps, n_c64, tail_w;        // tail_w: 0 or 8 channels per tap left to the gathered kernel
+    int n_atoms, tiles_k, cols_pad, m_tiles_n, num_kb, kb_per_split, splits, stages;
+    size_t smem_bytes, main_bytes, partial_bytes;      // partial = [main | remainder accumulators]
+};
+bool nn_tma_wgrad_plan(int Cin, int KH, int KW, int stride, int pad, int Cout, int64_t Mpix, int device, TmaWgradPlan* out);
+struct TmaWgradCall {
+    TmaWgradPlan pl;
+    int B, H, W, OH, OW, KH, KW, stride, pad, Cout;
+    const void* xp;               // layer input  [B, H, W, Cp] bf16
+    const void* gyp;              // grad_output  [B * OH * OW, Coutp] bf16
+    float* partial;               // [splits][Cout][cols_pad]
+    int* err_flag;
+};
+int nn_tma_wgrad_launch(const TmaWgradCall& c, int device, cudaStream_t st);

@@ -1370,6 +1370,63 @@ k_wgrad_umma_reduce(const float* __restrict__ partial, int splits, int Cout, int
     }
 }
 
+// partials of k_wgrad_tma -> gw [Cout][Cin][KHW], scale, STE mask.  Fixed summation order: deterministic.
+//   main [splits][Cout][cols_pad]:       column = (tap * n_c64 + chunk) * 64 + e   <->  channel chunk * 64 + e
+//     blocks [0, nb_main): one thread per (n, column), four independent partial chains
+//   tail [n_tail][Cout][256] (optional): column = tap * 8 + e                      <->  channel n_c64 * 64 + e
+//     blocks [nb_main, ...): 32 columns x 8 groups of partials (n_tail = splits x column tiles is large), as k_wgrad_umma_reduce2
+__global__ void __launch_bounds__(256)
+k_wgrad_tma_reduce(const float* __restrict__ partial, int splits, int Cout, int Cin, int KHW, int n_c64, int cols_pad, int nb_main,
+                   const float* __restrict__ tail, int n_tail, float scale, float* __restrict__ gw, const float* __restrict__ w_raw,
+                   float lo, float hi) {
+    __shared__ float sh[8][32];
+    if ((int)blockIdx.x >= nb_main) {
+        const unsigned total = (unsigned)Cout * 256u;
+        const size_t zstride = (size_t)Cout * 256;
+        const int col = threadIdx.x & 31, grp = threadIdx.x >> 5;
+        for (unsigned b0 = (blockIdx.x - nb_main) * 32u; b0 < total; b0 += (gridDim.x - nb_main) * 32u) {
+            const unsigned i = b0 + col;
+            const int n = (int)(i >> 8), ct = (int)(i & 255u), tap = ct >> 3, c = n_c64 * 64 + (ct & 7);
+            const bool live = tap < KHW && c < Cin;            // uniform per 8 columns; whole 32-column groups are often dead
+            float s = 0.f;
+            if (live)
+                for (int z = grp; z < n_tail; z += 8) s += tail[(size_t)z * zstride + i];
+            sh[grp][col] = s;
+            __syncthreads();
+            if (grp == 0 && live) {
+                float t = sh[0][col];
+#pragma unroll
+                for (int g = 1; g < 8; ++g) t += sh[g][col];
+                t *= scale;
+                const size_t o = ((size_t)n * Cin + c) * KHW + tap;
+                if (w_raw) { const float w = __ldg(w_raw + o); if (w > hi || w < lo) t = 0.f; }
+                gw[o] = t;
+            }
+            __syncthreads();
+        }
+        return;
+    }
+    const unsigned total = (unsigned)Cout * cols_pad;
+    const size_t zstride = (size_t)Cout * cols_pad;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nb_main * blockDim.x) {
+        const int n = (int)(i / cols_pad), col = (int)(i - (unsigned)n * cols_pad);
+        const int ga = col >> 6, tap = ga / n_c64, c = (ga - tap * n_c64) * 64 + (col & 63);
+        if (tap >= KHW || c >= Cin) continue;
+        const float* src = partial + i;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int z = 0;
+        for (; z + 3 < splits; z += 4) {
+            s0 += src[(size_t)z * zstride]; s1 += src[(size_t)(z + 1) * zstride];
+            s2 += src[(size_t)(z + 2) * zstride]; s3 += src[(size_t)(z + 3) * zstride];
+        }
+        for (; z < splits; ++z) s0 += src[(size_t)z * zstride];
+        float sum = ((s0 + s1) + (s2 + s3)) * scale;
+        const size_t o = ((size_t)n * Cin + c) * KHW + tap;
+        if (w_raw) { const float w = __ldg(w_raw + o); if (w > hi || w < lo) sum = 0.f; }
+        gw[o] = sum;
+    }
+}
+
 // ------------------------------------------------------------------ host-side planning
 struct Plan {
     int Cp, K_total, num_kb, n_tiles, n_t, n_mma, tmem_cols, stages, main_col, sig_col, wsum_col;
@@ -2197,7 +2254,16 @@ bool make_wg_shift_plan(const nn_conv_geom& g, int device, WgShiftPlan* out) {
 
 int64_t nn_umma_wgrad_workspace(const nn_conv_geom* g, int, int device) {
     WgPlan w = make_wg_plan(*g, device);
-    size_t need = align_up(w.xp_bytes, 1024) + align_up(w.gyp_bytes, 1024) + align_up(w.partial_bytes, 1024) + 2048;
+    size_t partial_bytes = w.partial_bytes;
+    {
+        int OH, OW;
+        nn_out_hw(*g, OH, OW);
+        TmaWgradPlan tw;
+        if (nn_tma_wgrad_plan(g->Cin, g->KH, g->KW, g->stride, g->pad, g->Cout, (int64_t)g->B * OH * OW, device, &tw) &&
+            tw.partial_bytes > partial_bytes)
+            partial_bytes = tw.partial_bytes;
+    }
+    size_t need = align_up(w.xp_bytes, 1024) + align_up(w.gyp_bytes, 1024) + align_up(partial_bytes, 1024) + 2048;
     WgShiftPlan sw;
     if (make_wg_shift_plan(*g, device, &sw)) {
         const size_t ns = align_up(sw.xp_bytes, 1024) + align_up(sw.gyv_bytes, 1024) + align_up(sw.partial_bytes, 1024) + 2048;
@@ -2306,6 +2372,9 @@ int nn_umma_conv_wgrad(const nn_conv_wgrad_args* a, int device, cudaStream_t st)
         }
     }
     WgPlan w = make_wg_plan(g, device);
+    TmaWgradPlan tw;
+    const bool use_tma = nn_tma_wgrad_plan(g.Cin, g.KH, g.KW, g.stride, g.pad, g.Cout, (int64_t)g.B * OH * OW, device, &tw);
+    if (use_tma) w.partial_bytes = tw.partial_bytes;
     const size_t need = align_up(w.xp_bytes, 1024) + align_up(w.gyp_bytes, 1024) + align_up(w.partial_bytes, 1024) + 1024;
     if (!a->workspace || (size_t)a->workspace_bytes < need)
         return nn_fail("nn_noisy_conv_wgrad: workspace too small%s (need %lld bytes)", "", (long long)need);
@@ -2332,6 +2401,26 @@ int nn_umma_conv_wgrad(const nn_conv_wgrad_args* a, int device, cudaStream_t st)
         k_pack_act<<<grid, 256, 0, st>>>(a->gy, gyp, g.B, g.Cout, OH * OW, w.Coutp, 0.f);
         NN_LAUNCH_OK();
     }
+    const float scale = a->a_code_scale > 0.f ? a->a_code_scale : 1.f;
+    if (use_tma) {      // both operands staged by the copy engine (im2col / tiled tensor maps)
+        TmaWgradCall c;
+        memset(&c, 0, sizeof(c));
+        c.pl = tw;
+        c.B = g.B; c.H = g.H; c.W = g.W; c.OH = OH; c.OW = OW; c.KH = g.KH; c.KW = g.KW; c.stride = g.stride; c.pad = g.pad;
+        c.Cout = g.Cout; c.xp = xp; c.gyp = gyp; c.partial = partial; c.err_flag = nn_umma_err_flag(device);
+        if (nn_tma_wgrad_launch(c, device, st)) return 1;
+        const int64_t n = (int64_t)g.Cout * tw.cols_pad;
+        int nb_main = (int)((n + 255) / 256);
+        if (nb_main > 8 * sms) nb_main = 8 * sms;
+        int nb_tail = tw.tail_w ? (g.Cout * 256 + 31) / 32 : 0;
+        if (nb_tail > 8 * sms) nb_tail = 8 * sms;
+        const float* tail = tw.tail_w ? reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(partial) + tw.main_bytes) : nullptr;
+        k_wgrad_tma_reduce<<<nb_main + nb_tail, 256, 0, st>>>(partial, tw.splits, g.Cout, g.Cin, g.KH * g.KW, tw.n_c64, tw.cols_pad, nb_main,
+                                                              tail, tw.splits * tw.tiles_k, scale, a->gw, a->w_raw, (float)a->w_lo,
+                                                              (float)a->w_hi);
+        NN_LAUNCH_OK();
+        return 0;
+    }
     WgUP p;
     memset(&p, 0, sizeof(p));
     p.B = g.B; p.H = g.H; p.W = g.W; p.Cp = w.Cp; p.KH = g.KH; p.KW = g.KW; p.stride = g.stride; p.pad = g.pad;
@@ -2346,7 +2435,6 @@ int nn_umma_conv_wgrad(const nn_conv_wgrad_args* a, int device, cudaStream_t st)
     k_wgrad_umma<<<grid, UM_THREADS, w.smem_bytes, st>>>(p);
     NN_LAUNCH_OK();
     const int64_t n = (int64_t)g.Cout * w.ktot_pad;
-    const float scale = a->a_code_scale > 0.f ? a->a_code_scale : 1.f;
     if (w.splits >= 64) {       // many splits, few columns (conv1): shorten the serial chain over splits 8x
         int rb = (int)((n + 31) / 32);
         if (rb > 16 * sms) rb = 16 * sms;

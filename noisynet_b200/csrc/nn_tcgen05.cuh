@@ -245,6 +245,10 @@ __device__ __forceinline__ void tma_im2col_4d_2cta(uint32_t dst, const void* map
     asm volatile("cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
                  ::"r"(dst), "l"(map), "r"(bar & NN_PEER_BIT_MASK), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
 }
+__device__ __forceinline__ void tma_tile_2d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_tile_2d_2cta(uint32_t dst, const void* map, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar & NN_PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");

@@ -17,3 +17,10 @@ gy = torch.randn_like(r["y_noisy"])
 for _ in range(3):
     ops.conv_dgrad(gy, wq, x.shape, precision="bf16", w_code_scale=1.0 / 15.0)
 torch.cuda.synchronize()
+for _ in range(3):
+    ops.conv_wgrad(gy, x, wq.shape, precision="bf16", a_code_scale=s_a)
+xf = torch.randint(0, 16, (B, 3000, 1, 1), device=dev).float() * s_a
+gyf = torch.randn(B, 390, 1, 1, device=dev)
+for _ in range(3):
+    ops.conv_wgrad(gyf, xf, (390, 3000, 1, 1), precision="bf16", a_code_scale=s_a)
+torch.cuda.synchronize()
