@@ -1372,58 +1372,79 @@ k_wgrad_umma_reduce(const float* __restrict__ partial, int splits, int Cout, int
 
 // partials of k_wgrad_tma -> gw [Cout][Cin][KHW], scale, STE mask.  Fixed summation order: deterministic.
 //   main [splits][Cout][cols_pad]:       column = (tap * n_c64 + chunk) * 64 + e   <->  channel chunk * 64 + e
-//     blocks [0, nb_main): one thread per (n, column), four independent partial chains
 //   tail [n_tail][Cout][256] (optional): column = tap * 8 + e                      <->  channel n_c64 * 64 + e
-//     blocks [nb_main, ...): 32 columns x 8 groups of partials (n_tail = splits x column tiles is large), as k_wgrad_umma_reduce2
+// One thread = four consecutive columns (float4 loads) of one group of partials; a block = (256 / G) column quads x G
+// groups, the G group sums are added in fixed order through shared memory.  G is picked per region so that each has
+// ~10^5 threads with a handful of independent 16-byte loads each (the partials sit in L2: the kernel is latency-bound).
+struct WgRedP {
+    const float *main, *tail;
+    int splits, n_tail, Cout, Cin, KHW, n_c64, cols_pad, nb_main, g_main, g_tail;
+    float scale, lo, hi;
+    float* gw;
+    const float* w_raw;
+};
+
 __global__ void __launch_bounds__(256)
-k_wgrad_tma_reduce(const float* __restrict__ partial, int splits, int Cout, int Cin, int KHW, int n_c64, int cols_pad, int nb_main,
-                   const float* __restrict__ tail, int n_tail, float scale, float* __restrict__ gw, const float* __restrict__ w_raw,
-                   float lo, float hi) {
-    __shared__ float sh[8][32];
-    if ((int)blockIdx.x >= nb_main) {
-        const unsigned total = (unsigned)Cout * 256u;
-        const size_t zstride = (size_t)Cout * 256;
-        const int col = threadIdx.x & 31, grp = threadIdx.x >> 5;
-        for (unsigned b0 = (blockIdx.x - nb_main) * 32u; b0 < total; b0 += (gridDim.x - nb_main) * 32u) {
-            const unsigned i = b0 + col;
-            const int n = (int)(i >> 8), ct = (int)(i & 255u), tap = ct >> 3, c = n_c64 * 64 + (ct & 7);
-            const bool live = tap < KHW && c < Cin;            // uniform per 8 columns; whole 32-column groups are often dead
-            float s = 0.f;
-            if (live)
-                for (int z = grp; z < n_tail; z += 8) s += tail[(size_t)z * zstride + i];
-            sh[grp][col] = s;
-            __syncthreads();
-            if (grp == 0 && live) {
-                float t = sh[0][col];
-#pragma unroll
-                for (int g = 1; g < 8; ++g) t += sh[g][col];
-                t *= scale;
-                const size_t o = ((size_t)n * Cin + c) * KHW + tap;
-                if (w_raw) { const float w = __ldg(w_raw + o); if (w > hi || w < lo) t = 0.f; }
-                gw[o] = t;
-            }
-            __syncthreads();
+k_wgrad_tma_reduce(const WgRedP p) {
+    __shared__ float4 sh[256];
+    const bool is_tail = (int)blockIdx.x >= p.nb_main;
+    const int G = is_tail ? p.g_tail : p.g_main, qpb = 256 / G;                  // G: power of two <= 32
+    const int row = is_tail ? 256 : p.cols_pad, cnt = is_tail ? p.n_tail : p.splits;
+    const float* src0 = is_tail ? p.tail : p.main;
+    const int g = threadIdx.x / qpb, ql = threadIdx.x - g * qpb;
+    const int quad = ((int)blockIdx.x - (is_tail ? p.nb_main : 0)) * qpb + ql;
+    const int quads_row = row >> 2, total = p.Cout * quads_row;
+    const size_t zstride = (size_t)p.Cout * row;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int n = 0, col = 0, tap = 0, c0 = 0;
+    bool live = false;
+    if (quad < total) {
+        n = quad / quads_row; col = (quad - n * quads_row) * 4;
+        if (is_tail) { tap = col >> 3; c0 = p.n_c64 * 64 + (col & 7); }
+        else { const int ga = col >> 6; tap = ga / p.n_c64; c0 = (ga - tap * p.n_c64) * 64 + (col & 63); }
+        live = tap < p.KHW && c0 < p.Cin;
+    }
+    if (live) {
+        const float4* src = reinterpret_cast<const float4*>(src0 + (size_t)n * row + col);
+        const size_t zs4 = zstride >> 2;
+        int z = g;
+        for (; z + 3 * G < cnt; z += 4 * G) {
+            const float4 a = __ldcg(src + (size_t)z * zs4), b = __ldcg(src + (size_t)(z + G) * zs4);
+            const float4 c = __ldcg(src + (size_t)(z + 2 * G) * zs4), d = __ldcg(src + (size_t)(z + 3 * G) * zs4);
+            s.x += (a.x + b.x) + (c.x + d.x); s.y += (a.y + b.y) + (c.y + d.y);
+            s.z += (a.z + b.z) + (c.z + d.z); s.w += (a.w + b.w) + (c.w + d.w);
         }
+        for (; z < cnt; z += G) { const float4 a = __ldcg(src + (size_t)z * zs4); s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w; }
+    }
+    if (G > 1) {
+        sh[threadIdx.x] = s;
+        __syncthreads();
+        if (g != 0) return;
+        for (int k = 1; k < G; ++k) { const float4 a = sh[k * qpb + ql]; s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w; }
+    }
+    if (!live) return;
+    if (p.KHW == 1 && (p.Cin & 3) == 0 && (((uintptr_t)p.gw | (uintptr_t)p.w_raw) & 15) == 0) {
+        // fully connected layers: the four columns are contiguous in gw
+        const size_t o = (size_t)n * p.Cin + c0;
+        float4 t = make_float4(s.x * p.scale, s.y * p.scale, s.z * p.scale, s.w * p.scale);
+        if (p.w_raw) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(p.w_raw + o));
+            if (w.x > p.hi || w.x < p.lo) t.x = 0.f;
+            if (w.y > p.hi || w.y < p.lo) t.y = 0.f;
+            if (w.z > p.hi || w.z < p.lo) t.z = 0.f;
+            if (w.w > p.hi || w.w < p.lo) t.w = 0.f;
+        }
+        *reinterpret_cast<float4*>(p.gw + o) = t;
         return;
     }
-    const unsigned total = (unsigned)Cout * cols_pad;
-    const size_t zstride = (size_t)Cout * cols_pad;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nb_main * blockDim.x) {
-        const int n = (int)(i / cols_pad), col = (int)(i - (unsigned)n * cols_pad);
-        const int ga = col >> 6, tap = ga / n_c64, c = (ga - tap * n_c64) * 64 + (col & 63);
-        if (tap >= KHW || c >= Cin) continue;
-        const float* src = partial + i;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int z = 0;
-        for (; z + 3 < splits; z += 4) {
-            s0 += src[(size_t)z * zstride]; s1 += src[(size_t)(z + 1) * zstride];
-            s2 += src[(size_t)(z + 2) * zstride]; s3 += src[(size_t)(z + 3) * zstride];
-        }
-        for (; z < splits; ++z) s0 += src[(size_t)z * zstride];
-        float sum = ((s0 + s1) + (s2 + s3)) * scale;
-        const size_t o = ((size_t)n * Cin + c) * KHW + tap;
-        if (w_raw) { const float w = __ldg(w_raw + o); if (w > hi || w < lo) sum = 0.f; }
-        gw[o] = sum;
+    const float v[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        if (c0 + e >= p.Cin) break;
+        float t = v[e] * p.scale;
+        const size_t o = ((size_t)n * p.Cin + c0 + e) * p.KHW + tap;
+        if (p.w_raw) { const float w = __ldg(p.w_raw + o); if (w > p.hi || w < p.lo) t = 0.f; }
+        p.gw[o] = t;
     }
 }
 
@@ -2409,15 +2430,23 @@ int nn_umma_conv_wgrad(const nn_conv_wgrad_args* a, int device, cudaStream_t st)
         c.B = g.B; c.H = g.H; c.W = g.W; c.OH = OH; c.OW = OW; c.KH = g.KH; c.KW = g.KW; c.stride = g.stride; c.pad = g.pad;
         c.Cout = g.Cout; c.xp = xp; c.gyp = gyp; c.partial = partial; c.err_flag = nn_umma_err_flag(device);
         if (nn_tma_wgrad_launch(c, device, st)) return 1;
-        const int64_t n = (int64_t)g.Cout * tw.cols_pad;
-        int nb_main = (int)((n + 255) / 256);
-        if (nb_main > 8 * sms) nb_main = 8 * sms;
-        int nb_tail = tw.tail_w ? (g.Cout * 256 + 31) / 32 : 0;
-        if (nb_tail > 8 * sms) nb_tail = 8 * sms;
-        const float* tail = tw.tail_w ? reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(partial) + tw.main_bytes) : nullptr;
-        k_wgrad_tma_reduce<<<nb_main + nb_tail, 256, 0, st>>>(partial, tw.splits, g.Cout, g.Cin, g.KH * g.KW, tw.n_c64, tw.cols_pad, nb_main,
-                                                              tail, tw.splits * tw.tiles_k, scale, a->gw, a->w_raw, (float)a->w_lo,
-                                                              (float)a->w_hi);
+        WgRedP r;
+        memset(&r, 0, sizeof(r));
+        r.main = partial;
+        r.tail = tw.tail_w ? reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(partial) + tw.main_bytes) : nullptr;
+        r.splits = tw.splits; r.n_tail = tw.splits * tw.tiles_k; r.Cout = g.Cout; r.Cin = g.Cin; r.KHW = g.KH * g.KW; r.n_c64 = tw.n_c64;
+        r.cols_pad = tw.cols_pad; r.scale = scale; r.lo = (float)a->w_lo; r.hi = (float)a->w_hi; r.gw = a->gw; r.w_raw = a->w_raw;
+        auto groups = [](int64_t quads, int cnt) {      // ~128 k threads, at least ~4 partials per thread
+            int G = 1;
+            while (G < 32 && quads * G < 131072 && cnt >= 8 * G) G <<= 1;
+            return G;
+        };
+        const int64_t q_main = (int64_t)g.Cout * (tw.cols_pad / 4), q_tail = (int64_t)g.Cout * 64;
+        r.g_main = groups(q_main, r.splits);
+        r.g_tail = tw.tail_w ? groups(q_tail, r.n_tail) : 1;
+        r.nb_main = (int)((q_main + 256 / r.g_main - 1) / (256 / r.g_main));
+        const int nb_tail = tw.tail_w ? (int)((q_tail + 256 / r.g_tail - 1) / (256 / r.g_tail)) : 0;
+        k_wgrad_tma_reduce<<<r.nb_main + nb_tail, 256, 0, st>>>(r);
         NN_LAUNCH_OK();
         return 0;
     }

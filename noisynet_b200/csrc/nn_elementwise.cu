@@ -540,21 +540,20 @@ struct AdamWP {
     nn_adamw_tensor t[NN_ADAMW_MAX_TENSORS];
     int count;
     float beta1, beta2, eps, grad_scale;
-    const int64_t* step_dev;
-    const float* consts;                       // device: 1 - beta1^step, sqrt(1 - beta2^step) (written by k_step_inc)
+    int64_t* step_dev;                         // the step counter: read by every block, incremented by the last one
+    unsigned* ctl;                             // per-device control words, see AW_*
     int first_block[NN_ADAMW_MAX_TENSORS];     // first 1024-element slab of each tensor in the flat block list
 };
+// control words: [0] arrival ticket (self-resetting); [4 + 4 * parity + {0,1,2}] the two bias-correction constants of a
+// step and the step they belong to, double-buffered by step parity; [16 + 32 * parity + tensor] max|w| bits of the tensor
+constexpr int AW_CONST = 4, AW_MAX = 16, AW_WORDS = 16 + 2 * 32;
+static_assert(NN_ADAMW_MAX_TENSORS <= 32, "control block layout");
 
-// step += 1 and the two bias-correction constants of the step, once (not per block): consts[0] = 1 - beta1^step,
-// consts[1] = sqrt(1 - beta2^step)
-__global__ void k_step_inc(int64_t* s, float beta1, float beta2, float* consts) {
-    *s += 1;
-    const double step = (double)(*s);
-    consts[0] = (float)(1.0 - pow((double)beta1, step));
-    consts[1] = (float)sqrt(1.0 - pow((double)beta2, step));
-}
-
-// blockIdx.x enumerates the 1024-element slabs of all tensors back to back (first_block[i] = first slab of tensor i)
+// blockIdx.x enumerates the 1024-element slabs of all tensors back to back (first_block[i] = first slab of tensor i).
+// ONE launch per step, no memset nodes: the bias-correction constants of step s are prepared during step s - 1 (by its
+// block 0, off the critical path: two fp64 pow); max|w| is an atomic max on the floats' bit patterns (order-independent,
+// so deterministic) into the parity slot that the previous step's last block cleared; the last block to finish publishes
+// the maxima, clears the other slot and advances the counter.
 __global__ void __launch_bounds__(256)
 k_adamw(const AdamWP p) {
     int ti = 0;
@@ -562,7 +561,28 @@ k_adamw(const AdamWP p) {
     const nn_adamw_tensor t = p.t[ti];
     const int64_t base = (int64_t)((int)blockIdx.x - p.first_block[ti]) * blockDim.x * 4;
     __shared__ float s_red[8];
-    const float step_size = (float)((double)t.lr / (double)p.consts[0]), bc2s = p.consts[1];
+    __shared__ float s_c[2];
+    __shared__ int s_par, s_last;
+    if (threadIdx.x == 0) {
+        const int64_t step = *p.step_dev + 1;
+        const int par = (int)(step & 1);
+        const float* cs = reinterpret_cast<const float*>(p.ctl + AW_CONST + 4 * par);
+        if (__float_as_int(__ldcg(cs + 2)) == (int)step) {     // the usual case: two loads instead of two fp64 pow per block
+            s_c[0] = __ldcg(cs); s_c[1] = __ldcg(cs + 1);
+        } else {                                                // first launch, or the counter was set from outside (checkpoint)
+            s_c[0] = (float)(1.0 - pow((double)p.beta1, (double)step));
+            s_c[1] = (float)sqrt(1.0 - pow((double)p.beta2, (double)step));
+        }
+        s_par = par;
+        if (blockIdx.x == 0) {                                  // constants of the NEXT step into the other slot
+            float* nx = reinterpret_cast<float*>(p.ctl + AW_CONST + 4 * (par ^ 1));
+            nx[0] = (float)(1.0 - pow((double)p.beta1, (double)(step + 1)));
+            nx[1] = (float)sqrt(1.0 - pow((double)p.beta2, (double)(step + 1)));
+            nx[2] = __int_as_float((int)(step + 1));
+        }
+    }
+    __syncthreads();
+    const float step_size = (float)((double)t.lr / (double)s_c[0]), bc2s = s_c[1];
     const float decay = 1.0f - t.lr * t.weight_decay;
     const float om1 = 1.0f - p.beta1, om2 = 1.0f - p.beta2;
     float amax = 0.f;
@@ -582,17 +602,29 @@ k_adamw(const AdamWP p) {
             amax = fmaxf(amax, fabsf(w));
         }
     }
-    if (t.absmax_out) {
-        amax = nn_warp_max(amax);
-        const int wi = threadIdx.x >> 5, l = threadIdx.x & 31;
-        if (l == 0) s_red[wi] = amax;
-        __syncthreads();
-        if (wi == 0) {
-            amax = (l < 8) ? s_red[l] : 0.f;
-            amax = nn_warp_max(amax);
-            if (l == 0) nn_atomic_max_float(t.absmax_out, amax);
-        }
+    const int wi = threadIdx.x >> 5, l = threadIdx.x & 31;
+    amax = nn_warp_max(amax);
+    if (l == 0) s_red[wi] = amax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float bm = s_red[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) bm = fmaxf(bm, s_red[w]);
+        unsigned* mx = p.ctl + AW_MAX + 32 * s_par;
+        if (t.absmax_out && bm > 0.f) atomicMax(mx + ti, __float_as_uint(bm));      // bm >= 0: bit order == value order
+        __threadfence();
+        s_last = atomicAdd(p.ctl, 1u) == gridDim.x - 1;
     }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if ((int)threadIdx.x < p.count) {
+        unsigned* mx = p.ctl + AW_MAX + 32 * s_par;
+        if (p.t[threadIdx.x].absmax_out) *p.t[threadIdx.x].absmax_out = __uint_as_float(__ldcg(mx + threadIdx.x));
+        p.ctl[AW_MAX + 32 * (s_par ^ 1) + threadIdx.x] = 0u;         // the next step's slot
+        mx[threadIdx.x] = 0u;                                        // (and this one, for a step counter set from outside)
+    }
+    if (threadIdx.x == 0) { p.ctl[0] = 0u; *p.step_dev += 1; }
 }
 
 extern "C" int nn_adamw_step(const nn_adamw_tensor* tensors, int count, float beta1, float beta2, float eps,
@@ -603,20 +635,20 @@ extern "C" int nn_adamw_step(const nn_adamw_tensor* tensors, int count, float be
     NN_SET_DEVICE(device);
     AdamWP p;
     p.count = count; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.grad_scale = grad_scale; p.step_dev = step_dev;
-    static float* consts[64] = {nullptr};
     if (device < 0 || device >= 64) return nn_fail("nn_adamw_step: bad device%s", "");
-    if (!consts[device]) NN_CUDA_OK(cudaMalloc(&consts[device], 2 * sizeof(float)));
-    p.consts = consts[device];
     int blocks = 0;
     for (int i = 0; i < count; ++i) {
         p.t[i] = tensors[i];
         p.first_block[i] = blocks;
         blocks += (int)((tensors[i].n + 1023) / 1024);
-        if (tensors[i].absmax_out) NN_CUDA_OK(cudaMemsetAsync(tensors[i].absmax_out, 0, sizeof(float), (cudaStream_t)stream));
     }
-    k_step_inc<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, beta1, beta2, consts[device]);
-    NN_LAUNCH_OK();
-    if (blocks == 0) return 0;
+    if (blocks == 0) return nn_fail("nn_adamw_step: empty tensors%s", "");
+    static unsigned* ctl[64] = {nullptr};        // allocated by the first (uncaptured) step of a device
+    if (!ctl[device]) {
+        NN_CUDA_OK(cudaMalloc(&ctl[device], AW_WORDS * sizeof(unsigned)));
+        NN_CUDA_OK(cudaMemset(ctl[device], 0, AW_WORDS * sizeof(unsigned)));
+    }
+    p.ctl = ctl[device];
     k_adamw<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
     NN_LAUNCH_OK();
     return 0;

@@ -35,12 +35,53 @@ __device__ __forceinline__ float quant_code(float v, float s, float qmax, float 
     return rintf(fminf(fmaxf(t, 0.f), qmax));
 }
 
+// The per-channel reductions end in the LAST slice's block of each channel (a self-resetting arrival counter behind the
+// partials): it adds the slices in fixed order -- deterministic whichever block happens to be last -- and writes the
+// statistics, so no separate finalize launch sits on the step's critical path.
+struct BnFinP {
+    double count;
+    float eps, momentum;
+    float *mean, *invstd, *running_mean, *running_var, *xmax_out;
+    int eval_mode;
+};
+
+__device__ __forceinline__ bool stage_last_slice(unsigned* counters, int c, int slices) {
+    __threadfence();                                   // this block's partial is visible before its arrival
+    const unsigned done = atomicAdd(counters + c, 1u);
+    if (done != (unsigned)slices - 1u) return false;
+    counters[c] = 0u;                                  // ready for the next launch that uses this scratch
+    __threadfence();
+    return true;
+}
+
+// mean / invstd (biased var) + running stats update (momentum, unbiased var), noisynet.py:1560-1567 for eval
+__device__ __forceinline__ void bn_finalize_channel(const double* partial, int splits, int c, const BnFinP& f) {
+    if (f.eval_mode) {          // model.eval(): normalise with the running statistics, update nothing
+        f.mean[c] = f.running_mean[c];
+        f.invstd[c] = (float)(1.0 / sqrt((double)f.running_var[c] + (double)f.eps));
+        return;
+    }
+    double s1 = 0, s2 = 0;
+    for (int s = 0; s < splits; ++s) { s1 += __ldcg(partial + ((int64_t)c * splits + s) * 2); s2 += __ldcg(partial + ((int64_t)c * splits + s) * 2 + 1); }
+    const double m = s1 / f.count;
+    double var = s2 / f.count - m * m;
+    if (var < 0) var = 0;
+    f.mean[c] = (float)m;
+    f.invstd[c] = (float)(1.0 / sqrt(var + (double)f.eps));
+    if (f.running_mean) {
+        const double unb = f.count > 1 ? var * f.count / (f.count - 1) : var;
+        f.running_mean[c] = (float)((1.0 - f.momentum) * f.running_mean[c] + f.momentum * m);
+        f.running_var[c] = (float)((1.0 - f.momentum) * f.running_var[c] + f.momentum * unb);
+    }
+}
+
 // ------------------------------------------------------------------ F1: 2x2 max pool + per-channel partial sums
 // grid (C, ST_SPLITS); block 256.  y [B,C,OH,OW] -> pooled [B,C,PH,PW], argmax (0..3), partial [C][SPLITS][2] (double)
 __global__ void __launch_bounds__(256)
 k_pool_stats(const float* __restrict__ y, float* __restrict__ pooled, uint8_t* __restrict__ amax, double* __restrict__ partial,
-             int B, int C, int OH, int OW) {
+             unsigned* __restrict__ counters, const BnFinP fin, int B, int C, int OH, int OW) {
     const int c = blockIdx.x, sp = blockIdx.y;
+    if (c == 0 && sp == 0 && threadIdx.x == 0 && fin.xmax_out) *fin.xmax_out = 0.f;      // the pack kernel that follows maxes into it
     const int PH = OH >> 1, PW = OW >> 1, PHW = PH * PW;
     const int b0 = (int)((int64_t)B * sp / (int)gridDim.y), b1 = (int)((int64_t)B * (sp + 1) / (int)gridDim.y);
     const int n = (b1 - b0) * PHW;
@@ -83,13 +124,16 @@ k_pool_stats(const float* __restrict__ y, float* __restrict__ pooled, uint8_t* _
         for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
         partial[((int64_t)c * gridDim.y + sp) * 2 + 0] = a;
         partial[((int64_t)c * gridDim.y + sp) * 2 + 1] = b;
+        if (stage_last_slice(counters, c, (int)gridDim.y)) bn_finalize_channel(partial, (int)gridDim.y, c, fin);
     }
 }
 
 // statistics only (fc stages / no pooling): x [B,C,HW]
 __global__ void __launch_bounds__(256)
-k_chan_stats(const float* __restrict__ x, double* __restrict__ partial, int B, int C, int HW) {
+k_chan_stats(const float* __restrict__ x, double* __restrict__ partial, unsigned* __restrict__ counters, const BnFinP fin,
+             int B, int C, int HW) {
     const int c = blockIdx.x, sp = blockIdx.y;
+    if (c == 0 && sp == 0 && threadIdx.x == 0 && fin.xmax_out) *fin.xmax_out = 0.f;
     const int b0 = (int)((int64_t)B * sp / (int)gridDim.y), b1 = (int)((int64_t)B * (sp + 1) / (int)gridDim.y);
     const int n = (b1 - b0) * HW;
     double s1 = 0.0, s2 = 0.0;
@@ -111,32 +155,7 @@ k_chan_stats(const float* __restrict__ x, double* __restrict__ partial, int B, i
         for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
         partial[((int64_t)c * gridDim.y + sp) * 2 + 0] = a;
         partial[((int64_t)c * gridDim.y + sp) * 2 + 1] = b;
-    }
-}
-
-// finalize BN statistics: mean / invstd (biased var) + running stats update (momentum, unbiased var)
-__global__ void k_bn_finalize(const double* __restrict__ partial, int splits, int C, double count, float eps, float momentum,
-                              float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
-                              float* __restrict__ running_var, float* __restrict__ xmax_out, int eval_mode) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && xmax_out) *xmax_out = 0.f;
-    if (c >= C) return;
-    if (eval_mode) {          // model.eval(): normalise with the running statistics, update nothing (noisynet.py:1560-1567)
-        mean[c] = running_mean[c];
-        invstd[c] = (float)(1.0 / sqrt((double)running_var[c] + (double)eps));
-        return;
-    }
-    double s1 = 0, s2 = 0;
-    for (int s = 0; s < splits; ++s) { s1 += partial[((int64_t)c * splits + s) * 2]; s2 += partial[((int64_t)c * splits + s) * 2 + 1]; }
-    const double m = s1 / count;
-    double var = s2 / count - m * m;
-    if (var < 0) var = 0;
-    mean[c] = (float)m;
-    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-    if (running_mean) {
-        const double unb = count > 1 ? var * count / (count - 1) : var;
-        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
-        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+        if (stage_last_slice(counters, c, (int)gridDim.y)) bn_finalize_channel(partial, (int)gridDim.y, c, fin);
     }
 }
 
@@ -249,6 +268,8 @@ k_bn_act_pack_lean(const BnActP p) {
 struct BnBwdP {
     const float *g, *x, *mean, *invstd, *gamma, *beta;
     double* partial;              // [C][SPLITS][2]
+    unsigned* counters;           // [C] arrivals (self-resetting)
+    float *dbeta, *dgamma;        // written by the last slice's block of each channel
     int B, C, HW;
     float act_max, q_hi;
 };
@@ -291,16 +312,14 @@ k_bn_bwd_stats(const BnBwdP p) {
         for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
         p.partial[((int64_t)c * gridDim.y + sp) * 2 + 0] = a;
         p.partial[((int64_t)c * gridDim.y + sp) * 2 + 1] = b;
+        if (stage_last_slice(p.counters, c, (int)gridDim.y)) {
+            const int splits = (int)gridDim.y;
+            double s1 = 0, s2 = 0;
+            for (int s = 0; s < splits; ++s) { s1 += __ldcg(p.partial + ((int64_t)c * splits + s) * 2); s2 += __ldcg(p.partial + ((int64_t)c * splits + s) * 2 + 1); }
+            p.dbeta[c] = (float)s1;        // grads are OVERWRITTEN (the step zeroes them anyway)
+            p.dgamma[c] = (float)s2;
+        }
     }
-}
-
-__global__ void k_bn_bwd_finalize(const double* __restrict__ partial, int splits, int C, float* __restrict__ dbeta, float* __restrict__ dgamma) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s1 = 0, s2 = 0;
-    for (int s = 0; s < splits; ++s) { s1 += partial[((int64_t)c * splits + s) * 2]; s2 += partial[((int64_t)c * splits + s) * 2 + 1]; }
-    dbeta[c] = (float)s1;        // grads are OVERWRITTEN (the step zeroes them anyway)
-    dgamma[c] = (float)s2;
 }
 
 // ------------------------------------------------------------------ B2: BN backward + max-pool routing -> NHWC bf16
@@ -977,7 +996,8 @@ static inline int grid_cap(int64_t items, int device, int waves = 8) {
 
 }  // namespace
 
-extern "C" int64_t nn_stage_scratch_bytes(int C) { return (int64_t)C * ST_SPLITS * 2 * sizeof(double); }
+// [C][ST_SPLITS][2] double partial sums, then [C] arrival counters
+extern "C" int64_t nn_stage_scratch_bytes(int C) { return (int64_t)C * ST_SPLITS * 2 * sizeof(double) + (int64_t)((C + 3) / 4 * 4) * sizeof(unsigned); }
 
 extern "C" int nn_stage_fwd(const nn_stage_args* a, int device, void* stream) {
     if (!a || !a->in || !a->xp || !a->scratch || !a->mean || !a->invstd)
@@ -990,24 +1010,27 @@ extern "C" int nn_stage_fwd(const nn_stage_args* a, int device, void* stream) {
     const float* bn_in = a->in;
     int HW = a->H * a->W;
     double* partial = (double*)a->scratch;
+    unsigned* counters = (unsigned*)(partial + (size_t)a->C * ST_SPLITS * 2);
     int splits = ST_SPLITS;
+    BnFinP fin;
+    fin.eps = a->eps; fin.momentum = a->momentum; fin.mean = a->mean; fin.invstd = a->invstd; fin.running_mean = a->running_mean;
+    fin.running_var = a->running_var; fin.xmax_out = a->xmax_out; fin.eval_mode = a->eval_mode;
     if (a->pool) {
         if (!a->pooled || !a->argmax) return nn_fail("nn_stage_fwd: pooled/argmax buffers missing%s", "");
         HW = (a->H / 2) * (a->W / 2);
         splits = stage_splits((int64_t)a->B * HW);
         dim3 grid(a->C, splits);
-        k_pool_stats<<<grid, 256, 0, st>>>(a->in, a->pooled, a->argmax, partial, a->B, a->C, a->H, a->W);
+        fin.count = (double)a->B * HW;
+        k_pool_stats<<<grid, 256, 0, st>>>(a->in, a->pooled, a->argmax, partial, counters, fin, a->B, a->C, a->H, a->W);
         NN_LAUNCH_OK();
         bn_in = a->pooled;
     } else {
         splits = stage_splits((int64_t)a->B * HW);
         dim3 grid(a->C, splits);
-        k_chan_stats<<<grid, 256, 0, st>>>(a->in, partial, a->B, a->C, HW);
+        fin.count = (double)a->B * HW;
+        k_chan_stats<<<grid, 256, 0, st>>>(a->in, partial, counters, fin, a->B, a->C, HW);
         NN_LAUNCH_OK();
     }
-    k_bn_finalize<<<(a->C + 127) / 128, 128, 0, st>>>(partial, splits, a->C, (double)a->B * HW, a->eps, a->momentum, a->mean,
-                                                      a->invstd, a->running_mean, a->running_var, a->xmax_out, a->eval_mode);
-    NN_LAUNCH_OK();
     BnActP p;
     p.x = bn_in; p.mean = a->mean; p.invstd = a->invstd; p.gamma = a->gamma; p.beta = a->beta; p.u_inject = a->u_inject;
     p.xp = (__nv_bfloat16*)a->xp; p.act = a->act; p.xmax_out = a->xmax_out;
@@ -1033,13 +1056,12 @@ extern "C" int nn_stage_bwd(const nn_stage_bwd_args* a, int device, void* stream
     const int PH = a->pool ? a->H / 2 : a->H, PW = a->pool ? a->W / 2 : a->W;
     BnBwdP q;
     q.g = a->g; q.x = a->x; q.mean = a->mean; q.invstd = a->invstd; q.gamma = a->gamma; q.beta = a->beta;
-    q.partial = (double*)a->scratch; q.B = a->B; q.C = a->C; q.HW = PH * PW; q.act_max = a->act_max;
+    q.partial = (double*)a->scratch; q.counters = (unsigned*)(q.partial + (size_t)a->C * ST_SPLITS * 2);
+    q.dbeta = a->dbeta; q.dgamma = a->dgamma; q.B = a->B; q.C = a->C; q.HW = PH * PW; q.act_max = a->act_max;
     q.q_hi = a->q_bits > 0 ? (float)a->q_hi : 0.f;
     const int splits = stage_splits((int64_t)a->B * PH * PW);
     dim3 grid(a->C, splits);
     k_bn_bwd_stats<<<grid, 256, 0, st>>>(q);
-    NN_LAUNCH_OK();
-    k_bn_bwd_finalize<<<(a->C + 127) / 128, 128, 0, st>>>(q.partial, splits, a->C, a->dbeta, a->dgamma);
     NN_LAUNCH_OK();
     BnBwdApplyP p;
     p.g = a->g; p.x = a->x; p.mean = a->mean; p.invstd = a->invstd; p.gamma = a->gamma; p.beta = a->beta;
