@@ -680,11 +680,12 @@ k_conv_shift(const ShiftP p) {
             } else
             // 4-channel groups (one Philox call each), dealt round-robin to the warps of this lane quarter; the deal
             // rotates with the tile so that an uneven group count (17 for 65 channels) averages out across tiles
-            for (int g4 = (jq + i) % per_q; g4 < ngrp; g4 += per_q) {
+            {
+            auto one_group = [&](int g4) {
                 float am[4], as[4];
                 if (NOISY) tmem_ld4x2(t_lane + (uint32_t)(p.main_col + g4 * 4), t_lane + (uint32_t)(p.sig_col + g4 * 4), am, as);
                 else tmem_ld4(t_lane + (uint32_t)(p.main_col + g4 * 4), am);
-                if (!row_ok) continue;
+                if (!row_ok) return;
                 const int nb = g4 * 4;
                 float z[4];
                 if (MODE == 1) nn_normal4(rs, grp_row + (uint64_t)g4, z);
@@ -699,7 +700,7 @@ k_conv_shift(const ShiftP p) {
                         st_global_f32(o_run, NOISY ? __fadd_rn(yv, __fmul_rn(z[j], nn_sigma(coef, as[j] * s_scale))) : yv);
                         o_run += ohw;
                     }
-                    continue;
+                    return;
                 }
                 const int nvalid = min(4, p.Cout - nb);
                 float* oy = out_y ? out_y + (size_t)nb * ohw : nullptr;
@@ -717,6 +718,34 @@ k_conv_shift(const ShiftP p) {
                         }
                     }
                 }
+            };
+            const bool hot = MODE == 1 && out_y == nullptr;
+            for (int g4 = (jq + i) % per_q; g4 < ngrp; g4 += 2 * per_q) {
+                const int g4b = g4 + per_q;
+                if (hot && g4b * 4 + 4 <= p.Cout) {
+                    // two groups per trip: one TMEM wait for both, and two independent Philox / Box-Muller chains for the
+                    // scheduler to interleave (the epilogue is latency-bound: one chain per warp left it at ~0.3 IPC)
+                    float am[4], as[4], bm[4], bs[4];
+                    tmem_ld4x4(t_lane + (uint32_t)(p.main_col + g4 * 4), t_lane + (uint32_t)(p.sig_col + g4 * 4),
+                               t_lane + (uint32_t)(p.main_col + g4b * 4), t_lane + (uint32_t)(p.sig_col + g4b * 4), am, as, bm, bs);
+                    if (!row_ok) continue;
+                    float za[4], zb[4];
+                    nn_normal4(rs, grp_row + (uint64_t)g4, za);
+                    nn_normal4(rs, grp_row + (uint64_t)g4b, zb);
+                    float* oa = out_main + (size_t)(g4 * 4) * ohw;
+                    float* ob = out_main + (size_t)(g4b * 4) * ohw;
+                    asm volatile("" : "+l"(oa), "+l"(ob));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        st_global_f32(oa, __fadd_rn(am[j] * y_scale, __fmul_rn(za[j], nn_sigma(coef, as[j] * s_scale))));
+                        st_global_f32(ob, __fadd_rn(bm[j] * y_scale, __fmul_rn(zb[j], nn_sigma(coef, bs[j] * s_scale))));
+                        oa += ohw; ob += ohw;
+                    }
+                    continue;
+                }
+                one_group(g4);
+                if (g4b < ngrp) one_group(g4b);
+            }
             }
             tc_fence_before();
             __syncwarp();

@@ -139,7 +139,19 @@ k_chan_stats(const float* __restrict__ x, double* __restrict__ partial, unsigned
     double s1 = 0.0, s2 = 0.0;
     const unsigned step_b = blockDim.x / (unsigned)HW, step_r = blockDim.x - step_b * (unsigned)HW;
     unsigned bi = threadIdx.x / (unsigned)HW, r = threadIdx.x - bi * (unsigned)HW;
-    for (unsigned i = threadIdx.x; i < (unsigned)n; i += blockDim.x) {
+    unsigned i = threadIdx.x;
+    for (; i + 3 * blockDim.x < (unsigned)n; i += 4 * blockDim.x) {         // four loads in flight, sums in element order
+        float m[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            m[k] = __ldg(x + ((int64_t)(b0 + (int)bi) * C + c) * HW + r);
+            bi += step_b; r += step_r;
+            if (r >= (unsigned)HW) { r -= (unsigned)HW; ++bi; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s1 += m[k]; s2 += (double)m[k] * m[k]; }
+    }
+    for (; i < (unsigned)n; i += blockDim.x) {
         const int b = b0 + (int)bi;
         const float m = __ldg(x + ((int64_t)b * C + c) * HW + r);
         s1 += m; s2 += (double)m * m;
@@ -264,6 +276,65 @@ k_bn_act_pack_lean(const BnActP p) {
     }
 }
 
+// Tiled variant of the hot path for HW >= 32 (the conv stages): same arithmetic and the same Philox counter per (pixel,
+// chunk) as k_bn_act_pack_lean, but the thread mapping follows the memory instead of the output.  A block owns 32
+// consecutive pixels: lane = pixel, so every channel read is one 128-byte line of the NCHW input (the chunk-fastest
+// mapping touched 32 different lines per load instruction); the codes are staged in shared memory as the tile's NHWC
+// image and leave as one contiguous 32 x Cp x 2 byte run.  Measured at batch 512, 65 channels 14x14: 43.5 -> see DESIGN.
+__global__ void __launch_bounds__(256)
+k_bn_act_pack_tiled(const BnActP p) {
+    extern __shared__ uint4 s_tile[];                       // [32 pixels][pitch] 16-byte chunks
+    const NnRng rs = nn_rng_load(p.rng);
+    const unsigned chunks = (unsigned)(p.Cp >> 3), HW = (unsigned)p.HW, C = (unsigned)p.C;
+    const unsigned pitch = chunks | 1u;                      // odd pitch: conflict-free 16-byte column writes
+    const unsigned npix = (unsigned)p.B * HW;
+    const float act_hi = p.act_max > 0.f ? p.act_max : __int_as_float(0x7f800000);
+    const float two_s = __fmul_rn(2.0f, p.stoch), q_scale = p.q_scale, q_max = p.q_max, stoch = p.stoch;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    float vmax = 0.f;
+    for (unsigned tile = blockIdx.x; tile * 32u < npix; tile += gridDim.x) {
+        const unsigned pixel = tile * 32u + lane;
+        const bool pix_ok = pixel < npix;
+        const unsigned b = pixel / HW, r = pixel - b * HW;
+        for (unsigned chunk = warp; chunk < chunks; chunk += 8u) {
+            const unsigned c0 = chunk * 8u;
+            __align__(16) __nv_bfloat16 out[8];
+            if (pix_ok) {
+                const unsigned i = pixel * chunks + chunk;
+                const float* src = p.x + (b * C + c0) * HW + r;           // element index < 2^31 (host check)
+                const uint4 r0 = nn_philox(rs, (uint64_t)i * 2), r1 = nn_philox(rs, (uint64_t)i * 2 + 1);
+                const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (unsigned j = 0; j < 8; ++j) {
+                    float code = 0.f;
+                    const unsigned c = c0 + j;
+                    if (c < C) {
+                        float v = (__ldg(src + j * HW) - __ldg(p.mean + c)) * __ldg(p.invstd + c) * __ldg(p.gamma + c) + __ldg(p.beta + c);
+                        v = fminf(fmaxf(v, 0.f), act_hi);                                   // ReLU, clamp(max=act_max)
+                        const float u = __fadd_rn(__fmul_rn(nn_u01(rr[j]), two_s), -stoch);    // == nn_usym(rr[j], stoch)
+                        code = quant_code(v, q_scale, q_max, u);
+                        vmax = fmaxf(vmax, __fmul_rn(code, q_scale));
+                    }
+                    out[j] = __float2bfloat16_rn(code);
+                }
+                s_tile[lane * pitch + chunk] = *reinterpret_cast<const uint4*>(out);
+            }
+        }
+        __syncthreads();
+        const unsigned valid = min(32u, npix - tile * 32u) * chunks;        // 16-byte chunks of this tile's NHWC image
+        uint4* dst = reinterpret_cast<uint4*>(p.xp + (size_t)tile * 32u * p.Cp);
+        for (unsigned k = threadIdx.x; k < valid; k += 256u) {
+            const unsigned px = k / chunks, ch = k - px * chunks;
+            dst[k] = s_tile[px * pitch + ch];
+        }
+        __syncthreads();
+    }
+    if (p.xmax_out) {
+        vmax = nn_warp_max(vmax);
+        if ((threadIdx.x & 31) == 0 && vmax > 0.f) nn_atomic_max_float(p.xmax_out, vmax);
+    }
+}
+
 // ------------------------------------------------------------------ B1: masks + per-channel sums of dv, dv*xhat
 struct BnBwdP {
     const float *g, *x, *mean, *invstd, *gamma, *beta;
@@ -294,7 +365,24 @@ k_bn_bwd_stats(const BnBwdP p) {
     double s1 = 0.0, s2 = 0.0;
     const unsigned step_b = blockDim.x / (unsigned)p.HW, step_r = blockDim.x - step_b * (unsigned)p.HW;
     unsigned bi = threadIdx.x / (unsigned)p.HW, r = threadIdx.x - bi * (unsigned)p.HW;
-    for (unsigned i = threadIdx.x; i < (unsigned)n; i += blockDim.x) {
+    unsigned i = threadIdx.x;
+    for (; i + 3 * blockDim.x < (unsigned)n; i += 4 * blockDim.x) {         // eight loads in flight, sums in element order
+        float gv[4], xv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t o = ((int64_t)(b0 + (int)bi) * p.C + c) * p.HW + r;
+            gv[k] = __ldg(p.g + o); xv[k] = __ldg(p.x + o);
+            bi += step_b; r += step_r;
+            if (r >= (unsigned)p.HW) { r -= (unsigned)p.HW; ++bi; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float xhat;
+            const float dv = stage_dv(gv[k], xv[k], mean, invstd, gamma, beta, p.act_max, p.q_hi, xhat);
+            s1 += dv; s2 += (double)dv * xhat;
+        }
+    }
+    for (; i < (unsigned)n; i += blockDim.x) {
         const int b = b0 + (int)bi;
         const int64_t o = ((int64_t)b * p.C + c) * p.HW + r;
         float xhat;
@@ -1043,7 +1131,12 @@ extern "C" int nn_stage_fwd(const nn_stage_args* a, int device, void* stream) {
     const int64_t items = (int64_t)a->B * HW * (a->Cp / 8);
     const bool lean = ST_CHUNK_FAST && p.quant && p.stoch > 0.f && !p.u_inject && !p.act &&
                       (int64_t)a->B * a->C * HW < ((int64_t)1 << 31) && items < ((int64_t)1 << 31);
-    if (lean) k_bn_act_pack_lean<<<grid_cap(items, device), 256, 0, st>>>(p);
+    const size_t tile_smem = (size_t)32 * ((a->Cp / 8) | 1) * 16;
+    if (lean && HW >= 32 && tile_smem <= 48 * 1024) {
+        const int64_t tiles = ((int64_t)a->B * HW + 31) / 32;
+        const int64_t cap = (int64_t)nn_num_sms(device) * 16;
+        k_bn_act_pack_tiled<<<(int)(tiles < cap ? tiles : cap), 256, tile_smem, st>>>(p);
+    } else if (lean) k_bn_act_pack_lean<<<grid_cap(items, device), 256, 0, st>>>(p);
     else k_bn_act_pack<<<grid_cap(items, device), 256, 0, st>>>(p);
     NN_LAUNCH_OK();
     return 0;

@@ -204,6 +204,22 @@ __device__ __forceinline__ void tmem_ld4x2(uint32_t ta, uint32_t tb, float a[4],
 #pragma unroll
     for (int i = 0; i < 4; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[4 + i]); }
 }
+__device__ __forceinline__ void tmem_ld4x4(uint32_t ta, uint32_t tb, uint32_t tc, uint32_t td, float a[4], float b[4], float c[4], float d[4]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%16];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4,%5,%6,%7}, [%17];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%8,%9,%10,%11}, [%18];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%12,%13,%14,%15}, [%19];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(ta), "r"(tb), "r"(tc), "r"(td) : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[4 + i]); c[i] = __uint_as_float(r[8 + i]); d[i] = __uint_as_float(r[12 + i]);
+    }
+}
 // K-major SWIZZLE_NONE descriptor: core matrix = 8 rows x 16 B contiguous; lbo = distance between the two
 // K chunks of one MMA, sbo = distance between 8-row groups (both in 16-byte units).
 __device__ __forceinline__ uint64_t umma_desc_none(uint32_t smem_addr, uint32_t lbo_units, uint32_t sbo_units) {

@@ -114,6 +114,47 @@ def test_stage_fwd_bwd_vs_torch(dev, shape, pool):
     assert (packed - ref).abs().max().item() <= 4e-3 * ref.abs().max().item() + 1e-6       # bf16 rounding of the pack
 
 
+@pytest.mark.parametrize("shape,pool", [((7, 65, 28, 28), 1), ((5, 120, 10, 10), 1), ((3, 16, 12, 12), 0), ((40, 390, 1, 1), 0)])
+def test_stage_fwd_hot_path_kernels_match_general(dev, shape, pool):
+    """The training hot path (Philox stochastic rounding, no fp32 copy) runs k_bn_act_pack_tiled (HW >= 32) or
+    k_bn_act_pack_lean; asking for the fp32 copy routes the same call through the general kernel.  Same Philox counter
+    per (pixel, chunk) -> the packed codes must be bit-identical (ragged last tile, even/odd chunk counts)."""
+    from noisynet_b200 import _lib, ops
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11 + sum(shape))
+    B, Cc, H, W = shape
+    x = (torch.randn(shape, generator=g) * 1.5 + 0.3).to(dev)
+    gamma, beta = (torch.rand(Cc, generator=g) + 0.5).to(dev), (torch.randn(Cc, generator=g) * 0.5 + 0.5).to(dev)
+    PH, PW = (H // 2, W // 2) if pool else (H, W)
+    Cp = (Cc + 7) // 8 * 8
+    outs = []
+    for want_act in (False, True):
+        pooled = torch.empty(B, Cc, PH, PW, device=dev)
+        amax = torch.empty(B, Cc, PH, PW, dtype=torch.uint8, device=dev)
+        mean, invstd = torch.empty(Cc, device=dev), torch.empty(Cc, device=dev)
+        rm, rv = torch.zeros(Cc, device=dev), torch.ones(Cc, device=dev)
+        xp = torch.full((B, PH, PW, Cp), 7.0, dtype=torch.bfloat16, device=dev)
+        act = torch.empty(B, Cc, PH, PW, device=dev)
+        xmax = torch.zeros(1, device=dev)
+        scratch = torch.zeros(int(lib.nn_stage_scratch_bytes(Cc)) + 64, dtype=torch.uint8, device=dev)
+        a = _lib.StageArgs()
+        a.in_ = x.data_ptr(); a.B, a.C, a.H, a.W, a.pool = B, Cc, H, W, pool
+        a.pooled, a.argmax = pooled.data_ptr(), amax.data_ptr()
+        a.gamma, a.beta, a.running_mean, a.running_var = gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr()
+        a.momentum, a.eps = 0.1, 1e-5
+        a.mean, a.invstd = mean.data_ptr(), invstd.data_ptr()
+        a.act_max, a.q_bits, a.q_hi, a.stochastic = 5.0, 4, 4.0, 0.5
+        a.u_inject = None
+        a.rng = ops._fixed_rng(21, 4)
+        a.xp, a.Cp, a.act, a.xmax_out, a.scratch = xp.data_ptr(), Cp, act.data_ptr() if want_act else None, xmax.data_ptr(), scratch.data_ptr()
+        _lib.check(lib.nn_stage_fwd(C.byref(a), 0, torch.cuda.current_stream().cuda_stream), "nn_stage_fwd")
+        torch.cuda.synchronize()
+        outs.append((xp.float().cpu(), xmax.item()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert outs[0][1] == outs[1][1]
+    assert 0.0 < outs[0][0][..., :Cc].mean().item() < 15.0 and torch.all(outs[0][0][..., Cc:] == 0)
+
+
 @pytest.mark.parametrize("B", [200, 512, 37, 1500])      # 1500 > 1024 rows: the strided single-block kernel
 def test_head_vs_torch(dev, B):
     from noisynet_b200 import _lib
