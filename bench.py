@@ -510,15 +510,17 @@ def run_b200(args):
             k_ms = sum(tms) / len(tms)
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r1_conv2_fwd_traffic.json")) as f:
-                traffic = {"dram_bytes_per_launch": json.load(f)["dram_bytes_per_launch"], "unit": "B",
-                           "from": "profiles/r1_ncu_full_k_conv_umma_raw.csv (ncu --set full, batch 512)"} if B == 512 else None
+            with open(os.path.join(ROOT, "profiles", "r2_conv2_fwd_traffic.json")) as f:
+                tj = json.load(f)
+                traffic = {"dram_bytes_per_launch": tj["dram_bytes_per_launch"], "l2_to_sm_bytes_per_launch": tj["l2_to_sm_bytes"],
+                           "unit": "B", "from": tj["source"]} if (B == 512 and precision == "bf16") else None
         except Exception:
             traffic = None
         flops = FLOP_FWD["conv2"] * B
         achieved = flops / (k_ms * 1e-3) / 1e12
         peak = peaks.get("bf16_tflops", 1590.0)
-        roof = {"kernel": "fused noisy conv forward, conv2 (M=%d, N=2x120, K=1625), precision=%s" % (B * 100, precision),
+        roof = {"kernel": "k_conv_tma<1>: fused noisy conv forward of conv2 (M=%d, N=2x120, K=1625; persistent CTA pairs, "
+                          "TMA-im2col operands), precision=%s" % (B * 100, precision),
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_kind": peak_kind + " (burst, kernel timed alone)", "kernel_ms": k_ms,
                 "flop_per_launch": flops, "traffic": traffic,

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NN_ABI_VERSION 13
+#define NN_ABI_VERSION 14
 
 /* ---- common ---------------------------------------------------------------------- */
 
@@ -104,6 +104,12 @@ typedef struct nn_adamw_tensor {
 } nn_adamw_tensor;
 int nn_adamw_step(const nn_adamw_tensor* tensors, int count, float beta1, float beta2, float eps,
                   float grad_scale, int64_t* step_dev, int device, void* stream);
+/* The same update for a SUBSET of the step's tensors: launches with advance = 0 use step count *step_dev + 1 and leave
+ * the counter alone, the step's last launch passes advance = 1 (nn_adamw_step == advance 1).  Lets the engine update
+ * the layers whose gradients are final early (and already exchanged) under the rest of the backward pass; launches of
+ * one step must not overlap each other (they share the per-device control words). */
+int nn_adamw_step_part(const nn_adamw_tensor* tensors, int count, float beta1, float beta2, float eps,
+                       float grad_scale, int64_t* step_dev, int advance, int device, void* stream);
 
 /* ---- a7 (unfused form): y_noisy = y + z * sqrt(0.1 * (scale / I) * S) --------------- */
 /* hardware_model.py:59 / :81-83 / :125.  scale_dev: device scalar (max|W| merged DAC,

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NN_LIB_PATH") or os.path.join(_HERE, "lib", "libnoisynet_b200.so")   # NN_LIB_PATH: instrumented debug builds
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 NOISE_NONE, NOISE_MERGED, NOISE_EXTERNAL = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
@@ -123,6 +123,8 @@ SIGNATURES = {
     "nn_quantize_bwd_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
     "nn_weight_noise_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, Rng,
                                       C.c_int, C.c_void_p]),
+    "nn_adamw_step_part": (C.c_int, [C.POINTER(AdamWTensor), C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                    C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "nn_adamw_step": (C.c_int, [C.POINTER(AdamWTensor), C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_void_p, C.c_int, C.c_void_p]),
     "nn_weight_pack_bytes": (C.c_int64, [C.POINTER(WPrepJob)]),

@@ -541,6 +541,7 @@ struct AdamWP {
     int count;
     float beta1, beta2, eps, grad_scale;
     int64_t* step_dev;                         // the step counter: read by every block, incremented by the last one
+    int advance;                               // 0: a partial launch of the step (more tensors follow; the counter stays)
     unsigned* ctl;                             // per-device control words, see AW_*
     int first_block[NN_ADAMW_MAX_TENSORS];     // first 1024-element slab of each tensor in the flat block list
 };
@@ -567,18 +568,20 @@ k_adamw(const AdamWP p) {
         const int64_t step = *p.step_dev + 1;
         const int par = (int)(step & 1);
         const float* cs = reinterpret_cast<const float*>(p.ctl + AW_CONST + 4 * par);
-        if (__float_as_int(__ldcg(cs + 2)) == (int)step) {     // the usual case: two loads instead of two fp64 pow per block
+        const int tag = __float_as_int(p.beta1) ^ (__float_as_int(p.beta2) * 31);      // the slot is shared by every optimizer of the device
+        if (__float_as_int(__ldcg(cs + 2)) == (int)step && __float_as_int(__ldcg(cs + 3)) == tag) {     // usual case: no fp64 pow
             s_c[0] = __ldcg(cs); s_c[1] = __ldcg(cs + 1);
         } else {                                                // first launch, or the counter was set from outside (checkpoint)
             s_c[0] = (float)(1.0 - pow((double)p.beta1, (double)step));
             s_c[1] = (float)sqrt(1.0 - pow((double)p.beta2, (double)step));
         }
         s_par = par;
-        if (blockIdx.x == 0) {                                  // constants of the NEXT step into the other slot
+        if (blockIdx.x == 0 && p.advance) {                     // constants of the NEXT step into the other slot
             float* nx = reinterpret_cast<float*>(p.ctl + AW_CONST + 4 * (par ^ 1));
             nx[0] = (float)(1.0 - pow((double)p.beta1, (double)(step + 1)));
             nx[1] = (float)sqrt(1.0 - pow((double)p.beta2, (double)(step + 1)));
             nx[2] = __int_as_float((int)(step + 1));
+            nx[3] = __int_as_float(tag);
         }
     }
     __syncthreads();
@@ -624,17 +627,23 @@ k_adamw(const AdamWP p) {
         p.ctl[AW_MAX + 32 * (s_par ^ 1) + threadIdx.x] = 0u;         // the next step's slot
         mx[threadIdx.x] = 0u;                                        // (and this one, for a step counter set from outside)
     }
-    if (threadIdx.x == 0) { p.ctl[0] = 0u; *p.step_dev += 1; }
+    if (threadIdx.x == 0) { p.ctl[0] = 0u; if (p.advance) *p.step_dev += 1; }
 }
 
 extern "C" int nn_adamw_step(const nn_adamw_tensor* tensors, int count, float beta1, float beta2, float eps,
                              float grad_scale, int64_t* step_dev, int device, void* stream) {
+    return nn_adamw_step_part(tensors, count, beta1, beta2, eps, grad_scale, step_dev, 1, device, stream);
+}
+
+extern "C" int nn_adamw_step_part(const nn_adamw_tensor* tensors, int count, float beta1, float beta2, float eps,
+                                  float grad_scale, int64_t* step_dev, int advance, int device, void* stream) {
     if (count <= 0) return 0;
     if (count > NN_ADAMW_MAX_TENSORS) return nn_fail("nn_adamw_step: too many tensors%s (%lld)", "", count);
     if (!step_dev) return nn_fail("nn_adamw_step: step_dev missing%s", "");
     NN_SET_DEVICE(device);
     AdamWP p;
     p.count = count; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.grad_scale = grad_scale; p.step_dev = step_dev;
+    p.advance = advance ? 1 : 0;
     if (device < 0 || device >= 64) return nn_fail("nn_adamw_step: bad device%s", "");
     int blocks = 0;
     for (int i = 0; i < count; ++i) {

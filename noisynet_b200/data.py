@@ -47,7 +47,7 @@ class EpochBatches:
 
 
 def reference_batch(train_inputs, idx, aug, augment=True):
-    """The batch exactly as the script's torch ops would build it (slice, crop, flip) -- test oracle for the kernel."""
+    """The batch exactly as the script's torch ops would build it (slice, crop, flip) -- the torch restatement the gather kernel is tested against."""
     x = train_inputs[idx]
     k, j, flip = (int(v) for v in aug.tolist())
     if augment:

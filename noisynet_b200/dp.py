@@ -82,6 +82,12 @@ class FlatGradAllReduce:
         if self.world > 1 and k < len(self._works) and self._works[k] is None and self.bounds[k + 1] > self.bounds[k]:
             self._works[k] = dist.all_reduce(self.flat[self.bounds[k]:self.bounds[k + 1]], op=dist.ReduceOp.SUM, async_op=True)
 
+    def wait_early(self, k=0):
+        """The current stream waits for early bucket ``k``'s sums (so that its parameters can be updated before the
+        step's last exchange); all_reduce_sum_ still joins everything."""
+        if self.world > 1 and k < len(self._works) and self._works[k] is not None:
+            self._works[k].wait()
+
     def all_reduce_sum_(self):
         if self.world > 1:
             # buckets never started are folded into the final all-reduce together with the remaining parameters
@@ -164,7 +170,7 @@ class SymmGradAllReduce(FlatGradAllReduce):
                 o += p.numel()
         self.nbytes = total * 4
         self.n_buckets = len(self.ranges)
-        self._started = [False] * self.n_buckets
+        self._started = [0] * self.n_buckets      # 0 idle, 1 exchange enqueued, 2 sums already waited for on some stream
         ptrs = list(self.hdl.buffer_ptrs)
         self._peer = (C.c_void_p * self.world)(*ptrs)
         self._mc = 0 if os.environ.get("NN_DP_MULTICAST", "1") == "0" else int(self.hdl.multicast_ptr or 0)
@@ -192,11 +198,19 @@ class SymmGradAllReduce(FlatGradAllReduce):
             self.comm.wait_stream(torch.cuda.current_stream(self.dev_index))
             self._lib_mod.check(lib.nn_allreduce_start(self._peer, self._mc or None, self.rank, self.world, k, self.ctl + o * 4, n,
                                                        self.ctas, self.dev_index, self.comm.cuda_stream), "nn_allreduce_start")
-            self._started[k] = True
+            self._started[k] = 1
 
     def start_early(self, k=0):
         if self.world > 1 and k < self.n_buckets - 1:
             self._start(k)
+
+    def wait_early(self, k=0):
+        if self.world > 1 and self._started[k] == 1:
+            cur = torch.cuda.current_stream(self.dev_index)
+            cur.wait_stream(self.comm)
+            self._lib_mod.check(self._lib_mod.load().nn_allreduce_wait(self._local, self.world, k, self.dev_index, cur.cuda_stream),
+                                "nn_allreduce_wait")
+            self._started[k] = 2
 
     def all_reduce_sum_(self):
         if self.world > 1:
@@ -205,9 +219,9 @@ class SymmGradAllReduce(FlatGradAllReduce):
                 self._start(k)                   # whatever has not been started yet, the tail range included
             torch.cuda.current_stream(self.dev_index).wait_stream(self.comm)
             for k in range(self.n_buckets):
-                if self._started[k]:
+                if self._started[k] == 1:
                     self._lib_mod.check(lib.nn_allreduce_wait(self._local, self.world, k, self.dev_index, self._st()), "nn_allreduce_wait")
-                    self._started[k] = False
+                self._started[k] = 0
         return self.flat
 
 

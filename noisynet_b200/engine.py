@@ -157,6 +157,10 @@ class NoisyNetEngine:
         self.steps_done = 0         # training steps since the last sync_bn_counters()
         self.logits = f32(B, 10)    # eval_forward output
 
+    def _late_params(self, W):
+        early = {id(W[1]), id(W[2]), id(W[3])}
+        return [p for _, p in self.opt._params() if id(p) not in early]
+
     def sync_bn_counters(self):
         """BatchNorm.num_batches_tracked of the four BN modules (state_dict key of the reference model): the kernels keep
         the running statistics, this host-side counter keeps the step count -- call before saving a checkpoint."""
@@ -446,6 +450,16 @@ class NoisyNetEngine:
                     self.red.start_early(1)
             else:
                 self.red.start_early(1)
+        early_update = self.opt is not None and self.side is not None and hasattr(self.opt, "step_part")
+        if early_update:
+            # fc2, fc1 and conv2 (99.8 % of the parameters): gradients final (and exchanged) -> AdamW + clamp + max|W| now, on
+            # the side stream under conv2's dgrad and the stage-1 backward; only conv1 and the BatchNorm vectors wait for
+            # the end of the step.  Nothing left on the main stream reads these weights (dgrad uses the packed images).
+            with torch.cuda.stream(self.side):
+                if self.red is not None:
+                    self.red.wait_early(0)
+                    self.red.wait_early(1)
+                self.opt.step_part([W[3], W[2], W[1]], advance=False)
         self._dgrad(self.geom[1], self.gyp2, 1, self.gx2)
         self._stage_bwd(self.gx2, self.pool1, self.amax1, C1, H1, 1, m.bn1, "bn1", a.q_a2, qh2, self.gyp1,
                         planes_grid=(32, 32) if self.gy1_layout else None, act_max=am1)
@@ -456,7 +470,10 @@ class NoisyNetEngine:
         if self.red is not None:
             self.red.all_reduce_sum_()
         if self.opt is not None:
-            self.opt.step()
+            if early_update:
+                self.opt.step_part(self._late_params(W), advance=True)
+            else:
+                self.opt.step()
             for idx, w in enumerate(W):
                 m.w_absmax[idx] = (w._version, self.opt.absmax_of(w))
         return self.loss

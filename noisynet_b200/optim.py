@@ -84,11 +84,37 @@ class FusedAdamW:
         if self._table is None or key != self._table_key:
             self._build()
             self._table_key = key
+            self._parts = {}
         b1, b2 = self.param_groups[0]["betas"]
         dev = _dev(self.step_dev)
         _lib.check(_lib.load().nn_adamw_step(self._table, self._n, float(b1), float(b2),
                                              float(self.param_groups[0]["eps"]), self.grad_scale,
                                              self.step_dev.data_ptr(), dev, _stream(dev)), "nn_adamw_step")
+
+    @torch.no_grad()
+    def step_part(self, params, advance):
+        """The update of a subset of the step's tensors (``nn_adamw_step_part``): the engine updates the layers whose
+        gradients are final (and exchanged) early, under the rest of the backward pass, and passes ``advance=True`` with
+        the last subset only.  The subsets of one step must cover every parameter exactly once."""
+        key = self._key()
+        if self._table is None or key != self._table_key:
+            self._build()
+            self._table_key = key
+            self._parts = {}
+        ids = tuple(id(p) for p in params)
+        part = self._parts.get(ids) if hasattr(self, "_parts") else None
+        if part is None:
+            if not hasattr(self, "_parts"):
+                self._parts = {}
+            arr = (_lib.AdamWTensor * len(params))()
+            for j, p in enumerate(params):
+                C.memmove(C.byref(arr[j]), C.byref(self._table[self.index[p]]), C.sizeof(_lib.AdamWTensor))
+            part = self._parts[ids] = arr
+        b1, b2 = self.param_groups[0]["betas"]
+        dev = _dev(self.step_dev)
+        _lib.check(_lib.load().nn_adamw_step_part(part, len(params), float(b1), float(b2), float(self.param_groups[0]["eps"]),
+                                                  self.grad_scale, self.step_dev.data_ptr(), 1 if advance else 0, dev, _stream(dev)),
+                   "nn_adamw_step_part")
 
     def absmax_of(self, p):
         i = self.index[p]

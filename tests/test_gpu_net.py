@@ -171,3 +171,35 @@ def test_fused_adamw_matches_torch(dev):
     assert fus.absmax_of(ps[0]).item() == pytest.approx(ps[0].abs().max().item())
     assert fus.absmax_of(ps[2]).item() == pytest.approx(ps[2].abs().max().item())
     assert fus.step_dev.item() == 5
+
+
+def test_fused_adamw_partial_steps_equal_one_step(dev):
+    """nn_adamw_step_part: a step split into an early subset (advance = 0) and the rest (advance = 1) gives bit-identical
+    parameters, moments, max|W| and step count to the single launch; also across a step counter set from outside."""
+    from noisynet_b200.optim import FusedAdamW
+    torch.manual_seed(1)
+    shapes = [(65, 3, 5, 5), (120, 65, 5, 5), (390, 3000), (10,), (7,)]
+    ps = [torch.nn.Parameter(torch.randn(s, device=dev) * 0.2) for s in shapes]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    groups = lambda xs: [{"params": [xs[0]], "lr": 0.005, "weight_decay": 0.0005, "clamp": 0.3},
+                         {"params": [xs[1], xs[2]], "lr": 0.002, "weight_decay": 0.0, "clamp": 0.25},
+                         {"params": [xs[3], xs[4]], "lr": 0.005, "weight_decay": 0.01, "clamp": 0.0}]
+    one, two = FusedAdamW(groups(qs), lr=0.005), FusedAdamW(groups(ps), lr=0.005)
+    for step in range(6):
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(p)
+            p.grad = g.clone() if p.grad is None else p.grad.copy_(g)
+            q.grad = g.clone() if q.grad is None else q.grad.copy_(g)
+        if step == 3:                       # e.g. a checkpoint restored: the cached bias-correction constants are stale
+            one.step_dev.fill_(40)
+            two.step_dev.fill_(40)
+        one.step()
+        two.step_part([ps[2], ps[1]], advance=False)
+        assert two.step_dev.item() == one.step_dev.item() - 1
+        two.step_part([ps[0], ps[3], ps[4]], advance=True)
+        for p, q in zip(ps, qs):
+            assert torch.equal(p, q), (step, (p - q).abs().max())
+            assert torch.equal(two.state[p]["exp_avg_sq"], one.state[q]["exp_avg_sq"])
+        for p, q in zip(ps, qs):
+            assert two.absmax_of(p).item() == one.absmax_of(q).item() == p.abs().max().item()
+    assert two.step_dev.item() == one.step_dev.item() == 43
