@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NN_ABI_VERSION 14
+#define NN_ABI_VERSION 15
 
 /* ---- common ---------------------------------------------------------------------- */
 
@@ -180,7 +180,19 @@ typedef struct nn_conv_fwd_args {
                                 output, [B,Cout,OH/2,OW/2]; y / y_noisy are then NOT written.  Served where
                                 nn_conv_pool_fusable() says so (the shift kernel on a 32-wide input grid).          */
     uint8_t* argmax_out;     /* window position 0..3 of the first maximum in row-major order (nn.MaxPool2d)      */
+    /* optional, with pooled_out: the BatchNorm that follows the pool (noisynet.py:419-431) gets its batch statistics
+     * from the same launch -- per-CTA partial sums of the pooled values, finalized by the last CTA (fixed order:
+     * deterministic).  bn_mean != NULL selects it; the stage that follows is then called with stats_ready = 1. */
+    float* bn_mean;          /* out [Cout] batch mean   (eval: the running mean)                                   */
+    float* bn_invstd;        /* out [Cout] 1 / sqrt(biased var + eps)                                               */
+    float* bn_running_mean;  /* [Cout] updated with momentum (unbiased var), or NULL                                */
+    float* bn_running_var;
+    float bn_eps, bn_momentum;
+    int32_t bn_eval_mode;    /* 1: normalise with the running statistics, update nothing                            */
+    void* bn_scratch;        /* nn_conv_bn_scratch_bytes(Cout) bytes, zeroed once by the caller                     */
+    float* zero_out;         /* optional device float set to 0 by the launch (the max-accumulator of the next stage) */
 } nn_conv_fwd_args;
+int64_t nn_conv_bn_scratch_bytes(int Cout);
 
 /* Packed-weight layouts.  NN_PACK_TILED: 128B-swizzled [n-tile][k-block] shared-memory images (every geometry).
  * NN_PACK_SHIFT: [tap][row][8] image of the persistent shift-GEMM forward kernel, served for stride-1 unpadded
@@ -313,6 +325,8 @@ typedef struct nn_stage_args {
                                  consistent); shared by the forward and backward of all stages          */
     int32_t eval_mode;        /* 1: model.eval() -- BatchNorm normalises with running_mean / running_var and updates
                                  nothing (noisynet.py:1560-1567); the caller passes stochastic = 0 (hardware_model.py:283-286) */
+    int32_t stats_ready;      /* 1: mean / invstd (and the running statistics, and *xmax_out = 0) were already produced by
+                                 the conv launch (nn_conv_fwd_args.bn_mean): skip the statistics pass (pool must be 0)  */
 } nn_stage_args;
 int64_t nn_stage_scratch_bytes(int C);
 int nn_stage_fwd(const nn_stage_args* a, int device, void* stream);

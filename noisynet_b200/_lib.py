@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NN_LIB_PATH") or os.path.join(_HERE, "lib", "libnoisynet_b200.so")   # NN_LIB_PATH: instrumented debug builds
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 NOISE_NONE, NOISE_MERGED, NOISE_EXTERNAL = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
@@ -40,7 +40,10 @@ class ConvFwdArgs(C.Structure):
                 ("a_code_scale", C.c_float), ("w_code_scale", C.c_float),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("x_packed", C.c_void_p),
                 ("w_packed", C.c_void_p), ("w_packed_layout", C.c_int32),
-                ("pooled_out", C.c_void_p), ("argmax_out", C.c_void_p)]
+                ("pooled_out", C.c_void_p), ("argmax_out", C.c_void_p),
+                ("bn_mean", C.c_void_p), ("bn_invstd", C.c_void_p), ("bn_running_mean", C.c_void_p), ("bn_running_var", C.c_void_p),
+                ("bn_eps", C.c_float), ("bn_momentum", C.c_float), ("bn_eval_mode", C.c_int32), ("bn_scratch", C.c_void_p),
+                ("zero_out", C.c_void_p)]
 
 
 class ConvDgradArgs(C.Structure):
@@ -81,7 +84,8 @@ class StageArgs(C.Structure):
                 ("momentum", C.c_float), ("eps", C.c_float), ("mean", C.c_void_p), ("invstd", C.c_void_p),
                 ("act_max", C.c_float), ("q_bits", C.c_int32), ("q_hi", C.c_double), ("stochastic", C.c_float),
                 ("u_inject", C.c_void_p), ("rng", Rng), ("xp", C.c_void_p), ("Cp", C.c_int32),
-                ("act", C.c_void_p), ("xmax_out", C.c_void_p), ("scratch", C.c_void_p), ("eval_mode", C.c_int32)]
+                ("act", C.c_void_p), ("xmax_out", C.c_void_p), ("scratch", C.c_void_p), ("eval_mode", C.c_int32),
+                ("stats_ready", C.c_int32)]
 
 
 class StageBwdArgs(C.Structure):
@@ -130,6 +134,7 @@ SIGNATURES = {
     "nn_weight_pack_bytes": (C.c_int64, [C.POINTER(WPrepJob)]),
     "nn_prepare_weights": (C.c_int, [C.POINTER(WPrepJob), C.c_int, C.c_int, C.c_void_p]),
     "nn_stage_scratch_bytes": (C.c_int64, [C.c_int]),
+    "nn_conv_bn_scratch_bytes": (C.c_int64, [C.c_int]),
     "nn_stage_fwd": (C.c_int, [C.POINTER(StageArgs), C.c_int, C.c_void_p]),
     "nn_stage_bwd": (C.c_int, [C.POINTER(StageBwdArgs), C.c_int, C.c_void_p]),
     "nn_input_quant_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -168,3 +168,32 @@ static inline void nn_out_hw(const nn_conv_geom& g, int& OH, int& OW) {
     OH = (g.H + 2 * g.pad - g.KH) / g.stride + 1;
     OW = (g.W + 2 * g.pad - g.KW) / g.stride + 1;
 }
+
+// ---- BatchNorm batch statistics from fixed-order partial sums (shared by the stage kernels and the conv1 epilogue fusion)
+struct BnFinP {
+    double count;
+    float eps, momentum;
+    float *mean, *invstd, *running_mean, *running_var, *xmax_out;
+    int eval_mode;
+};
+// partial[s * stride + {0, 1}] = (sum, sum of squares) of slice s of channel c.  mean / invstd (biased var) + running
+// statistics update (momentum, unbiased var); eval_mode: noisynet.py:1560-1567
+__device__ __forceinline__ void bn_finalize_channel(const double* partial, int splits, int64_t stride, int c, const BnFinP& f) {
+    if (f.eval_mode) {          // model.eval(): normalise with the running statistics, update nothing
+        f.mean[c] = f.running_mean[c];
+        f.invstd[c] = (float)(1.0 / sqrt((double)f.running_var[c] + (double)f.eps));
+        return;
+    }
+    double s1 = 0, s2 = 0;
+    for (int s = 0; s < splits; ++s) { s1 += __ldcg(partial + (int64_t)s * stride); s2 += __ldcg(partial + (int64_t)s * stride + 1); }
+    const double m = s1 / f.count;
+    double var = s2 / f.count - m * m;
+    if (var < 0) var = 0;
+    f.mean[c] = (float)m;
+    f.invstd[c] = (float)(1.0 / sqrt(var + (double)f.eps));
+    if (f.running_mean) {
+        const double unb = f.count > 1 ? var * f.count / (f.count - 1) : var;
+        f.running_mean[c] = (float)((1.0 - f.momentum) * f.running_mean[c] + f.momentum * m);
+        f.running_var[c] = (float)((1.0 - f.momentum) * f.running_var[c] + f.momentum * unb);
+    }
+}

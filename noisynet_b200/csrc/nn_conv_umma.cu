@@ -459,6 +459,7 @@ k_splitk_epilogue(const SplitEpiP p) {
 constexpr int SH_MAX_PAIRS = 64;
 constexpr int SH_STAGES = 4;
 constexpr int SH_ACC_STRIDE = 256;                  // TMEM columns between the two accumulator buffers
+constexpr int SH_POOL_IT = 5;                       // pooled launches: 4-channel groups per epilogue warp (<= 80 channels at 16 warps)
 
 struct ShiftP {
     int H, W, OH, OW, KH, KW, Cout;
@@ -470,6 +471,13 @@ struct ShiftP {
     float *y, *y_noisy;
     float* pooled;            // optional: fused MaxPool2d(2,2) of the (noisy) output [B,Cout,OH/2,OW/2]; then y / y_noisy are not written
     uint8_t* pool_arg;        // window position 0..3 of the maximum (first maximum in row-major order, as nn.MaxPool2d)
+    // pooled launches use BLOCK tiles: 16 image rows x 8 columns (blk = 1; the 8-pixel row groups of the A operand are one
+    // image row apart, SBO = W), so that every 2x2 window lies inside one warp of the epilogue
+    int blk, tiles_x, tiles_per_img, sbo_units;
+    double* stat_partial;     // optional [gridDim.x][Cout][2]: per-CTA sums of the pooled values (BatchNorm statistics)
+    unsigned* stat_ticket;
+    BnFinP fin;               // the last CTA to finish turns the partials into mean / invstd / running statistics
+    float* zero_out;
     const float* z_inject;
     float current;
     const float* scale_dev;
@@ -478,9 +486,21 @@ struct ShiftP {
     long long* dbg;          // optional [cta][32 tiles][4] clock64 stamps: MMA ready / issued, accumulator seen / epilogue done
 };
 
+// first pixel of tile t (block tiles: image b, rows 16 rb .., columns 8 cb ..)
+__device__ __forceinline__ long long shift_tile_v0(const ShiftP& p, int t, int& b, int& r0, int& c0) {
+    if (!p.blk) { b = 0; r0 = 0; c0 = 0; return (long long)t * UM_BLOCK_M; }
+    b = t / p.tiles_per_img;
+    const int rem = t - b * p.tiles_per_img, rb = rem / p.tiles_x;
+    r0 = rb * 16; c0 = (rem - rb * p.tiles_x) * 8;
+    return ((long long)b * p.H + r0) * p.W + c0;
+}
 // a tile is skipped when none of its 128 positions can be a real output (whole rows oh >= OH of one image).
 // 32-bit arithmetic: the host rejects inputs with 2^31 pixels or more.
 __device__ __forceinline__ bool shift_tile_live(const ShiftP& p, int t) {
+    if (p.blk) {
+        const int rem = t % p.tiles_per_img, rb = rem / p.tiles_x;
+        return rb * 16 < p.OH && (rem - rb * p.tiles_x) * 8 < p.OW;
+    }
     const unsigned v0 = (unsigned)t * UM_BLOCK_M, total = (unsigned)p.total_pixels;
     unsigned v1 = v0 + UM_BLOCK_M - 1;
     if (v1 >= total) v1 = total - 1;
@@ -492,7 +512,7 @@ __device__ __forceinline__ bool shift_tile_live(const ShiftP& p, int t) {
 
 // MODE: 0 plain, 1 noisy (Philox z), 2 noisy with injected z (parity hook); SH_EPI_WARPS: epilogue warps, a
 // multiple of 4 (one TMEM lane quarter per warp % 4)
-template <int MODE, int SH_EPI_WARPS>
+template <int MODE, int SH_EPI_WARPS, bool POOL>
 __global__ void __launch_bounds__((2 + SH_EPI_WARPS) * 32, 1)
 k_conv_shift(const ShiftP p) {
     constexpr bool NOISY = MODE != 0;
@@ -554,7 +574,8 @@ k_conv_shift(const ShiftP p) {
             if (!shift_tile_live(p, t)) continue;
             if (!mbar_wait(a_empty + 8 * s, ph)) { *abort_g = 1; break; }
             if (*abort_g) break;
-            const long long v0 = (long long)t * UM_BLOCK_M;
+            int tb, tr0, tc0;
+            const long long v0 = shift_tile_v0(p, t, tb, tr0, tc0);
             long long px = p.total_pixels - v0;
             if (px > p.a_pixels) px = p.a_pixels;
             const uint32_t bytes = (uint32_t)px * 16u;
@@ -573,7 +594,7 @@ k_conv_shift(const ShiftP p) {
         int i = 0, s = 0;
         uint32_t ph = 0u;
         const uint64_t bd0 = umma_desc_none(b_base, (uint32_t)p.n_mma, 8u);
-        const uint64_t ad_t = umma_desc_none(0u, 0u, 8u);           // A template: start address and LBO vary per tap pair
+        const uint64_t ad_t = umma_desc_none(0u, 0u, (uint32_t)p.sbo_units);   // A template: start address and LBO vary per tap pair
         for (int t = blockIdx.x; t < p.n_tiles && ok; t += gridDim.x) {
             if (!shift_tile_live(p, t)) continue;
             const int buf = i & 1;
@@ -608,7 +629,9 @@ k_conv_shift(const ShiftP p) {
         if (NOISY) coef = nn_noise_coef(*p.scale_dev, p.current);
         if (MODE == 1) rs = nn_rng_load(p.rng);
         const float y_scale = p.y_scale, s_scale = p.s_scale;
-        int pool_buf = 0;
+        float st1[SH_POOL_IT], st2[SH_POOL_IT];          // pooled launches: per-thread sums of the pooled values it finalized
+#pragma unroll
+        for (int it = 0; it < SH_POOL_IT; ++it) { st1[it] = 0.f; st2[it] = 0.f; }
         int i = 0;
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
             if (!shift_tile_live(p, t)) continue;
@@ -617,65 +640,81 @@ k_conv_shift(const ShiftP p) {
             if (*abort_g) break;
             tc_fence_after();
             if (p.dbg && i < 32 && warp == 2 && lane == 0) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 2] = clock64();
-            const unsigned v = (unsigned)t * UM_BLOCK_M + q * 32 + lane;
-            const int b = (int)(v / (unsigned)hw);
-            const int rem = (int)(v - (unsigned)b * (unsigned)hw);
-            const int ih = (int)((unsigned)rem / (unsigned)p.W), iw = rem - ih * p.W;
-            const bool row_ok = v < (unsigned)p.total_pixels && ih < p.OH && iw < p.OW;
+            int b, ih, iw;
+            bool row_ok;
+            if (p.blk) {        // block tile: TMEM lane = 8 * (row in tile) + column, so a warp holds 4 rows x 8 columns
+                int r0, c0;
+                shift_tile_v0(p, t, b, r0, c0);
+                ih = r0 + q * 4 + (lane >> 3); iw = c0 + (lane & 7);
+                row_ok = ih < p.OH && iw < p.OW;
+            } else {
+                const unsigned v = (unsigned)t * UM_BLOCK_M + q * 32 + lane;
+                b = (int)(v / (unsigned)hw);
+                const int rem = (int)(v - (unsigned)b * (unsigned)hw);
+                ih = (int)((unsigned)rem / (unsigned)p.W); iw = rem - ih * p.W;
+                row_ok = v < (unsigned)p.total_pixels && ih < p.OH && iw < p.OW;
+            }
             const int pix = ih * p.OW + iw;
             const uint64_t grp_row = (uint64_t)((long long)b * ohw + pix) * ngrp;
             const size_t out_row = (size_t)b * p.Cout * ohw + pix;
             float* const out_main = (NOISY ? p.y_noisy : p.y) + out_row;
             float* const out_y = (NOISY && p.y) ? p.y + out_row : nullptr;
             const uint32_t t_lane = tmem_base + (uint32_t)(buf * SH_ACC_STRIDE) + ((uint32_t)(q * 32) << 16);
-            if (p.pooled) {
-                // Fused MaxPool2d(2,2) (host guarantees W == 32: a warp is one image row, a tile four rows): horizontal
-                // pairs by shuffle, vertical pairs between the two warps of a row pair (same jq, hence the same group
-                // sequence) through a double-buffered shared-memory slot and a 64-thread named barrier per group.
+            if (POOL) {
+                // Fused MaxPool2d(2,2) on block tiles: the window of lane l is {l, l^1, l^8, l^9} (columns iw, iw+1 of rows
+                // ih, ih+1).  The four lanes of a window SHARE the work: the lane at window position w finalizes channel w of
+                // the 4-channel group -- it collects that channel from its three partners (each lane offers the channel its
+                // partner wants: 3 shuffles per group instead of 12), takes the first maximum in row-major order (as
+                // nn.MaxPool2d), stores ONE pooled value + window index (all 32 lanes store) and keeps ONE pair of sums for the
+                // BatchNorm statistics of the stage that follows.  No shared memory, no barrier.  The first 4 * (ngrp / 4)
+                // groups of a lane quarter are dealt FIXED (g4 = jq + it * per_q: their sums live in registers for the whole
+                // kernel), a remaining odd group rotates over the warps with the tile index (its sums are added over all warps).
                 const int PW = p.OW >> 1, PHW = (p.OH >> 1) * PW;
-                const int pair = jq * 2 + (q >> 1);
-                float* xs = reinterpret_cast<float*>(gen0 + (pool_slot - base)) + pair * 256;
-                const bool top = (q & 1) == 0, left = (lane & 1) == 0;
-                const size_t pbase = (size_t)b * p.Cout * PHW + (size_t)(ih >> 1) * PW + (iw >> 1);
-                for (int g4 = (jq + i) % per_q; g4 < ngrp; g4 += per_q) {
+                const int w = (lane & 1) | ((lane >> 2) & 2);
+                const bool w1 = (w & 1) != 0, w2 = (w & 2) != 0;
+                const size_t pbase = (size_t)b * p.Cout * PHW + (size_t)(ih >> 1) * PW + (iw >> 1);      // same for the 4 lanes of a window
+                const bool warp_live = __any_sync(0xffffffffu, row_ok);
+                const int n_fix = ngrp / per_q, g_extra = n_fix * per_q;
+#pragma unroll
+                for (int it = 0; it < SH_POOL_IT; ++it) {
+                    int g4;
+                    if (it < SH_POOL_IT - 1) { g4 = jq + it * per_q; if (it >= n_fix) continue; }
+                    else { g4 = g_extra; if (g4 >= ngrp || (i % per_q) != jq) continue; }
+                    if (!warp_live) continue;
                     float am[4], as[4];
                     if (NOISY) tmem_ld4x2(t_lane + (uint32_t)(p.main_col + g4 * 4), t_lane + (uint32_t)(p.sig_col + g4 * 4), am, as);
                     else tmem_ld4(t_lane + (uint32_t)(p.main_col + g4 * 4), am);
                     const int nb = g4 * 4;
                     float z[4] = {0.f, 0.f, 0.f, 0.f};
                     if (MODE == 1) nn_normal4(rs, grp_row + (uint64_t)g4, z);
-                    float m[4];
-                    int a[4];
+                    float v[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        float v = am[j] * y_scale;
+                        v[j] = am[j] * y_scale;
                         if (NOISY) {
                             const float zz = MODE == 2 ? ((row_ok && nb + j < p.Cout) ? __ldg(p.z_inject + out_row + (size_t)(nb + j) * ohw) : 0.f) : z[j];
-                            v = __fadd_rn(v, __fmul_rn(zz, nn_sigma(coef, as[j] * s_scale)));
-                        }
-                        const float o = __shfl_xor_sync(0xffffffffu, v, 1);
-                        m[j] = v; a[j] = 0;
-                        if (o > v) { m[j] = o; a[j] = 1; }           // meaningful on the left (even) lane of a pair
-                    }
-                    float* slot = xs + pool_buf * 128;
-                    if (!top && left) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) { slot[j * 16 + (lane >> 1)] = m[j]; slot[64 + j * 16 + (lane >> 1)] = (float)a[j]; }
-                    }
-                    asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
-                    if (top && left && row_ok) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (nb + j < p.Cout) {
-                                const float mb = slot[j * 16 + (lane >> 1)];
-                                if (mb > m[j]) { m[j] = mb; a[j] = 2 + (int)slot[64 + j * 16 + (lane >> 1)]; }
-                                const size_t o = pbase + (size_t)(nb + j) * PHW;
-                                p.pooled[o] = m[j];
-                                p.pool_arg[o] = (uint8_t)a[j];
-                            }
+                            v[j] = __fadd_rn(v[j], __fmul_rn(zz, nn_sigma(coef, as[j] * s_scale)));
                         }
                     }
-                    pool_buf ^= 1;
+                    // v[w ^ k] for k = 0..3 (w is a per-thread constant: two predicates)
+                    const float s01 = w1 ? v[1] : v[0], s10 = w1 ? v[0] : v[1], s23 = w1 ? v[3] : v[2], s32 = w1 ? v[2] : v[3];
+                    const float own = w2 ? s23 : s01;           // v[w]
+                    const float c1 = w2 ? s32 : s10;            // v[w ^ 1]: what the horizontal partner finalizes
+                    const float c2 = w2 ? s01 : s23;            // v[w ^ 2]: the vertical partner
+                    const float c3 = w2 ? s10 : s32;            // v[w ^ 3]: the diagonal partner
+                    const float a1 = __shfl_xor_sync(0xffffffffu, c1, 1), a2 = __shfl_xor_sync(0xffffffffu, c2, 8),
+                                a3 = __shfl_xor_sync(0xffffffffu, c3, 9);
+                    // candidates of channel w at window positions w (own), w^1, w^2, w^3: maximum, ties to the lowest position
+                    float m = own; int a = w;
+                    if (a1 > m || (a1 == m && (w ^ 1) < a)) { m = a1; a = w ^ 1; }
+                    if (a2 > m || (a2 == m && (w ^ 2) < a)) { m = a2; a = w ^ 2; }
+                    if (a3 > m || (a3 == m && (w ^ 3) < a)) { m = a3; a = w ^ 3; }
+                    if (row_ok && nb + w < p.Cout) {            // OH, OW even: a window is valid as a whole
+                        const size_t o = pbase + (size_t)(nb + w) * PHW;
+                        p.pooled[o] = m;
+                        p.pool_arg[o] = (uint8_t)a;
+                        st1[it] += m; st2[it] = fmaf(m, m, st2[it]);
+                    }
                 }
             } else
             // 4-channel groups (one Philox call each), dealt round-robin to the warps of this lane quarter; the deal
@@ -752,6 +791,54 @@ k_conv_shift(const ShiftP p) {
             if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
             if (p.dbg && i < 32 && warp == 2 && lane == 0) p.dbg[((size_t)blockIdx.x * 32 + i) * 4 + 3] = clock64();
             ++i;
+        }
+        if (POOL && p.stat_partial) {
+            // ---- BatchNorm statistics of the pooled output: lanes -> warp -> CTA partial (fixed order), once per kernel
+            float* ssum = reinterpret_cast<float*>(gen0 + (pool_slot - base));      // [epilogue warp][SH_POOL_IT][4 channels][2]
+            const int w = (lane & 1) | ((lane >> 2) & 2);
+#pragma unroll
+            for (int it = 0; it < SH_POOL_IT; ++it) {
+                float a1 = st1[it], a2 = st2[it];
+#pragma unroll
+                for (int o = 2; o <= 16; o <<= 1) {             // lanes of equal window position: bits 1, 2, 4 (not 3)
+                    if (o == 8) continue;
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                }
+                if ((lane & ~9) == 0) { ssum[(((warp - 2) * SH_POOL_IT + it) * 4 + w) * 2] = a1; ssum[(((warp - 2) * SH_POOL_IT + it) * 4 + w) * 2 + 1] = a2; }
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(SH_EPI_WARPS * 32) : "memory");
+            const int et = tid - 64;                                               // epilogue thread index
+            if (et < p.Cout) {
+                const int g4 = et >> 2, j = et & 3, n_fix = ngrp / per_q;
+                double d1 = 0.0, d2 = 0.0;
+                if (g4 < n_fix * per_q) {           // fixed deal: the four lane quarters of group column wj (warps 4 wj .. 4 wj + 3)
+                    const int it = g4 / per_q, wj = g4 - it * per_q;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        d1 += (double)ssum[(((wj * 4 + k) * SH_POOL_IT + it) * 4 + j) * 2];
+                        d2 += (double)ssum[(((wj * 4 + k) * SH_POOL_IT + it) * 4 + j) * 2 + 1];
+                    }
+                } else {                            // the rotating odd group: every warp may hold a share
+                    for (int k = 0; k < SH_EPI_WARPS; ++k) {
+                        d1 += (double)ssum[((k * SH_POOL_IT + SH_POOL_IT - 1) * 4 + j) * 2];
+                        d2 += (double)ssum[((k * SH_POOL_IT + SH_POOL_IT - 1) * 4 + j) * 2 + 1];
+                    }
+                }
+                p.stat_partial[((size_t)blockIdx.x * p.Cout + et) * 2] = d1;
+                p.stat_partial[((size_t)blockIdx.x * p.Cout + et) * 2 + 1] = d2;
+                __threadfence();
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(SH_EPI_WARPS * 32) : "memory");
+            volatile int* last_g = reinterpret_cast<volatile int*>(ssum);
+            if (et == 0) *last_g = (atomicAdd(p.stat_ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+            asm volatile("bar.sync 1, %0;" ::"r"(SH_EPI_WARPS * 32) : "memory");
+            if (*last_g) {          // the last CTA: sums over the CTAs in index order (deterministic), then the statistics
+                __threadfence();
+                if (et < p.Cout) bn_finalize_channel(p.stat_partial + (size_t)et * 2, (int)gridDim.x, (int64_t)p.Cout * 2, et, p.fin);
+                if (et == 0) { *p.stat_ticket = 0u; if (p.zero_out) *p.zero_out = 0.f; }
+            }
+        } else if (p.zero_out && blockIdx.x == 0 && tid == 64) {
+            *p.zero_out = 0.f;
         }
     }
     tc_fence_before();
@@ -1556,7 +1643,10 @@ static bool make_shift_plan(const nn_conv_geom& g, bool noisy, ShiftPlan* out) {
     sp.a_stage = pad_to(sp.a_pixels * 16, 128);
     sp.b_bytes = sp.n_chunks * sp.n_mma * 16;
     sp.n_tiles = (int)(((int64_t)g.B * g.H * g.W + UM_BLOCK_M - 1) / UM_BLOCK_M);
-    sp.smem_bytes = 128 + (size_t)sp.b_bytes + (size_t)SH_STAGES * sp.a_stage + 16 * SH_STAGES + 64 + 4 * SH_MAX_PAIRS + 16 + 12 * 1024;
+    // (the A ring is sized for the block tiles of the pooled launches: 16 + KH - 1 image rows)
+    const int a_stage_blk = pad_to(((15 + g.KH - 1) * g.W + 8 + (g.KW - 1) + 8) * 16, 128);
+    sp.smem_bytes = 128 + (size_t)sp.b_bytes + (size_t)SH_STAGES * (a_stage_blk > sp.a_stage ? a_stage_blk : sp.a_stage) + 16 * SH_STAGES + 64 +
+                    4 * SH_MAX_PAIRS + 16 + 12 * 1024;
     if (sp.n_pairs > SH_MAX_PAIRS) return false;
     sp.wp_bytes = (size_t)sp.b_bytes;
     if (sp.smem_bytes > 200 * 1024) return false;
@@ -1789,8 +1879,29 @@ static int shift_conv_fwd(const nn_conv_fwd_args* a, const ShiftPlan& sp, int de
     p.pooled = a->pooled_out; p.pool_arg = a->argmax_out;
     p.current = a->current; p.scale_dev = a->scale_dev; p.rng = a->rng;
     p.err_flag = nn_umma_err_flag(device);
+    p.sbo_units = 8; p.zero_out = a->zero_out;
+    if (p.pooled) {
+        // block tiles (16 rows x 8 columns of the input grid): one stage = the rows r0 .. r0 + 15 + KH - 1 from column c0 on
+        p.blk = 1; p.tiles_x = g.W / 8; p.tiles_per_img = (g.H / 16) * p.tiles_x; p.sbo_units = g.W;
+        p.n_tiles = g.B * p.tiles_per_img;
+        p.a_pixels = (15 + g.KH - 1) * g.W + 8 + (g.KW - 1) + 8;
+        p.a_stage = pad_to(p.a_pixels * 16, 128);
+        if (a->bn_mean) {
+            if (!a->bn_invstd || !a->bn_scratch) return nn_fail("nn_noisy_conv_fwd: bn_mean needs bn_invstd and bn_scratch%s", "");
+            if (a->bn_eval_mode && (!a->bn_running_mean || !a->bn_running_var))
+                return nn_fail("nn_noisy_conv_fwd: bn_eval_mode needs the running statistics%s", "");
+            p.stat_ticket = (unsigned*)a->bn_scratch;
+            p.stat_partial = (double*)((uint8_t*)a->bn_scratch + 16);
+            p.fin.count = (double)g.B * (OH / 2) * (OW / 2);
+            p.fin.eps = a->bn_eps; p.fin.momentum = a->bn_momentum; p.fin.mean = a->bn_mean; p.fin.invstd = a->bn_invstd;
+            p.fin.running_mean = a->bn_running_mean; p.fin.running_var = a->bn_running_var; p.fin.xmax_out = nullptr;
+            p.fin.eval_mode = a->bn_eval_mode;
+        }
+    } else if (a->bn_mean) {
+        return nn_fail("nn_noisy_conv_fwd: bn_mean is served together with pooled_out only%s", "");
+    }
     int grid = nn_num_sms(device);
-    if (grid > sp.n_tiles) grid = sp.n_tiles;
+    if (grid > p.n_tiles) grid = p.n_tiles;
 #ifdef NN_KDEBUG
     static const bool want_dbg = getenv("NN_UMMA_DEBUG") != nullptr;
 #else
@@ -1812,14 +1923,18 @@ static int shift_conv_fwd(const nn_conv_fwd_args* a, const ShiftPlan& sp, int de
         cudaEventRecord(g_ev0, st);
     }
     const int mode = !noise ? 0 : (a->z_inject ? 2 : 1);      // 16 epilogue warps (12 / 20 / 24 measured slower)
-#define NN_SHIFT_LAUNCH(MODE, EW)                                                                                      \
+#define NN_SHIFT_LAUNCH(MODE, EW, POOL)                                                                                \
     do {                                                                                                               \
         NN_ONCE_PER_DEVICE({ \
-            NN_CUDA_OK(cudaFuncSetAttribute(k_conv_shift<MODE, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+            NN_CUDA_OK(cudaFuncSetAttribute(k_conv_shift<MODE, EW, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
         });                                                                                                              \
-        k_conv_shift<MODE, EW><<<grid, (2 + EW) * 32, sp.smem_bytes, st>>>(p);                                          \
+        k_conv_shift<MODE, EW, POOL><<<grid, (2 + EW) * 32, sp.smem_bytes, st>>>(p);                                    \
     } while (0)
-    if (mode == 0) NN_SHIFT_LAUNCH(0, 16); else if (mode == 1) NN_SHIFT_LAUNCH(1, 16); else NN_SHIFT_LAUNCH(2, 16);
+    if (p.pooled) {
+        if (mode == 0) NN_SHIFT_LAUNCH(0, 16, true); else if (mode == 1) NN_SHIFT_LAUNCH(1, 16, true); else NN_SHIFT_LAUNCH(2, 16, true);
+    } else {
+        if (mode == 0) NN_SHIFT_LAUNCH(0, 16, false); else if (mode == 1) NN_SHIFT_LAUNCH(1, 16, false); else NN_SHIFT_LAUNCH(2, 16, false);
+    }
 #undef NN_SHIFT_LAUNCH
     if (g_time_main) cudaEventRecord(g_ev1, st);
     NN_LAUNCH_OK();
@@ -1843,8 +1958,12 @@ extern "C" int nn_conv_pool_fusable(const nn_conv_geom* g, int32_t noise_mode, i
     if (!make_shift_plan(*g, noise_mode != NN_NOISE_NONE, nullptr)) return 0;
     int OH, OW;
     nn_out_hw(*g, OH, OW);
-    return g->W == 32 && g->H % 4 == 0 && OH % 2 == 0 && OW % 2 == 0;
+    // block tiles of 16 rows x 8 columns; the epilogue keeps SH_POOL_IT 4-channel groups per warp (16 warps)
+    const int ngrp = (g->Cout + 3) / 4;      // 16 epilogue warps: 4 per lane quarter; fixed groups + at most one rotating group
+    return g->W % 8 == 0 && g->H % 16 == 0 && OH % 2 == 0 && OW % 2 == 0 && ngrp / 4 <= SH_POOL_IT - 1 && ngrp % 4 <= 1;
 }
+// [ticket | per-CTA partial sums of the pooled values]: 16 + SMs x Cout x 2 doubles (sized for 256 CTAs)
+extern "C" int64_t nn_conv_bn_scratch_bytes(int Cout) { return 16 + (int64_t)256 * Cout * 2 * sizeof(double); }
 extern "C" int nn_debug_shift_enable(int enable) {
     const int prev = g_shift_enable;
     if (enable >= 0) g_shift_enable = enable;

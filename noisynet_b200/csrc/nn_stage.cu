@@ -38,13 +38,6 @@ __device__ __forceinline__ float quant_code(float v, float s, float qmax, float 
 // The per-channel reductions end in the LAST slice's block of each channel (a self-resetting arrival counter behind the
 // partials): it adds the slices in fixed order -- deterministic whichever block happens to be last -- and writes the
 // statistics, so no separate finalize launch sits on the step's critical path.
-struct BnFinP {
-    double count;
-    float eps, momentum;
-    float *mean, *invstd, *running_mean, *running_var, *xmax_out;
-    int eval_mode;
-};
-
 __device__ __forceinline__ bool stage_last_slice(unsigned* counters, int c, int slices) {
     __threadfence();                                   // this block's partial is visible before its arrival
     const unsigned done = atomicAdd(counters + c, 1u);
@@ -52,27 +45,6 @@ __device__ __forceinline__ bool stage_last_slice(unsigned* counters, int c, int 
     counters[c] = 0u;                                  // ready for the next launch that uses this scratch
     __threadfence();
     return true;
-}
-
-// mean / invstd (biased var) + running stats update (momentum, unbiased var), noisynet.py:1560-1567 for eval
-__device__ __forceinline__ void bn_finalize_channel(const double* partial, int splits, int c, const BnFinP& f) {
-    if (f.eval_mode) {          // model.eval(): normalise with the running statistics, update nothing
-        f.mean[c] = f.running_mean[c];
-        f.invstd[c] = (float)(1.0 / sqrt((double)f.running_var[c] + (double)f.eps));
-        return;
-    }
-    double s1 = 0, s2 = 0;
-    for (int s = 0; s < splits; ++s) { s1 += __ldcg(partial + ((int64_t)c * splits + s) * 2); s2 += __ldcg(partial + ((int64_t)c * splits + s) * 2 + 1); }
-    const double m = s1 / f.count;
-    double var = s2 / f.count - m * m;
-    if (var < 0) var = 0;
-    f.mean[c] = (float)m;
-    f.invstd[c] = (float)(1.0 / sqrt(var + (double)f.eps));
-    if (f.running_mean) {
-        const double unb = f.count > 1 ? var * f.count / (f.count - 1) : var;
-        f.running_mean[c] = (float)((1.0 - f.momentum) * f.running_mean[c] + f.momentum * m);
-        f.running_var[c] = (float)((1.0 - f.momentum) * f.running_var[c] + f.momentum * unb);
-    }
 }
 
 // ------------------------------------------------------------------ F1: 2x2 max pool + per-channel partial sums
@@ -124,7 +96,7 @@ k_pool_stats(const float* __restrict__ y, float* __restrict__ pooled, uint8_t* _
         for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
         partial[((int64_t)c * gridDim.y + sp) * 2 + 0] = a;
         partial[((int64_t)c * gridDim.y + sp) * 2 + 1] = b;
-        if (stage_last_slice(counters, c, (int)gridDim.y)) bn_finalize_channel(partial, (int)gridDim.y, c, fin);
+        if (stage_last_slice(counters, c, (int)gridDim.y)) bn_finalize_channel(partial + (int64_t)c * gridDim.y * 2, (int)gridDim.y, 2, c, fin);
     }
 }
 
@@ -167,7 +139,7 @@ k_chan_stats(const float* __restrict__ x, double* __restrict__ partial, unsigned
         for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
         partial[((int64_t)c * gridDim.y + sp) * 2 + 0] = a;
         partial[((int64_t)c * gridDim.y + sp) * 2 + 1] = b;
-        if (stage_last_slice(counters, c, (int)gridDim.y)) bn_finalize_channel(partial, (int)gridDim.y, c, fin);
+        if (stage_last_slice(counters, c, (int)gridDim.y)) bn_finalize_channel(partial + (int64_t)c * gridDim.y * 2, (int)gridDim.y, 2, c, fin);
     }
 }
 
@@ -1103,7 +1075,10 @@ extern "C" int nn_stage_fwd(const nn_stage_args* a, int device, void* stream) {
     BnFinP fin;
     fin.eps = a->eps; fin.momentum = a->momentum; fin.mean = a->mean; fin.invstd = a->invstd; fin.running_mean = a->running_mean;
     fin.running_var = a->running_var; fin.xmax_out = a->xmax_out; fin.eval_mode = a->eval_mode;
-    if (a->pool) {
+    if (a->stats_ready) {
+        // mean / invstd / running statistics / *xmax_out = 0 come from the conv launch that produced `in` (fused pool + stats)
+        if (a->pool) return nn_fail("nn_stage_fwd: stats_ready goes with pool = 0 (the conv launch pooled already)%s", "");
+    } else if (a->pool) {
         if (!a->pooled || !a->argmax) return nn_fail("nn_stage_fwd: pooled/argmax buffers missing%s", "");
         HW = (a->H / 2) * (a->W / 2);
         splits = stage_splits((int64_t)a->B * HW);

@@ -105,15 +105,16 @@ class NoisyNetEngine:
         self.geom_fc1_lin = ConvGeom(B, C2 * P2 * P2, 1, 1, FC, 1, 1, 1, 0)
         # conv1 weight gradient through the in-place (shift) kernel: its grad_output lives in the planes layout on the
         # 32x32 input grid, zeroed once here -- nn_stage_bwd only ever writes the 28x28 output positions
-        # MaxPool2d fused into the conv1 epilogue (pooled_out): exact, saves the 104 MB y1n round trip, but measured
-        # SLOWER overall at batch 512 (conv1 forward 86 -> 123 us: the per-group pair barrier puts the two warps of a row
-        # pair in lock-step; pool+stats 36 -> 18 us) -- off unless NN_ENGINE_FUSE_POOL=1
+        # MaxPool2d and the batch statistics of bn1 fused into the conv1 epilogue (pooled_out + bn_mean): exact, the 104 MB y1n
+        # round trip and the pool+statistics pass (33 us) disappear; conv1 forward 78 -> 97 us on block tiles whose 2x2
+        # windows lie inside one warp (round 1's per-group pair barrier made it 123 us).  NN_ENGINE_FUSE_POOL=0: separate stage
         # fc2 + bn4 + loss + their backward as ONE 8-CTA cluster launch (nn_classifier_tail): exact and tested, but 43 us
         # against 37 us for the three separate launches it replaces (8 SMs, ten latency-bound phases) -- off unless
         # NN_ENGINE_FUSED_TAIL=1
         self.fused_tail = B <= 2048 and self.q_w[3] > 0 and self.q_a[3] > 0 and os.environ.get("NN_ENGINE_FUSED_TAIL", "0") == "1"
         self.fuse_pool1 = bool(self.lib.nn_conv_pool_fusable(C.byref(self.geom[0]), self.noise_modes[0], PREC_BF16)) and \
-            os.environ.get("NN_ENGINE_FUSE_POOL", "0") == "1"
+            os.environ.get("NN_ENGINE_FUSE_POOL", "1") == "1"
+        self.bn_scratch = torch.zeros(int(self.lib.nn_conv_bn_scratch_bytes(C1)), dtype=torch.uint8, device=dev)
         self.gy1_layout = self.lib.nn_conv_wgrad_pack_layout(C.byref(self.geom[0]), PREC_BF16, self.di)
         if self.gy1_layout:
             nbytes = int(self.lib.nn_conv_gy_planes_bytes(C.byref(self.geom[0])))
@@ -242,7 +243,8 @@ class NoisyNetEngine:
             return hit[1]
         return ops.tensor_stats(w.detach())[1:2]
 
-    def _fwd_gemm(self, idx, xp, a_cs, y_noisy, mode, scale_dev, z=None, pooled=None, argmax=None):
+    def _fwd_gemm(self, idx, xp, a_cs, y_noisy, mode, scale_dev, z=None, pooled=None, argmax=None, bn=None, key=None, zero=None,
+                  eval_mode=False):
         a = ConvFwdArgs()
         a.g = self.geom[idx]
         a.x = None
@@ -261,6 +263,11 @@ class NoisyNetEngine:
         if pooled is not None:                  # MaxPool2d(2,2) fused into the conv epilogue: the full-size output is never written
             a.y, a.y_noisy = None, None
             a.pooled_out, a.argmax_out = _p(pooled), _p(argmax)
+            if bn is not None:                  # ... and the BatchNorm statistics of the pooled output come from the same launch
+                a.bn_mean, a.bn_invstd = _p(self.stat[key][0]), _p(self.stat[key][1])
+                a.bn_running_mean, a.bn_running_var = _p(bn.running_mean), _p(bn.running_var)
+                a.bn_eps, a.bn_momentum, a.bn_eval_mode = float(bn.eps), float(bn.momentum), 1 if eval_mode else 0
+                a.bn_scratch, a.zero_out = _p(self.bn_scratch), _p(zero)
         a.precision = PREC_BF16
         a.a_code_scale, a.w_code_scale = a_cs, self.w_cs[idx]
         a.workspace, a.workspace_bytes = _p(self.ws), self.ws.numel()
@@ -293,9 +300,11 @@ class NoisyNetEngine:
         a.workspace, a.workspace_bytes = _p(self.ws), self.ws.numel()
         _lib.check(self.lib.nn_noisy_conv_dgrad(C.byref(a), self.di, self._st()), "nn_noisy_conv_dgrad")
 
-    def _stage_fwd(self, x_in, C_, H, pool, pooled, amax, bn, key, q_bits, q_hi, xp, xmax, u=None, act_max=None, eval_mode=False):
+    def _stage_fwd(self, x_in, C_, H, pool, pooled, amax, bn, key, q_bits, q_hi, xp, xmax, u=None, act_max=None, eval_mode=False,
+                   stats_ready=False):
         a = StageArgs()
         a.eval_mode = 1 if eval_mode else 0
+        a.stats_ready = 1 if stats_ready else 0
         a.in_ = _p(x_in)
         a.B, a.C, a.H, a.W, a.pool = self.B, C_, H, H, pool
         a.pooled, a.argmax = _p(pooled), _p(amax)
@@ -393,9 +402,12 @@ class NoisyNetEngine:
         input_pack(st)
         # ---- forward
         if self.fuse_pool1:
+            # conv1 + analog noise + MaxPool2d + the batch statistics of bn1 in ONE launch: the 104 MB fp32 conv output is
+            # never written; the stage that follows only normalises, quantizes and packs
             self._fwd_gemm(0, self.xp1, s1, None, self.noise_modes[0], self._absmax(0, W[0]), self._take("z"),
-                           pooled=self.pool1, argmax=self.amax1)
-            self._stage_fwd(self.pool1, C1, P1, 0, None, None, m.bn1, "bn1", a.q_a2, qh2, self.xp2, self.xmax2, self._take("u"), act_max=am1)
+                           pooled=self.pool1, argmax=self.amax1, bn=m.bn1, key="bn1", zero=self.xmax2)
+            self._stage_fwd(self.pool1, C1, P1, 0, None, None, m.bn1, "bn1", a.q_a2, qh2, self.xp2, self.xmax2, self._take("u"), act_max=am1,
+                            stats_ready=True)
         else:
             self._fwd_gemm(0, self.xp1, s1, self.y1n, self.noise_modes[0], self._absmax(0, W[0]), self._take("z"))
             self._stage_fwd(self.y1n, C1, H1, 1, self.pool1, self.amax1, m.bn1, "bn1", a.q_a2, qh2, self.xp2, self.xmax2, self._take("u"), act_max=am1)

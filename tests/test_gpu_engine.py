@@ -322,7 +322,8 @@ def test_engine_eval_forward_vs_oracle(dev):
 GRAD_REL_TOL, GRAD_COS_TOL = 0.25, 0.98        # measured: rel-L2 0.005 .. 0.17, cosine 0.985 .. 0.99999 (2.7 % of fc2's input codes differ)
 
 
-def test_engine_benchmark_config_vs_oracle(dev):
+@pytest.mark.parametrize("fuse_pool", ["1", "0"])
+def test_engine_benchmark_config_vs_oracle(dev, monkeypatch, fuse_pool):
     """The configuration bench.py measures -- NoisyNetEngine.train_step at batch 512, full widths (65 / 120 / 390),
     q_a = q_w = 4, I = 1 nA on every layer -- against the CPU oracle's training step (oracle/noisynet_oracle.py, pinned to
     the unmodified reference by tests/golden) with the SAME injected draws (stochastic-rounding uniforms of the four
@@ -339,6 +340,7 @@ def test_engine_benchmark_config_vs_oracle(dev):
       * gradients of every parameter against the ORACLE's: relative L2 error <= GRAD_REL_TOL, cosine >= GRAD_COS_TOL
         (bf16 grad_output operands + the flipped codes, whose STE masks and ReLU gates switch whole gradient paths).
     """
+    monkeypatch.setenv("NN_ENGINE_FUSE_POOL", fuse_pool)      # conv1 + pool + bn1 statistics in one launch / separate stage
     from noisynet_b200 import ops
     from noisynet_b200.engine import NoisyNetEngine
     from noisynet_b200.net import NoisyNet, default_args, make_fused_optimizer, with_quant

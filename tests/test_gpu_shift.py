@@ -209,7 +209,7 @@ def test_stage_bwd_planes_layout(dev):
     assert float(grid[mask].abs().max()) == 0.0 and float(planes[:, B * vH * vW:].abs().max() if P > B * vH * vW else 0.0) == 0.0
 
 
-@pytest.mark.parametrize("B,Cout,k", [(4, 65, 5), (3, 20, 3), (2, 7, 1)])
+@pytest.mark.parametrize("B,Cout,k", [(4, 65, 5), (3, 20, 3), (2, 4, 1), (2, 64, 3)])
 def test_shift_fused_maxpool(dev, B, Cout, k):
     """pooled_out / argmax_out of the shift kernel == MaxPool2d(2,2) (values and first-maximum window position) of the
     output the same launch configuration writes without the fusion (same Philox stream -> bit-identical noise)."""
@@ -250,7 +250,27 @@ def test_shift_fused_maxpool(dev, B, Cout, k):
         a.precision, a.a_code_scale, a.w_code_scale = PREC_BF16, s_a, 1.0 / 15.0
         ws = torch.empty(int(lib.nn_conv_workspace_bytes(C.byref(g), PREC_BF16)) + 4096, dtype=torch.uint8, device=dev)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
-        _lib.check(lib.nn_noisy_conv_fwd(C.byref(a), 0, torch.cuda.current_stream().cuda_stream), "nn_noisy_conv_fwd")
-        assert ops.error_flag() == 0
-        assert torch.equal(pooled, pv)
-        assert torch.equal(arg, pos)
+        # ... and the batch statistics of the BatchNorm that follows the pool, from the same launch
+        mean, invstd = torch.empty(Cout, device=dev), torch.empty(Cout, device=dev)
+        rm, rv = torch.full((Cout,), 0.25, device=dev), torch.full((Cout,), 2.0, device=dev)
+        scratch = torch.zeros(int(lib.nn_conv_bn_scratch_bytes(Cout)), dtype=torch.uint8, device=dev)
+        zero = torch.full((1,), 7.0, device=dev)
+        a.bn_mean, a.bn_invstd, a.bn_running_mean, a.bn_running_var = mean.data_ptr(), invstd.data_ptr(), rm.data_ptr(), rv.data_ptr()
+        a.bn_eps, a.bn_momentum, a.bn_eval_mode, a.bn_scratch, a.zero_out = 1e-5, 0.1, 0, scratch.data_ptr(), zero.data_ptr()
+        for rep in range(2):                # twice: the arrival ticket resets itself, the running statistics move on
+            _lib.check(lib.nn_noisy_conv_fwd(C.byref(a), 0, torch.cuda.current_stream().cuda_stream), "nn_noisy_conv_fwd")
+            assert ops.error_flag() == 0
+            assert torch.equal(pooled, pv)
+            assert torch.equal(arg, pos)
+            m_ref = pv.double().mean(dim=(0, 2, 3))
+            v_ref = pv.double().var(dim=(0, 2, 3), unbiased=False)
+            assert torch.allclose(mean.double(), m_ref, rtol=1e-5, atol=1e-6)
+            assert torch.allclose(invstd.double(), 1.0 / torch.sqrt(v_ref + 1e-5), rtol=1e-5)
+            assert zero.item() == 0.0
+        n = pv[:, 0].numel()
+        rm_ref, rv_ref = torch.full((Cout,), 0.25, dtype=torch.float64, device=dev), torch.full((Cout,), 2.0, dtype=torch.float64, device=dev)
+        for rep in range(2):
+            rm_ref = 0.9 * rm_ref + 0.1 * m_ref
+            rv_ref = 0.9 * rv_ref + 0.1 * v_ref * n / (n - 1)
+        assert torch.allclose(rm.double(), rm_ref, rtol=1e-5, atol=1e-6) and torch.allclose(rv.double(), rv_ref, rtol=1e-5)
+        assert int(scratch[:4].view(torch.int32).item()) == 0
