@@ -576,8 +576,10 @@ k_adamw(const AdamWP p) {
             s_c[1] = (float)sqrt(1.0 - pow((double)p.beta2, (double)step));
         }
         s_par = par;
-        if (blockIdx.x == 0 && p.advance) {                     // constants of the NEXT step into the other slot
-            float* nx = reinterpret_cast<float*>(p.ctl + AW_CONST + 4 * (par ^ 1));
+        // constants of the NEXT step into the other slot (nobody reads it during this step): by the first launch of the step
+        // that gets here -- with partial launches that is the early, large one, not the small one on the critical path
+        float* nx = reinterpret_cast<float*>(p.ctl + AW_CONST + 4 * (par ^ 1));
+        if (blockIdx.x == 0 && !(__float_as_int(__ldcg(nx + 2)) == (int)(step + 1) && __float_as_int(__ldcg(nx + 3)) == tag)) {
             nx[0] = (float)(1.0 - pow((double)p.beta1, (double)(step + 1)));
             nx[1] = (float)sqrt(1.0 - pow((double)p.beta2, (double)(step + 1)));
             nx[2] = __int_as_float((int)(step + 1));

@@ -492,6 +492,39 @@ k_bn_bwd_apply_lean(const BnBwdApplyP p) {
     }
 }
 
+// Per-image variant for pooled stages with NHWC output (stage 2: 120 x 5x5 -> 10x10): one block = one sample.  Its g / x /
+// argmax slices are CONTIGUOUS (C * PH * PW elements): thread t reads element t, t + 256, ... (the chunk-fastest mapping of
+// k_bn_bwd_apply_lean touched 32 cache lines per load instruction); the sample's NHWC bf16 gradient image (zeros included)
+// is assembled in shared memory and leaves as one contiguous run.  Same arithmetic as k_bn_bwd_apply.
+__global__ void __launch_bounds__(256)
+k_bn_bwd_apply_img(const BnBwdApplyP p) {
+    extern __shared__ uint4 s_img4[];
+    __nv_bfloat16* s_img = reinterpret_cast<__nv_bfloat16*>(s_img4);
+    const unsigned C = (unsigned)p.C, PH = p.OH >> 1, PW = p.OW >> 1, PHW = PH * PW, n = C * PHW;
+    const unsigned img16 = (unsigned)(p.OH * p.OW * p.Cp) >> 3;          // 16-byte chunks of the sample's output image
+    const float inv_count = p.inv_count;
+    for (unsigned b = blockIdx.x; b < (unsigned)p.B; b += gridDim.x) {
+        for (unsigned k = threadIdx.x; k < img16; k += 256u) s_img4[k] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        const unsigned o0 = b * n;                                       // element index < 2^31 (host check)
+        for (unsigned e = threadIdx.x; e < n; e += 256u) {
+            const unsigned c = e / PHW, r = e - c * PHW, ph = r / PW, pw = r - ph * PW;
+            float xhat;
+            const float invstd = __ldg(p.invstd + c), gamma = __ldg(p.gamma + c);
+            const float dv = stage_dv(__ldg(p.g + o0 + e), __ldg(p.x + o0 + e), __ldg(p.mean + c), invstd, gamma, __ldg(p.beta + c),
+                                      p.act_max, p.q_hi, xhat);
+            const float d = gamma * invstd * (dv - __ldg(p.dbeta + c) * inv_count - xhat * __ldg(p.dgamma + c) * inv_count);
+            const unsigned pos = __ldg(p.amax + o0 + e);
+            const unsigned oh = 2 * ph + (pos >> 1), ow = 2 * pw + (pos & 1);
+            s_img[(oh * p.OW + ow) * p.Cp + c] = __float2bfloat16_rn(d);
+        }
+        __syncthreads();
+        uint4* dst = reinterpret_cast<uint4*>(p.gyp + (size_t)b * p.OH * p.OW * p.Cp);
+        for (unsigned k = threadIdx.x; k < img16; k += 256u) dst[k] = s_img4[k];
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------ input quantize + pack (noisynet.py:390-393)
 __global__ void __launch_bounds__(256)
 k_quant_pack_input(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, float* __restrict__ act, int B, int C, int HW,
@@ -1148,7 +1181,11 @@ extern "C" int nn_stage_bwd(const nn_stage_bwd_args* a, int device, void* stream
     const int64_t items = (int64_t)a->B * PH * PW * (a->Cp / 8);
     const int agrid = grid_cap(items, device);
     const bool lean = !p.gy_f32 && (int64_t)a->B * a->C * PH * PW < ((int64_t)1 << 31) && items < ((int64_t)1 << 31);
-    if (!lean) k_bn_bwd_apply<<<agrid, 256, 0, st>>>(p);
+    const size_t img_bytes = (size_t)a->H * a->W * a->Cp * 2;
+    if (lean && a->pool && !p.planes && img_bytes <= 48 * 1024 && PH * PW >= 16) {
+        const int cap = nn_num_sms(device) * 8;
+        k_bn_bwd_apply_img<<<a->B < cap ? a->B : cap, 256, img_bytes, st>>>(p);
+    } else if (!lean) k_bn_bwd_apply<<<agrid, 256, 0, st>>>(p);
     else if (a->pool && p.planes) k_bn_bwd_apply_lean<true, true><<<agrid, 256, 0, st>>>(p);
     else if (a->pool) k_bn_bwd_apply_lean<true, false><<<agrid, 256, 0, st>>>(p);
     else if (p.planes) k_bn_bwd_apply_lean<false, true><<<agrid, 256, 0, st>>>(p);

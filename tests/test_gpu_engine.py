@@ -155,6 +155,44 @@ def test_stage_fwd_hot_path_kernels_match_general(dev, shape, pool):
     assert 0.0 < outs[0][0][..., :Cc].mean().item() < 15.0 and torch.all(outs[0][0][..., Cc:] == 0)
 
 
+@pytest.mark.parametrize("shape,pool", [((6, 120, 10, 10), 1), ((3, 65, 28, 28), 1), ((5, 16, 12, 12), 1), ((40, 390, 1, 1), 0)])
+def test_stage_bwd_hot_path_kernels_match_general(dev, shape, pool):
+    """nn_stage_bwd without the fp32 copy runs the hot-path kernels (k_bn_bwd_apply_img for pooled NHWC stages whose
+    image fits shared memory, k_bn_bwd_apply_lean otherwise); with gy_f32 it runs the general kernel.  Same arithmetic ->
+    the packed bf16 gradients must be bit-identical."""
+    from noisynet_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5 + sum(shape))
+    B, Cc, H, W = shape
+    x = (torch.randn(shape, generator=g) * 1.5 + 0.3).to(dev)
+    gamma, beta = (torch.rand(Cc, generator=g) + 0.5).to(dev), (torch.randn(Cc, generator=g) * 0.5 + 0.5).to(dev)
+    PH, PW = (H // 2, W // 2) if pool else (H, W)
+    u = (torch.rand(B, Cc, PH, PW, generator=g) - 0.5).to(dev)
+    gout = torch.randn(B, Cc, PH, PW, generator=g).to(dev)
+    rm, rv = torch.zeros(Cc, device=dev), torch.ones(Cc, device=dev)
+    r = _stage_call(dev, x, gamma, beta, rm, rv, pool, 5.0, 4, 4.0, u)
+    Cp = (Cc + 7) // 8 * 8
+    outs = []
+    for want_f32 in (False, True):
+        gyp = torch.full((B, H, W, Cp), 3.0, dtype=torch.bfloat16, device=dev)
+        gyf = torch.empty(B, Cc, H, W, device=dev)
+        dg, db = torch.empty(Cc, device=dev), torch.empty(Cc, device=dev)
+        b = _lib.StageBwdArgs()
+        b.g = gout.data_ptr()
+        b.x = (r["pooled"] if pool else x).data_ptr(); b.argmax = r["amax"].data_ptr()
+        b.B, b.C, b.H, b.W, b.pool = B, Cc, H, W, pool
+        b.mean, b.invstd, b.gamma, b.beta = r["mean"].data_ptr(), r["invstd"].data_ptr(), gamma.data_ptr(), beta.data_ptr()
+        b.act_max, b.q_bits, b.q_hi = 5.0, 4, 4.0
+        b.dgamma, b.dbeta = dg.data_ptr(), db.data_ptr()
+        b.gyp, b.Cp, b.gy_f32, b.scratch = gyp.data_ptr(), Cp, gyf.data_ptr() if want_f32 else None, r["scratch"].data_ptr()
+        _lib.check(lib.nn_stage_bwd(C.byref(b), 0, torch.cuda.current_stream().cuda_stream), "nn_stage_bwd")
+        torch.cuda.synchronize()
+        outs.append((gyp.float().cpu(), dg.cpu(), db.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    assert outs[0][0].abs().sum().item() > 0
+
+
 @pytest.mark.parametrize("B", [200, 512, 37, 1500])      # 1500 > 1024 rows: the strided single-block kernel
 def test_head_vs_torch(dev, B):
     from noisynet_b200 import _lib
