@@ -120,13 +120,14 @@ class QuantMeasure(nn.Module):
         """Host value of a scalar buffer, re-read (one sync) only when the buffer object or its
         version changed -- the reference syncs on every call (hm:265-271)."""
         t = getattr(self, name)
-        key = (id(t), t._version)
         cache = self.__dict__.setdefault('_host_cache', {})
         hit = cache.get(name)
-        if hit is None or hit[0] != key:
-            hit = (key, float(t.reshape(-1)[0].item()))
+        # the cache holds the tensor OBJECT (a strong reference: the scripts replace the buffer, noisynet.py:1258, and a freed
+        # wrapper's id can be reused) and its version counter
+        if hit is None or hit[0] is not t or hit[1] != t._version:
+            hit = (t, t._version, float(t.reshape(-1)[0].item()))
             cache[name] = hit
-        return hit[1]
+        return hit[2]
 
     def _range(self, input):
         """Returns (min_value, max_value, stoch, range_dev).  range_dev (float32[2] device tensor) is set where the

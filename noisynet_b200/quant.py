@@ -34,12 +34,12 @@ class QuantMeasure(nn.Module):
 
     def _host_running_max(self):
         t = self.running_max
-        key = (id(t), t._version)
         hit = self.__dict__.get('_rm_cache')
-        if hit is None or hit[0] != key:
-            hit = (key, float(t.item()))
+        # keyed on the tensor OBJECT (strong reference; the scripts replace the buffer and ids are reused) + its version
+        if hit is None or hit[0] is not t or hit[1] != t._version:
+            hit = (t, t._version, float(t.item()))
             self.__dict__['_rm_cache'] = hit
-        return hit[1]
+        return hit[2]
 
     def forward(self, input):
         from . import ops
