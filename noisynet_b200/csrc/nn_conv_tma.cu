@@ -600,6 +600,22 @@ int nn_tma_conv_launch(const TmaConvCall& c, int device, cudaStream_t st) {
     return 0;
 }
 
+// Tiled 2-D map of a row-major bf16 matrix [rows][cols] (row pitch in bytes, a multiple of 16), box = 64 columns x 128 rows,
+// SWIZZLE_128B: the K-major A tile of the gathered kernels when the layer is linear (out-of-range rows / columns read as 0).
+int nn_tma_encode_rows(void* map_out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_bytes) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return nn_fail("nn_conv_tma: cuTensorMapEncodeTiled is not available%s", "");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(reinterpret_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return nn_fail("nn_conv_tma: cuTensorMapEncodeTiled (matrix rows) failed%s (CUresult %lld)", "", (long long)r);
+    return 0;
+}
+
 // ================================================================== weight gradient with TMA-staged operands
 //   D[n, (tap, c)] = sum over output pixels m of gy[m, n] * x[pixel(m) + tap, c]
 // Both operands are NHWC bf16, i.e. contiguous along their M / N dimension: they are staged as MN-major SWIZZLE_128B atoms

@@ -52,3 +52,6 @@ struct TmaWgradCall {
     int* err_flag;
 };
 int nn_tma_wgrad_launch(const TmaWgradCall& c, int device, cudaStream_t st);
+
+// 128-byte tensor map (CUtensorMap) of a row-major bf16 matrix for the linear layers of the gathered kernel (k_conv_umma)
+int nn_tma_encode_rows(void* map_out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_bytes);

@@ -61,7 +61,9 @@ struct UmmaP {
     int m_pad;
     int inc_taps;                  // producers track (tap, channel) incrementally instead of dividing per k-block
     long long* kdbg;               // optional per-k-block stamps [cta][num_kb][4]: producer woke / arrived, MMA woke / committed
+    int a_tma;                     // linear layers (the im2col row of sample m is row m of a row-major matrix): A by ONE tensor-map copy
 };
+struct UmmaAMap { alignas(64) unsigned char bytes[128]; };      // CUtensorMap of the activation matrix (a_tma)
 
 // EPI selects the epilogue at compile time: 0 = generic (every option), 1 = lean noisy (main + sigma, Philox z,
 // y_noisy [+ y], no bias / mask / inject / export / stats) -- the training hot path, 2 = lean plain (y only).
@@ -72,7 +74,7 @@ struct UmmaP {
 #endif
 template <int EPI>
 __global__ void __launch_bounds__(UM_THREADS, EPI == 2 ? 3 : (EPI == 1 ? NN_EPI1_MINBLOCKS : 2))
-k_conv_umma(const UmmaP p) {
+k_conv_umma(const UmmaP p, const __grid_constant__ UmmaAMap amap) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int S = p.stages;
@@ -100,7 +102,7 @@ k_conv_umma(const UmmaP p) {
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_bar + 8 * s, 128 + 1);                  // 128 producer arrivals + 1 expect_tx arrival of the weights
+            mbar_init(full_bar + 8 * s, p.a_tma ? 2 : 128 + 1);   // 128 producer arrivals (or 1 expect_tx of the A copy) + 1 expect_tx of the weights
             mbar_init(empty_bar + 8 * s, 1);                       // tcgen05.commit: the stage may be refilled
         }
         mbar_init(tfull_bar, 1);
@@ -115,7 +117,24 @@ k_conv_umma(const UmmaP p) {
     if (dbg && tid == 0) dbg[1] = clock64();
 
     // ================================================================ main loop roles
-    if (warp < 4) {
+    if (warp < 4 && p.a_tma) {
+        // ---------------- A by the copy engine (linear layers): the 128 x 64 tile of the row-major activation matrix is one
+        // cp.async.bulk.tensor.2d into the SWIZZLE_128B stage; rows >= M and columns >= K read as zeros
+        if (warp == 0) {
+            int s = 0;
+            uint32_t ph = 1u;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                if (!mbar_wait(empty_bar + 8 * s, ph)) { *abort_g = 1; break; }
+                if (*abort_g) break;
+                if (elect_one_sync()) {
+                    mbar_arrive_expect_tx(full_bar + 8 * s, UM_A_STAGE);
+                    tma_tile_2d(a_base + (uint32_t)s * UM_A_STAGE, &amap, full_bar + 8 * s, kb * UM_BLOCK_K, m0);
+                }
+                __syncwarp();
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp < 4) {
         // ---------------- A producers.  Lane mapping: 8 consecutive lanes fetch the 8 consecutive 16-byte
         // chunks of ONE tile row (contiguous channels of one tap, 128 B), so a warp instruction touches 4 rows
         // = 4-8 cache lines instead of 32 (the gather is L1-wavefront-bound otherwise).  Thread t owns chunk
@@ -1733,9 +1752,19 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* sp
         if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
         cudaEventRecord(g_ev0, st);
     }
-    if (epi == 1) k_conv_umma<1><<<grid, UM_THREADS, pl.smem_bytes, st>>>(pd);
-    else if (epi == 2) k_conv_umma<2><<<grid, UM_THREADS, pl.smem_bytes, st>>>(pd);
-    else k_conv_umma<0><<<grid, UM_THREADS, pl.smem_bytes, st>>>(pd);
+    UmmaAMap amap;
+    memset(&amap, 0, sizeof(amap));
+    // linear layers: one output position per sample and the kernel covers the whole (unpadded) input map, so the im2col row of
+    // sample m is the sample's packed activation itself = row m of a row-major [B][KH * KW * Cp] matrix
+    if (nn_debug_tma_enable(-1) && p.OH * p.OW == 1 && p.pad == 0 && p.KH == p.H && p.KW == p.W && pd.rows_tile == UM_BLOCK_M &&
+        (((size_t)p.KH * p.KW * p.Cp * 2) % 16) == 0 && ((uintptr_t)p.xp % 16) == 0) {
+        const uint64_t k_total = (uint64_t)p.KH * p.KW * p.Cp;
+        if (nn_tma_encode_rows(&amap, p.xp, (uint64_t)p.M, k_total, k_total * 2)) return 1;
+        pd.a_tma = 1;
+    }
+    if (epi == 1) k_conv_umma<1><<<grid, UM_THREADS, pl.smem_bytes, st>>>(pd, amap);
+    else if (epi == 2) k_conv_umma<2><<<grid, UM_THREADS, pl.smem_bytes, st>>>(pd, amap);
+    else k_conv_umma<0><<<grid, UM_THREADS, pl.smem_bytes, st>>>(pd, amap);
     if (g_time_main) cudaEventRecord(g_ev1, st);
     NN_LAUNCH_OK();
     if (splits > 1) {
