@@ -430,6 +430,8 @@ def run_b200(args):
     bufs = [(torch.empty_like(dev_x[0]), torch.empty_like(dev_y[0])) for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    host_loss = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
 
     def prefetch(i):
         k = i & 1
@@ -455,7 +457,15 @@ def run_b200(args):
                 prefetch(i + 1)
             step_body(bufs[k][0], bufs[k][1])
             consumed[k].record(cur)
-        return loss_out.item()          # device -> host read of the step's result
+        # device -> host read of every step's result: the copy of THIS step's loss into pinned host memory is enqueued behind
+        # the step, and the host reads the PREVIOUS step's value while this one runs (a synchronous .item() per step left the
+        # GPU idle for the host's launch time of the next step)
+        host_loss[k].copy_(loss_out, non_blocking=True)
+        loss_ev[k].record(cur)
+        if i > 0:
+            loss_ev[k ^ 1].synchronize()
+            return float(host_loss[k ^ 1])
+        return None
 
     for k in range(2):
         consumed[k].record(torch.cuda.current_stream())
@@ -467,6 +477,8 @@ def run_b200(args):
     e2.record()
     for i in range(3, 3 + args.steps):
         e2e_step(i, i == 2 + args.steps)
+    loss_ev[(2 + args.steps) & 1].synchronize()        # the last step's loss is on the host before the clock stops
+    e2e_last_loss = float(host_loss[(2 + args.steps) & 1])
     e3.record()
     barrier()
     t2 = torch.tensor([e2.elapsed_time(e3)], device=dev)
@@ -556,7 +568,9 @@ def run_b200(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[precision],
         "data": "synthetic", "config": workload_config(args, world),
-        "e2e": {"value": e2e_val, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "e2e": {"value": e2e_val, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "readback": "loss of every step copied to pinned host memory and read by the host one step later (last one before the clock stops)",
+                "last_loss": e2e_last_loss},
         "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
         "cuda_graph": graph is not None, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "library_baseline": lib_base, "second_variant": other,
         "final_loss": final_loss,

@@ -453,3 +453,30 @@ def test_linearity_and_determinism_at_full_size(dev):
     r4 = ops.noisy_conv_fwd(x1, w, w, None, noise_mode=NOISE_EXTERNAL, current=4.0, scale_dev=sc, want_sigma=True,
                             precision="fp32")
     assert (r1["sigma"] >= 0).all() and torch.allclose(r1["sigma"], 2.0 * r4["sigma"], rtol=1e-5, atol=1e-7)
+
+
+def test_distort_tensor_semantics(dev):
+    """hardware_model.distort_tensor (reference hardware_model.py:426-458, called by the ImageNet models' forward,
+    models/resnet.py:40-55): fixed Gaussian offsets drawn once per tensor slot (--offset), or a fresh uniform
+    multiplicative distortion x * (1 + U(-noise, noise)) per call."""
+    from types import SimpleNamespace
+    from noisynet_b200 import hardware_model as hm
+    torch.manual_seed(0)
+    x = torch.randn(8, 16, 12, 12, device=dev)
+    owner = SimpleNamespace(generate_offsets=True)
+    args = SimpleNamespace(offset=0.1, offset_input=0.0, noise=0.0, debug=False)
+    y1 = hm.distort_tensor(owner, args, x, scale=0.1)
+    assert torch.equal(y1 - x, owner.act1_offsets) or torch.allclose(y1 - x, owner.act1_offsets, atol=1e-6)
+    assert owner.act1_offsets.std().item() == pytest.approx(0.1, rel=0.1) and owner.generate_offsets
+    y2 = hm.distort_tensor(owner, args, x * 2, scale=0.1, stop=True)            # last layer: offsets are frozen afterwards
+    assert not owner.generate_offsets and torch.allclose(y2 - 2 * x, owner.act2_offsets, atol=1e-6)
+    frozen = owner.act1_offsets.clone()
+    y3 = hm.distort_tensor(owner, args, x, scale=0.1)
+    assert torch.equal(owner.act1_offsets, frozen) and torch.allclose(y3, x + frozen, atol=1e-6)
+    # multiplicative distortion (nn_alt_noise kind "distort_act"): |y / x - 1| <= noise, fresh per call, mean ~ 0
+    args = SimpleNamespace(offset=0.0, offset_input=0.0, noise=0.05, debug=False)
+    ya, yb = hm.distort_tensor(owner, args, x), hm.distort_tensor(owner, args, x)
+    r = ya / x - 1.0
+    assert r.abs().max().item() <= 0.05 + 1e-5 and abs(r.mean().item()) < 2e-3
+    assert r.std().item() == pytest.approx(0.05 / 3 ** 0.5, rel=0.05)
+    assert not torch.equal(ya, yb)
