@@ -694,27 +694,8 @@ k_conv_shift(const ShiftP p) {
                 const size_t pbase = (size_t)b * p.Cout * PHW + (size_t)(ih >> 1) * PW + (iw >> 1);      // same for the 4 lanes of a window
                 const bool warp_live = __any_sync(0xffffffffu, row_ok);
                 const int n_fix = ngrp / per_q, g_extra = n_fix * per_q;
-#pragma unroll
-                for (int it = 0; it < SH_POOL_IT; ++it) {
-                    int g4;
-                    if (it < SH_POOL_IT - 1) { g4 = jq + it * per_q; if (it >= n_fix) continue; }
-                    else { g4 = g_extra; if (g4 >= ngrp || (i % per_q) != jq) continue; }
-                    if (!warp_live) continue;
-                    float am[4], as[4];
-                    if (NOISY) tmem_ld4x2(t_lane + (uint32_t)(p.main_col + g4 * 4), t_lane + (uint32_t)(p.sig_col + g4 * 4), am, as);
-                    else tmem_ld4(t_lane + (uint32_t)(p.main_col + g4 * 4), am);
-                    const int nb = g4 * 4;
-                    float z[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (MODE == 1) nn_normal4(rs, grp_row + (uint64_t)g4, z);
-                    float v[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        v[j] = am[j] * y_scale;
-                        if (NOISY) {
-                            const float zz = MODE == 2 ? ((row_ok && nb + j < p.Cout) ? __ldg(p.z_inject + out_row + (size_t)(nb + j) * ohw) : 0.f) : z[j];
-                            v[j] = __fadd_rn(v[j], __fmul_rn(zz, nn_sigma(coef, as[j] * s_scale)));
-                        }
-                    }
+                // window exchange + first maximum + store + statistics of one group's four values (channel w of this lane)
+                auto pool_group = [&](const float (&v)[4], int nb, float& s1, float& s2) {
                     // v[w ^ k] for k = 0..3 (w is a per-thread constant: two predicates)
                     const float s01 = w1 ? v[1] : v[0], s10 = w1 ? v[0] : v[1], s23 = w1 ? v[3] : v[2], s32 = w1 ? v[2] : v[3];
                     const float own = w2 ? s23 : s01;           // v[w]
@@ -732,8 +713,53 @@ k_conv_shift(const ShiftP p) {
                         const size_t o = pbase + (size_t)(nb + w) * PHW;
                         p.pooled[o] = m;
                         p.pool_arg[o] = (uint8_t)a;
-                        st1[it] += m; st2[it] = fmaf(m, m, st2[it]);
+                        s1 += m; s2 = fmaf(m, m, s2);
                     }
+                };
+                auto noisy_values = [&](const float (&am)[4], const float (&as)[4], const float (&z)[4], int nb, float (&v)[4]) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        v[j] = am[j] * y_scale;
+                        if (NOISY) {
+                            const float zz = MODE == 2 ? ((row_ok && nb + j < p.Cout) ? __ldg(p.z_inject + out_row + (size_t)(nb + j) * ohw) : 0.f) : z[j];
+                            v[j] = __fadd_rn(v[j], __fmul_rn(zz, nn_sigma(coef, as[j] * s_scale)));
+                        }
+                    }
+                };
+#pragma unroll
+                for (int it = 0; it < SH_POOL_IT; ++it) {
+                    if (MODE == 1 && (it & 1) == 0 && it + 1 < SH_POOL_IT - 1) {
+                        // two fixed groups per trip where there are two: one TMEM wait, two independent Philox chains
+                        if (it + 1 < n_fix) {
+                            if (!warp_live) continue;
+                            const int ga = jq + it * per_q, gb = ga + per_q;
+                            float am[4], as[4], bm[4], bs[4], za[4], zb[4], va[4], vb[4];
+                            tmem_ld4x4(t_lane + (uint32_t)(p.main_col + ga * 4), t_lane + (uint32_t)(p.sig_col + ga * 4),
+                                       t_lane + (uint32_t)(p.main_col + gb * 4), t_lane + (uint32_t)(p.sig_col + gb * 4), am, as, bm, bs);
+                            nn_normal4(rs, grp_row + (uint64_t)ga, za);
+                            nn_normal4(rs, grp_row + (uint64_t)gb, zb);
+                            noisy_values(am, as, za, ga * 4, va);
+                            noisy_values(bm, bs, zb, gb * 4, vb);
+                            pool_group(va, ga * 4, st1[it], st2[it]);
+                            pool_group(vb, gb * 4, st1[it + 1], st2[it + 1]);
+                            continue;
+                        }
+                    } else if (MODE == 1 && (it & 1) == 1 && it < SH_POOL_IT - 1) {
+                        if (it < n_fix) continue;               // done with its even neighbour
+                    }
+                    int g4;
+                    if (it < SH_POOL_IT - 1) { g4 = jq + it * per_q; if (it >= n_fix) continue; }
+                    else { g4 = g_extra; if (g4 >= ngrp || (i % per_q) != jq) continue; }
+                    if (!warp_live) continue;
+                    float am[4], as[4];
+                    if (NOISY) tmem_ld4x2(t_lane + (uint32_t)(p.main_col + g4 * 4), t_lane + (uint32_t)(p.sig_col + g4 * 4), am, as);
+                    else tmem_ld4(t_lane + (uint32_t)(p.main_col + g4 * 4), am);
+                    const int nb = g4 * 4;
+                    float z[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (MODE == 1) nn_normal4(rs, grp_row + (uint64_t)g4, z);
+                    float v[4];
+                    noisy_values(am, as, z, nb, v);
+                    pool_group(v, nb, st1[it], st2[it]);
                 }
             } else
             // 4-channel groups (one Philox call each), dealt round-robin to the warps of this lane quarter; the deal
@@ -1931,6 +1957,7 @@ static int shift_conv_fwd(const nn_conv_fwd_args* a, const ShiftPlan& sp, int de
     }
     int grid = nn_num_sms(device);
     if (grid > p.n_tiles) grid = p.n_tiles;
+    if (p.stat_partial && grid > 256) grid = 256;         // nn_conv_bn_scratch_bytes holds 256 per-CTA partials
 #ifdef NN_KDEBUG
     static const bool want_dbg = getenv("NN_UMMA_DEBUG") != nullptr;
 #else
