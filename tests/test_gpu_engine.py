@@ -155,6 +155,29 @@ def test_stage_fwd_hot_path_kernels_match_general(dev, shape, pool):
     assert 0.0 < outs[0][0][..., :Cc].mean().item() < 15.0 and torch.all(outs[0][0][..., Cc:] == 0)
 
 
+@pytest.mark.parametrize("B,Cc", [(7, 3), (2, 1), (5, 4)])
+def test_input_quant_pack_hot_path_matches_general(dev, B, Cc):
+    """nn_input_quant_pack: the 4-pixels-per-thread kernel of the training hot path (no fp32 copy) against the general kernel
+    (fp32 copy requested) with the same Philox stream: bit-identical codes; the codes dequantise to the fp32 copy."""
+    from noisynet_b200 import _lib, ops
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(B * 10 + Cc)
+    x = (torch.rand(B, Cc, 32, 32, generator=g)).to(dev)
+    outs = []
+    for want_act in (False, True):
+        xp = torch.full((B, 32, 32, 8), 9.0, dtype=torch.bfloat16, device=dev)
+        act = torch.empty_like(x)
+        _lib.check(lib.nn_input_quant_pack(x.data_ptr(), xp.data_ptr(), act.data_ptr() if want_act else None, B, Cc, 32 * 32, 8, 4, 1.0, 0.5,
+                                           None, ops._fixed_rng(5, 17), 0, torch.cuda.current_stream().cuda_stream), "nn_input_quant_pack")
+        torch.cuda.synchronize()
+        outs.append((xp.float().cpu(), act.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    codes = outs[0][0][..., :Cc].permute(0, 3, 1, 2)
+    assert torch.all(outs[0][0][..., Cc:] == 0) and codes.max() <= 15 and codes.min() >= 0
+    assert torch.allclose(codes * np.float32(1.0 / 15.0), outs[1][1], rtol=0, atol=1e-7)
+    assert (codes - x.cpu() * 15).abs().max() <= 1.0 + 1e-4            # stochastic rounding moves a value by less than one level
+
+
 @pytest.mark.parametrize("shape,pool", [((6, 120, 10, 10), 1), ((3, 65, 28, 28), 1), ((5, 16, 12, 12), 1), ((40, 390, 1, 1), 0)])
 def test_stage_bwd_hot_path_kernels_match_general(dev, shape, pool):
     """nn_stage_bwd without the fp32 copy runs the hot-path kernels (k_bn_bwd_apply_img for pooled NHWC stages whose
