@@ -45,7 +45,14 @@ def _worker(rank, world, port, out_dir, two_buckets=False):
     red.start_early()                                            # async bucket, joined by all_reduce_mean_
     if two_buckets:
         red.start_early(1)
+        # the engine updates the early buckets' parameters before the step's last exchange (optim.FusedAdamW.step_part):
+        # their sums must be complete after wait_early
+        red.wait_early(0)
+        red.wait_early(1)
+        early_now = red.flat[:red.n_early].clone()
     red.all_reduce_mean_()
+    if two_buckets:
+        assert torch.allclose(red.flat[:red.n_early], early_now / world)      # all_reduce_mean_ only rescaled them
     assert red._work is None
     torch.save({"flat": red.flat.clone(), "params": [p.detach().clone() for p in model.parameters()]},
                os.path.join(out_dir, "rank%d.pt" % rank))
