@@ -1299,7 +1299,8 @@ struct WgShiftP {
     int b_pixels, a_stage, b_stage, stages, tmem_cols, order;
     long long total_pixels, plane_stride;   // plane_stride = total_pixels rounded up to WS_KP (zeros in the padding)
     const __nv_bfloat16 *xp, *gyv;
-    float* partial;                         // [gridDim.x][Cout][KH*KW*8]
+    float* partial;                         // [gridDim.x][Cout][row_pitch], column tap * 8 + c
+    int row_pitch;
     int* err_flag;
     long long* dbg;                         // optional [cta][32 chunks][4]: before wait, operands landed, MMAs issued
 };
@@ -1425,8 +1426,7 @@ k_wgrad_shift(const WgShiftP p) {
         if (!ok) *abort_g = 3;
         const int q = warp & 3;
         const int n = q * 32 + lane;
-        const int kcols = p.KH * p.KW * 8;
-        float* dst = p.partial + ((size_t)blockIdx.x * p.Cout + n) * kcols;
+        float* dst = p.partial + ((size_t)blockIdx.x * p.Cout + n) * p.row_pitch;      // row pitch 256: k_wgrad_tma_reduce's tail format
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         if (ok && !*abort_g) {
             for (int kh = 0; kh < p.KH; ++kh)
@@ -2471,7 +2471,10 @@ bool make_wg_shift_plan(const nn_conv_geom& g, int device, WgShiftPlan* out) {
     if (w.grid > w.n_chunks) w.grid = w.n_chunks;
     w.xp_bytes = (size_t)total * 16;
     w.gyv_bytes = (size_t)w.n_planes * w.plane_stride * 16;
-    w.partial_bytes = (size_t)w.grid * g.Cout * g.KH * g.KW * 8 * sizeof(float);
+    {   // rows of 256 columns (k_wgrad_tma_reduce's remainder format) when the taps fit, else packed rows
+        const int kc = g.KH * g.KW * 8;
+        w.partial_bytes = (size_t)w.grid * g.Cout * (kc <= 256 ? 256 : kc) * sizeof(float);
+    }
     if (out) *out = w;
     return true;
 }
@@ -2568,11 +2571,28 @@ static int shift_conv_wgrad(const nn_conv_wgrad_args* a, const WgShiftPlan& w, i
         p.dbg = g_dbg_buf;
         g_dbg_last = rows;
     }
+    const int kcols = g.KH * g.KW * 8;
+    p.row_pitch = kcols <= 256 ? 256 : kcols;
     k_wgrad_shift<<<w.grid, WS_THREADS, w.smem_bytes, st>>>(p);
     NN_LAUNCH_OK();
-    const int kcols = g.KH * g.KW * 8;
-    const int64_t n = (int64_t)g.Cout * kcols;
     const float scale = a->a_code_scale > 0.f ? a->a_code_scale : 1.f;
+    if (kcols <= 256) {
+        // the per-CTA partials are [grid][Cout][256] with column tap * 8 + c: the remainder format of k_wgrad_tma_reduce
+        // (float4 loads, groups of partials per block; w.grid = 2 x SMs partials is a long chain for one thread)
+        WgRedP r;
+        memset(&r, 0, sizeof(r));
+        r.tail = partial; r.n_tail = w.grid; r.Cout = g.Cout; r.Cin = g.Cin; r.KHW = g.KH * g.KW; r.n_c64 = 0; r.cols_pad = 0;
+        r.scale = scale; r.lo = (float)a->w_lo; r.hi = (float)a->w_hi; r.gw = a->gw; r.w_raw = a->w_raw;
+        r.nb_main = 0; r.g_main = 1;
+        const int64_t q_tail = (int64_t)g.Cout * 64;
+        int G = 1;
+        while (G < 32 && q_tail * G < 131072 && r.n_tail >= 8 * G) G <<= 1;
+        r.g_tail = G;
+        k_wgrad_tma_reduce<<<(int)((q_tail + 256 / G - 1) / (256 / G)), 256, 0, st>>>(r);
+        NN_LAUNCH_OK();
+        return 0;
+    }
+    const int64_t n = (int64_t)g.Cout * kcols;
     int rb = (int)((n + 31) / 32);
     if (rb > 16 * sms) rb = 16 * sms;
     k_wgrad_umma_reduce2<<<rb, 256, 0, st>>>(partial, w.grid, g.Cout, g.Cin, g.KH * g.KW, 8, kcols, scale, a->gw, a->w_raw,
