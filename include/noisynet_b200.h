@@ -193,6 +193,10 @@ typedef struct nn_conv_fwd_args {
     float* zero_out;         /* optional device float set to 0 by the launch (the max-accumulator of the next stage) */
 } nn_conv_fwd_args;
 int64_t nn_conv_bn_scratch_bytes(int Cout);
+/* bn_mean is also served for LINEAR layers whose launch is split over K (fully connected layers at training batch sizes:
+ * the split-K epilogue adds the per-channel sums; BatchNorm1d, noisynet.py:540-546): 1 if this geometry qualifies.  There
+ * bn_scratch is nn_stage_scratch_bytes(Cout) bytes (the stage kernels' scratch can be shared), zeroed once. */
+int nn_conv_linear_bn_fusable(const nn_conv_geom* g, int32_t noise_mode, int32_t precision, int device);
 
 /* Packed-weight layouts.  NN_PACK_TILED: 128B-swizzled [n-tile][k-block] shared-memory images (every geometry).
  * NN_PACK_SHIFT: [tap][row][8] image of the persistent shift-GEMM forward kernel, served for stride-1 unpadded

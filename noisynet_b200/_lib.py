@@ -135,6 +135,7 @@ SIGNATURES = {
     "nn_prepare_weights": (C.c_int, [C.POINTER(WPrepJob), C.c_int, C.c_int, C.c_void_p]),
     "nn_stage_scratch_bytes": (C.c_int64, [C.c_int]),
     "nn_conv_bn_scratch_bytes": (C.c_int64, [C.c_int]),
+    "nn_conv_linear_bn_fusable": (C.c_int, [C.POINTER(ConvGeom), C.c_int32, C.c_int32, C.c_int]),
     "nn_stage_fwd": (C.c_int, [C.POINTER(StageArgs), C.c_int, C.c_void_p]),
     "nn_stage_bwd": (C.c_int, [C.POINTER(StageBwdArgs), C.c_int, C.c_void_p]),
     "nn_input_quant_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

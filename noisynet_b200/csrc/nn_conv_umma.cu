@@ -62,6 +62,10 @@ struct UmmaP {
     int inc_taps;                  // producers track (tap, channel) incrementally instead of dividing per k-block
     long long* kdbg;               // optional per-k-block stamps [cta][num_kb][4]: producer woke / arrived, MMA woke / committed
     int a_tma;                     // linear layers (the im2col row of sample m is row m of a row-major matrix): A by ONE tensor-map copy
+    // optional (split-K linear layers): BatchNorm batch statistics of the output from the split-K epilogue (nn_conv_fwd_args.bn_mean)
+    BnFinP bn_fin;                 // bn_fin.mean != nullptr selects it
+    void* bn_scratch;              // nn_stage_scratch_bytes(Cout): [Cout][16][2] double partial sums, then [Cout] arrival counters
+    float* zero_out;
 };
 struct UmmaAMap { alignas(64) unsigned char bytes[128]; };      // CUtensorMap of the activation matrix (a_tma)
 
@@ -426,6 +430,10 @@ k_conv_umma(const UmmaP p, const __grid_constant__ UmmaAMap amap) {
 struct SplitEpiP {
     const float* partial; int splits, n_tiles, n_mma, n_t, main_col, sig_col, m_pad, M, Cout;
     float y_scale, s_scale, current; const float* scale_dev; nn_rng rng; float *y, *y_noisy; int noisy;
+    // optional: per-channel sums of the outputs (the BatchNorm1d that follows a fully connected layer, noisynet.py:540-546).
+    // Needs M % 256 == 0 and one block per 256 rows of one 4-channel group: the block is slice blockIdx.x % (M / 256) of its
+    // four channels; the last slice of a channel finalizes it (fixed order: deterministic).
+    double* stat_partial; unsigned* stat_counters; BnFinP fin; float* zero_out;
 };
 __global__ void __launch_bounds__(256)
 k_splitk_epilogue(const SplitEpiP p) {
@@ -450,12 +458,42 @@ k_splitk_epilogue(const SplitEpiP p) {
         float zz[4] = {0.f, 0.f, 0.f, 0.f};
         if (p.noisy) nn_normal4(rs, (uint64_t)m * ngrp + (uint64_t)g, zz);
         float* o = (p.noisy ? p.y_noisy : p.y) + (size_t)m * p.Cout + n0;
+        float ov[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (n0 + j < p.Cout) {
                 const float yv = am[j] * p.y_scale;
-                o[j] = p.noisy ? __fadd_rn(yv, __fmul_rn(zz[j], nn_sigma(coef, as[j] * p.s_scale))) : yv;
+                ov[j] = p.noisy ? __fadd_rn(yv, __fmul_rn(zz[j], nn_sigma(coef, as[j] * p.s_scale))) : yv;
+                o[j] = ov[j];
                 if (p.noisy && p.y) p.y[(size_t)m * p.Cout + n0 + j] = yv;
+            }
+        }
+        if (p.stat_partial) {
+            // (the host launched exactly one trip per thread: this block = 256 consecutive rows of group g)
+            __shared__ double sh[8][8];
+            const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double s1 = (double)ov[j], s2 = (double)ov[j] * (double)ov[j];
+#pragma unroll
+                for (int o2 = 16; o2 > 0; o2 >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o2); s2 += __shfl_xor_sync(0xffffffffu, s2, o2); }
+                if (lane == 0) { sh[wi][2 * j] = s1; sh[wi][2 * j + 1] = s2; }
+            }
+            __syncthreads();
+            if (threadIdx.x < 4 && n0 + (int)threadIdx.x < p.Cout) {
+                const int j = threadIdx.x, c = n0 + j, slices = p.M >> 8, slice = (m >> 8);
+                double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { a1 += sh[w][2 * j]; a2 += sh[w][2 * j + 1]; }
+                double* part = p.stat_partial + (size_t)c * slices * 2;
+                part[slice * 2] = a1; part[slice * 2 + 1] = a2;
+                __threadfence();
+                if (atomicAdd(p.stat_counters + c, 1u) == (unsigned)slices - 1u) {
+                    p.stat_counters[c] = 0u;
+                    __threadfence();
+                    bn_finalize_channel(part, slices, 2, c, p.fin);
+                    if (c == 0 && p.zero_out) *p.zero_out = 0.f;
+                }
             }
         }
     }
@@ -1800,9 +1838,17 @@ static int launch_umma(const UmmaP& p, const Plan& pl, cudaStream_t st, void* sp
         e.main_col = pl.main_col; e.sig_col = pl.sig_col; e.m_pad = pd.m_pad; e.M = p.M; e.Cout = p.Cout;
         e.y_scale = p.y_scale; e.s_scale = p.s_scale; e.current = p.current; e.scale_dev = p.scale_dev; e.rng = p.rng;
         e.y = p.y; e.y_noisy = p.y_noisy; e.noisy = epi == 1;
+        if (p.bn_fin.mean) {
+            if (p.M % 256) return nn_fail("nn_noisy_conv_fwd: bn_mean on a linear layer needs a batch that is a multiple of 256%s", "");
+            e.stat_partial = (double*)p.bn_scratch;
+            e.stat_counters = (unsigned*)(e.stat_partial + (size_t)p.Cout * 16 * 2);
+            e.fin = p.bn_fin; e.fin.count = (double)p.M; e.zero_out = p.zero_out;
+        }
         const int total = p.M * ((p.Cout + 3) / 4);
         k_splitk_epilogue<<<(total + 255) / 256, 256, 0, st>>>(e);
         NN_LAUNCH_OK();
+    } else if (p.bn_fin.mean) {
+        return nn_fail("nn_noisy_conv_fwd: bn_mean on a linear layer is served by the split-K epilogue only%s (see nn_conv_linear_bn_fusable)", "");
     }
     return 0;
 }
@@ -2018,6 +2064,18 @@ extern "C" int nn_conv_pool_fusable(const nn_conv_geom* g, int32_t noise_mode, i
     const int ngrp = (g->Cout + 3) / 4;      // 16 epilogue warps: 4 per lane quarter; fixed groups + at most one rotating group
     return g->W % 8 == 0 && g->H % 16 == 0 && OH % 2 == 0 && OW % 2 == 0 && ngrp / 4 <= SH_POOL_IT - 1 && ngrp % 4 <= 1;
 }
+// 1 if nn_noisy_conv_fwd serves bn_mean for this LINEAR layer (its split-K epilogue adds the per-channel sums): the launch must be
+// split (few CTAs, >= 8 k-blocks) and the batch a multiple of 256 (<= 4096)
+extern "C" int nn_conv_linear_bn_fusable(const nn_conv_geom* g, int32_t noise_mode, int32_t precision, int device) {
+    if (!g || precision != NN_PREC_BF16) return 0;
+    int OH, OW;
+    nn_out_hw(*g, OH, OW);
+    const int M = g->B * OH * OW;
+    if (OH * OW != 1 || M % 256 || M > 4096) return 0;
+    const Plan pl = make_plan(g->Cin, g->KH * g->KW, g->Cout, true, noise_mode != NN_NOISE_NONE, false, (int64_t)g->B * g->H * g->W, (M + 127) / 128);
+    const int ctas = ((M + UM_BLOCK_M - 1) / UM_BLOCK_M) * pl.n_tiles;
+    return ctas * 2 <= nn_num_sms(device) && pl.num_kb >= 8 && pl.num_kb / 2 >= 4;
+}
 // [ticket | per-CTA partial sums of the pooled values]: 16 + SMs x Cout x 2 doubles (sized for 256 CTAs)
 extern "C" int64_t nn_conv_bn_scratch_bytes(int Cout) { return 16 + (int64_t)256 * Cout * 2 * sizeof(double); }
 extern "C" int nn_debug_shift_enable(int enable) {
@@ -2041,7 +2099,7 @@ static bool tma_fwd_plan(const nn_conv_fwd_args* a, TmaPlan* tp) {
     nn_out_hw(g, OH, OW);
     const bool noise = a->noise_mode != NN_NOISE_NONE;
     const bool has_main = a->w_eff != nullptr || a->w_packed != nullptr;
-    const bool lean = has_main && !a->bias && !a->z_export && !a->sigma_export && !a->stats && !a->pooled_out && !(noise && a->y);
+    const bool lean = has_main && !a->bias && !a->z_export && !a->sigma_export && !a->stats && !a->pooled_out && !a->bn_mean && !(noise && a->y);
     return lean && nn_tma_make_plan(g.Cin, g.KH, g.KW, g.stride, g.pad, g.Cout, noise, OH, OW, tp);
 }
 
@@ -2179,6 +2237,16 @@ int nn_umma_conv_fwd(const nn_conv_fwd_args* a, int device, cudaStream_t st) {
     p.noise_mode = a->noise_mode; p.current = a->current; p.scale_dev = a->scale_dev; p.z_inject = a->z_inject;
     p.z_export = a->z_export; p.sigma_export = a->sigma_export; p.stats = a->stats; p.rng = a->rng;
     p.mask_x = nullptr; p.err_flag = err;
+    if (a->bn_mean && !a->pooled_out) {       // BatchNorm1d statistics of a linear layer's output from the split-K epilogue
+        if (!a->bn_invstd || !a->bn_scratch) return nn_fail("nn_noisy_conv_fwd: bn_mean needs bn_invstd and bn_scratch%s", "");
+        if (a->bn_eval_mode && (!a->bn_running_mean || !a->bn_running_var))
+            return nn_fail("nn_noisy_conv_fwd: bn_eval_mode needs the running statistics%s", "");
+        if (g.Cout > 0 && ((g.B * OH * OW) >> 8) > 16) return nn_fail("nn_noisy_conv_fwd: bn_mean on a linear layer serves batches up to 4096%s", "");
+        p.bn_fin.mean = a->bn_mean; p.bn_fin.invstd = a->bn_invstd; p.bn_fin.running_mean = a->bn_running_mean;
+        p.bn_fin.running_var = a->bn_running_var; p.bn_fin.eps = a->bn_eps; p.bn_fin.momentum = a->bn_momentum;
+        p.bn_fin.eval_mode = a->bn_eval_mode; p.bn_fin.xmax_out = nullptr;
+        p.bn_scratch = a->bn_scratch; p.zero_out = a->zero_out;
+    }
     // what is left of the workspace after the operand packs serves the split-K partial sums
     uint8_t* rest = ws + align_up(pl.xp_bytes, 1024) + align_up(pl.wp_bytes, 1024);
     uint8_t* ws_end = (uint8_t*)a->workspace + a->workspace_bytes;

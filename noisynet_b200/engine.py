@@ -115,6 +115,10 @@ class NoisyNetEngine:
         self.fuse_pool1 = bool(self.lib.nn_conv_pool_fusable(C.byref(self.geom[0]), self.noise_modes[0], PREC_BF16)) and \
             os.environ.get("NN_ENGINE_FUSE_POOL", "1") == "1"
         self.bn_scratch = torch.zeros(int(self.lib.nn_conv_bn_scratch_bytes(C1)), dtype=torch.uint8, device=dev)
+        # fc1's split-K epilogue also adds the per-channel sums of bn3 (the separate statistics pass is one launch less)
+        self.fuse_bn3 = bool(self.lib.nn_conv_linear_bn_fusable(C.byref(self.geom[2]), self.noise_modes[2], PREC_BF16, self.di)) and \
+            os.environ.get("NN_ENGINE_FUSE_BN3", "1") == "1"
+        self.bn3_scratch = torch.zeros(int(self.lib.nn_stage_scratch_bytes(FC)) + 64, dtype=torch.uint8, device=dev)
         self.gy1_layout = self.lib.nn_conv_wgrad_pack_layout(C.byref(self.geom[0]), PREC_BF16, self.di)
         if self.gy1_layout:
             nbytes = int(self.lib.nn_conv_gy_planes_bytes(C.byref(self.geom[0])))
@@ -263,11 +267,11 @@ class NoisyNetEngine:
         if pooled is not None:                  # MaxPool2d(2,2) fused into the conv epilogue: the full-size output is never written
             a.y, a.y_noisy = None, None
             a.pooled_out, a.argmax_out = _p(pooled), _p(argmax)
-            if bn is not None:                  # ... and the BatchNorm statistics of the pooled output come from the same launch
-                a.bn_mean, a.bn_invstd = _p(self.stat[key][0]), _p(self.stat[key][1])
-                a.bn_running_mean, a.bn_running_var = _p(bn.running_mean), _p(bn.running_var)
-                a.bn_eps, a.bn_momentum, a.bn_eval_mode = float(bn.eps), float(bn.momentum), 1 if eval_mode else 0
-                a.bn_scratch, a.zero_out = _p(self.bn_scratch), _p(zero)
+        if bn is not None:                      # the BatchNorm statistics of the (pooled) output come from the same launch
+            a.bn_mean, a.bn_invstd = _p(self.stat[key][0]), _p(self.stat[key][1])
+            a.bn_running_mean, a.bn_running_var = _p(bn.running_mean), _p(bn.running_var)
+            a.bn_eps, a.bn_momentum, a.bn_eval_mode = float(bn.eps), float(bn.momentum), 1 if eval_mode else 0
+            a.bn_scratch, a.zero_out = _p(self.bn_scratch if pooled is not None else self.bn3_scratch), _p(zero)
         a.precision = PREC_BF16
         a.a_code_scale, a.w_code_scale = a_cs, self.w_cs[idx]
         a.workspace, a.workspace_bytes = _p(self.ws), self.ws.numel()
@@ -415,8 +419,14 @@ class NoisyNetEngine:
             torch.cuda.current_stream(di).wait_stream(self.side)
         self._fwd_gemm(1, self.xp2, s2, self.y2n, self.noise_modes[1], self.xmax2, self._take("z"))
         self._stage_fwd(self.y2n, C2, H2, 1, self.pool2, self.amax2, m.bn2, "bn2", a.q_a3, qh3, self.xp3, None, self._take("u"), act_max=am2)
-        self._fwd_gemm(2, self.xp3, s3, self.l1n, self.noise_modes[2], self._absmax(2, W[2]), self._take("z"))
-        self._stage_fwd(self.l1n, FC, 1, 0, None, None, m.bn3, "bn3", a.q_a4, qh4, self.xp4, self.xmax4, self._take("u"), act_max=am3)
+        z3 = self._take("z")
+        if self.fuse_bn3 and z3 is None:        # (injected draws run the general epilogue, which is not split over K)
+            self._fwd_gemm(2, self.xp3, s3, self.l1n, self.noise_modes[2], self._absmax(2, W[2]), None, bn=m.bn3, key="bn3", zero=self.xmax4)
+            self._stage_fwd(self.l1n, FC, 1, 0, None, None, m.bn3, "bn3", a.q_a4, qh4, self.xp4, self.xmax4, self._take("u"), act_max=am3,
+                            stats_ready=True)
+        else:
+            self._fwd_gemm(2, self.xp3, s3, self.l1n, self.noise_modes[2], self._absmax(2, W[2]), z3)
+            self._stage_fwd(self.l1n, FC, 1, 0, None, None, m.bn3, "bn3", a.q_a4, qh4, self.xp4, self.xmax4, self._take("u"), act_max=am3)
         bn4 = m.bn4
         if self.fused_tail:
             # fc2 forward + noise, bn4, cross entropy, their backward and the fc2 dgrad: one 8-CTA cluster launch

@@ -133,3 +133,53 @@ def test_full_size_conv2_properties(dev):
     assert torch.equal(ys, y[sl])
     y2 = ops.noisy_conv_fwd(xd, -wqd, precision="bf16", a_code_scale=s_a, w_code_scale=1 / 15.0)["y"]
     assert torch.equal(y2, -y)
+
+
+def test_linear_bn_statistics_from_splitk_epilogue(dev):
+    """bn_mean on a fully connected layer (nn_conv_linear_bn_fusable): the split-K epilogue adds the per-channel sums of its
+    output, the last slice finalizes -- mean / invstd / running statistics against torch on the output the same launch
+    wrote, twice in a row (self-resetting counters), and the zero_out side effect."""
+    import ctypes as C
+    from noisynet_b200 import _lib, ops
+    from noisynet_b200._lib import NOISE_MERGED, PREC_BF16, ConvFwdArgs, ConvGeom
+    lib = _lib.load()
+    B, K, N = 512, 3000, 390
+    g = ConvGeom(B, K, 1, 1, N, 1, 1, 1, 0)
+    assert lib.nn_conv_linear_bn_fusable(C.byref(g), NOISE_MERGED, PREC_BF16, 0) == 1
+    assert lib.nn_conv_linear_bn_fusable(C.byref(ConvGeom(500, K, 1, 1, N, 1, 1, 1, 0)), NOISE_MERGED, PREC_BF16, 0) == 0
+    gen = torch.Generator().manual_seed(3)
+    s_a = 5.0 / 15.0
+    ka, x = _codes((B, K, 1, 1), gen, s_a)
+    cw, wq = _wcodes((N, K, 1, 1), gen)
+    w_raw = torch.randn(N, K, 1, 1, generator=gen) * 0.05
+    xd, wqd, wrd = x.to(dev), wq.to(dev), w_raw.to(dev)
+    scale = ops.tensor_stats(wrd)[1:2]
+    y = torch.empty(B, N, 1, 1, device=dev)
+    mean, invstd = torch.empty(N, device=dev), torch.empty(N, device=dev)
+    rm, rv = torch.zeros(N, device=dev), torch.ones(N, device=dev)
+    scratch = torch.zeros(int(lib.nn_stage_scratch_bytes(N)) + 64, dtype=torch.uint8, device=dev)
+    zero = torch.full((1,), 3.0, device=dev)
+    ws = torch.empty(int(lib.nn_conv_workspace_bytes(C.byref(g), PREC_BF16)) + 4096, dtype=torch.uint8, device=dev)
+    a = ConvFwdArgs()
+    a.g = g
+    a.x, a.w_eff, a.w_raw, a.y_noisy = xd.data_ptr(), wqd.data_ptr(), wrd.data_ptr(), y.data_ptr()
+    a.noise_mode, a.current, a.scale_dev, a.rng = NOISE_MERGED, 1.0, scale.data_ptr(), ops._fixed_rng(4, 4)
+    a.precision, a.a_code_scale, a.w_code_scale = PREC_BF16, s_a, 1.0 / 15.0
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    a.bn_mean, a.bn_invstd, a.bn_running_mean, a.bn_running_var = mean.data_ptr(), invstd.data_ptr(), rm.data_ptr(), rv.data_ptr()
+    a.bn_eps, a.bn_momentum, a.bn_eval_mode, a.bn_scratch, a.zero_out = 1e-5, 0.1, 0, scratch.data_ptr(), zero.data_ptr()
+    for rep in range(2):
+        zero.fill_(3.0)
+        _lib.check(lib.nn_noisy_conv_fwd(C.byref(a), 0, torch.cuda.current_stream().cuda_stream), "nn_noisy_conv_fwd")
+        assert ops.error_flag() == 0
+        yy = y.view(B, N).double()
+        m_ref, v_ref = yy.mean(0), yy.var(0, unbiased=False)
+        assert torch.allclose(mean.double(), m_ref, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(invstd.double(), 1.0 / torch.sqrt(v_ref + 1e-5), rtol=1e-5)
+        assert zero.item() == 0.0
+    assert torch.allclose(rm.double(), (0.9 * 0.1 + 0.1) * m_ref, rtol=1e-4, atol=1e-6)       # two updates from 0 with the same batch
+    # the same call without bn_mean writes the same output (same Philox stream)
+    y2 = torch.empty_like(y)
+    a.y_noisy, a.bn_mean = y2.data_ptr(), None
+    _lib.check(lib.nn_noisy_conv_fwd(C.byref(a), 0, torch.cuda.current_stream().cuda_stream), "nn_noisy_conv_fwd")
+    assert torch.equal(y, y2)
