@@ -45,7 +45,8 @@ class NoisyNetEngine:
         if max(self.q_w) > 7:
             raise ValueError("NoisyNetEngine: weight codes are int8 (q_w <= 7)")
         if a.use_bias or a.dropout > 0 or a.dropout_conv > 0:
-            raise NotImplementedError("NoisyNetEngine: bias / dropout are served by the module path (net.NoisyNet), not the engine")
+            raise NotImplementedError("NoisyNetEngine: bias / dropout are served by the module path (net.NoisyNet(fused=True), or the "
+                                      "unchanged script on the drop-in modules), not the engine")
         if any(getattr(a, k, 0) for k in ("distort_act", "uniform_ind", "uniform_dep", "normal_ind", "normal_dep")):
             raise NotImplementedError("NoisyNetEngine: alternative noise models are served by the module path")
         for li, mod in enumerate((model.conv1, model.conv2, model.linear1, model.linear2)):

@@ -73,6 +73,8 @@ class NoisyNet(nn.Module):
         self.bn2 = nn.BatchNorm2d(a.fm2 * a.width, track_running_stats=a.track_running_stats)
         self.bn3 = nn.BatchNorm1d(a.fc * a.width, track_running_stats=a.track_running_stats)
         self.bn4 = nn.BatchNorm1d(10, track_running_stats=a.track_running_stats)
+        if a.dropout > 0 or a.dropout_conv > 0:     # noisynet.py:375-376 (the script creates it for --dropout only and then
+            self.dropout = nn.Dropout(p=a.dropout)   # fails on --dropout_conv alone; here p = --dropout in both cases)
         for m in (self.conv1, self.conv2, self.linear1, self.linear2):
             m.precision = precision
         self.power = [[] for _ in range(4)]
@@ -147,12 +149,16 @@ class NoisyNet(nn.Module):
         h = self.relu(h)                                                       # :430
         if a.act_max1 > 0:
             h = torch.clamp(h, max=a.act_max1)                                 # :438
+        if a.dropout_conv > 0:
+            h = self.dropout(h)                                                # :456-457
         if a.q_a2 > 0:
             h = self.quantize2(h)                                              # :460
         h = self._layer(h, self.conv2, 1, "conv", False, i)                    # :462-481
         h = self.relu(self.bn2(self.pool(h)))
         if a.act_max2 > 0:
             h = torch.clamp(h, max=a.act_max2)
+        if a.dropout > 0:
+            h = self.dropout(h)                                                # :512-513
         h = h.view(h.size(0), -1)                                              # :515
         if a.q_a3 > 0:
             h = self.quantize3(h)                                              # :520
@@ -160,6 +166,8 @@ class NoisyNet(nn.Module):
         h = self.relu(self.bn3(h))
         if a.act_max3 > 0:
             h = torch.clamp(h, max=a.act_max3)
+        if a.dropout > 0:
+            h = self.dropout(h)                                                # :565-566
         if a.q_a4 > 0:
             h = self.quantize4(h)                                              # :569
         h = self._layer(h, self.linear2, 3, "linear", False, i)                # :571-591

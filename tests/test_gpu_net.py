@@ -145,6 +145,39 @@ def test_training_reduces_loss(dev):
     assert all(np.isfinite(losses))
 
 
+def test_training_with_dropout_module_path(dev):
+    """--dropout / --dropout_conv (noisynet.py:456, :512, :565: nn.Dropout between clamp and the next quantizer; quantize3's
+    range is act_max / (1 - p), :346) on the module path: trains, drops ~p of the activations in train mode and nothing in eval."""
+    from noisynet_b200.net import NoisyNet, default_args, init_like_reference, make_optimizer, train_step, with_quant
+    torch.manual_seed(0)
+    a = with_quant(default_args(dropout=0.2, dropout_conv=0.2), 4, 4)
+    nm = init_like_reference(NoisyNet(a, fused=True)).to(dev)
+    assert nm.quantize3.max_value == pytest.approx(5.0 / 0.8)
+    nm.quantize2.running_max = torch.tensor(5.0, device=dev)
+    nm.quantize4.running_max = torch.tensor(5.0, device=dev)
+    nm.collect_stats = False
+    opt = make_optimizer(nm, a)
+    g = torch.Generator().manual_seed(3)
+    protos = torch.randint(0, 16, (10, 3, 32, 32), generator=g).float() / 15
+    lab = torch.randint(0, 10, (256,), generator=g)
+    x = (protos[lab] * 0.7 + 0.3 * torch.randint(0, 16, (256, 3, 32, 32), generator=g).float() / 15)
+    x = ((x * 15).round() / 15).to(dev)
+    lab = lab.to(dev)
+    seen = {}
+    hook = nm.dropout.register_forward_hook(                # fraction of the nonzero activations that were dropped
+        lambda m, i, o: seen.setdefault("z", []).append((((o == 0) & (i[0] != 0)).sum() / (i[0] != 0).sum().clamp(min=1)).item()))
+    nm.train()
+    losses = [train_step(nm, opt, x, lab, i=100 + s)[0].item() for s in range(30)]
+    assert losses[-1] < 0.6 * losses[0] and all(np.isfinite(losses)), losses
+    assert len(seen["z"]) == 90 and all(0.15 < f < 0.25 for f in seen["z"][-3:])            # three dropout sites per step
+    seen["z"] = []
+    nm.eval()
+    with torch.no_grad():
+        nm(x, 0, 100)
+    hook.remove()
+    assert all(f == 0.0 for f in seen["z"])
+
+
 def test_fused_adamw_matches_torch(dev):
     """nn_adamw_step == torch.optim.AdamW + clamp_ over several steps (rtol 1e-5), incl. per-group lr / weight
     decay, the fused clamp and the max|W| side output."""
