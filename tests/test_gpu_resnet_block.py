@@ -137,3 +137,38 @@ def test_basic_block_matches_oracle(dev, stride, precision):
     for i, m in enumerate((blk.bn1, blk.bn2, blk.bn3)):
         close(m.weight.grad, bo[i][0].grad, rel, "dgamma%d" % i)
         close(m.bias.grad, bo[i][1].grad, rel, "dbeta%d" % i)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_batchnorm_folded_into_noisy_conv_inference(dev, precision):
+    """main.py:540-654 (merge_batchnorm, the ImageNet drivers' inference mode): the BatchNorm scale gamma / sqrt(var + eps) is
+    multiplied into the conv weights through the state_dict (same keys as the reference's modules) and the shift
+    beta - mean * scale becomes the conv bias, so that conv'(x) == bn_eval(conv(x)).  Exercises the bias path of
+    nn_noisy_conv_fwd on the drop-in NoisyConv2d (3x3 pad 1 and 1x1 stride 2, unquantized weights as in merge mode)."""
+    from noisynet_b200 import ops
+    from noisynet_b200.hardware_model import NoisyConv2d
+    gen = torch.Generator().manual_seed(4)
+    for (Cin, Cout, k, s, p) in ((16, 32, 3, 1, 1), (32, 48, 1, 2, 0)):
+        kw = dict(num_bits=0, num_bits_weight=0, noise=0.0, test_noise=0.0, stochastic=0.0)
+        conv = NoisyConv2d(Cin, Cout, kernel_size=k, stride=s, padding=p, bias=False, **kw).to(dev)
+        bn = nn.BatchNorm2d(Cout).to(dev)
+        with torch.no_grad():
+            conv.weight.copy_(torch.randn(conv.weight.shape, generator=gen) * 0.2)
+            bn.weight.copy_(torch.rand(Cout, generator=gen) + 0.5); bn.bias.copy_(torch.randn(Cout, generator=gen) * 0.3)
+            bn.running_mean.copy_(torch.randn(Cout, generator=gen) * 0.2); bn.running_var.copy_(torch.rand(Cout, generator=gen) + 0.3)
+        conv.precision = precision
+        conv.eval(); bn.eval()
+        x = torch.randn(4, Cin, 12, 12, generator=gen).to(dev)
+        with torch.no_grad():
+            ref = bn(conv(x))
+            merged = NoisyConv2d(Cin, Cout, kernel_size=k, stride=s, padding=p, bias=True, **kw).to(dev)
+            merged.precision = precision
+            merged.eval()
+            sd = merged.state_dict()
+            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            sd["weight"].copy_(conv.weight * scale.view(-1, 1, 1, 1))            # main.py:598: param.data *= bn_weight / sqrt(var + eps)
+            sd["bias"].copy_(bn.bias - bn.running_mean * scale)
+            out = merged(x)
+        assert ops.error_flag() == 0
+        tol = (2e-5 if precision == "fp32" else 1.5e-2) * ref.abs().max().item()
+        assert (out - ref).abs().max().item() <= tol, (precision, k, (out - ref).abs().max().item(), tol)
